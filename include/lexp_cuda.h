@@ -1,0 +1,134 @@
+/* lexp_cuda.h -- C-ABI of the B200-native unary-cost engine for Local Expansion Stereo.
+ *
+ * This is the drop-in boundary for ONE path of t-taniai/LocalExpStereo: the per-cell
+ * slanted-plane unary cost evaluation + guided-filter aggregation.  Every entry point
+ * names the reference interface it replaces (paths relative to
+ * /root/reference/LocalExpansionStereo/).  Plain C types only; no torch / OpenCV types.
+ * All functions return 0 on success and a negative lexp_status on failure;
+ * lexp_last_error() returns a thread-local message.  There is NO CPU fallback: every
+ * evaluation runs hand-written sm_100a kernels, or fails.
+ *
+ * Threading: a context may be used from several host threads (the reference calls the
+ * virtuals from OpenMP threads, FastGCStereo.h:30-49); calls are serialised internally.
+ */
+#ifndef LEXP_CUDA_H_
+#define LEXP_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LEXP_API __declspec(dllexport)
+#else
+#define LEXP_API __attribute__((visibility("default")))
+#endif
+
+typedef enum lexp_status {
+    LEXP_OK = 0,
+    LEXP_ERR_INVALID = -1, /* bad argument / precondition violated        */
+    LEXP_ERR_CUDA = -2,    /* CUDA runtime error (message in last_error)   */
+    LEXP_ERR_STATE = -3,   /* images / volume not uploaded yet             */
+    LEXP_ERR_NOMEM = -4
+} lexp_status;
+
+/* cv::Rect layout (x, y, width, height), image coordinates. */
+typedef struct lexp_rect { int x, y, width, height; } lexp_rect;
+
+/* struct Plane {a,b,c,v}  (Plane.h:4-8); d(x,y) = a*x + b*y + c (Plane.h:51-58). */
+typedef struct lexp_plane { float a, b, c, v; } lexp_plane;
+
+/* Subset of `struct Parameters` (StereoEnergy.h:13-40) + the CostVolumeEnergy constructor
+ * arguments (CostVolumeEnergy.h:16) that the unary path uses. */
+typedef struct lexp_params {
+    int height, width;  /* image size (imL.rows, imL.cols)                                    */
+    int ndisp;          /* D = vol.size[0]; volume is float[D][H][W] (main.cpp:353-354)        */
+    int windR;          /* Parameters::windR; guided-filter box radius R = windR/2 (CostVolumeEnergy.h:30) */
+    float eps;          /* Parameters::filter_param1 (GF regulariser, main.cpp:73: 1e-4)       */
+    float th_col;       /* Parameters::th_col (truncation, CostVolumeEnergy.h:96)              */
+    float min_disp;     /* MIN_DISPARITY (0 in main.cpp)                                       */
+    float max_disp;     /* MAX_DISPARITY (= ndisp-1 in main.cpp:385-386)                       */
+    int device;         /* CUDA device ordinal                                                  */
+    int reserved[7];
+} lexp_params;
+
+typedef struct lexp_ctx lexp_ctx;   /* replaces a CostVolumeEnergy instance (CostVolumeEnergy.h:6-184) */
+typedef struct lexp_plan lexp_plan; /* device-side work list for a fixed set of (filterRect, targetRect) */
+
+LEXP_API const char* lexp_last_error(void);
+LEXP_API int lexp_version(void);
+
+/* CostVolumeEnergy::CostVolumeEnergy(imL, imR, volL, volR, params, MAX, MIN) -- CostVolumeEnergy.h:16-43.
+ * Split in three so that volumes may already live on the device. */
+LEXP_API int lexp_create(const lexp_params* params, lexp_ctx** out_ctx);
+LEXP_API int lexp_destroy(lexp_ctx* ctx);
+
+/* Guide image of view `mode` (0 = left, 1 = right): uint8 BGR, `step_bytes` per row (cv::Mat::step).
+ * Runs the one-time guided-filter statistics on the device
+ * (FastGuidedImageFilter<double>(im, windR/2, eps, 1/255): CostVolumeEnergy.h:30-31, GuidedFilter.h:58-102). */
+LEXP_API int lexp_set_image(lexp_ctx* ctx, int mode, const uint8_t* bgr_host, ptrdiff_t step_bytes);
+
+/* vol[mode] = float[D][H][W] contiguous (CostVolumeEnergy.h:20-21).  _host copies it to HBM;
+ * _device borrows an existing device pointer (no copy; caller keeps it alive). */
+LEXP_API int lexp_set_volume_host(lexp_ctx* ctx, int mode, const float* vol_host);
+LEXP_API int lexp_set_volume_device(lexp_ctx* ctx, int mode, const float* vol_device);
+
+/* Debug / parity: copy the 9 statistics planes [mean_r,g,b, inv_rr,rg,rb,gg,gb,bb] (float[9][H][W]) to the host. */
+LEXP_API int lexp_get_stats(lexp_ctx* ctx, int mode, float* out9_host);
+
+/* StereoEnergy::ComputeUnaryPotential / ComputeUnaryPotentialWithoutCheck (StereoEnergy.h:625-626,
+ * CostVolumeEnergy.h:55-183) for ONE cell.  `costs` is the pointer the reference passes as
+ * `costs.data` -- element (filterRect.y, filterRect.x) of the caller's cost image, row pitch
+ * `costs_step_bytes` (cv::Mat::step).  Only costs(targetRect - filterRect.tl()) is written
+ * (CostVolumeEnergy.h:169-171,180-182).  Blocking.  with_check != 0 selects ComputeUnaryPotential. */
+LEXP_API int lexp_eval_cell(lexp_ctx* ctx, int mode, const lexp_rect* filter_rect, const lexp_rect* target_rect,
+                            const lexp_plane* plane, float* costs, ptrdiff_t costs_step_bytes, int with_check);
+
+/* One batched step = the independent cells of one disjoint group with one proposal each
+ * (the `#pragma omp parallel for` body at FastGCStereo.h:30-49).  `cost_image` is element (0,0)
+ * of the caller's H x W cost image (proposalCost, FastGCStereo.h:25); call i writes
+ * cost_image(target_rects[i]).  Host pointers; blocking. */
+LEXP_API int lexp_eval_batch(lexp_ctx* ctx, int mode, int n, const lexp_rect* filter_rects,
+                             const lexp_rect* target_rects, const lexp_plane* planes, float* cost_image,
+                             ptrdiff_t cost_step_bytes, int with_check);
+
+/* Plans: the rects of a (layer, group) never change (LayerManager.h:14-24), only the planes do.
+ * A plan tiles every call into CTA work items once and keeps them in HBM. */
+LEXP_API int lexp_plan_create(lexp_ctx* ctx, int n, const lexp_rect* filter_rects, const lexp_rect* target_rects,
+                              lexp_plan** out_plan);
+LEXP_API int lexp_plan_destroy(lexp_plan* plan);
+LEXP_API int lexp_plan_num_calls(const lexp_plan* plan);
+LEXP_API int lexp_plan_num_items(const lexp_plan* plan);
+/* Sum over calls of filterRect pixels (= "evals" of one step), of targetRect pixels, and the
+ * algorithmic bytes 20*F + 36*A + 4*S of SURVEY.md section 8(d). */
+LEXP_API int lexp_plan_work(const lexp_plan* plan, int64_t* sum_filter_px, int64_t* sum_target_px,
+                            int64_t* algorithmic_bytes);
+
+/* Asynchronous evaluation on the context stream; outputs stay in HBM.
+ * planes: n planes, on the host (planes_on_device == 0; copied H2D, 16 B each) or on the device.
+ * d_cost_image: device pointer to element (0,0) of an H x W float image with row pitch step_bytes. */
+LEXP_API int lexp_plan_eval_device(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
+                                   int planes_on_device, float* d_cost_image, ptrdiff_t step_bytes, int with_check);
+/* Same, host in / host out (planes H2D, compact tiles D2H, scattered into cost_image); blocking. */
+LEXP_API int lexp_plan_eval_host(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
+                                 float* cost_image, ptrdiff_t cost_step_bytes, int with_check);
+
+LEXP_API int lexp_sync(lexp_ctx* ctx);
+/* cudaStream_t of the context (so a caller can order its own device work / events after ours). */
+LEXP_API void* lexp_stream(lexp_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);
+
+/* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
+ * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
+LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,
+                                 int* width_blocks, lexp_rect* unit_regions, lexp_rect* shared_regions,
+                                 lexp_rect* filter_regions, int* group_of);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEXP_CUDA_H_ */

@@ -1,0 +1,437 @@
+// lexp_capi.cu -- host side of the C-ABI declared in include/lexp_cuda.h.
+// Owns device memory (guide, statistics, volumes, plans), tiles calls into CTA work items and
+// launches the sm_100a kernels of lexp_kernels.cuh.  No CPU compute fallback exists here.
+#include "../../include/lexp_cuda.h"
+#include "lexp_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace lexp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define LEXP_CUDA(expr)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(LEXP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+struct lexp_plan {
+    lexp_ctx* ctx = nullptr;
+    int ncalls = 0, nitems = 0, max_vw = 0;
+    std::vector<lexp_rect> filt, targ;
+    std::vector<int> compact_off;  // per call
+    int64_t sum_f = 0, sum_s = 0, alg_bytes = 0;
+    Item* d_items = nullptr;
+    Plane4* d_planes = nullptr;   // staging for host planes
+    float* d_compact = nullptr;   // lazily allocated compact output (host path)
+    float* h_compact = nullptr;   // pinned
+};
+
+struct lexp_ctx {
+    lexp_params p{};
+    int R = 0;
+    cudaStream_t stream = nullptr;
+    uchar4* d_guide[2] = {nullptr, nullptr};
+    float* d_stats[2] = {nullptr, nullptr};
+    const float* d_vol[2] = {nullptr, nullptr};
+    float* d_vol_owned[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    std::mutex mu;
+    int ch = 4;           // rows per chunk (template CH)
+    int tile_oh = 128;    // max output rows per work item
+    size_t smem_limit = 0;
+    bool smem_configured = false;
+};
+
+namespace {
+
+template <int R_T, int CH>
+int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
+    auto kern = lexp_fused_kernel<R_T, CH>;
+    if (!c->smem_configured) {  // one (R, CH) instantiation per context
+        LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
+        c->smem_configured = true;
+    }
+    kern<<<nitems, kThreads, smem, c->stream>>>(kp);
+    LEXP_CUDA(cudaGetLastError());
+    c->launches++;
+    return LEXP_OK;
+}
+
+template <int CH>
+int launch_fused_ch(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
+    switch (c->R) {
+        case 10: return launch_fused_t<10, CH>(c, kp, nitems, smem);
+        case 16: return launch_fused_t<16, CH>(c, kp, nitems, smem);
+        default: return launch_fused_t<0, CH>(c, kp, nitems, smem);
+    }
+}
+
+int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, int max_vw) {
+    const size_t smem = fused_smem_bytes(max_vw, c->R, c->ch);
+    if (smem > c->smem_limit) return fail(LEXP_ERR_INVALID, "tile needs more shared memory than the device offers");
+    if (c->ch == 2) return launch_fused_ch<2>(c, kp, nitems, smem);
+    return launch_fused_ch<4>(c, kp, nitems, smem);
+}
+
+int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
+    const int H = c->p.height, W = c->p.width;
+    if (f.width <= 0 || f.height <= 0 || t.width <= 0 || t.height <= 0) return fail(LEXP_ERR_INVALID, "empty rect");
+    if (f.x < 0 || f.y < 0 || f.x + f.width > W || f.y + f.height > H) return fail(LEXP_ERR_INVALID, "filterRect outside image");
+    if (t.x < f.x || t.y < f.y || t.x + t.width > f.x + f.width || t.y + t.height > f.y + f.height)
+        return fail(LEXP_ERR_INVALID, "targetRect not inside filterRect");
+    return LEXP_OK;
+}
+
+int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float* d_out, long long pitch, int compact,
+             int with_check) {
+    if (mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "mode must be 0 or 1");
+    if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
+    KParams kp{};
+    kp.vol = c->d_vol[mode];
+    kp.guide = c->d_guide[mode];
+    kp.stats = c->d_stats[mode];
+    kp.items = pl->d_items;
+    kp.planes = d_planes;
+    kp.out = d_out;
+    kp.out_pitch = pitch;
+    kp.out_compact = compact;
+    kp.H = c->p.height; kp.W = c->p.width; kp.D = c->p.ndisp;
+    kp.th_col = c->p.th_col; kp.min_disp = c->p.min_disp; kp.max_disp = c->p.max_disp;
+    kp.with_check = with_check;
+    kp.R = c->R;
+    return launch_fused(c, kp, pl->nitems, pl->max_vw);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lexp_last_error(void) { return g_err.c_str(); }
+int lexp_version(void) { return 100; }
+
+int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
+    if (!params || !out_ctx) return fail(LEXP_ERR_INVALID, "null argument");
+    if (params->height <= 0 || params->width <= 0 || params->ndisp < 2) return fail(LEXP_ERR_INVALID, "bad H/W/D");
+    if (params->windR < 2 || params->windR / 2 > 24) return fail(LEXP_ERR_INVALID, "windR/2 must be in [1, 24]");
+    int ndev = 0;
+    LEXP_CUDA(cudaGetDeviceCount(&ndev));
+    if (params->device < 0 || params->device >= ndev) return fail(LEXP_ERR_INVALID, "bad device ordinal");
+    LEXP_CUDA(cudaSetDevice(params->device));
+    cudaDeviceProp prop;
+    LEXP_CUDA(cudaGetDeviceProperties(&prop, params->device));
+    if (prop.major < 10) return fail(LEXP_ERR_INVALID, "this library is built for sm_100a (B200) only");
+    lexp_ctx* c = new lexp_ctx();
+    c->p = *params;
+    c->R = params->windR / 2;  // CostVolumeEnergy.h:30
+    c->smem_limit = prop.sharedMemPerBlockOptin;
+    c->ch = env_int("LEXP_CH", 4) == 2 ? 2 : 4;
+    c->tile_oh = std::max(8, env_int("LEXP_TILE_OH", 128));
+    if (4 * c->R + 8 > kThreads) { delete c; return fail(LEXP_ERR_INVALID, "windR too large for the tile width"); }
+    LEXP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out_ctx = c;
+    return LEXP_OK;
+}
+
+int lexp_destroy(lexp_ctx* c) {
+    if (!c) return LEXP_OK;
+    cudaSetDevice(c->p.device);
+    cudaStreamSynchronize(c->stream);
+    for (int m = 0; m < 2; m++) {
+        cudaFree(c->d_guide[m]);
+        cudaFree(c->d_stats[m]);
+        cudaFree(c->d_vol_owned[m]);
+    }
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return LEXP_OK;
+}
+
+int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
+    if (!c || !bgr || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const int H = c->p.height, W = c->p.width;
+    const size_t HW = (size_t)H * W;
+    std::vector<uchar4> tmp(HW);
+    for (int y = 0; y < H; y++) {
+        const uint8_t* row = bgr + (ptrdiff_t)y * step;
+        for (int x = 0; x < W; x++) tmp[(size_t)y * W + x] = make_uchar4(row[3 * x], row[3 * x + 1], row[3 * x + 2], 0);
+    }
+    if (!c->d_guide[mode]) LEXP_CUDA(cudaMalloc(&c->d_guide[mode], HW * sizeof(uchar4)));
+    if (!c->d_stats[mode]) LEXP_CUDA(cudaMalloc(&c->d_stats[mode], 9 * HW * sizeof(float)));
+    LEXP_CUDA(cudaMemcpyAsync(c->d_guide[mode], tmp.data(), HW * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
+    int* d_rs = nullptr;
+    LEXP_CUDA(cudaMalloc(&d_rs, 9 * HW * sizeof(int)));
+    dim3 blk(128), grd((W + 127) / 128, H);
+    lexp_stats_rowsum<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], d_rs, H, W, c->R);
+    lexp_stats_finish<<<grd, blk, 0, c->stream>>>(d_rs, c->d_stats[mode], H, W, c->R, (double)c->p.eps);
+    c->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_rs);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("statistics kernels: ") + cudaGetErrorString(e));
+    return LEXP_OK;
+}
+
+int lexp_set_volume_host(lexp_ctx* c, int mode, const float* vol) {
+    if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const size_t n = (size_t)c->p.ndisp * c->p.height * c->p.width;
+    if (!c->d_vol_owned[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol_owned[mode], n * sizeof(float)));
+    LEXP_CUDA(cudaMemcpy(c->d_vol_owned[mode], vol, n * sizeof(float), cudaMemcpyHostToDevice));
+    c->d_vol[mode] = c->d_vol_owned[mode];
+    return LEXP_OK;
+}
+
+int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) {
+    if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaPointerAttributes at;
+    LEXP_CUDA(cudaPointerGetAttributes(&at, vol));
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+        return fail(LEXP_ERR_INVALID, "lexp_set_volume_device needs a device pointer");
+    c->d_vol[mode] = vol;
+    return LEXP_OK;
+}
+
+int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {
+    if (!c || !out9 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_stats[mode]) return fail(LEXP_ERR_STATE, "image not set");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    LEXP_CUDA(cudaMemcpy(out9, c->d_stats[mode], 9 * (size_t)c->p.height * c->p.width * sizeof(float), cudaMemcpyDeviceToHost));
+    return LEXP_OK;
+}
+
+int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect* targ, lexp_plan** out_plan) {
+    if (!c || !filt || !targ || !out_plan || n <= 0) return fail(LEXP_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n; i++) {
+        int rc = check_rects(c, filt[i], targ[i]);
+        if (rc) return rc;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const int R = c->R;
+    const int ow_max = kThreads - 4 * R;
+    const int oh_max = c->tile_oh;
+    lexp_plan* pl = new lexp_plan();
+    pl->ctx = c;
+    pl->ncalls = n;
+    pl->filt.assign(filt, filt + n);
+    pl->targ.assign(targ, targ + n);
+    pl->compact_off.resize(n);
+    std::vector<Item> items;
+    int64_t coff = 0;
+    for (int i = 0; i < n; i++) {
+        const lexp_rect &f = filt[i], &t = targ[i];
+        pl->compact_off[i] = (int)coff;
+        const int ncol = (t.width + ow_max - 1) / ow_max, nrow = (t.height + oh_max - 1) / oh_max;
+        for (int rj = 0; rj < nrow; rj++) {
+            const int y0 = t.y + (int)((int64_t)t.height * rj / nrow), y1 = t.y + (int)((int64_t)t.height * (rj + 1) / nrow);
+            for (int cj = 0; cj < ncol; cj++) {
+                const int x0 = t.x + (int)((int64_t)t.width * cj / ncol), x1 = t.x + (int)((int64_t)t.width * (cj + 1) / ncol);
+                Item it{};
+                it.fx = f.x; it.fy = f.y; it.fw = f.width; it.fh = f.height;
+                it.ox0 = x0; it.oy0 = y0; it.ow = x1 - x0; it.oh = y1 - y0;
+                it.call = i;
+                it.compact_off = (int)(coff + (int64_t)(y0 - t.y) * t.width + (x0 - t.x));
+                it.compact_stride = t.width;
+                it.flags = (t.width == 1 && t.height == 1) ? 1 : 0;
+                items.push_back(it);
+                pl->max_vw = std::max(pl->max_vw, it.ow + 4 * R);
+            }
+        }
+        coff += (int64_t)t.width * t.height;
+        // work accounting: F = filterRect px, S = targetRect px,
+        // A = targetRect dilated by R, clipped to filterRect
+        const int64_t F = (int64_t)f.width * f.height, S = (int64_t)t.width * t.height;
+        const int ax0 = std::max(t.x - R, f.x), ax1 = std::min(t.x + t.width + R, f.x + f.width);
+        const int ay0 = std::max(t.y - R, f.y), ay1 = std::min(t.y + t.height + R, f.y + f.height);
+        const int64_t A = (int64_t)(ax1 - ax0) * (ay1 - ay0);
+        pl->sum_f += F; pl->sum_s += S;
+        pl->alg_bytes += 20 * F + 36 * A + 4 * S;
+    }
+    if (coff > 0x7fffffffLL) { delete pl; return fail(LEXP_ERR_INVALID, "plan output too large"); }
+    // big items first: the hardware scheduler then back-fills with small ones
+    std::stable_sort(items.begin(), items.end(), [R](const Item& a, const Item& b) {
+        return (int64_t)(a.ow + 4 * R) * (a.oh + 4 * R) > (int64_t)(b.ow + 4 * R) * (b.oh + 4 * R);
+    });
+    pl->nitems = (int)items.size();
+    cudaError_t e = cudaMalloc(&pl->d_items, items.size() * sizeof(Item));
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_planes, (size_t)n * sizeof(Plane4));
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(pl->d_items); cudaFree(pl->d_planes);
+        delete pl;
+        return fail(LEXP_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
+    }
+    *out_plan = pl;
+    return LEXP_OK;
+}
+
+int lexp_plan_destroy(lexp_plan* pl) {
+    if (!pl) return LEXP_OK;
+    cudaSetDevice(pl->ctx->p.device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    cudaFree(pl->d_items);
+    cudaFree(pl->d_planes);
+    cudaFree(pl->d_compact);
+    if (pl->h_compact) cudaFreeHost(pl->h_compact);
+    delete pl;
+    return LEXP_OK;
+}
+
+int lexp_plan_num_calls(const lexp_plan* pl) { return pl ? pl->ncalls : 0; }
+int lexp_plan_num_items(const lexp_plan* pl) { return pl ? pl->nitems : 0; }
+
+int lexp_plan_work(const lexp_plan* pl, int64_t* sf, int64_t* ss, int64_t* ab) {
+    if (!pl) return fail(LEXP_ERR_INVALID, "null plan");
+    if (sf) *sf = pl->sum_f;
+    if (ss) *ss = pl->sum_s;
+    if (ab) *ab = pl->alg_bytes;
+    return LEXP_OK;
+}
+
+int lexp_plan_eval_device(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, int planes_on_device,
+                          float* d_cost_image, ptrdiff_t step_bytes, int with_check) {
+    if (!c || !pl || !planes || !d_cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (step_bytes % 4 != 0 || step_bytes < (ptrdiff_t)c->p.width * 4) return fail(LEXP_ERR_INVALID, "bad row pitch");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const Plane4* dp = reinterpret_cast<const Plane4*>(planes);
+    if (!planes_on_device) {
+        LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+        dp = pl->d_planes;
+    }
+    return run_plan(c, pl, mode, dp, d_cost_image, step_bytes / 4, 0, with_check);
+}
+
+int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, float* cost_image,
+                        ptrdiff_t step_bytes, int with_check) {
+    if (!c || !pl || !planes || !cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const size_t nout = (size_t)pl->sum_s;
+    if (!pl->d_compact) {
+        LEXP_CUDA(cudaMalloc(&pl->d_compact, nout * sizeof(float)));
+        LEXP_CUDA(cudaHostAlloc(&pl->h_compact, nout * sizeof(float), cudaHostAllocDefault));
+    }
+    LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+    int rc = run_plan(c, pl, mode, pl->d_planes, pl->d_compact, 0, 1, with_check);
+    if (rc) return rc;
+    LEXP_CUDA(cudaMemcpyAsync(pl->h_compact, pl->d_compact, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    // scatter the per-call tiles into the caller's image: costs(targetRect) only (CostVolumeEnergy.h:169-171)
+    for (int i = 0; i < pl->ncalls; i++) {
+        const lexp_rect& t = pl->targ[i];
+        const float* src = pl->h_compact + pl->compact_off[i];
+        for (int y = 0; y < t.height; y++) {
+            float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(cost_image) + (ptrdiff_t)(t.y + y) * step_bytes) + t.x;
+            memcpy(dst, src + (size_t)y * t.width, (size_t)t.width * sizeof(float));
+        }
+    }
+    return LEXP_OK;
+}
+
+int lexp_eval_batch(lexp_ctx* c, int mode, int n, const lexp_rect* filt, const lexp_rect* targ, const lexp_plane* planes,
+                    float* cost_image, ptrdiff_t step_bytes, int with_check) {
+    lexp_plan* pl = nullptr;
+    int rc = lexp_plan_create(c, n, filt, targ, &pl);
+    if (rc) return rc;
+    rc = lexp_plan_eval_host(c, pl, mode, planes, cost_image, step_bytes, with_check);
+    std::string keep = g_err;
+    lexp_plan_destroy(pl);
+    g_err = keep;
+    return rc;
+}
+
+int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect* targ, const lexp_plane* plane, float* costs,
+                   ptrdiff_t step_bytes, int with_check) {
+    if (!filt || !targ || !plane || !costs) return fail(LEXP_ERR_INVALID, "null argument");
+    // `costs` addresses element (filterRect.y, filterRect.x); rebase to image element (0,0)
+    float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(costs) - (ptrdiff_t)filt->y * step_bytes) - filt->x;
+    return lexp_eval_batch(c, mode, 1, filt, targ, plane, base, step_bytes, with_check);
+}
+
+int lexp_sync(lexp_ctx* c) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    return LEXP_OK;
+}
+
+void* lexp_stream(lexp_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t lexp_launch_count(const lexp_ctx* c) { return c ? c->launches : 0; }
+
+// LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).
+int lexp_layer_geometry(int width, int height, int windR, int u, int* hb_out, int* wb_out, lexp_rect* unit, lexp_rect* shared,
+                        lexp_rect* filt, int* group_of) {
+    if (width <= 0 || height <= 0 || u <= 0 || windR < 0) return fail(LEXP_ERR_INVALID, "bad layer arguments");
+    const int minsize = std::max(2, u / 2);
+    const int frac_h = height % u, frac_w = width % u;
+    const int split_h = frac_h >= minsize ? 1 : 0, split_w = frac_w >= minsize ? 1 : 0;
+    const int hb = height / u + split_h, wb = width / u + split_w;
+    if (hb_out) *hb_out = hb;
+    if (wb_out) *wb_out = wb;
+    if (!unit || !shared || !filt) return LEXP_OK;
+    auto clip = [&](int x, int y, int w, int h) {
+        const int x0 = std::max(x, 0), y0 = std::max(y, 0), x1 = std::min(x + w, width), y1 = std::min(y + h, height);
+        lexp_rect r{0, 0, 0, 0};
+        if (x1 > x0 && y1 > y0) { r.x = x0; r.y = y0; r.width = x1 - x0; r.height = y1 - y0; }
+        return r;
+    };
+    for (int i = 0; i < hb; i++)
+        for (int j = 0; j < wb; j++) {
+            const int r = i * wb + j;
+            unit[r] = clip(j * u, i * u, u, u);
+            shared[r] = clip((j - 1) * u, (i - 1) * u, 3 * u, 3 * u);
+            filt[r] = clip((j - 1) * u - windR, (i - 1) * u - windR, 3 * u + 2 * windR, 3 * u + 2 * windR);
+            if (group_of) group_of[r] = (i % 4) * 4 + (j % 4);
+        }
+    if (!split_w) {
+        for (int i = 0; i < hb; i++) unit[i * wb + wb - 1].width += frac_w;
+        if (wb >= 2)
+            for (int i = 0; i < hb; i++) {
+                const int r = i * wb + wb - 2;
+                shared[r].width += frac_w;
+                filt[r] = clip(filt[r].x, filt[r].y, filt[r].width + frac_w, filt[r].height);
+            }
+    }
+    if (!split_h) {
+        for (int j = 0; j < wb; j++) unit[(hb - 1) * wb + j].height += frac_h;
+        if (hb >= 2)
+            for (int j = 0; j < wb; j++) {
+                const int r = (hb - 2) * wb + j;
+                shared[r].height += frac_h;
+                filt[r] = clip(filt[r].x, filt[r].y, filt[r].width, filt[r].height + frac_h);
+            }
+    }
+    return LEXP_OK;
+}
+
+}  // extern "C"

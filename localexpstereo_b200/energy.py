@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's operator interface for the unary-cost path.
+
+Same names, argument meaning and error behaviour as the reference classes
+(`/root/reference/LocalExpansionStereo/`): `Plane` (Plane.h:4-106), `Parameters`
+(StereoEnergy.h:13-40), `LayerManager` / `Layer` (LayerManager.h:7-186) and
+`CostVolumeEnergy` with `ComputeUnaryPotential[WithoutCheck]` (StereoEnergy.h:625-626,
+CostVolumeEnergy.h:55-183).  All arithmetic of the hot path runs in the CUDA library behind
+the C-ABI (`include/lexp_cuda.h`); this file only marshals numpy arrays (the cv::Mat stand-in).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import LexpError, PlaneC, Rect, check, lib
+
+COST_FOR_INVALID = 1000000.0  # StereoEnergy.h:45
+
+
+@dataclass
+class Parameters:  # StereoEnergy.h:13-40 (defaults of the constructor at :26)
+    lambda_: float = 20.0
+    windR: int = 20
+    filterName: str = "GF"
+    filter_param1: float = 1e-4
+    alpha: float = 0.9
+    omega: float = 10.0
+    th_grad: float = 2.0
+    th_col: float = 10.0
+    th_smooth: float = 1.0
+    epsilon: float = 0.01
+    neighborNum: int = 8
+
+
+class Plane:
+    """struct Plane {a,b,c,v} (Plane.h:4-12)."""
+    __slots__ = ("a", "b", "c", "v")
+
+    def __init__(self, a=0.0, b=0.0, c=0.0, v=0.0):
+        self.a, self.b, self.c, self.v = (float(np.float32(t)) for t in (a, b, c, v))
+
+    @staticmethod
+    def CreatePlane(nx, ny, nz, z, x, y, v=0.0):  # Plane.h:14-32, float arithmetic
+        f = np.float32
+        nx, ny, nz, z, x, y = (f(t) for t in (nx, ny, nz, z, x, y))
+        a = f(-nx / nz)
+        b = f(-ny / nz)
+        c = f(f(z - f(a * x)) - f(b * y))
+        return Plane(a, b, c, v)
+
+    def GetZ(self, x, y):  # Plane.h:51-54
+        f = np.float32
+        return float(f(f(f(f(self.a) * f(x)) + f(f(self.b) * f(y))) + f(self.c)))
+
+    def toVec4(self):
+        return np.array([self.a, self.b, self.c, self.v], dtype=np.float32)
+
+    def __iter__(self):
+        return iter((self.a, self.b, self.c, self.v))
+
+
+def _as_rect(r) -> Rect:
+    if isinstance(r, Rect):
+        return r
+    x, y, w, h = (int(t) for t in r)
+    return Rect(x, y, w, h)
+
+
+def _rect_array(rects) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray([tuple(r) if not isinstance(r, Rect) else (r.x, r.y, r.width, r.height) for r in rects],
+                                        dtype=np.int32))
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+def _plane_array(planes) -> np.ndarray:
+    if isinstance(planes, np.ndarray):
+        a = np.ascontiguousarray(planes, dtype=np.float32)
+    else:
+        a = np.ascontiguousarray(np.asarray([tuple(p) for p in planes], dtype=np.float32))
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+@dataclass
+class Layer:  # LayerManager.h:14-24
+    heightBlocks: int
+    widthBlocks: int
+    regionUnitSize: int
+    unitRegions: List[tuple]
+    sharedRegions: List[tuple]
+    filterRegions: List[tuple]
+    disjointRegionSets: List[List[int]]
+    proposers: list = field(default_factory=list)
+
+
+class LayerManager:
+    """LayerManager (LayerManager.h:7-186); geometry computed by the C++ library (lexp_layer_geometry)."""
+
+    def __init__(self, width, height, windowR, localLabelSetNum=0):
+        self.width, self.height, self.windowR = int(width), int(height), int(windowR)
+        self.layers: List[Layer] = []
+
+    def addLayer(self, unitRegionSize):
+        u = int(unitRegionSize)
+        hb, wb = C.c_int(), C.c_int()
+        check(lib().lexp_layer_geometry(self.width, self.height, self.windowR, u, C.byref(hb), C.byref(wb), None, None, None, None))
+        n = hb.value * wb.value
+        unit = np.zeros((n, 4), np.int32)
+        shared = np.zeros((n, 4), np.int32)
+        filt = np.zeros((n, 4), np.int32)
+        grp = np.zeros(n, np.int32)
+        check(lib().lexp_layer_geometry(self.width, self.height, self.windowR, u, C.byref(hb), C.byref(wb),
+                                        unit.ctypes.data, shared.ctypes.data, filt.ctypes.data, grp.ctypes.data))
+        sets = [[] for _ in range(16)]
+        for r in range(n):
+            sets[int(grp[r])].append(r)
+        sets = [s for s in sets if s]  # empty groups erased (LayerManager.h:174-182)
+        self.layers.append(Layer(hb.value, wb.value, u, [tuple(map(int, r)) for r in unit], [tuple(map(int, r)) for r in shared],
+                                 [tuple(map(int, r)) for r in filt], sets))
+        return self.layers[-1]
+
+
+class Plan:
+    """Device-resident work list for a fixed list of (filterRect, targetRect) (see lexp_plan_create)."""
+
+    def __init__(self, energy: "CostVolumeEnergy", filter_rects, target_rects):
+        self.energy = energy
+        self._fr = _rect_array(filter_rects)
+        self._tr = _rect_array(target_rects)
+        assert len(self._fr) == len(self._tr)
+        h = C.c_void_p()
+        check(lib().lexp_plan_create(energy._h, len(self._fr), self._fr.ctypes.data, self._tr.ctypes.data, C.byref(h)))
+        self._h = h
+        sf, ss, ab = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib().lexp_plan_work(self._h, C.byref(sf), C.byref(ss), C.byref(ab)))
+        self.filter_px, self.target_px, self.algorithmic_bytes = sf.value, ss.value, ab.value
+        self.num_calls = lib().lexp_plan_num_calls(self._h)
+        self.num_items = lib().lexp_plan_num_items(self._h)
+
+    def eval_host(self, planes, cost_image: np.ndarray, with_check=True, mode=0):
+        pl = _plane_array(planes)
+        assert len(pl) == self.num_calls
+        assert cost_image.dtype == np.float32 and cost_image.ndim == 2 and cost_image.strides[1] == 4
+        check(lib().lexp_plan_eval_host(self.energy._h, self._h, mode, pl.ctypes.data, cost_image.ctypes.data,
+                                        cost_image.strides[0], int(with_check)))
+        return cost_image
+
+    def eval_device(self, planes, d_cost_ptr: int, step_bytes: int, with_check=True, mode=0, planes_on_device=False):
+        """planes: numpy [n][4] (host) or an int device pointer when planes_on_device."""
+        if planes_on_device:
+            ptr = int(planes)
+        else:
+            self._pl_keep = _plane_array(planes)
+            assert len(self._pl_keep) == self.num_calls
+            ptr = self._pl_keep.ctypes.data
+        check(lib().lexp_plan_eval_device(self.energy._h, self._h, mode, ptr, int(planes_on_device), int(d_cost_ptr),
+                                          int(step_bytes), int(with_check)))
+
+    def close(self):
+        if self._h:
+            lib().lexp_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CostVolumeEnergy:
+    """CostVolumeEnergy (CostVolumeEnergy.h:6-184) backed by the sm_100a kernels.
+
+    imL / imR: uint8 [H][W][3] BGR; volL / volR: float32 [D][H][W] numpy arrays, or torch CUDA tensors /
+    integer device pointers (then no copy is made).  `params.filterName` must be "GF" or "GFfloat"
+    (both run the same FP32 kernel, within the 1e-4 tolerance of the reference's double filter)."""
+
+    def __init__(self, imL, imR, volL, volR, params: Parameters, MAX_DISPARITY, MIN_DISPARITY=0.0, MAX_VDISPARITY=0.0,
+                 device: int = 0):
+        if params.filterName not in ("GF", "GFfloat"):
+            raise LexpError('only filterName "GF" / "GFfloat" is implemented on the GPU path')
+        if MAX_VDISPARITY != 0:
+            raise LexpError("MAX_VDISPARITY != 0 is not supported (main.cpp never sets it)")
+        imL = np.ascontiguousarray(imL, dtype=np.uint8)
+        self.height, self.width = imL.shape[:2]
+        self.params = params
+        self.MAX_DISPARITY, self.MIN_DISPARITY = float(MAX_DISPARITY), float(MIN_DISPARITY)
+        D = self._ndisp(volL)
+        p = _capi.Params(self.height, self.width, D, int(params.windR), float(params.filter_param1), float(params.th_col),
+                         float(MIN_DISPARITY), float(MAX_DISPARITY), int(device))
+        h = C.c_void_p()
+        check(lib().lexp_create(C.byref(p), C.byref(h)))
+        self._h = h
+        self._keep = []
+        self.ndisp = D
+        for mode, (im, vol) in enumerate(((imL, volL), (imR, volR))):
+            if im is not None:
+                im = np.ascontiguousarray(im, dtype=np.uint8)
+                assert im.shape == (self.height, self.width, 3)
+                check(lib().lexp_set_image(self._h, mode, im.ctypes.data, im.strides[0]))
+            if vol is not None:
+                self._set_volume(mode, vol)
+
+    @staticmethod
+    def _ndisp(vol):
+        return int(vol.shape[0])
+
+    def _set_volume(self, mode, vol):
+        if isinstance(vol, np.ndarray):
+            v = np.ascontiguousarray(vol, dtype=np.float32)
+            assert v.shape == (self.ndisp, self.height, self.width)
+            check(lib().lexp_set_volume_host(self._h, mode, v.ctypes.data))
+        else:  # torch CUDA tensor (duck-typed): borrowed, kept alive here
+            assert tuple(vol.shape) == (self.ndisp, self.height, self.width) and vol.is_contiguous() and vol.is_cuda
+            self._keep.append(vol)
+            check(lib().lexp_set_volume_device(self._h, mode, vol.data_ptr()))
+
+    # --- the two virtuals of StereoEnergy (StereoEnergy.h:625-626) -------------------------------
+    def ComputeUnaryPotentialWithoutCheck(self, filterRect, targetRect, costs: np.ndarray, plane, reusable=None, mode=0):
+        self._eval_cell(filterRect, targetRect, costs, plane, mode, 0)
+
+    def ComputeUnaryPotential(self, filterRect, targetRect, costs: np.ndarray, plane, reusable=None, mode=0):
+        self._eval_cell(filterRect, targetRect, costs, plane, mode, 1)
+
+    def _eval_cell(self, filterRect, targetRect, costs, plane, mode, with_check):
+        """`costs` is the numpy view proposalCost[fy:fy+fh, fx:fx+fw] (cv::Mat ROI at filterRect)."""
+        fr, tr = _as_rect(filterRect), _as_rect(targetRect)
+        assert costs.dtype == np.float32 and costs.shape == (fr.height, fr.width) and costs.strides[1] == 4
+        pl = PlaneC(*[float(t) for t in plane])
+        check(lib().lexp_eval_cell(self._h, mode, C.byref(fr), C.byref(tr), C.byref(pl), costs.ctypes.data, costs.strides[0],
+                                   with_check))
+
+    # --- batched forms ------------------------------------------------------------------------------
+    def ComputeUnaryPotentialBatch(self, filterRects, targetRects, cost_image: np.ndarray, planes, mode=0, with_check=True):
+        fr, tr, pl = _rect_array(filterRects), _rect_array(targetRects), _plane_array(planes)
+        assert cost_image.dtype == np.float32 and cost_image.shape == (self.height, self.width) and cost_image.strides[1] == 4
+        check(lib().lexp_eval_batch(self._h, mode, len(fr), fr.ctypes.data, tr.ctypes.data, pl.ctypes.data,
+                                    cost_image.ctypes.data, cost_image.strides[0], int(with_check)))
+        return cost_image
+
+    def make_plan(self, filterRects, targetRects) -> Plan:
+        return Plan(self, filterRects, targetRects)
+
+    def stats(self, mode=0) -> np.ndarray:
+        out = np.empty((9, self.height, self.width), dtype=np.float32)
+        check(lib().lexp_get_stats(self._h, mode, out.ctypes.data))
+        return out
+
+    def sync(self):
+        check(lib().lexp_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().lexp_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().lexp_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().lexp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

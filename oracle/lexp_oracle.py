@@ -1,0 +1,487 @@
+"""CPU oracle for the LocalExpStereo unary-cost hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in numpy, the arithmetic of the reference's hot path
+(`/root/reference/LocalExpansionStereo/*`; citations below are file:line in that
+directory).  It is the *checker* for the CUDA path: only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+legs may import it.  Nothing under `localexpstereo_b200/` imports it.
+
+PARITY STATUS: **parity unpinned by the reference** -- the reference ships no
+tests, golden vectors or known-answer values for this path (SURVEY.md section 4
+and 8c) and cannot be compiled in this container (MSVC dialect, OpenCV C++ 3.1.0
+headers absent).  What pins this restatement instead:
+  * `tests/test_oracle_cv2.py` checks the box filter / reduce order / warpAffine
+    emulation against the OpenCV kernels the reference calls (`cv2` 4.13 Python
+    wheel, the only OpenCV in the image),
+  * `oracle/lexp_oracle.c` is an independent plain-C restatement cross-checked
+    against this file,
+  * `tests/golden/*.npz` are vectors minted by `tests/golden/make_golden.py`.
+
+Conventions: rect = (x, y, w, h) in image coordinates (cv::Rect); plane =
+(a, b, c, v) float32 (Plane.h:4-8); volume = float32[D][H][W] (main.cpp:353-354);
+guide image = uint8[H][W][3] in OpenCV BGR channel order.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+COST_FOR_INVALID = np.float32(1000000.0)  # StereoEnergy.h:45
+
+f32 = np.float32
+
+
+# ----------------------------------------------------------------------------
+# Plane (Plane.h:4-106)
+# ----------------------------------------------------------------------------
+def create_plane(nx, ny, nz, z, x, y, v=0.0):
+    """Plane::CreatePlane (Plane.h:14-32): all arithmetic in float."""
+    nx, ny, nz, z, x, y = (f32(t) for t in (nx, ny, nz, z, x, y))
+    a = f32(-nx / nz)
+    b = f32(-ny / nz)
+    c = f32(f32(z - f32(a * x)) - f32(b * y))
+    return np.array([a, b, c, f32(v)], dtype=np.float32)
+
+
+def plane_normal(plane):
+    """Plane::GetNormal (Plane.h:42-50): sqrt in double, then cast to float."""
+    a, b = f32(plane[0]), f32(plane[1])
+    # `1.0 + a*a + b*b`: a*a is float*float (rounded to float), then promoted to double
+    nz = f32(1.0 / np.sqrt(1.0 + float(f32(a * a)) + float(f32(b * b))))
+    nx = f32(-a * nz)
+    ny = f32(-b * nz)
+    return np.array([nx, ny, nz], dtype=np.float32)
+
+
+def plane_get_z(plane, x, y):
+    """Plane::GetZ (Plane.h:51-58): (a*x + b*y) + c in float, no contraction."""
+    a, b, c = f32(plane[0]), f32(plane[1]), f32(plane[2])
+    x = np.asarray(x, dtype=np.float32)
+    y = np.asarray(y, dtype=np.float32)
+    return (a * x + b * y) + c
+
+
+# ----------------------------------------------------------------------------
+# cv::RNG restatement (OpenCV core, multiply-with-carry; used by
+# StereoEnergy.h:120-129, Proposer.h:38-45,120-148, Utilities.hpp:254-261)
+# ----------------------------------------------------------------------------
+class CvRNG:
+    """cv::RNG: state = (uint32)state * 4164903690 + (state >> 32)."""
+
+    def __init__(self, seed=0xFFFFFFFF):
+        self.state = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if self.state == 0:
+            self.state = 0xFFFFFFFF
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * 4164903690 + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform_int(self, a, b):
+        return a if a == b else int(self.next() % (b - a) + a)
+
+    def uniform_float(self, a, b):
+        a, b = f32(a), f32(b)
+        r = f32(f32(self.next()) * f32(2.3283064365386962890625e-10))
+        return f32(f32(r * f32(b - a)) + a)
+
+    def uniform_double(self, a, b):
+        t = self.next()
+        t = (t << 32) | self.next()
+        # (uint64)t * 5.4210108624275221700372640043497e-20  -> [0, 1)
+        r = float(t) * 5.4210108624275221700372640043497e-20
+        return r * (b - a) + a
+
+
+def random_unit_vector(rng: CvRNG, theta_range=np.pi):
+    """cvutils::getRandomUnitVector (Utilities.hpp:254-261)."""
+    theta = rng.uniform_double(0.0, theta_range)
+    phi = rng.uniform_double(0.0, np.pi * 2.0)
+    ct, st = np.cos(theta), np.sin(theta)
+    cp, sp = np.cos(phi), np.sin(phi)
+    return np.array([st * cp, st * sp, ct], dtype=np.float64)
+
+
+def create_random_label(rng: CvRNG, sx, sy, min_disp, max_disp):
+    """StereoEnergy::createRandomLabel (StereoEnergy.h:120-129), MAX_VDISPARITY == 0."""
+    zs = rng.uniform_float(min_disp, max_disp)
+    n = random_unit_vector(rng, np.pi / 3)
+    nf = n.astype(np.float32)  # Vec3d -> Vec<float,3> conversion at the call
+    return create_plane(nf[0], nf[1], nf[2], zs, f32(sx), f32(sy), 0.0)
+
+
+def random_proposal(rng: CvRNG, plane_in, sx, sy, m, min_disp, max_disp):
+    """RandomProposer::getNextProposal (Proposer.h:120-148) for a given source
+    label `plane_in` taken at pixel (sx, sy); m = outerIter + iter; MAX_VDISPARITY == 0."""
+    zs = plane_get_z(plane_in, f32(sx), f32(sy))
+    dz = f32(f32(max_disp - min_disp) * f32(np.power(f32(0.5), m + 1)))
+    minz = max(f32(min_disp), f32(zs - dz))
+    maxz = min(f32(max_disp), f32(zs + dz))
+    zs = rng.uniform_float(minz, maxz)
+    nr = f32(f32(1.0) * f32(np.power(f32(0.5), m)))
+    rv = random_unit_vector(rng).astype(np.float32)
+    nv = plane_normal(plane_in) + rv * nr
+    nv = nv.astype(np.float32)
+    nrm = np.sqrt(float(nv[0]) * float(nv[0]) + float(nv[1]) * float(nv[1]) + float(nv[2]) * float(nv[2]))
+    nv = (nv.astype(np.float64) / nrm).astype(np.float32)
+    return create_plane(nv[0], nv[1], nv[2], zs, f32(sx), f32(sy), plane_in[3])
+
+
+# ----------------------------------------------------------------------------
+# LayerManager::addLayer (LayerManager.h:88-185)
+# ----------------------------------------------------------------------------
+def _clip(r, W, H):
+    x0, y0 = max(r[0], 0), max(r[1], 0)
+    x1, y1 = min(r[0] + r[2], W), min(r[1] + r[3], H)
+    if x1 <= x0 or y1 <= y0:
+        return (0, 0, 0, 0)  # cv::Rect & of disjoint rects is the empty Rect()
+    return (x0, y0, x1 - x0, y1 - y0)
+
+
+def make_layer(W, H, windR, u):
+    """Returns dict(heightBlocks, widthBlocks, unit, shared, filter, groups)."""
+    minsize = max(2, u // 2)
+    frac_h, frac_w = H % u, W % u
+    split_h = 1 if frac_h >= minsize else 0
+    split_w = 1 if frac_w >= minsize else 0
+    hb, wb = H // u + split_h, W // u + split_w
+    unit, shared, filt = [], [], []
+    for i in range(hb):
+        for j in range(wb):
+            unit.append(_clip((j * u, i * u, u, u), W, H))
+            shared.append(_clip(((j - 1) * u, (i - 1) * u, 3 * u, 3 * u), W, H))
+            filt.append(_clip(((j - 1) * u - windR, (i - 1) * u - windR, 3 * u + 2 * windR, 3 * u + 2 * windR), W, H))
+    if split_w == 0:
+        for i in range(hb):
+            x1 = i * wb + wb - 1
+            r = unit[x1]
+            unit[x1] = (r[0], r[1], r[2] + frac_w, r[3])
+        if wb >= 2:
+            for i in range(hb):
+                x1 = i * wb + wb - 2
+                r = shared[x1]
+                shared[x1] = (r[0], r[1], r[2] + frac_w, r[3])
+                r = filt[x1]
+                filt[x1] = _clip((r[0], r[1], r[2] + frac_w, r[3]), W, H)
+    if split_h == 0:
+        for j in range(wb):
+            y1 = (hb - 1) * wb + j
+            r = unit[y1]
+            unit[y1] = (r[0], r[1], r[2], r[3] + frac_h)
+        if hb >= 2:
+            for j in range(wb):
+                y1 = (hb - 2) * wb + j
+                r = shared[y1]
+                shared[y1] = (r[0], r[1], r[2], r[3] + frac_h)
+                r = filt[y1]
+                filt[y1] = _clip((r[0], r[1], r[2], r[3] + frac_h), W, H)
+    groups = [[] for _ in range(16)]
+    for i in range(hb):
+        for j in range(wb):
+            groups[(i % 4) * 4 + (j % 4)].append(i * wb + j)
+    groups = [g for g in groups if g]
+    return dict(heightBlocks=hb, widthBlocks=wb, unitSize=u, unit=unit, shared=shared, filter=filt, groups=groups)
+
+
+# ----------------------------------------------------------------------------
+# Box filter: cv::boxFilter(ksize=2R+1, normalize=false, BORDER_CONSTANT)
+# (GuidedFilter.h:40-45).  OpenCV accumulates 32F/64F sources in double.
+# ----------------------------------------------------------------------------
+def box_sum(X, R):
+    X64 = np.asarray(X, dtype=np.float64)
+    h, w = X64.shape
+    P = np.zeros((h + 2 * R + 1, w + 2 * R + 1), dtype=np.float64)
+    P[R + 1:R + 1 + h, R + 1:R + 1 + w] = X64
+    # windowed sums by explicit sliding accumulation along each axis (same
+    # operation order as a running row/column sum; no integral-image cancellation)
+    k = 2 * R + 1
+    rows = np.zeros((h + 2 * R + 1, w), dtype=np.float64)
+    acc = P[:, 1:k + 1].sum(axis=1)
+    rows[:, 0] = acc
+    for x in range(1, w):
+        acc = acc + P[:, x + k] - P[:, x]
+        rows[:, x] = acc
+    out = np.zeros((h, w), dtype=np.float64)
+    acc = rows[1:k + 1, :].sum(axis=0)
+    out[0, :] = acc
+    for y in range(1, h):
+        acc = acc + rows[y + k, :] - rows[y, :]
+        out[y, :] = acc
+    return out.astype(np.asarray(X).dtype if np.asarray(X).dtype in (np.float32, np.float64) else np.float64)
+
+
+def box_sum_fast(X, R):
+    """Same quantity through a float64 summed-area table (used for big inputs;
+    agrees with box_sum to ~1e-13 relative)."""
+    X64 = np.asarray(X, dtype=np.float64)
+    h, w = X64.shape
+    S = np.zeros((h + 1, w + 1), dtype=np.float64)
+    np.cumsum(X64, axis=0, out=S[1:, 1:])
+    np.cumsum(S[1:, 1:], axis=1, out=S[1:, 1:])
+    y0 = np.clip(np.arange(h) - R, 0, h)
+    y1 = np.clip(np.arange(h) + R + 1, 0, h)
+    x0 = np.clip(np.arange(w) - R, 0, w)
+    x1 = np.clip(np.arange(w) + R + 1, 0, w)
+    out = S[np.ix_(y1, x1)] - S[np.ix_(y0, x1)] - S[np.ix_(y1, x0)] + S[np.ix_(y0, x0)]
+    dt = np.asarray(X).dtype
+    return out.astype(dt if dt in (np.float32, np.float64) else np.float64)
+
+
+# ----------------------------------------------------------------------------
+# GuidedImageFilter<T> statistics (GuidedFilter.h:58-102) and
+# FastGuidedImageFilter<T>::createSubregionFilter (:301-326)
+# ----------------------------------------------------------------------------
+class GuidedFilterStats:
+    """One-time per-image statistics: realI, mean_I_{r,g,b}, inv{rr,rg,rb,gg,gb,bb}."""
+
+    def __init__(self, I8, R, eps, dtype=np.float64, scaling=1.0 / 255, box=box_sum_fast):
+        T = np.dtype(dtype).type
+        self.T, self.R, self.eps, self.box = T, int(R), float(eps), box
+        I8 = np.asarray(I8)
+        assert I8.ndim == 3 and I8.shape[2] == 3
+        if T is np.float64:
+            real = I8.astype(np.float64) * float(scaling)  # convertTo(..., DEPTH, scaling) (:62-65)
+        else:
+            real = I8.astype(np.float32) * np.float32(scaling)
+        self.I = [np.ascontiguousarray(real[:, :, k]) for k in range(3)]  # cv::split (:67)
+        ones = np.ones(real.shape[:2], dtype=T)
+        bx = lambda X: box(X.astype(T), self.R)
+        N = bx(ones)  # (:69)
+        self.N_image = N
+        Ir, Ig, Ib = self.I
+        self.mean = [bx(Ir) / N, bx(Ig) / N, bx(Ib) / N]  # (:70-72)
+        mr, mg, mb = self.mean
+        e = T(eps)
+        vrr = bx(Ir * Ir) / N - mr * mr + e  # (:79-84)
+        vrg = bx(Ir * Ig) / N - mr * mg
+        vrb = bx(Ir * Ib) / N - mr * mb
+        vgg = bx(Ig * Ig) / N - mg * mg + e
+        vgb = bx(Ig * Ib) / N - mg * mb
+        vbb = bx(Ib * Ib) / N - mb * mb + e
+        irr = vgg * vbb - vgb * vgb  # (:87-92)
+        irg = vgb * vrb - vrg * vbb
+        irb = vrg * vgb - vgg * vrb
+        igg = vrr * vbb - vrb * vrb
+        igb = vrb * vrg - vrr * vgb
+        ibb = vrr * vgg - vrg * vrg
+        det = irr * vrr + irg * vrg + irb * vrb  # (:94)
+        self.inv = [irr / det, irg / det, irb / det, igg / det, igb / det, ibb / det]  # (:96-101)
+
+    def stats_f32(self):
+        """[9][H][W] float32: mean_r, mean_g, mean_b, irr, irg, irb, igg, igb, ibb."""
+        return np.stack([m.astype(np.float32) for m in self.mean] + [m.astype(np.float32) for m in self.inv])
+
+
+def subregion_N(rect, R, T=np.float64):
+    """N = boxfilter(ones(rect.size())) (GuidedFilter.h:324): window counts
+    clipped at the *filterRect* border."""
+    _, _, w, h = rect
+    xs = np.arange(w)
+    ys = np.arange(h)
+    nx = np.minimum(xs + R, w - 1) - np.maximum(xs - R, 0) + 1
+    ny = np.minimum(ys + R, h - 1) - np.maximum(ys - R, 0) + 1
+    return (ny[:, None] * nx[None, :]).astype(T)
+
+
+def guided_filter_sub(stats: GuidedFilterStats, rect, p_f32):
+    """GuidedImageFilter<T>::filter -> filter_raw (GuidedFilter.h:248-266, 142-247)
+    on the sub-region filter created for `rect` (:301-326).  Returns float32."""
+    T, R, box = stats.T, stats.R, stats.box
+    x, y, w, h = rect
+    sl = (slice(y, y + h), slice(x, x + w))
+    I = [c[sl] for c in stats.I]
+    m = [c[sl] for c in stats.mean]
+    irr, irg, irb, igg, igb, ibb = [c[sl] for c in stats.inv]
+    N = subregion_N(rect, R, T)
+    p = p_f32.astype(T)  # (:250-252)
+    bx = lambda X: box(np.ascontiguousarray(X, dtype=T), R)
+    Bp = bx(p)  # (:145)
+    Br, Bg, Bb_ = bx(I[0] * p), bx(I[1] * p), bx(I[2] * p)  # (:151-172)
+    mp = Bp / N  # (:206)
+    cr = Br / N - m[0] * mp  # (:212-214)
+    cg = Bg / N - m[1] * mp
+    cb = Bb_ / N - m[2] * mp
+    ar = irr * cr + irg * cg + irb * cb  # (:216-218)
+    ag = irg * cr + igg * cg + igb * cb
+    ab = irb * cr + igb * cg + ibb * cb
+    bb = mp - ar * m[0] - ag * m[1] - ab * m[2]  # (:220)
+    q = (bx(bb) + bx(ar) * I[0] + bx(ag) * I[1] + bx(ab) * I[2]) / N  # (:224-227, :243)
+    return q.astype(np.float32)  # (:260-263)
+
+
+# ----------------------------------------------------------------------------
+# CostVolumeEnergy (CostVolumeEnergy.h:55-183) and validity (StereoEnergy.h:560-610)
+# ----------------------------------------------------------------------------
+def sample_plane_cost(vol, rect, plane, th_col, min_disp=0.0, max_disp=None):
+    """HOT LOOP 1 (CostVolumeEnergy.h:69-98), interpolate == 1.  Returns pIL float32[h][w]."""
+    D = vol.shape[0]
+    MIN = f32(min_disp)
+    MAX = f32(D - 1 if max_disp is None else max_disp)
+    D0 = int(-float(MIN))
+    x, y, w, h = rect
+    a, b, c = f32(plane[0]), f32(plane[1]), f32(plane[2])
+    ys = np.arange(y, y + h, dtype=np.int64)
+    xs = np.arange(x, x + w, dtype=np.int64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        d_base = (b * ys.astype(np.float32) + c).astype(np.float32)  # (:73)
+        d = (a * xs.astype(np.float32))[None, :] + d_base[:, None]  # (:76)
+        d = d.astype(np.float32)
+        lo = d < MIN
+        hi = (~lo) & (d >= MAX)
+        bad = (~lo) & (~hi) & ~np.isfinite(d)
+        ok = ~(lo | hi | bad)
+        dd = np.where(ok, d, f32(0))
+        d0 = dd.astype(np.int32) + D0  # int(d): truncation toward zero (:83)
+        f1 = (dd - np.floor(dd)).astype(np.float32)  # (:85)
+        f0 = (f32(1.0) - f1).astype(np.float32)
+        d1 = d0 + 1
+        oob = ok & ((d1 >= D) | (d0 < 0))  # (:87-90)
+        d0c = np.clip(d0, 0, D - 1)
+        d1c = np.clip(d1, 0, D - 1)
+        Y = ys[:, None] + np.zeros((1, w), dtype=np.int64)
+        X = xs[None, :] + np.zeros((h, 1), dtype=np.int64)
+        v0 = vol[d0c, Y, X]
+        v1 = vol[d1c, Y, X]
+        C = (f0 * v0).astype(np.float32) + (f1 * v1).astype(np.float32)  # (:92)
+        C = np.where(lo, vol[0][Y, X], C)  # (:78)
+        C = np.where(hi, vol[D - 1][Y, X], C)  # (:79)
+        C = np.where(bad | oob, COST_FOR_INVALID, C).astype(np.float32)  # (:80,:89)
+        th = f32(th_col)
+        p = np.where(th < C, th, C).astype(np.float32)  # std::min(C, th_col) (:96)
+    return p
+
+
+def is_valid_label(plane, rect, min_disp, max_disp):
+    """StereoEnergy::IsValiLabel(Plane, Rect) (StereoEnergy.h:577-610) -> bool[h][w].
+    ds follows cvutils::channelSum(coordinates(pos).mul(label.toScalar()))
+    (Utilities.hpp:224-229): float products summed left to right,
+    ((x*a + y*b) + 1*c) + 0*v  (order verified against cv2.reduce, see tests)."""
+    x, y, w, h = rect
+    a, b, c, v = (f32(t) for t in plane[:4])
+    MIN, MAX = f32(min_disp), f32(max_disp)
+    with np.errstate(invalid="ignore", over="ignore"):
+        a5 = f32(a * f32(5))
+        b5 = f32(b * f32(5))
+        if w == 1 and h == 1:  # 1x1 fast path (:579-583 -> :560-574): Plane::GetZ(cv::Point)
+            ds = np.array([[(a * f32(x) + b * f32(y)) + c]], dtype=np.float32)
+        else:
+            xs = np.arange(x, x + w).astype(np.float32)[None, :]
+            ys = np.arange(y, y + h).astype(np.float32)[:, None]
+            ds = ((xs * a + ys * b).astype(np.float32) + c * f32(1)).astype(np.float32) + f32(0) * v
+            ds = ds.astype(np.float32)
+        ok = (ds >= MIN) & (ds <= MAX)
+        for sa, sb in ((1, 1), (1, -1), (-1, 1), (-1, -1)):
+            t = (ds + a5) if sa > 0 else (ds - a5)
+            t = t.astype(np.float32)
+            t = (t + b5) if sb > 0 else (t - b5)
+            t = t.astype(np.float32)
+            ok &= (t >= MIN) & (t <= MAX)
+    return ok
+
+
+class CostVolumeEnergyOracle:
+    """CostVolumeEnergy (CostVolumeEnergy.h:6-184) with filterName "GF" (T=double,
+    default, main.cpp:73) or "GFfloat" (T=float) or "" (no filter)."""
+
+    def __init__(self, imL, imR, volL, volR, windR, eps, th_col, max_disp, min_disp=0.0,
+                 filter_name="GF", box=box_sum_fast):
+        self.im = [np.asarray(imL), np.asarray(imR) if imR is not None else None]
+        self.vol = [volL, volR]
+        self.windR, self.eps, self.th_col = int(windR), float(eps), f32(th_col)
+        self.MAX, self.MIN = f32(max_disp), f32(min_disp)
+        self.filter_name = filter_name
+        self.filter = [None, None]
+        if filter_name in ("GF", "GFfloat"):
+            T = np.float64 if filter_name == "GF" else np.float32
+            for m in range(2):
+                if self.im[m] is not None:
+                    self.filter[m] = GuidedFilterStats(self.im[m], self.windR // 2, eps, T, box=box)  # (:30-31)
+
+    def raw(self, filter_rect, plane, mode=0):
+        return sample_plane_cost(self.vol[mode], filter_rect, plane, self.th_col, self.MIN, self.MAX)
+
+    def compute_unary_potential_without_check(self, filter_rect, target_rect, plane, mode=0):
+        """Returns float32[th][tw]: the values written to costs(targetRect - filterRect.tl()) (:169-171)."""
+        p = self.raw(filter_rect, plane, mode)
+        fx, fy, _, _ = filter_rect
+        tx, ty, tw, th = target_rect
+        q = guided_filter_sub(self.filter[mode], filter_rect, p) if self.filter_name else p
+        return q[ty - fy:ty - fy + th, tx - fx:tx - fx + tw].copy()
+
+    def compute_unary_potential(self, filter_rect, target_rect, plane, mode=0):
+        out = self.compute_unary_potential_without_check(filter_rect, target_rect, plane, mode)
+        valid = is_valid_label(plane, target_rect, self.MIN, self.MAX)  # (:179)
+        out[~valid] = COST_FOR_INVALID  # (:180-182)
+        return out
+
+
+# ----------------------------------------------------------------------------
+# Volume preparation (main.cpp:146-199)
+# ----------------------------------------------------------------------------
+def fill_out_of_view(vol, mode, margin=0):
+    """fillOutOfView (main.cpp:146-176), in place."""
+    D, H, W = vol.shape
+    for d in range(D):
+        k = d + margin
+        if mode == 0:
+            if k > 0:
+                vol[d, :, :k] = vol[d, :, k:k + 1]
+        else:
+            if k > 0:
+                vol[d, :, W - k:] = vol[d, :, W - k - 1:W - k]
+    return vol
+
+
+def convert_volume_l2r(vol, margin=0):
+    """convertVolumeL2R (main.cpp:178-199)."""
+    D, H, W = vol.shape
+    dst = vol.copy()
+    for d in range(D):
+        dst[d, :, :W - d] = vol[d, :, d:]
+        edge1 = vol[d, :, W - 1 - margin].copy()
+        edge0 = vol[d, :, d + margin].copy()
+        for x in range(W - 1 - d - margin, W):
+            dst[d, :, x] = edge1
+        for x in range(margin):
+            dst[d, :, x] = edge0
+    return dst
+
+
+# ----------------------------------------------------------------------------
+# Synthetic inputs -- shared by tests and bench so that the
+# GPU arm, the oracle and the CPU baseline see identical data.
+# ----------------------------------------------------------------------------
+def synthetic_image(H, W, seed):
+    """8UC3 guide: smooth random field stretched to 0..255 plus +-8 white noise."""
+    rng = np.random.default_rng(seed)
+    img = np.empty((H, W, 3), dtype=np.uint8)
+    # separable binomial-ish blur (sigma ~ 3) of uniform noise, numpy only
+    k = np.exp(-0.5 * (np.arange(-9, 10) / 3.0) ** 2)
+    k /= k.sum()
+    for c in range(3):
+        z = rng.random((H + 18, W + 18))
+        z = np.apply_along_axis(lambda r: np.convolve(r, k, mode="valid"), 1, z)
+        z = np.apply_along_axis(lambda r: np.convolve(r, k, mode="valid"), 0, z)
+        z = (z - z.min()) / max(z.max() - z.min(), 1e-12) * 255.0
+        z = z + rng.integers(-8, 9, size=(H, W))
+        img[:, :, c] = np.clip(np.rint(z), 0, 255).astype(np.uint8)
+    return img
+
+
+def synthetic_volume(D, H, W, seed):
+    rng = np.random.default_rng(seed)
+    return rng.random((D, H, W), dtype=np.float32)
+
+
+def synthetic_planes(cells_unit, n_steps, D, seed):
+    """Per cell, per step: createRandomLabel anchored at a random pixel of the unit
+    cell for step 0, RandomProposer perturbations (m = step-1) of it afterwards."""
+    rng = CvRNG(seed if seed else 1)
+    out = np.zeros((n_steps, len(cells_unit), 4), dtype=np.float32)
+    for i, (ux, uy, uw, uh) in enumerate(cells_unit):
+        n = rng.uniform_int(0, uw * uh)
+        sx, sy = ux + n % uw, uy + n // uw
+        base = create_random_label(rng, sx, sy, 0.0, float(D - 1))
+        out[0, i] = base
+        for s in range(1, n_steps):
+            out[s, i] = random_proposal(rng, base, sx, sy, s - 1, 0.0, float(D - 1))
+    return out

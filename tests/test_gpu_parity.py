@@ -1,0 +1,121 @@
+"""GPU parity: CUDA path (through the C-ABI) vs the numpy oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+from oracle import lexp_oracle as O
+from lexp_testlib import assert_costs_close, make_scene, random_planes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    import localexpstereo_b200 as L
+    H, W, D, windR = 150, 210, 24, 20
+    imL, imR, volL, volR = make_scene(H, W, D)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(imL, imR, volL, volR, prm, D - 1)
+    Or = O.CostVolumeEnergyOracle(imL, imR, volL, volR, windR, 1e-4, 0.5, D - 1)
+    yield dict(H=H, W=W, D=D, windR=windR, E=E, O=Or, L=L)
+    E.close()
+
+
+def test_stats_match_oracle(scene):
+    for mode in (0, 1):
+        got = scene["E"].stats(mode)
+        ref = scene["O"].filter[mode].stats_f32()
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)
+        assert rel.max() < 1e-5, rel.max()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("unit", [10, 31])
+def test_cells_of_a_layer(scene, mode, unit):
+    L, E, Or = scene["L"], scene["E"], scene["O"]
+    lm = L.LayerManager(scene["W"], scene["H"], scene["windR"])
+    lay = lm.addLayer(unit)
+    rng = O.CvRNG(7 + unit + mode)
+    worst = 0.0
+    for g in lay.disjointRegionSets[:6]:
+        planes = random_planes(rng, [lay.unitRegions[r] for r in g], scene["D"])
+        fr = [lay.filterRegions[r] for r in g]
+        tr = [lay.sharedRegions[r] for r in g]
+        img = np.full((scene["H"], scene["W"]), -7.0, np.float32)
+        E.ComputeUnaryPotentialBatch(fr, tr, img, planes, mode=mode, with_check=True)
+        touched = np.zeros_like(img, dtype=bool)
+        for f, t, p in zip(fr, tr, planes):
+            ref = Or.compute_unary_potential(f, t, p, mode)
+            got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+            worst = max(worst, assert_costs_close(got, ref, f"cell f={f} t={t}"))
+            touched[t[1]:t[1] + t[3], t[0]:t[0] + t[2]] = True
+        assert (img[~touched] == -7.0).all(), "wrote outside targetRect"
+    print("worst rel err", worst)
+
+
+def test_single_cell_virtuals(scene):
+    """The two StereoEnergy virtuals, called the way FastGCStereo.h:49 / :113 does."""
+    L, E, Or = scene["L"], scene["E"], scene["O"]
+    H, W, D = scene["H"], scene["W"], scene["D"]
+    rng = O.CvRNG(99)
+    proposal = np.zeros((H, W), np.float32)
+    for (f, t) in [((30, 20, 100, 90), (50, 40, 60, 50)), ((0, 0, 70, 60), (0, 0, 50, 40)), ((110, 60, 100, 90), (130, 80, 80, 70)),
+                   ((40, 40, 41, 41), (60, 60, 1, 1))]:
+        p = O.create_random_label(rng, t[0], t[1], 0, D - 1)
+        view = proposal[f[1]:f[1] + f[3], f[0]:f[0] + f[2]]
+        E.ComputeUnaryPotentialWithoutCheck(f, t, view, p)
+        ref = Or.compute_unary_potential_without_check(f, t, p)
+        assert_costs_close(proposal[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"nocheck {f} {t}")
+        E.ComputeUnaryPotential(f, t, view, p)
+        ref = Or.compute_unary_potential(f, t, p)
+        assert_costs_close(proposal[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"check {f} {t}")
+
+
+def test_branches_of_the_sampler(scene):
+    """d < MIN, d >= MAX, NaN planes, invalid-corner mask (CostVolumeEnergy.h:78-92, StereoEnergy.h:577-610)."""
+    E, Or, D = scene["E"], scene["O"], scene["D"]
+    f, t = (20, 10, 120, 100), (40, 30, 80, 60)
+    H, W = scene["H"], scene["W"]
+    planes = [
+        (0.0, 0.0, -5.0, 0.0),            # everywhere below MIN
+        (0.0, 0.0, D + 3.0, 0.0),         # everywhere above MAX
+        (0.35, -0.2, 3.0, 0.0),           # crosses both ends
+        (float("nan"), 0.0, 1.0, 0.0),    # NaN disparity
+        (0.0, 0.0, float(D - 1), 0.0),    # exactly MAX
+        (0.0, 0.0, 0.0, 0.0),             # exactly MIN
+        (1.7, 1.7, -100.0, 0.0),          # steep
+        (0.0, 0.0, 5.5, float("inf")),    # v = inf poisons channelSum
+    ]
+    for p in planes:
+        p = np.array(p, np.float32)
+        for chk in (False, True):
+            img = np.zeros((H, W), np.float32)
+            view = img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]]
+            (E.ComputeUnaryPotential if chk else E.ComputeUnaryPotentialWithoutCheck)(f, t, view, p)
+            ref = (Or.compute_unary_potential if chk else Or.compute_unary_potential_without_check)(f, t, p)
+            got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+            if np.isnan(ref).any():
+                assert np.array_equal(np.isnan(ref), np.isnan(got))
+                ref = np.nan_to_num(ref, nan=0.0); got = np.nan_to_num(got, nan=0.0)
+            assert_costs_close(got, ref, f"plane {p} chk={chk}")
+
+
+def test_filter_rect_smaller_than_dependency_cone(scene):
+    """N is clipped at the *filterRect* (GuidedFilter.h:324), also when filterRect < targetRect +- 2R."""
+    E, Or, D = scene["E"], scene["O"], scene["D"]
+    H, W = scene["H"], scene["W"]
+    rng = O.CvRNG(3)
+    for (f, t) in [((50, 40, 60, 50), (55, 45, 50, 40)), ((50, 40, 60, 50), (50, 40, 60, 50)), ((10, 10, 25, 130), (12, 30, 20, 90))]:
+        p = O.create_random_label(rng, t[0], t[1], 0, D - 1)
+        img = np.zeros((H, W), np.float32)
+        E.ComputeUnaryPotential(f, t, img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], p)
+        ref = Or.compute_unary_potential(f, t, p)
+        assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"{f} {t}")
+
+
+def test_errors_are_reported(scene):
+    L, E = scene["L"], scene["E"]
+    img = np.zeros((scene["H"], scene["W"]), np.float32)
+    with pytest.raises(L.LexpError):
+        E.ComputeUnaryPotentialBatch([(0, 0, 50, 50)], [(40, 40, 20, 20)], img, np.zeros((1, 4), np.float32))  # target not inside filter
+    with pytest.raises(L.LexpError):
+        E.ComputeUnaryPotentialBatch([(-5, 0, 50, 50)], [(0, 0, 20, 20)], img, np.zeros((1, 4), np.float32))  # outside the image
