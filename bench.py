@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- plane-hypothesis cost evals/sec of the unary-cost hot path (BASELINE.json metric).
+
+A *step* is one local-expansion sweep over one view: 3 layers x <=16 disjoint groups x K proposal
+steps = 240 batched evaluations (FastGCStereo.h:22-72), on synthetic inputs of the shape
+BASELINE.json names.  `value` = filterRect-pixel evals of the whole job / device time, inputs
+resident in HBM.  `e2e` = same sweep through the host-buffer API (planes H2D, costs D2H).
+`--impl reference` times the CPU restatement of the reference (oracle/lexp_oracle.c; the reference
+itself cannot be compiled here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (W, H, D, windR)   -- BASELINE.json configs[2] / [1] / [4]
+    "synthetic_2048x1536x256_r20": (2048, 1536, 256, 20),
+    "adirondack_shape_1436x992x290_r20": (1436, 992, 290, 20),
+    "synthetic_4k_3840x2160x512_r32": (3840, 2160, 512, 32),
+    "tiny_450x375x64_r20": (450, 375, 64, 20),
+}
+TH_COL, EPS = 0.5, 1e-4  # main.cpp:26,351 / main.cpp:73
+METRIC = "plane-hypothesis cost evals/sec"
+UNIT = "evals/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(W, H, D, need_right=False):
+    from localexpstereo_b200 import synth
+    imL = synth.synthetic_image(H, W, 42)
+    rng = np.random.default_rng(1234)
+    vol = rng.random((D, H, W), dtype=np.float32)
+    return imL, vol
+
+
+def all_planes(sweep, D):
+    from localexpstereo_b200 import synth
+    per_layer = [synth.synthetic_planes(sweep.layer(li).unitRegions, sweep.steps[li], D, 7 + li) for li in range(len(sweep.steps))]
+    return [np.ascontiguousarray(per_layer[g.layer][:, g.cells, :]) for g in sweep.groups]  # [K][n][4] per group plan
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, W, H, D, windR, rank, world):
+    """CPU arm: oracle/lexp_oracle.c (kind "port") with all host threads, on a bounded sample of the sweep."""
+    if rank != 0:
+        return
+    from oracle.c_oracle import COracle, max_threads
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import V3_STEPS, v3_layer_units
+    from localexpstereo_b200 import synth
+    imL, vol = make_inputs(W, H, D)
+    orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
+    orc.set_image(0, imL)
+    orc.set_volume(0, vol)
+    lm = L.LayerManager(W, H, windR)
+    units = v3_layer_units(W)
+    sample = []  # (layer, group 0, step k) for every layer: 15 of the 240 batched evaluations
+    for li, u in enumerate(units):
+        lay = lm.addLayer(u)
+        cells = lay.disjointRegionSets[0]
+        pls = synth.synthetic_planes(lay.unitRegions, V3_STEPS[li], D, 7 + li)[:, cells, :]
+        fr = [lay.filterRegions[r] for r in cells]
+        tr = [lay.sharedRegions[r] for r in cells]
+        for k in range(V3_STEPS[li]):
+            sample.append((fr, tr, pls[k]))
+    evals = sum(sum(f[2] * f[3] for f in fr) for fr, _, _ in sample)
+    out = np.zeros((H, W), np.float32)
+    nthr = max_threads()
+
+    def step():
+        for fr, tr, pl in sample:
+            orc.unary_batch(0, fr, tr, pl, out, True, nthr)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = evals / dt
+    desc = f"group 0 of each of the 3 layers, all K=9/3/3 steps ({len(sample)} of 240 batched evaluations, {evals} evals per step)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 guided filter / f32 sampling", "data": "synthetic",
+        "config": {"workload": args.workload, "W": W, "H": H, "ndisp": D, "windR": windR, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, W, H, D, windR, rank, world, local_rank):
+    import torch
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import UnarySweep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    imL, vol_h = make_inputs(W, H, D)
+    vol_d = torch.from_numpy(vol_h).to(dev)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS, th_col=TH_COL)
+    E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    E.set_stream(stream.cuda_stream)
+    sweep = UnarySweep(E, rank=rank, world=world)
+    planes_h = all_planes(sweep, D)
+    planes_d = [torch.from_numpy(p).to(dev) for p in planes_h]
+    cost_d = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    pitch = W * 4
+
+    # cell-shard exchange buffers: per group, every rank contributes its per-cell unary tiles (padded to the max)
+    gather = None
+    if world > 1:
+        sizes = torch.tensor([g.plan.target_px for g in sweep.groups], device=dev)
+        # groups are identical in count on all ranks only if every group has >= world cells; align by (layer, group) key
+        keys = [(g.layer, g.group) for g in sweep.groups]
+        all_keys = [None] * world
+        dist.all_gather_object(all_keys, keys)
+        common = [k for k in all_keys[0] if all(k in ak for ak in all_keys)]
+        mx = torch.zeros(len(common), dtype=torch.int64, device=dev)
+        mine = {k: g.plan.target_px for k, g in zip(keys, sweep.groups)}
+        loc = torch.tensor([mine[k] for k in common], dtype=torch.int64, device=dev)
+        dist.all_reduce(loc, op=dist.ReduceOp.MAX)
+        gather = {k: (torch.zeros(int(n), device=dev), torch.zeros(int(n) * world, device=dev)) for k, n in zip(common, loc.tolist())}
+
+    def sweep_device(record=None):
+        """One step of the bench: all batched evaluations of a sweep, outputs resident in HBM."""
+        for gi, g in enumerate(sweep.groups):
+            base = planes_d[gi].data_ptr()
+            n = g.plan.num_calls
+            key = (g.layer, g.group)
+            for k in range(g.n_steps):
+                if record is not None:
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+                last = (k == g.n_steps - 1)
+                if gather is not None and last and key in gather:
+                    g.plan.eval_device_tiles(base + k * n * 16, gather[key][0].data_ptr(), True, 0, planes_on_device=True)
+                else:
+                    g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), pitch, True, 0, planes_on_device=True)
+                if record is not None:
+                    e1 = torch.cuda.Event(enable_timing=True); e1.record(stream)
+                    record.append((gi, e0, e1))
+            if gather is not None and key in gather:
+                dist.all_gather_into_tensor(gather[key][1], gather[key][0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        sweep_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = E.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sweep_device()
+    ev1.record(stream)
+    barrier()
+    launches = E.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    evals_per_step = sweep.total_filter_px  # whole job, all ranks
+    value = evals_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (lexp_fused_kernel): algorithmic bytes / per-launch device time
+    rec = []
+    sweep_device(rec)
+    torch.cuda.synchronize(dev)
+    kern_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rec)
+    peak, peak_src = measured_peak_gbs()
+    achieved = sweep.local_alg_bytes / (kern_ms * 1e-3) / 1e9
+    by_layer = {}
+    for gi, e0, e1 in rec:
+        li = sweep.groups[gi].layer
+        by_layer.setdefault(li, [0.0, 0])
+        by_layer[li][0] += e0.elapsed_time(e1); by_layer[li][1] += 1
+
+    # ---- end to end through the host-buffer API: planes H2D + unary tiles D2H every evaluation
+    cost_h = np.zeros((H, W), np.float32)
+
+    def sweep_host():
+        for gi, g in enumerate(sweep.groups):
+            for k in range(g.n_steps):
+                g.plan.eval_host(planes_h[gi][k], cost_h, True, 0)
+
+    sweep_host()  # warm-up (allocates the pinned staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        sweep_host()
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = evals_per_step / float(dt.item())
+    h2d = sum(g.plan.num_calls * 16 * g.n_steps for g in sweep.groups)
+    d2h = sweep.local_target_px * 4
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on a bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.c_oracle import COracle, max_threads
+        orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
+        orc.set_image(0, imL)
+        orc.set_volume(0, vol_h)
+        nthr = max_threads()
+        out = np.zeros((H, W), np.float32)
+        tot_e, tot_t, used = 0, 0.0, []
+        for gi, g in enumerate(sweep.groups):
+            if g.group != 0:
+                continue
+            lay = sweep.layer(g.layer)
+            fr = [lay.filterRegions[r] for r in g.cells]
+            tr = [lay.sharedRegions[r] for r in g.cells]
+            orc.unary_batch(0, fr, tr, planes_h[gi][0], out, True, nthr)  # warm
+            t0 = time.perf_counter()
+            for k in range(g.n_steps):
+                orc.unary_batch(0, fr, tr, planes_h[gi][k], out, True, nthr)
+            tot_t += time.perf_counter() - t0
+            tot_e += g.plan.filter_px * g.n_steps
+            used.append(f"L{g.layer}g0x{g.n_steps}")
+        cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": nthr, "kind": "port",
+               "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s)"}
+        orc.close()
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "W": W, "H": H, "ndisp": D, "windR": windR, "th_col": TH_COL, "eps": EPS,
+                       "layers_unit": sweep.unit_sizes, "steps_per_layer": sweep.steps,
+                       "evals_per_step": evals_per_step, "target_px_per_step": sweep.total_target_px,
+                       "batched_evaluations_per_step": sweep.launches_per_sweep,
+                       "parallelism": f"cell-shard x{world}" + (", all-gather of per-cell unary tiles per group" if world > 1 else ""),
+                       "l2": "inputs larger than L2 (cost volume %.2f GB, random planes)" % (vol_h.nbytes / 1e9)},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "lexp_fused_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": sweep.local_alg_bytes, "kernel_ms_per_step": kern_ms,
+                         "ms_by_layer": {str(k): round(v[0], 4) for k, v in by_layer.items()}},
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    sweep.close()
+    E.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synthetic_2048x1536x256_r20", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    W, H, D, windR = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, W, H, D, windR, rank, world)
+    else:
+        run_ours(args, W, H, D, windR, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,11 @@ LEXP_API int lexp_plan_work(const lexp_plan* plan, int64_t* sum_filter_px, int64
  * d_cost_image: device pointer to element (0,0) of an H x W float image with row pitch step_bytes. */
 LEXP_API int lexp_plan_eval_device(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
                                    int planes_on_device, float* d_cost_image, ptrdiff_t step_bytes, int with_check);
+/* Same, but call i writes its targetRect as a contiguous tile (row pitch = targetRect.width) at
+ * d_tiles + offset_i, offset_i = sum of targetRect areas of calls 0..i-1 (the layout that is
+ * all-gathered between GPUs on the cell-shard path). */
+LEXP_API int lexp_plan_eval_device_tiles(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
+                                         int planes_on_device, float* d_tiles, int with_check);
 /* Same, host in / host out (planes H2D, compact tiles D2H, scattered into cost_image); blocking. */
 LEXP_API int lexp_plan_eval_host(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
                                  float* cost_image, ptrdiff_t cost_step_bytes, int with_check);
@@ -119,6 +124,8 @@ LEXP_API int lexp_plan_eval_host(lexp_ctx* ctx, lexp_plan* plan, int mode, const
 LEXP_API int lexp_sync(lexp_ctx* ctx);
 /* cudaStream_t of the context (so a caller can order its own device work / events after ours). */
 LEXP_API void* lexp_stream(lexp_ctx* ctx);
+/* Run all subsequent work of this context on the caller's stream (e.g. torch's current stream). */
+LEXP_API int lexp_set_stream(lexp_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);
 

@@ -48,9 +48,11 @@ SYMBOLS = {
     "lexp_plan_num_items": (C.c_int, [_P]),
     "lexp_plan_work": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lexp_plan_eval_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_ssize_t, C.c_int]),
+    "lexp_plan_eval_device_tiles": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int]),
     "lexp_plan_eval_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_ssize_t, C.c_int]),
     "lexp_sync": (C.c_int, [_P]),
     "lexp_stream": (_P, [_P]),
+    "lexp_set_stream": (C.c_int, [_P, _P]),
     "lexp_launch_count": (C.c_int64, [_P]),
     "lexp_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, _P, _P]),
 }

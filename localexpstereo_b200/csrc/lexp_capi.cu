@@ -63,6 +63,7 @@ struct lexp_ctx {
     int tile_oh = 128;    // max output rows per work item
     size_t smem_limit = 0;
     bool smem_configured = false;
+    bool own_stream = true;
 };
 
 namespace {
@@ -164,7 +165,7 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_stats[m]);
         cudaFree(c->d_vol_owned[m]);
     }
-    cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return LEXP_OK;
 }
@@ -331,6 +332,19 @@ int lexp_plan_eval_device(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane
     return run_plan(c, pl, mode, dp, d_cost_image, step_bytes / 4, 0, with_check);
 }
 
+int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, int planes_on_device,
+                                float* d_tiles, int with_check) {
+    if (!c || !pl || !planes || !d_tiles || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const Plane4* dp = reinterpret_cast<const Plane4*>(planes);
+    if (!planes_on_device) {
+        LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+        dp = pl->d_planes;
+    }
+    return run_plan(c, pl, mode, dp, d_tiles, 0, 1, with_check);
+}
+
 int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, float* cost_image,
                         ptrdiff_t step_bytes, int with_check) {
     if (!c || !pl || !planes || !cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
@@ -386,6 +400,16 @@ int lexp_sync(lexp_ctx* c) {
 }
 
 void* lexp_stream(lexp_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int lexp_set_stream(lexp_ctx* c, void* s) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)s;
+    return LEXP_OK;
+}
 int64_t lexp_launch_count(const lexp_ctx* c) { return c ? c->launches : 0; }
 
 // LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).

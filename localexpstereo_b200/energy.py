@@ -161,6 +161,16 @@ class Plan:
         check(lib().lexp_plan_eval_device(self.energy._h, self._h, mode, ptr, int(planes_on_device), int(d_cost_ptr),
                                           int(step_bytes), int(with_check)))
 
+    def eval_device_tiles(self, planes, d_tiles_ptr: int, with_check=True, mode=0, planes_on_device=False):
+        """Per-call contiguous tiles at d_tiles + sum of previous targetRect areas (floats)."""
+        if planes_on_device:
+            ptr = int(planes)
+        else:
+            self._pl_keep = _plane_array(planes)
+            ptr = self._pl_keep.ctypes.data
+        check(lib().lexp_plan_eval_device_tiles(self.energy._h, self._h, mode, ptr, int(planes_on_device), int(d_tiles_ptr),
+                                                int(with_check)))
+
     def close(self):
         if self._h:
             lib().lexp_plan_destroy(self._h)
@@ -257,6 +267,10 @@ class CostVolumeEnergy:
     @property
     def stream(self) -> int:
         return int(lib().lexp_stream(self._h) or 0)
+
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(lib().lexp_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     @property
     def launch_count(self) -> int:
