@@ -40,6 +40,7 @@ int env_int(const char* name, int dflt) {
 struct lexp_plan {
     lexp_ctx* ctx = nullptr;
     int ncalls = 0, nitems = 0, max_vw = 0;
+    size_t smem = 0;  // dynamic shared memory of the largest item
     std::vector<lexp_rect> filt, targ;
     std::vector<int> compact_off;  // per call
     int64_t sum_f = 0, sum_s = 0, alg_bytes = 0;
@@ -54,12 +55,13 @@ struct lexp_ctx {
     int R = 0;
     cudaStream_t stream = nullptr;
     uchar4* d_guide[2] = {nullptr, nullptr};
-    float* d_stats[2] = {nullptr, nullptr};
+    float4* d_statA[2] = {nullptr, nullptr};
+    float4* d_statB[2] = {nullptr, nullptr};
+    float* d_statC[2] = {nullptr, nullptr};
     const float* d_vol[2] = {nullptr, nullptr};
     float* d_vol_owned[2] = {nullptr, nullptr};
     int64_t launches = 0;
     std::mutex mu;
-    int ch = 4;           // rows per chunk (template CH)
     int tile_oh = 128;    // max output rows per work item
     size_t smem_limit = 0;
     bool smem_configured = false;
@@ -68,10 +70,10 @@ struct lexp_ctx {
 
 namespace {
 
-template <int R_T, int CH>
+template <int R_T>
 int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
-    auto kern = lexp_fused_kernel<R_T, CH>;
-    if (!c->smem_configured) {  // one (R, CH) instantiation per context
+    auto kern = lexp_fused_kernel<R_T>;
+    if (!c->smem_configured) {  // one R instantiation per context
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
         c->smem_configured = true;
     }
@@ -81,20 +83,13 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
     return LEXP_OK;
 }
 
-template <int CH>
-int launch_fused_ch(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
-    switch (c->R) {
-        case 10: return launch_fused_t<10, CH>(c, kp, nitems, smem);
-        case 16: return launch_fused_t<16, CH>(c, kp, nitems, smem);
-        default: return launch_fused_t<0, CH>(c, kp, nitems, smem);
-    }
-}
-
-int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, int max_vw) {
-    const size_t smem = fused_smem_bytes(max_vw, c->R, c->ch);
+int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
     if (smem > c->smem_limit) return fail(LEXP_ERR_INVALID, "tile needs more shared memory than the device offers");
-    if (c->ch == 2) return launch_fused_ch<2>(c, kp, nitems, smem);
-    return launch_fused_ch<4>(c, kp, nitems, smem);
+    switch (c->R) {
+        case 10: return launch_fused_t<10>(c, kp, nitems, smem);
+        case 16: return launch_fused_t<16>(c, kp, nitems, smem);
+        default: return launch_fused_t<0>(c, kp, nitems, smem);
+    }
 }
 
 int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
@@ -113,7 +108,9 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     KParams kp{};
     kp.vol = c->d_vol[mode];
     kp.guide = c->d_guide[mode];
-    kp.stats = c->d_stats[mode];
+    kp.statA = c->d_statA[mode];
+    kp.statB = c->d_statB[mode];
+    kp.statC = c->d_statC[mode];
     kp.items = pl->d_items;
     kp.planes = d_planes;
     kp.out = d_out;
@@ -123,7 +120,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     kp.th_col = c->p.th_col; kp.min_disp = c->p.min_disp; kp.max_disp = c->p.max_disp;
     kp.with_check = with_check;
     kp.R = c->R;
-    return launch_fused(c, kp, pl->nitems, pl->max_vw);
+    return launch_fused(c, kp, pl->nitems, pl->smem);
 }
 
 }  // namespace
@@ -148,9 +145,8 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->p = *params;
     c->R = params->windR / 2;  // CostVolumeEnergy.h:30
     c->smem_limit = prop.sharedMemPerBlockOptin;
-    c->ch = env_int("LEXP_CH", 4) == 2 ? 2 : 4;
     c->tile_oh = std::max(8, env_int("LEXP_TILE_OH", 128));
-    if (4 * c->R + 8 > kThreads) { delete c; return fail(LEXP_ERR_INVALID, "windR too large for the tile width"); }
+    if (max_tile_ow(c->R) < 8) { delete c; return fail(LEXP_ERR_INVALID, "windR too large for the tile width"); }
     LEXP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out_ctx = c;
     return LEXP_OK;
@@ -162,7 +158,9 @@ int lexp_destroy(lexp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int m = 0; m < 2; m++) {
         cudaFree(c->d_guide[m]);
-        cudaFree(c->d_stats[m]);
+        cudaFree(c->d_statA[m]);
+        cudaFree(c->d_statB[m]);
+        cudaFree(c->d_statC[m]);
         cudaFree(c->d_vol_owned[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -182,13 +180,17 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
         for (int x = 0; x < W; x++) tmp[(size_t)y * W + x] = make_uchar4(row[3 * x], row[3 * x + 1], row[3 * x + 2], 0);
     }
     if (!c->d_guide[mode]) LEXP_CUDA(cudaMalloc(&c->d_guide[mode], HW * sizeof(uchar4)));
-    if (!c->d_stats[mode]) LEXP_CUDA(cudaMalloc(&c->d_stats[mode], 9 * HW * sizeof(float)));
+    if (!c->d_statA[mode]) {
+        LEXP_CUDA(cudaMalloc(&c->d_statA[mode], HW * sizeof(float4)));
+        LEXP_CUDA(cudaMalloc(&c->d_statB[mode], HW * sizeof(float4)));
+        LEXP_CUDA(cudaMalloc(&c->d_statC[mode], HW * sizeof(float)));
+    }
     LEXP_CUDA(cudaMemcpyAsync(c->d_guide[mode], tmp.data(), HW * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
     int* d_rs = nullptr;
     LEXP_CUDA(cudaMalloc(&d_rs, 9 * HW * sizeof(int)));
     dim3 blk(128), grd((W + 127) / 128, H);
     lexp_stats_rowsum<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], d_rs, H, W, c->R);
-    lexp_stats_finish<<<grd, blk, 0, c->stream>>>(d_rs, c->d_stats[mode], H, W, c->R, (double)c->p.eps);
+    lexp_stats_finish<<<grd, blk, 0, c->stream>>>(d_rs, c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], H, W, c->R, (double)c->p.eps);
     c->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -221,11 +223,18 @@ int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) {
 
 int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {
     if (!c || !out9 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
-    if (!c->d_stats[mode]) return fail(LEXP_ERR_STATE, "image not set");
+    if (!c->d_statA[mode]) return fail(LEXP_ERR_STATE, "image not set");
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
-    LEXP_CUDA(cudaStreamSynchronize(c->stream));
-    LEXP_CUDA(cudaMemcpy(out9, c->d_stats[mode], 9 * (size_t)c->p.height * c->p.width * sizeof(float), cudaMemcpyDeviceToHost));
+    const size_t HW = (size_t)c->p.height * c->p.width;
+    float* d9 = nullptr;
+    LEXP_CUDA(cudaMalloc(&d9, 9 * HW * sizeof(float)));
+    lexp_stats_unpack<<<(unsigned)((HW + 255) / 256), 256, 0, c->stream>>>(c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], d9, HW);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out9, d9, 9 * HW * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d9);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("get_stats: ") + cudaGetErrorString(e));
     return LEXP_OK;
 }
 
@@ -238,7 +247,7 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int R = c->R;
-    const int ow_max = kThreads - 4 * R;
+    const int ow_max = max_tile_ow(R);
     const int oh_max = c->tile_oh;
     lexp_plan* pl = new lexp_plan();
     pl->ctx = c;
@@ -265,6 +274,7 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
                 it.flags = (t.width == 1 && t.height == 1) ? 1 : 0;
                 items.push_back(it);
                 pl->max_vw = std::max(pl->max_vw, it.ow + 4 * R);
+                pl->smem = std::max(pl->smem, fused_smem_bytes(it.ow + 4 * R, it.oh, R));
             }
         }
         coff += (int64_t)t.width * t.height;

@@ -8,21 +8,33 @@
 //                       (StereoEnergy.h:577-610, CostVolumeEnergy.h:176-183).
 // File:line citations are relative to /root/reference/LocalExpansionStereo/.
 //
-// Design: one CTA = one output tile of one (cell, plane) call.  The CTA
-// streams top-to-bottom over the rows of the tile's dependency cone (tile +- 2R):
-//   V-phase (thread = column): gather p, running column sums of {p, I*p} (stage 1) and of
-//            {a, b} (stage 2) kept in registers, the 2R+1 rows they will subtract later
-//            kept in a thread-private shared-memory ring; epilogue q = (Bb + Ba.I)/N.
-//   H-phase (thread = run of 8 columns): horizontal window sums over the rows of the chunk.
-// Two CTA barriers per chunk of CH rows; intermediates never leave the SM.
+// Design: one CTA = one output tile (<= 64 columns) of one (cell, plane)
+// call.  The CTA streams top-to-bottom over the rows of the tile's dependency cone
+// (tile +- 2R) in chunks of CH rows.  Five warp teams form a software pipeline, one CTA
+// barrier per chunk, all intermediates in shared memory / registers:
+//   A (4 warps, thread = column): gather p = min(lerp(V, plane), th) (register prefetch three
+//       chunks ahead), products {p, I0 p, I1 p, I2 p}, running column sums over 2R+1 rows
+//       (thread-private ring of the rows to subtract later)            -> hb1
+//   H (2 warps, thread = run of 8 columns): horizontal window sums of hb1 -> ho1, hb2 -> ho2
+//   C (3 warps, thread = column): (a, b) from the stage-1 box sums and the precomputed
+//       statistics, running column sums of {a0, a1, a2, b}              -> hb2
+//   E (2 warps, thread = column): q = (Bb + Ba.I) / N, validity mask, store.
+// float4 quantities are held as two packed f32x2 registers and added with Blackwell's
+// FADD2 (add.rn.f32x2): two FP32 adds per issue slot.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace lexp {
 
-constexpr int kThreads = 128;          // CTA size == max virtual tile width (ow + 4R)
-constexpr int kRun = 8;                // columns per H-phase task
+constexpr int kWarpsA = 4, kWarpsH = 2, kWarpsC = 3, kWarpsE = 2;
+constexpr int kThreads = 32 * (kWarpsA + kWarpsH + kWarpsC + kWarpsE);  // 352
+constexpr int kMaxVW = 32 * kWarpsA;   // virtual tile width  ow + 4R
+constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
+constexpr int kMaxOW = 32 * kWarpsE;   // output columns
+constexpr int kRun = 8;                // columns per H task
+constexpr int kCH = 2;                 // rows per pipeline chunk
+constexpr int kPD = 3;                 // gather prefetch distance (chunks)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
 
 struct __align__(16) Item {  // one CTA work item (64 B)
@@ -40,7 +52,9 @@ struct Plane4 { float a, b, c, v; };
 struct KParams {
     const float* __restrict__ vol;      // float[D][H][W]
     const uchar4* __restrict__ guide;   // uchar4[H][W] = (c0,c1,c2,0), OpenCV BGR order
-    const float* __restrict__ stats;    // float[9][H][W]: mean c0,c1,c2, inv 00,01,02,11,12,22
+    const float4* __restrict__ statA;   // float4[H][W] = {mean0, mean1, mean2, inv00}
+    const float4* __restrict__ statB;   // float4[H][W] = {inv01, inv02, inv11, inv12}
+    const float* __restrict__ statC;    // float [H][W] =  inv22
     const Item* __restrict__ items;
     const Plane4* __restrict__ planes;
     float* __restrict__ out;
@@ -52,244 +66,361 @@ struct KParams {
     int R;                              // guided-filter box radius (windR / 2)
 };
 
-__host__ __device__ __forceinline__ int sidx(int x) { return x + (x >> 3); }  // bank-conflict padding
-__host__ __device__ __forceinline__ int srow_stride(int vw) {
+// largest output-tile width the team sizes allow for box radius R
+__host__ __device__ inline int max_tile_ow(int R) {
+    int a = kMaxVW - 4 * R, b = kMaxW2 - 2 * R, c = kMaxOW;
+    int m = a < b ? a : b;
+    return m < c ? m : c;
+}
+__host__ __device__ __forceinline__ int sidx(int x) { return x + (x >> 3); }  // 1 pad slot per 8 columns
+__host__ __device__ inline int srow_stride(int vw) {
     int s = sidx(vw + kRun + 7) + 1;
-    return s + ((10 - (s & 7)) & 7);  // == 2 (mod 8) in float4 units
+    return s + ((12 - (s & 7)) & 7);  // == 4 (mod 8) float4 units: the 2 rows x 4 runs of a quarter-warp hit 8 bank groups
 }
-// dynamic shared memory (bytes) of the fused kernel for a tile of virtual width vw
-__host__ __device__ __forceinline__ size_t fused_smem_bytes(int vw, int R, int CH) {
+__host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
-    return (size_t)(K * vw + K * (vw - 2 * R) + 4 * CH * srow_stride(vw)) * sizeof(float4);
+    const int vh = oh + 4 * R;
+    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + (vh + 3) / 4) * 16;
 }
 
-__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-
-// Plane disparity at (X, y): two separately rounded operations each, like the reference's
-// `d_base = b*y + c; d = a*x + d_base` compiled without FMA contraction (CostVolumeEnergy.h:73,76).
-__device__ __forceinline__ float plane_d(float a, float d_base, int X) {
-    return __fadd_rn(__fmul_rn(a, (float)X), d_base);
+// ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
+typedef unsigned long long u64;
+struct __align__(16) F4 { u64 lo, hi; };  // lo = (x, y), hi = (z, w)
+__device__ __forceinline__ u64 pk2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
 }
+__device__ __forceinline__ void up2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
+__device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
+__device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
 
-// Classify d (CostVolumeEnergy.h:78-92).  Returns the interpolation weight f1 >= 0 and the two
-// slice indices, or f1 = -1 (clamped: C = V[i0]) or f1 = -2 (C = COST_FOR_INVALID, nothing to load).
-__device__ __forceinline__ float classify_d(float d, float minD, float maxD, int D0, int D, int& i0, int& i1) {
-    if (d < minD) { i0 = i1 = 0; return -1.f; }
-    if (d >= maxD) { i0 = i1 = D - 1; return -1.f; }
-    if (isnan(d) || isinf(d)) { i0 = i1 = 0; return -2.f; }
-    const int d0 = (int)d + D0;  // int(d): truncation toward zero (:83)
-    if (d0 + 1 >= D || d0 < 0) { i0 = i1 = 0; return -2.f; }  // (:87-90)
-    i0 = d0; i1 = d0 + 1;
-    return d - floorf(d);        // (:85)
-}
-
-template <int R_T, int CH>
-__global__ void __launch_bounds__(kThreads) lexp_fused_kernel(const KParams P) {
+template <int R_T>
+__global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
     const int K = 2 * R + 1;
-    extern __shared__ float4 smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    F4* smem = reinterpret_cast<F4*>(smem_raw);
 
     const Item it = P.items[blockIdx.x];
     const Plane4 pl = P.planes[it.call];
-    const int t = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int VW = it.ow + 4 * R, VH = it.oh + 4 * R;
     const int X0 = it.ox0 - 2 * R, Y0 = it.oy0 - 2 * R;
-    const int W2 = VW - 2 * R;            // stage-2 (a,b) columns
+    const int W2 = VW - 2 * R;
     const int SW = srow_stride(VW);
-    float4* ring1 = smem;                  // [K][VW]   raw {p, I0 p, I1 p, I2 p} rows
-    float4* ring2 = ring1 + K * VW;        // [K][W2]   {a0, a1, a2, b} rows
-    float4* hbuf1 = ring2 + K * W2;        // [CH][SW]  stage-1 column sums of the chunk
-    float4* hout1 = hbuf1 + CH * SW;       // [CH][SW]  stage-1 box sums
-    float4* hbuf2 = hout1 + CH * SW;       // [CH][SW]  stage-2 column sums
-    float4* hout2 = hbuf2 + CH * SW;       // [CH][SW]  stage-2 box sums
-
-    {   // zero-fill (box filter is zero padded, GuidedFilter.h:43 BORDER_CONSTANT)
-        const int total = K * VW + K * W2 + 4 * CH * SW;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = t; i < total; i += kThreads) smem[i] = z;
-    }
+    F4* ring1 = smem;                      // [K][VW]
+    F4* ring2 = ring1 + K * VW;            // [K][W2]
+    F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
+    F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW] stage-1 box sums      (index: column - X0 - R)
+    F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
+    F4* ho2 = hb2 + 2 * kCH * SW;          // [2][CH][SW] stage-2 box sums      (index: column - X0 - 2R)
+    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VH] 1 / (#rows of the window inside filterRect)
 
     const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
-    const size_t HW = (size_t)P.H * P.W;
-    const int D0 = (int)(-P.min_disp);
-    const float th = P.th_col;
-
-    // column roles of this thread
-    const int XA = X0 + t;                       // stage-1 gather column
-    const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
-    const int XC = X0 + R + t;                   // (a,b) column
-    const bool colC = (t < W2) && XC >= it.fx && XC < fx1;
-    const int XE = it.ox0 + t;                   // output column
-    const bool colE = t < it.ow;
-    float inv_nxC = 0.f, inv_nxE = 0.f;          // 1 / (#columns of the window inside filterRect), GuidedFilter.h:324
-    if (colC) inv_nxC = 1.0f / (float)(min(XC + R, fx1 - 1) - max(XC - R, it.fx) + 1);
-    if (colE) inv_nxE = 1.0f / (float)(min(XE + R, fx1 - 1) - max(XE - R, it.fx) + 1);
-
-    const int nChunks = (VH + CH - 1) / CH;
-    const int n1 = (W2 + kRun - 1) / kRun;       // stage-1 runs per row
-    const int n2 = (it.ow + kRun - 1) / kRun;    // stage-2 runs per row
-    const int T1 = ((CH * n1 + 31) / 32) * 32;   // stage-1 tasks padded to a warp boundary
-    const int Ttot = T1 + CH * n2;
-
-    float4 acc1 = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc1;
-    int slot1 = 0, slot2 = 0;
-
-    // prefetch registers for the gather of one chunk
-    float pv0[CH], pv1[CH], pf1[CH];
-    uint32_t pg[CH];
-
-    auto prefetch = [&](int chunk) {
-#pragma unroll
-        for (int r = 0; r < CH; r++) {
-            const int v = chunk * CH + r;
+    {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
+        const int total = K * VW + K * W2 + 8 * kCH * SW;
+        for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
+        for (int v = tid; v < VH; v += kThreads) {
             const int y = Y0 + v;
-            pf1[r] = -3.f;  // outside filterRect: contributes zero
-            pv0[r] = 0.f; pv1[r] = 0.f; pg[r] = 0u;
-            if (colA && v < VH && y >= it.fy && y < fy1) {
-                const float d_base = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);
-                const float d = plane_d(pl.a, d_base, XA);
-                int i0, i1;
-                const float f1 = classify_d(d, P.min_disp, P.max_disp, D0, P.D, i0, i1);
-                pf1[r] = f1;
-                const size_t pix = (size_t)y * P.W + XA;
-                if (f1 > -2.f) pv0[r] = __ldg(P.vol + (size_t)i0 * HW + pix);
-                if (f1 >= 0.f) pv1[r] = __ldg(P.vol + (size_t)i1 * HW + pix);
-                pg[r] = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + pix);
-            }
+            s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
         }
-    };
-
-    prefetch(0);
+    }
     __syncthreads();
 
-    for (int itn = 0; itn < nChunks + 2; itn++) {
-        // ------------------------------------------------------------------ V-phase
-        // (A) stage-1 rows of chunk itn: consume the prefetched samples
-        if (itn < nChunks) {
-            float cv0[CH], cv1[CH], cf1[CH];
-            uint32_t cg[CH];
+    const size_t HW = (size_t)P.H * P.W;
+    const int nChunks = (VH + kCH - 1) / kCH;
+    const int nIter = nChunks + 4;
+
+    if (warp < kWarpsA) {
+        // =========================================================================== team A
+        const int t = tid;
+        const int XA = X0 + t;
+        const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
+        const float ax = __fmul_rn(pl.a, (float)XA);  // CostVolumeEnergy.h:76 (product rounded separately)
+        const int D0 = (int)(-P.min_disp);
+        const float th = P.th_col;
+        const float s255 = 1.0f / 255.0f;
+        F4 acc = f4zero();
+        int slot = 0;
+        float bv0[kPD][kCH], bv1[kPD][kCH], bf1[kPD][kCH];
+        uint32_t bg[kPD][kCH];
+
+        auto issue = [&](int chunk, float* v0, float* v1, float* f1, uint32_t* g) {
 #pragma unroll
-            for (int r = 0; r < CH; r++) { cv0[r] = pv0[r]; cv1[r] = pv1[r]; cf1[r] = pf1[r]; cg[r] = pg[r]; }
-            if (itn + 1 < nChunks) prefetch(itn + 1);
-            if (t < VW) {
-#pragma unroll
-                for (int r = 0; r < CH; r++) {
-                    float4 nw = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float f1 = cf1[r];
-                    if (f1 > -3.f) {
-                        float C;
-                        if (f1 >= 0.f) C = __fadd_rn(__fmul_rn(1.0f - f1, cv0[r]), __fmul_rn(f1, cv1[r]));  // (:92)
-                        else if (f1 > -2.f) C = cv0[r];                                                      // (:78-79)
-                        else C = kCostInvalid;                                                               // (:80,:89)
-                        const float p = (th < C) ? th : C;                                                   // std::min (:96)
-                        const float s = 1.0f / 255.0f;
-                        const float i0 = (float)(cg[r] & 0xffu) * s, i1 = (float)((cg[r] >> 8) & 0xffu) * s,
-                                    i2 = (float)((cg[r] >> 16) & 0xffu) * s;
-                        nw = make_float4(p, i0 * p, i1 * p, i2 * p);                                         // GuidedFilter.h:151-169
-                    }
-                    float4* slot = ring1 + slot1 * VW + t;
-                    const float4 old = *slot;
-                    *slot = nw;
-                    acc1 = f4sub(f4add(acc1, nw), old);
-                    hbuf1[r * SW + sidx(t)] = acc1;  // column sum centred on row v - R
-                    slot1 = (slot1 + 1 == K) ? 0 : slot1 + 1;
+            for (int r = 0; r < kCH; r++) {
+                const int v = chunk * kCH + r;
+                const int y = Y0 + v;
+                f1[r] = -1.f; v0[r] = 0.f; v1[r] = 0.f; g[r] = 0u;  // outside filterRect: zero
+                if (colA && v < VH && y >= it.fy && y < fy1) {
+                    const float d_base = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);  // :73
+                    const float d = __fadd_rn(ax, d_base);                             // :76
+                    const bool lo = d < P.min_disp;                                    // :78
+                    const bool hi = !lo && d >= P.max_disp;                            // :79
+                    bool bad = !lo && !hi && (isnan(d) || isinf(d));                   // :80
+                    const float dd = (lo || hi || bad) ? 0.f : d;
+                    int d0 = (int)dd + D0;                                             // :83
+                    float ff = dd - floorf(dd);                                        // :85
+                    if (d0 + 1 >= P.D || d0 < 0) bad = true;                           // :87-90
+                    if (lo) { d0 = 0; ff = 3.f; }
+                    if (hi) { d0 = P.D - 1; ff = 3.f; }
+                    if (bad && !lo && !hi) { d0 = 0; ff = 2.f; }
+                    const int d1 = min(d0 + 1, P.D - 1);
+                    const size_t pix = (size_t)y * P.W + XA;
+                    v0[r] = __ldg(P.vol + (size_t)d0 * HW + pix);
+                    v1[r] = __ldg(P.vol + (size_t)d1 * HW + pix);
+                    g[r] = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + pix);
+                    f1[r] = ff;
                 }
             }
-        }
-        // (C) (a,b) rows from the stage-1 box sums of chunk itn-1
-        if (itn >= 1 && itn - 1 < nChunks && t < W2) {
+        };
+
 #pragma unroll
-            for (int r = 0; r < CH; r++) {
-                const int v = (itn - 1) * CH + r;
-                if (v >= 2 * R && v < VH) {
-                    const int yc = Y0 + v - R;
-                    float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (colC && yc >= it.fy && yc < fy1) {
-                        const float inv_ny = 1.0f / (float)(min(yc + R, fy1 - 1) - max(yc - R, it.fy) + 1);
-                        const float invN = inv_nxC * inv_ny;
-                        const float4 B = hout1[r * SW + sidx(t + R)];
-                        const float* st = P.stats + (size_t)yc * P.W + XC;
-                        const float m0 = __ldg(st), m1 = __ldg(st + HW), m2 = __ldg(st + 2 * HW);
-                        const float i00 = __ldg(st + 3 * HW), i01 = __ldg(st + 4 * HW), i02 = __ldg(st + 5 * HW);
-                        const float i11 = __ldg(st + 6 * HW), i12 = __ldg(st + 7 * HW), i22 = __ldg(st + 8 * HW);
-                        const float mp = B.x * invN;                       // GuidedFilter.h:206
-                        const float c0 = fmaf(B.y, invN, -m0 * mp);        // :212-214
-                        const float c1 = fmaf(B.z, invN, -m1 * mp);
-                        const float c2 = fmaf(B.w, invN, -m2 * mp);
-                        ab.x = i00 * c0 + i01 * c1 + i02 * c2;             // :216-218
-                        ab.y = i01 * c0 + i11 * c1 + i12 * c2;
-                        ab.z = i02 * c0 + i12 * c1 + i22 * c2;
-                        ab.w = mp - ab.x * m0 - ab.y * m1 - ab.z * m2;     // :220
+        for (int u = 0; u < kPD; u++) issue(u, bv0[u], bv1[u], bf1[u], bg[u]);
+
+        for (int base = 0; base < nIter; base += kPD) {
+#pragma unroll
+            for (int u = 0; u < kPD; u++) {
+                const int itn = base + u;
+                if (itn >= nIter) break;
+                if (itn < nChunks) {
+                    float cv0[kCH], cv1[kCH], cf1[kCH];
+                    uint32_t cg[kCH];
+#pragma unroll
+                    for (int r = 0; r < kCH; r++) { cv0[r] = bv0[u][r]; cv1[r] = bv1[u][r]; cf1[r] = bf1[u][r]; cg[r] = bg[u][r]; }
+                    if (itn + kPD < nChunks) issue(itn + kPD, bv0[u], bv1[u], bf1[u], bg[u]);
+                    if (t < VW) {
+                        F4* hb = hb1 + (itn & 1) * kCH * SW;
+#pragma unroll
+                        for (int r = 0; r < kCH; r++) {
+                            F4 nw = f4zero();
+                            const float f1 = cf1[r];
+                            if (f1 >= 0.f) {
+                                float C;
+                                if (f1 < 1.5f) C = __fadd_rn(__fmul_rn(1.0f - f1, cv0[r]), __fmul_rn(f1, cv1[r]));  // :92
+                                else if (f1 > 2.5f) C = cv0[r];                                                       // :78-79
+                                else C = kCostInvalid;                                                                // :80,:89
+                                const float p = (th < C) ? th : C;                                                    // std::min (:96)
+                                const float ps = p * s255, nm = -8388608.0f * ps;
+                                const uint32_t g = cg[r];
+                                // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169)
+                                const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
+                                const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
+                                const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
+                                nw = F4{pk2(p, q0), pk2(q1, q2)};
+                            }
+                            F4* sl = ring1 + slot * VW + t;
+                            const F4 old = *sl;
+                            *sl = nw;
+                            acc = f4add(acc, f4sub(nw, old));
+                            hb[r * SW + sidx(t)] = acc;  // column sum centred on row v - R
+                            slot = (slot + 1 == K) ? 0 : slot + 1;
+                        }
                     }
-                    float4* slot = ring2 + slot2 * W2 + t;
-                    const float4 old = *slot;
-                    *slot = ab;
-                    acc2 = f4sub(f4add(acc2, ab), old);
-                    hbuf2[r * SW + sidx(t + R)] = acc2;  // column sum centred on row v - 2R
-                    slot2 = (slot2 + 1 == K) ? 0 : slot2 + 1;
+                }
+                __syncthreads();
+            }
+        }
+    } else if (warp < kWarpsA + kWarpsH) {
+        // =========================================================================== team H
+        // out[i] = sum_{m=0}^{2R} in[i + m]: lane = (row r of the chunk, run k of 8 columns)
+        const bool st2 = (warp == kWarpsA + 1);
+        const int r = lane & (kCH - 1), k = lane / kCH;
+        const int nruns = ((st2 ? it.ow : W2) + kRun - 1) / kRun;
+        const int lag = st2 ? 3 : 1;
+        const int vmin = st2 ? 4 * R : 2 * R;
+        const F4* inb = st2 ? hb2 : hb1;
+        F4* outb = st2 ? ho2 : ho1;
+        for (int itn = 0; itn < nIter; itn++) {
+            const int c = itn - lag;
+            const int v = c * kCH + r;
+            if (c >= 0 && c < nChunks && k < nruns && v >= vmin && v < VH) {
+                const F4* in = inb + ((c & 1) * kCH + r) * SW + 9 * k;
+                F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
+                if (R_T > 0) {
+                    F4 w[kRun - 1];
+                    F4 s = in[0];
+                    w[0] = s;
+#pragma unroll
+                    for (int j = 1; j < 2 * R_T + 1; j++) {
+                        const F4 x = in[j + (j >> 3)];
+                        if (j < kRun - 1) w[j] = x;
+                        s = f4add(s, x);
+                    }
+                    out[0] = s;
+#pragma unroll
+                    for (int j = 1; j < kRun; j++) {
+                        const int jn = 2 * R_T + j;
+                        s = f4add(s, f4sub(in[jn + (jn >> 3)], w[j - 1]));
+                        out[j] = s;
+                    }
+                } else {
+                    F4 s = in[0];
+                    for (int j = 1; j < K; j++) s = f4add(s, in[sidx(j)]);
+                    out[0] = s;
+                    for (int j = 1; j < kRun; j++) {
+                        s = f4add(s, f4sub(in[sidx(2 * R + j)], in[sidx(j - 1)]));
+                        out[j] = s;
+                    }
                 }
             }
+            __syncthreads();
         }
-        // (E) epilogue rows from the stage-2 box sums of chunk itn-2
-        if (itn >= 2 && colE) {
+    } else if (warp < kWarpsA + kWarpsH + kWarpsC) {
+        // =========================================================================== team C
+        const int t = tid - 32 * (kWarpsA + kWarpsH);
+        const int XC = X0 + R + t;
+        const bool colC = (t < W2) && XC >= it.fx && XC < fx1;
+        float inv_nx = 0.f;
+        if (colC) inv_nx = 1.0f / (float)(min(XC + R, fx1 - 1) - max(XC - R, it.fx) + 1);
+        F4 acc = f4zero();
+        int slot = 0;
+        constexpr int PDC = 2;
+        float4 sa[PDC][kCH], sb[PDC][kCH];
+        float sc[PDC][kCH];
+        auto issue = [&](int chunk, float4* a, float4* b, float* c) {
 #pragma unroll
-            for (int r = 0; r < CH; r++) {
-                const int v = (itn - 2) * CH + r;
-                if (v >= 4 * R && v < VH) {
-                    const int yq = Y0 + v - 2 * R;
-                    const float inv_ny = 1.0f / (float)(min(yq + R, fy1 - 1) - max(yq - R, it.fy) + 1);
-                    const float4 S = hout2[r * SW + sidx(t + 2 * R)];
-                    const uint32_t g = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + (size_t)yq * P.W + XE);
-                    const float s = 1.0f / 255.0f;
-                    const float i0 = (float)(g & 0xffu) * s, i1 = (float)((g >> 8) & 0xffu) * s,
-                                i2 = (float)((g >> 16) & 0xffu) * s;
-                    float q = (S.w + S.x * i0 + S.y * i1 + S.z * i2) * (inv_nxE * inv_ny);  // GuidedFilter.h:243
-                    if (P.with_check) {  // StereoEnergy.h:577-610
-                        const float xa = __fmul_rn((float)XE, pl.a), yb = __fmul_rn((float)yq, pl.b);
-                        float ds = __fadd_rn(__fadd_rn(xa, yb), pl.c);
-                        if (!(it.flags & 1)) ds = __fadd_rn(ds, __fmul_rn(0.0f, pl.v));  // channelSum's 4th term
-                        const float a5 = __fmul_rn(pl.a, 5.0f), b5 = __fmul_rn(pl.b, 5.0f);
-                        const float lo = P.min_disp, hi = P.max_disp;
-                        const float dpp = __fadd_rn(__fadd_rn(ds, a5), b5), dpm = __fsub_rn(__fadd_rn(ds, a5), b5);
-                        const float dmp = __fadd_rn(__fsub_rn(ds, a5), b5), dmm = __fsub_rn(__fsub_rn(ds, a5), b5);
-                        const bool ok = ds >= lo && ds <= hi && dpp >= lo && dpp <= hi && dpm >= lo && dpm <= hi &&
-                                        dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
-                        if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
-                    }
-                    const int ry = v - 4 * R;  // row inside the tile
-                    if (P.out_compact)
-                        P.out[(size_t)it.compact_off + (size_t)ry * it.compact_stride + t] = q;
-                    else
-                        P.out[(size_t)yq * P.out_pitch + XE] = q;
+            for (int r = 0; r < kCH; r++) {
+                const int v = chunk * kCH + r;
+                const int yc = Y0 + v - R;
+                a[r] = make_float4(0.f, 0.f, 0.f, 0.f); b[r] = a[r]; c[r] = 0.f;
+                if (colC && v >= 2 * R && v < VH && yc >= it.fy && yc < fy1) {
+                    const size_t pix = (size_t)yc * P.W + XC;
+                    a[r] = __ldg(P.statA + pix);
+                    b[r] = __ldg(P.statB + pix);
+                    c[r] = __ldg(P.statC + pix);
                 }
             }
-        }
-        __syncthreads();
-        // ------------------------------------------------------------------ H-phase
-        for (int task = t; task < Ttot; task += kThreads) {
-            const bool st2 = task >= T1;
-            const int tk = st2 ? task - T1 : task;
-            const int r = tk % CH, k = tk / CH;
-            const int chunk = st2 ? itn - 1 : itn;
-            if (chunk < 0 || chunk >= nChunks) continue;
-            if (!st2 && k >= n1) continue;
-            const int v = chunk * CH + r;
-            if (v >= VH || v < (st2 ? 4 * R : 2 * R)) continue;
-            const float4* in = (st2 ? hbuf2 : hbuf1) + r * SW;
-            float4* out = (st2 ? hout2 : hout1) + r * SW;
-            const int x0 = (st2 ? 2 * R : R) + k * kRun;  // first output column of the run
-            float4 s = in[sidx(x0 - R)];
-#pragma unroll 4
-            for (int j = 1; j < K; j++) s = f4add(s, in[sidx(x0 - R + j)]);
-            out[sidx(x0)] = s;
+        };
 #pragma unroll
-            for (int j = 1; j < kRun; j++) {
-                s = f4sub(f4add(s, in[sidx(x0 + R + j)]), in[sidx(x0 - R - 1 + j)]);
-                out[sidx(x0 + j)] = s;
+        for (int u = 0; u < PDC; u++) issue(u, sa[u], sb[u], sc[u]);
+        for (int base = 0; base < nIter; base += PDC) {
+#pragma unroll
+            for (int u = 0; u < PDC; u++) {
+                const int itn = base + u;
+                if (itn >= nIter) break;
+                const int c = itn - 2;
+                // the buffers of slot u hold chunk (itn - 2)'s statistics when itn >= 2; before that they hold
+                // chunks 0/1 which are consumed at itn = 2/3 (same slot): only refill after consuming
+                if (c >= 0 && c < nChunks) {
+                    float4 ca[kCH], cb[kCH];
+                    float cc[kCH];
+#pragma unroll
+                    for (int r = 0; r < kCH; r++) { ca[r] = sa[u][r]; cb[r] = sb[u][r]; cc[r] = sc[u][r]; }
+                    if (c + PDC < nChunks) issue(c + PDC, sa[u], sb[u], sc[u]);
+                    if (t < W2) {
+                        const F4* ho = ho1 + (c & 1) * kCH * SW;
+                        F4* hb = hb2 + (c & 1) * kCH * SW;
+#pragma unroll
+                        for (int r = 0; r < kCH; r++) {
+                            const int v = c * kCH + r;
+                            if (v >= 2 * R && v < VH) {
+                                const int yc = Y0 + v - R;
+                                F4 ab = f4zero();
+                                if (colC && yc >= it.fy && yc < fy1) {
+                                    const float invN = inv_nx * s_invny[v - R];
+                                    const F4 B = ho[r * SW + sidx(t)];
+                                    float Bp, B0, B1, B2;
+                                    up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
+                                    const float m0 = ca[r].x, m1 = ca[r].y, m2 = ca[r].z, i00 = ca[r].w;
+                                    const float i01 = cb[r].x, i02 = cb[r].y, i11 = cb[r].z, i12 = cb[r].w, i22 = cc[r];
+                                    const float mp = Bp * invN;                      // GuidedFilter.h:206
+                                    const float c0 = fmaf(B0, invN, -m0 * mp);       // :212-214
+                                    const float c1 = fmaf(B1, invN, -m1 * mp);
+                                    const float c2 = fmaf(B2, invN, -m2 * mp);
+                                    const float a0 = i00 * c0 + i01 * c1 + i02 * c2;  // :216-218
+                                    const float a1 = i01 * c0 + i11 * c1 + i12 * c2;
+                                    const float a2 = i02 * c0 + i12 * c1 + i22 * c2;
+                                    const float bb = mp - a0 * m0 - a1 * m1 - a2 * m2;  // :220
+                                    ab = F4{pk2(a0, a1), pk2(a2, bb)};
+                                }
+                                F4* sl = ring2 + slot * W2 + t;
+                                const F4 old = *sl;
+                                *sl = ab;
+                                acc = f4add(acc, f4sub(ab, old));
+                                hb[r * SW + sidx(t)] = acc;  // column sum centred on row v - 2R
+                                slot = (slot + 1 == K) ? 0 : slot + 1;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
+    } else {
+        // =========================================================================== team E
+        const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);
+        const int XE = it.ox0 + t;
+        const bool colE = t < it.ow;
+        float inv_nx = 0.f;
+        if (colE) inv_nx = 1.0f / (float)(min(XE + R, fx1 - 1) - max(XE - R, it.fx) + 1);
+        const float s255 = 1.0f / 255.0f;
+        const float xa = __fmul_rn((float)XE, pl.a);
+        const float a5 = __fmul_rn(pl.a, 5.0f), b5 = __fmul_rn(pl.b, 5.0f);
+        const float vz = __fmul_rn(0.0f, pl.v);
+        constexpr int PDE = 2;
+        uint32_t gq[PDE][kCH];
+        auto issue = [&](int chunk, uint32_t* g) {
+#pragma unroll
+            for (int r = 0; r < kCH; r++) {
+                const int v = chunk * kCH + r;
+                g[r] = 0u;
+                if (colE && v >= 4 * R && v < VH)
+                    g[r] = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + (size_t)(Y0 + v - 2 * R) * P.W + XE);
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < PDE; u++) issue(u, gq[u]);
+        for (int base = 0; base < nIter; base += PDE) {
+#pragma unroll
+            for (int u = 0; u < PDE; u++) {
+                const int itn = base + u;
+                if (itn >= nIter) break;
+                const int c = itn - 4;
+                if (c >= 0 && c < nChunks) {
+                    uint32_t cg[kCH];
+#pragma unroll
+                    for (int r = 0; r < kCH; r++) cg[r] = gq[u][r];
+                    if (c + PDE < nChunks) issue(c + PDE, gq[u]);
+                    if (colE) {
+                        const F4* ho = ho2 + (c & 1) * kCH * SW;
+#pragma unroll
+                        for (int r = 0; r < kCH; r++) {
+                            const int v = c * kCH + r;
+                            if (v >= 4 * R && v < VH) {
+                                const int yq = Y0 + v - 2 * R;
+                                const F4 S = ho[r * SW + sidx(t)];
+                                float S0, S1, S2, Sb;
+                                up2(S.lo, S0, S1); up2(S.hi, S2, Sb);
+                                const uint32_t g = cg[r];
+                                const float i0 = (float)(g & 0xffu) * s255, i1 = (float)((g >> 8) & 0xffu) * s255,
+                                            i2 = (float)((g >> 16) & 0xffu) * s255;
+                                float q = (Sb + S0 * i0 + S1 * i1 + S2 * i2) * (inv_nx * s_invny[v - 2 * R]);  // GuidedFilter.h:243
+                                if (P.with_check) {  // StereoEnergy.h:577-610
+                                    const float yb = __fmul_rn((float)yq, pl.b);
+                                    float ds = __fadd_rn(__fadd_rn(xa, yb), pl.c);
+                                    if (!(it.flags & 1)) ds = __fadd_rn(ds, vz);  // channelSum's 4th term (0 * v)
+                                    const float lo = P.min_disp, hi = P.max_disp;
+                                    const float dpp = __fadd_rn(__fadd_rn(ds, a5), b5), dpm = __fsub_rn(__fadd_rn(ds, a5), b5);
+                                    const float dmp = __fadd_rn(__fsub_rn(ds, a5), b5), dmm = __fsub_rn(__fsub_rn(ds, a5), b5);
+                                    const bool ok = ds >= lo && ds <= hi && dpp >= lo && dpp <= hi && dpm >= lo && dpm <= hi &&
+                                                    dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
+                                    if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
+                                }
+                                if (P.out_compact)
+                                    P.out[(size_t)it.compact_off + (size_t)(v - 4 * R) * it.compact_stride + t] = q;
+                                else
+                                    P.out[(size_t)yq * P.out_pitch + XE] = q;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
     }
 }
 
@@ -314,7 +445,8 @@ __global__ void lexp_stats_rowsum(const uchar4* __restrict__ guide, int* __restr
     for (int k = 0; k < 9; k++) rs[k * HW + (size_t)y * W + x] = s[k];
 }
 
-__global__ void lexp_stats_finish(const int* __restrict__ rs, float* __restrict__ stats, int H, int W, int R, double eps) {
+__global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict__ statA, float4* __restrict__ statB,
+                                  float* __restrict__ statC, int H, int W, int R, double eps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const size_t HW = (size_t)H * W;
@@ -334,9 +466,20 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float* __restrict_
     double i11 = v00 * v22 - v02 * v02, i12 = v02 * v01 - v00 * v12, i22 = v00 * v11 - v01 * v01;
     const double det = i00 * v00 + i01 * v01 + i02 * v02;                                          // :94
     const size_t p = (size_t)y * W + x;
-    stats[0 * HW + p] = (float)m0; stats[1 * HW + p] = (float)m1; stats[2 * HW + p] = (float)m2;
-    stats[3 * HW + p] = (float)(i00 / det); stats[4 * HW + p] = (float)(i01 / det); stats[5 * HW + p] = (float)(i02 / det);
-    stats[6 * HW + p] = (float)(i11 / det); stats[7 * HW + p] = (float)(i12 / det); stats[8 * HW + p] = (float)(i22 / det);
+    statA[p] = make_float4((float)m0, (float)m1, (float)m2, (float)(i00 / det));
+    statB[p] = make_float4((float)(i01 / det), (float)(i02 / det), (float)(i11 / det), (float)(i12 / det));
+    statC[p] = (float)(i22 / det);
+}
+
+// planar float[9][H][W] view of the statistics (lexp_get_stats)
+__global__ void lexp_stats_unpack(const float4* __restrict__ statA, const float4* __restrict__ statB, const float* __restrict__ statC,
+                                  float* __restrict__ out9, size_t HW) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float4 a = statA[p], b = statB[p];
+    out9[p] = a.x; out9[HW + p] = a.y; out9[2 * HW + p] = a.z; out9[3 * HW + p] = a.w;
+    out9[4 * HW + p] = b.x; out9[5 * HW + p] = b.y; out9[6 * HW + p] = b.z; out9[7 * HW + p] = b.w;
+    out9[8 * HW + p] = statC[p];
 }
 
 }  // namespace lexp
