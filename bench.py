@@ -30,6 +30,7 @@ WORKLOADS = {
     "adirondack_shape_1436x992x290_r20": (1436, 992, 290, 20),
     "synthetic_4k_3840x2160x512_r32": (3840, 2160, 512, 32),
     "tiny_450x375x64_r20": (450, 375, 64, 20),
+    "probe_2048x1536x16_r20": (2048, 1536, 16, 20),   # TLB / DRAM-locality probe (not a BASELINE config)
 }
 TH_COL, EPS = 0.5, 1e-4  # main.cpp:26,351 / main.cpp:73
 METRIC = "plane-hypothesis cost evals/sec"

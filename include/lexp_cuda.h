@@ -71,8 +71,9 @@ LEXP_API int lexp_destroy(lexp_ctx* ctx);
  * (FastGuidedImageFilter<double>(im, windR/2, eps, 1/255): CostVolumeEnergy.h:30-31, GuidedFilter.h:58-102). */
 LEXP_API int lexp_set_image(lexp_ctx* ctx, int mode, const uint8_t* bgr_host, ptrdiff_t step_bytes);
 
-/* vol[mode] = float[D][H][W] contiguous (CostVolumeEnergy.h:20-21).  _host copies it to HBM;
- * _device borrows an existing device pointer (no copy; caller keeps it alive). */
+/* vol[mode] = float[D][H][W] contiguous (CostVolumeEnergy.h:20-21).  Both calls re-lay the volume out
+ * into a context-owned blocked copy in HBM (4-pixel blocks, disparity contiguous) and scan it for
+ * NaN/Inf; the caller's buffer (host, or device for _device) is not referenced after the call returns. */
 LEXP_API int lexp_set_volume_host(lexp_ctx* ctx, int mode, const float* vol_host);
 LEXP_API int lexp_set_volume_device(lexp_ctx* ctx, int mode, const float* vol_device);
 

@@ -58,14 +58,14 @@ struct lexp_ctx {
     float4* d_statA[2] = {nullptr, nullptr};
     float4* d_statB[2] = {nullptr, nullptr};
     float* d_statC[2] = {nullptr, nullptr};
-    const float* d_vol[2] = {nullptr, nullptr};
-    float* d_vol_owned[2] = {nullptr, nullptr};
+    float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[H][Wb][D][4] (owned)
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
     size_t smem_limit = 0;
     bool smem_configured = false;
     bool own_stream = true;
+    bool vol_finite[2] = {false, false};
 };
 
 namespace {
@@ -107,6 +107,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
     KParams kp{};
     kp.vol = c->d_vol[mode];
+    kp.Wb = (c->p.width + 3) / 4;
     kp.guide = c->d_guide[mode];
     kp.statA = c->d_statA[mode];
     kp.statB = c->d_statB[mode];
@@ -120,7 +121,30 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     kp.th_col = c->p.th_col; kp.min_disp = c->p.min_disp; kp.max_disp = c->p.max_disp;
     kp.with_check = with_check;
     kp.R = c->R;
+    kp.fast_ok = (c->vol_finite[mode] && c->p.min_disp == 0.0f && c->p.max_disp == (float)(c->p.ndisp - 1) && c->p.th_col >= 0.0f) ? 1 : 0;
     return launch_fused(c, kp, pl->nitems, pl->smem);
+}
+
+// scan the caller's volume for NaN/Inf and re-lay it out into the context's blocked copy
+int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
+    const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4;
+    const size_t nblk = (size_t)H * Wb * D * 4;
+    if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], nblk * sizeof(float)));
+    int* d_flag = nullptr;
+    LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream);
+    lexp_scan_nonfinite<<<148 * 8, 256, 0, c->stream>>>(d_src, (size_t)D * H * W, d_flag);
+    dim3 grd((W + 31) / 32, H, (D + 31) / 32), blk(32, 8);
+    lexp_relayout_volume<<<grd, blk, 0, c->stream>>>(d_src, c->d_vol[mode], D, H, W, Wb);
+    c->launches += 2;
+    int h = 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("volume ingest: ") + cudaGetErrorString(e));
+    c->vol_finite[mode] = (h == 0);
+    return LEXP_OK;
 }
 
 }  // namespace
@@ -133,6 +157,7 @@ int lexp_version(void) { return 100; }
 int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     if (!params || !out_ctx) return fail(LEXP_ERR_INVALID, "null argument");
     if (params->height <= 0 || params->width <= 0 || params->ndisp < 2) return fail(LEXP_ERR_INVALID, "bad H/W/D");
+    if ((size_t)params->height * params->width >= (1ull << 30)) return fail(LEXP_ERR_INVALID, "image too large (H*W must be < 2^30)");
     if (params->windR < 2 || params->windR / 2 > 24) return fail(LEXP_ERR_INVALID, "windR/2 must be in [1, 24]");
     int ndev = 0;
     LEXP_CUDA(cudaGetDeviceCount(&ndev));
@@ -161,7 +186,7 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_statA[m]);
         cudaFree(c->d_statB[m]);
         cudaFree(c->d_statC[m]);
-        cudaFree(c->d_vol_owned[m]);
+        cudaFree(c->d_vol[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -204,10 +229,14 @@ int lexp_set_volume_host(lexp_ctx* c, int mode, const float* vol) {
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const size_t n = (size_t)c->p.ndisp * c->p.height * c->p.width;
-    if (!c->d_vol_owned[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol_owned[mode], n * sizeof(float)));
-    LEXP_CUDA(cudaMemcpy(c->d_vol_owned[mode], vol, n * sizeof(float), cudaMemcpyHostToDevice));
-    c->d_vol[mode] = c->d_vol_owned[mode];
-    return LEXP_OK;
+    float* tmp = nullptr;
+    LEXP_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+    cudaError_t e = cudaMemcpy(tmp, vol, n * sizeof(float), cudaMemcpyHostToDevice);
+    int rc = LEXP_OK;
+    if (e != cudaSuccess) rc = fail(LEXP_ERR_CUDA, std::string("volume upload: ") + cudaGetErrorString(e));
+    else rc = ingest_volume(c, mode, tmp);
+    cudaFree(tmp);
+    return rc;
 }
 
 int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) {
@@ -217,8 +246,8 @@ int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) {
     LEXP_CUDA(cudaPointerGetAttributes(&at, vol));
     if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
         return fail(LEXP_ERR_INVALID, "lexp_set_volume_device needs a device pointer");
-    c->d_vol[mode] = vol;
-    return LEXP_OK;
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    return ingest_volume(c, mode, vol);
 }
 
 int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {

@@ -34,7 +34,7 @@ constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
 constexpr int kMaxOW = 32 * kWarpsE;   // output columns
 constexpr int kRun = 8;                // columns per H task
 constexpr int kCH = 2;                 // rows per pipeline chunk
-constexpr int kPD = 3;                 // gather prefetch distance (chunks)
+constexpr int kG = 8;                  // rows per gather batch of team A (one batch of loads in flight)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
 
 struct __align__(16) Item {  // one CTA work item (64 B)
@@ -50,7 +50,8 @@ struct __align__(16) Item {  // one CTA work item (64 B)
 struct Plane4 { float a, b, c, v; };
 
 struct KParams {
-    const float* __restrict__ vol;      // float[D][H][W]
+    const float* __restrict__ vol;      // blocked cost volume float[H][Wb][D][4], Wb = ceil(W/4) (see lexp_relayout_volume)
+    int Wb;
     const uchar4* __restrict__ guide;   // uchar4[H][W] = (c0,c1,c2,0), OpenCV BGR order
     const float4* __restrict__ statA;   // float4[H][W] = {mean0, mean1, mean2, inv00}
     const float4* __restrict__ statB;   // float4[H][W] = {inv01, inv02, inv11, inv12}
@@ -64,6 +65,7 @@ struct KParams {
     float th_col, min_disp, max_disp;
     int with_check;
     int R;                              // guided-filter box radius (windR / 2)
+    int fast_ok;                        // MIN == 0, MAX == D-1, th_col >= 0 and the volume holds no NaN/Inf
 };
 
 // largest output-tile width the team sizes allow for box radius R
@@ -98,6 +100,18 @@ __device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), ad
 __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
 
+// cost-volume samples are used once: keep them from displacing the guide statistics in L2
+__device__ __forceinline__ u64 policy_evict_first() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ldg_stream(const float* p, u64 pol) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <int R_T>
 __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
@@ -108,31 +122,39 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     const Item it = P.items[blockIdx.x];
     const Plane4 pl = P.planes[it.call];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int VW = it.ow + 4 * R, VH = it.oh + 4 * R;
-    const int X0 = it.ox0 - 2 * R, Y0 = it.oy0 - 2 * R;
+    const int VW = it.ow + 4 * R;
+    const int X0 = it.ox0 - 2 * R;
     const int W2 = VW - 2 * R;
     const int SW = srow_stride(VW);
+    const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
+    // streamed rows y = ys + v, v in [0, VHs): the dependency cone of the tile, minus leading rows above
+    // the filterRect (they are zero padding).  Rows >= fy1 are zero rows that flush the running sums.
+    const int ys = max(it.oy0 - 2 * R, it.fy);
+    const int VHs = it.oy0 + it.oh + 2 * R - ys;
+    const int vReal = min(VHs, fy1 - ys);                    // rows [0, vReal) lie inside the filterRect
+    const int vC0 = max(it.oy0 - R, it.fy) + R - ys;         // first v whose stage-1 centre row (y - R) is needed
+    const int vC1 = min(VHs, fy1 + R - ys);                  // centre rows >= fy1 are zero rows
+    const int vE0 = it.oy0 + 2 * R - ys;                     // first v whose stage-2 centre row (y - 2R) is an output row
+
     F4* ring1 = smem;                      // [K][VW]
     F4* ring2 = ring1 + K * VW;            // [K][W2]
     F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
     F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW] stage-1 box sums      (index: column - X0 - R)
     F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
     F4* ho2 = hb2 + 2 * kCH * SW;          // [2][CH][SW] stage-2 box sums      (index: column - X0 - 2R)
-    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VH] 1 / (#rows of the window inside filterRect)
+    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VHs] 1 / (#rows of the window inside filterRect)
 
-    const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
         const int total = K * VW + K * W2 + 8 * kCH * SW;
         for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
-        for (int v = tid; v < VH; v += kThreads) {
-            const int y = Y0 + v;
+        for (int v = tid; v < VHs; v += kThreads) {
+            const int y = ys + v;
             s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
         }
     }
     __syncthreads();
 
-    const size_t HW = (size_t)P.H * P.W;
-    const int nChunks = (VH + kCH - 1) / kCH;
+    const int nChunks = (VHs + kCH - 1) / kCH;
     const int nIter = nChunks + 4;
 
     if (warp < kWarpsA) {
@@ -141,89 +163,123 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         const int XA = X0 + t;
         const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
         const float ax = __fmul_rn(pl.a, (float)XA);  // CostVolumeEnergy.h:76 (product rounded separately)
-        const int D0 = (int)(-P.min_disp);
         const float th = P.th_col;
         const float s255 = 1.0f / 255.0f;
+        // fast sampler: finite plane, MIN = 0, MAX = D-1, th >= 0, finite volume (checked at upload)
+        const bool fast = P.fast_ok && isfinite(pl.a) && isfinite(pl.b) && isfinite(pl.c);
+        const unsigned W4 = (unsigned)P.W * 4u;
+        const u64 pol = policy_evict_first();
+        const int XAc = colA ? XA : it.fx;
+        // blocked volume: element (d, y, x) lives at ((y * Wb + x / 4) * D + d) * 4 + x % 4
+        const size_t vstride = (size_t)P.Wb * P.D * 16;  // bytes per image row
+        const char* vrow = reinterpret_cast<const char*>(P.vol) + (size_t)ys * vstride + ((size_t)(XAc >> 2) * P.D * 4 + (XAc & 3)) * 4;
+        const char* grow = reinterpret_cast<const char*>(P.guide) + ((size_t)ys * P.W + XAc) * 4;
+        const float maxd = (float)(P.D - 1);
         F4 acc = f4zero();
         int slot = 0;
-        float bv0[kPD][kCH], bv1[kPD][kCH], bf1[kPD][kCH];
-        uint32_t bg[kPD][kCH];
-
-        auto issue = [&](int chunk, float* v0, float* v1, float* f1, uint32_t* g) {
+        // Gather batches of kG rows.  Exactly ONE batch of loads is in flight at any time: the hardware
+        // scoreboard cannot tell older from younger loads, so a deeper register pipeline would stall on the
+        // youngest load.  Order per batch: wait(batch b) -> issue(batch b+1) -> process(batch b).
+        float lv0[kG], lv1[kG];
+        uint32_t lg[kG];
+        // weight f1 and slice indices of row y (recomputed at the consume point instead of being kept in registers)
+        //   fast: d < 0 -> V[0]; d >= D-1 -> (1-1) V[D-2] + 1 V[D-1] = V[D-1]; else lerp (:78-92)
+        //   generic: f1 in [0,1] lerp | 2: COST_FOR_INVALID | 3: C = V[d0]
+        auto weights = [&](int y, int& d0, int& d1) -> float {
+            const float d_base = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);  // :73
+            const float d = __fadd_rn(ax, d_base);                             // :76
+            if (fast) {
+                const float dc = fminf(fmaxf(d, 0.f), maxd);
+                d0 = min(__float2int_rz(dc), P.D - 2);
+                d1 = d0 + 1;
+                return dc - (float)d0;
+            }
+            const int D0 = (int)(-P.min_disp);
+            const bool lo = d < P.min_disp;                                    // :78
+            const bool hi = !lo && d >= P.max_disp;                            // :79
+            bool bad = !lo && !hi && (isnan(d) || isinf(d));                   // :80
+            const float dd = (lo || hi || bad) ? 0.f : d;
+            d0 = (int)dd + D0;                                                 // :83
+            float ff = dd - floorf(dd);                                        // :85
+            if (d0 + 1 >= P.D || d0 < 0) bad = true;                           // :87-90
+            if (lo) { d0 = 0; ff = 3.f; }
+            if (hi) { d0 = P.D - 1; ff = 3.f; }
+            if (bad && !lo && !hi) { d0 = 0; ff = 2.f; }
+            d1 = min(d0 + 1, P.D - 1);
+            return ff;
+        };
+        int vi = 0;  // next virtual row to issue
+        auto issue = [&]() {
 #pragma unroll
-            for (int r = 0; r < kCH; r++) {
-                const int v = chunk * kCH + r;
-                const int y = Y0 + v;
-                f1[r] = -1.f; v0[r] = 0.f; v1[r] = 0.f; g[r] = 0u;  // outside filterRect: zero
-                if (colA && v < VH && y >= it.fy && y < fy1) {
-                    const float d_base = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);  // :73
-                    const float d = __fadd_rn(ax, d_base);                             // :76
-                    const bool lo = d < P.min_disp;                                    // :78
-                    const bool hi = !lo && d >= P.max_disp;                            // :79
-                    bool bad = !lo && !hi && (isnan(d) || isinf(d));                   // :80
-                    const float dd = (lo || hi || bad) ? 0.f : d;
-                    int d0 = (int)dd + D0;                                             // :83
-                    float ff = dd - floorf(dd);                                        // :85
-                    if (d0 + 1 >= P.D || d0 < 0) bad = true;                           // :87-90
-                    if (lo) { d0 = 0; ff = 3.f; }
-                    if (hi) { d0 = P.D - 1; ff = 3.f; }
-                    if (bad && !lo && !hi) { d0 = 0; ff = 2.f; }
-                    const int d1 = min(d0 + 1, P.D - 1);
-                    const size_t pix = (size_t)y * P.W + XA;
-                    v0[r] = __ldg(P.vol + (size_t)d0 * HW + pix);
-                    v1[r] = __ldg(P.vol + (size_t)d1 * HW + pix);
-                    g[r] = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + pix);
-                    f1[r] = ff;
+            for (int j = 0; j < kG; j++) {
+                lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u;  // outside filterRect: zero
+                if (colA && vi < vReal) {
+                    int d0, d1;
+                    weights(ys + vi, d0, d1);
+                    lv0[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 16), pol);
+                    lv1[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d1 * 16), pol);
+                    lg[j] = __ldg(reinterpret_cast<const unsigned int*>(grow));
                 }
+                vi++;
+                vrow += vstride;
+                grow += W4;
             }
         };
 
+        issue();
+        int c = 0;  // pipeline chunk
+        while (c < nChunks) {
+            float wv0[kG], wv1[kG];
+            uint32_t wg[kG];
 #pragma unroll
-        for (int u = 0; u < kPD; u++) issue(u, bv0[u], bv1[u], bf1[u], bg[u]);
-
-        for (int base = 0; base < nIter; base += kPD) {
+            for (int j = 0; j < kG; j++) {
+                // consume point of the batch: every load must have landed before the next batch is issued
+                asm volatile("" : "+f"(lv0[j]), "+f"(lv1[j]), "+r"(lg[j]) :: "memory");
+                wv0[j] = lv0[j]; wv1[j] = lv1[j]; wg[j] = lg[j];
+            }
+            issue();
 #pragma unroll
-            for (int u = 0; u < kPD; u++) {
-                const int itn = base + u;
-                if (itn >= nIter) break;
-                if (itn < nChunks) {
-                    float cv0[kCH], cv1[kCH], cf1[kCH];
-                    uint32_t cg[kCH];
-#pragma unroll
-                    for (int r = 0; r < kCH; r++) { cv0[r] = bv0[u][r]; cv1[r] = bv1[u][r]; cf1[r] = bf1[u][r]; cg[r] = bg[u][r]; }
-                    if (itn + kPD < nChunks) issue(itn + kPD, bv0[u], bv1[u], bf1[u], bg[u]);
+            for (int cc = 0; cc < kG / kCH; cc++) {
+                if (c < nChunks) {  // CTA-uniform
                     if (t < VW) {
-                        F4* hb = hb1 + (itn & 1) * kCH * SW;
+                        F4* hb = hb1 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
                         for (int r = 0; r < kCH; r++) {
-                            F4 nw = f4zero();
-                            const float f1 = cf1[r];
-                            if (f1 >= 0.f) {
-                                float C;
-                                if (f1 < 1.5f) C = __fadd_rn(__fmul_rn(1.0f - f1, cv0[r]), __fmul_rn(f1, cv1[r]));  // :92
-                                else if (f1 > 2.5f) C = cv0[r];                                                       // :78-79
-                                else C = kCostInvalid;                                                                // :80,:89
-                                const float p = (th < C) ? th : C;                                                    // std::min (:96)
-                                const float ps = p * s255, nm = -8388608.0f * ps;
-                                const uint32_t g = cg[r];
-                                // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169)
-                                const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
-                                const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
-                                const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
-                                nw = F4{pk2(p, q0), pk2(q1, q2)};
+                            const int j = cc * kCH + r;
+                            const int v = c * kCH + r;
+                            float p = 0.f;  // outside filterRect: zero padding
+                            if (fast || (colA && v < vReal)) {
+                                int d0, d1;
+                                const float f1 = weights(ys + v, d0, d1);
+                                float C = __fadd_rn(__fmul_rn(1.0f - f1, wv0[j]), __fmul_rn(f1, wv1[j]));  // :92
+                                if (!fast) {
+                                    if (f1 > 2.5f) C = wv0[j];             // :78-79
+                                    else if (f1 > 1.5f) C = kCostInvalid;  // :80,:89
+                                }
+                                p = (th < C) ? th : C;                     // std::min (:96); fast & outside: min(0, th) = 0
                             }
+                            const float ps = p * s255, nm = -8388608.0f * ps;
+                            const uint32_t g = wg[j];
+                            // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169)
+                            const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
+                            const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
+                            const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
+                            const F4 nw = F4{pk2(p, q0), pk2(q1, q2)};
                             F4* sl = ring1 + slot * VW + t;
                             const F4 old = *sl;
                             *sl = nw;
                             acc = f4add(acc, f4sub(nw, old));
-                            hb[r * SW + sidx(t)] = acc;  // column sum centred on row v - R
+                            hb[r * SW] = acc;  // column sum centred on row y - R
                             slot = (slot + 1 == K) ? 0 : slot + 1;
                         }
                     }
+                    __syncthreads();
+                    c++;
                 }
-                __syncthreads();
             }
         }
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) __syncthreads();
     } else if (warp < kWarpsA + kWarpsH) {
         // =========================================================================== team H
         // out[i] = sum_{m=0}^{2R} in[i + m]: lane = (row r of the chunk, run k of 8 columns)
@@ -231,13 +287,13 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         const int r = lane & (kCH - 1), k = lane / kCH;
         const int nruns = ((st2 ? it.ow : W2) + kRun - 1) / kRun;
         const int lag = st2 ? 3 : 1;
-        const int vmin = st2 ? 4 * R : 2 * R;
+        const int vmin = st2 ? vE0 : vC0, vmax = st2 ? VHs : vC1;
         const F4* inb = st2 ? hb2 : hb1;
         F4* outb = st2 ? ho2 : ho1;
         for (int itn = 0; itn < nIter; itn++) {
             const int c = itn - lag;
             const int v = c * kCH + r;
-            if (c >= 0 && c < nChunks && k < nruns && v >= vmin && v < VH) {
+            if (c >= 0 && c < nChunks && k < nruns && v >= vmin && v < vmax) {
                 const F4* in = inb + ((c & 1) * kCH + r) * SW + 9 * k;
                 F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
                 if (R_T > 0) {
@@ -278,78 +334,86 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         if (colC) inv_nx = 1.0f / (float)(min(XC + R, fx1 - 1) - max(XC - R, it.fx) + 1);
         F4 acc = f4zero();
         int slot = 0;
-        constexpr int PDC = 2;
-        float4 sa[PDC][kCH], sb[PDC][kCH];
-        float sc[PDC][kCH];
-        auto issue = [&](int chunk, float4* a, float4* b, float* c) {
+        // one batch (= one chunk) of statistics loads in flight: wait(c) -> issue(c + 1) -> process(c)
+        float4 sa[kCH], sb[kCH];
+        float sc[kCH];
+        // statistics of centre row yc = ys + v - R, issued chunk by chunk in order
+        int vi = 0;
+        const size_t pix0 = (size_t)(ys - R) * P.W + (colC ? XC : it.fx);  // rows above vC0 are never dereferenced
+        const float4* pa = P.statA + pix0;
+        const float4* pb = P.statB + pix0;
+        const float* pc = P.statC + pix0;
+        auto issue = [&]() {
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
-                const int v = chunk * kCH + r;
-                const int yc = Y0 + v - R;
-                a[r] = make_float4(0.f, 0.f, 0.f, 0.f); b[r] = a[r]; c[r] = 0.f;
-                if (colC && v >= 2 * R && v < VH && yc >= it.fy && yc < fy1) {
-                    const size_t pix = (size_t)yc * P.W + XC;
-                    a[r] = __ldg(P.statA + pix);
-                    b[r] = __ldg(P.statB + pix);
-                    c[r] = __ldg(P.statC + pix);
+                sa[r] = make_float4(0.f, 0.f, 0.f, 0.f); sb[r] = sa[r]; sc[r] = 0.f;
+#ifdef LEXP_X_NOSTATS
+                if (colC && vi >= vC0 && vi < vC1) { sa[r] = make_float4(0.5f, 0.5f, 0.5f, 10.f); sb[r] = make_float4(0.f, 0.f, 10.f, 0.f); sc[r] = 10.f; }
+                if (false) {
+#else
+                if (colC && vi >= vC0 && vi < vC1) {
+#endif
+                    sa[r] = __ldg(pa);
+                    sb[r] = __ldg(pb);
+                    sc[r] = __ldg(pc);
                 }
+                vi++;
+                pa += P.W; pb += P.W; pc += P.W;
             }
         };
+        issue();
+        __syncthreads();
+        __syncthreads();
+        for (int c = 0; c < nChunks; c++) {
+            {
+                float4 ca[kCH], cb[kCH];
+                float cc[kCH];
 #pragma unroll
-        for (int u = 0; u < PDC; u++) issue(u, sa[u], sb[u], sc[u]);
-        for (int base = 0; base < nIter; base += PDC) {
+                for (int r = 0; r < kCH; r++) {
+                    asm volatile("" : "+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
+                                 "+f"(sb[r].z), "+f"(sb[r].w), "+f"(sc[r]) :: "memory");
+                    ca[r] = sa[r]; cb[r] = sb[r]; cc[r] = sc[r];
+                }
+                issue();
+                if (t < W2) {
+                    const F4* ho = ho1 + (c & 1) * kCH * SW + sidx(t);
+                    F4* hb = hb2 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
-            for (int u = 0; u < PDC; u++) {
-                const int itn = base + u;
-                if (itn >= nIter) break;
-                const int c = itn - 2;
-                // the buffers of slot u hold chunk (itn - 2)'s statistics when itn >= 2; before that they hold
-                // chunks 0/1 which are consumed at itn = 2/3 (same slot): only refill after consuming
-                if (c >= 0 && c < nChunks) {
-                    float4 ca[kCH], cb[kCH];
-                    float cc[kCH];
-#pragma unroll
-                    for (int r = 0; r < kCH; r++) { ca[r] = sa[u][r]; cb[r] = sb[u][r]; cc[r] = sc[u][r]; }
-                    if (c + PDC < nChunks) issue(c + PDC, sa[u], sb[u], sc[u]);
-                    if (t < W2) {
-                        const F4* ho = ho1 + (c & 1) * kCH * SW;
-                        F4* hb = hb2 + (c & 1) * kCH * SW;
-#pragma unroll
-                        for (int r = 0; r < kCH; r++) {
-                            const int v = c * kCH + r;
-                            if (v >= 2 * R && v < VH) {
-                                const int yc = Y0 + v - R;
-                                F4 ab = f4zero();
-                                if (colC && yc >= it.fy && yc < fy1) {
-                                    const float invN = inv_nx * s_invny[v - R];
-                                    const F4 B = ho[r * SW + sidx(t)];
-                                    float Bp, B0, B1, B2;
-                                    up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
-                                    const float m0 = ca[r].x, m1 = ca[r].y, m2 = ca[r].z, i00 = ca[r].w;
-                                    const float i01 = cb[r].x, i02 = cb[r].y, i11 = cb[r].z, i12 = cb[r].w, i22 = cc[r];
-                                    const float mp = Bp * invN;                      // GuidedFilter.h:206
-                                    const float c0 = fmaf(B0, invN, -m0 * mp);       // :212-214
-                                    const float c1 = fmaf(B1, invN, -m1 * mp);
-                                    const float c2 = fmaf(B2, invN, -m2 * mp);
-                                    const float a0 = i00 * c0 + i01 * c1 + i02 * c2;  // :216-218
-                                    const float a1 = i01 * c0 + i11 * c1 + i12 * c2;
-                                    const float a2 = i02 * c0 + i12 * c1 + i22 * c2;
-                                    const float bb = mp - a0 * m0 - a1 * m1 - a2 * m2;  // :220
-                                    ab = F4{pk2(a0, a1), pk2(a2, bb)};
-                                }
-                                F4* sl = ring2 + slot * W2 + t;
-                                const F4 old = *sl;
-                                *sl = ab;
-                                acc = f4add(acc, f4sub(ab, old));
-                                hb[r * SW + sidx(t)] = acc;  // column sum centred on row v - 2R
-                                slot = (slot + 1 == K) ? 0 : slot + 1;
+                    for (int r = 0; r < kCH; r++) {
+                        const int v = c * kCH + r;
+                        if (v >= vC0 && v < VHs) {
+                            F4 ab = f4zero();
+                            if (colC && v < vC1) {
+                                const float invN = inv_nx * s_invny[v - R];
+                                const F4 B = ho[r * SW];
+                                float Bp, B0, B1, B2;
+                                up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
+                                const float m0 = ca[r].x, m1 = ca[r].y, m2 = ca[r].z, i00 = ca[r].w;
+                                const float i01 = cb[r].x, i02 = cb[r].y, i11 = cb[r].z, i12 = cb[r].w, i22 = cc[r];
+                                const float mp = Bp * invN;                      // GuidedFilter.h:206
+                                const float c0 = fmaf(B0, invN, -m0 * mp);       // :212-214
+                                const float c1 = fmaf(B1, invN, -m1 * mp);
+                                const float c2 = fmaf(B2, invN, -m2 * mp);
+                                const float a0 = i00 * c0 + i01 * c1 + i02 * c2;  // :216-218
+                                const float a1 = i01 * c0 + i11 * c1 + i12 * c2;
+                                const float a2 = i02 * c0 + i12 * c1 + i22 * c2;
+                                const float bb = mp - a0 * m0 - a1 * m1 - a2 * m2;  // :220
+                                ab = F4{pk2(a0, a1), pk2(a2, bb)};
                             }
+                            F4* sl = ring2 + slot * W2 + t;
+                            const F4 old = *sl;
+                            *sl = ab;
+                            acc = f4add(acc, f4sub(ab, old));
+                            hb[r * SW] = acc;  // column sum centred on row y - 2R
+                            slot = (slot + 1 == K) ? 0 : slot + 1;
                         }
                     }
                 }
                 __syncthreads();
             }
         }
+        __syncthreads();
+        __syncthreads();
     } else {
         // =========================================================================== team E
         const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);
@@ -361,60 +425,79 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         const float xa = __fmul_rn((float)XE, pl.a);
         const float a5 = __fmul_rn(pl.a, 5.0f), b5 = __fmul_rn(pl.b, 5.0f);
         const float vz = __fmul_rn(0.0f, pl.v);
-        constexpr int PDE = 2;
-        uint32_t gq[PDE][kCH];
-        auto issue = [&](int chunk, uint32_t* g) {
+        // conservative tile-level validity: if the plane stays inside [MIN, MAX] by a margin over the whole
+        // tile (+-5 px corners), every per-pixel test of StereoEnergy.h:577-610 passes and is skipped
+        bool check = P.with_check != 0;
+        if (check && isfinite(pl.a) && isfinite(pl.b) && isfinite(pl.c) && isfinite(pl.v)) {
+            const float x0 = (float)it.ox0, x1 = (float)(it.ox0 + it.ow - 1), y0 = (float)it.oy0, y1 = (float)(it.oy0 + it.oh - 1);
+            const float axl = fminf(pl.a * x0, pl.a * x1), axh = fmaxf(pl.a * x0, pl.a * x1);
+            const float byl = fminf(pl.b * y0, pl.b * y1), byh = fmaxf(pl.b * y0, pl.b * y1);
+            const float ext = 5.0f * (fabsf(pl.a) + fabsf(pl.b));
+            const float mag = fabsf(axl) + fabsf(axh) + fabsf(byl) + fabsf(byh) + fabsf(pl.c) + ext;
+            const float margin = 1e-5f * mag + 1e-30f;
+            if (axl + byl + pl.c - ext - margin >= P.min_disp && axh + byh + pl.c + ext + margin <= P.max_disp) check = false;
+        }
+        uint32_t gq[kCH];
+        int vi = 0;
+        const unsigned int* pg = reinterpret_cast<const unsigned int*>(P.guide) + (size_t)(ys - 2 * R) * P.W + (colE ? XE : it.ox0);
+        auto issue = [&]() {
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
-                const int v = chunk * kCH + r;
-                g[r] = 0u;
-                if (colE && v >= 4 * R && v < VH)
-                    g[r] = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + (size_t)(Y0 + v - 2 * R) * P.W + XE);
+                gq[r] = 0u;
+#ifdef LEXP_X_NOGUIDE_E
+                if (colE && vi >= vE0 && vi < VHs) gq[r] = 0x00808080u;
+#else
+                if (colE && vi >= vE0 && vi < VHs) gq[r] = __ldg(pg);
+#endif
+                vi++;
+                pg += P.W;
             }
         };
+        issue();
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) __syncthreads();
+        float* orow;  // output pointer of row yq = ys + v - 2R at column XE
+        long long ostride;
+        if (P.out_compact) { orow = P.out + (size_t)it.compact_off + t; ostride = it.compact_stride; }
+        else { orow = P.out + (size_t)it.oy0 * P.out_pitch + XE; ostride = P.out_pitch; }
+        for (int c = 0; c < nChunks; c++) {
+            {
+                uint32_t cg[kCH];
 #pragma unroll
-        for (int u = 0; u < PDE; u++) issue(u, gq[u]);
-        for (int base = 0; base < nIter; base += PDE) {
+                for (int r = 0; r < kCH; r++) {
+                    asm volatile("" : "+r"(gq[r]) :: "memory");
+                    cg[r] = gq[r];
+                }
+                issue();
+                if (colE) {
+                    const F4* ho = ho2 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
-            for (int u = 0; u < PDE; u++) {
-                const int itn = base + u;
-                if (itn >= nIter) break;
-                const int c = itn - 4;
-                if (c >= 0 && c < nChunks) {
-                    uint32_t cg[kCH];
-#pragma unroll
-                    for (int r = 0; r < kCH; r++) cg[r] = gq[u][r];
-                    if (c + PDE < nChunks) issue(c + PDE, gq[u]);
-                    if (colE) {
-                        const F4* ho = ho2 + (c & 1) * kCH * SW;
-#pragma unroll
-                        for (int r = 0; r < kCH; r++) {
-                            const int v = c * kCH + r;
-                            if (v >= 4 * R && v < VH) {
-                                const int yq = Y0 + v - 2 * R;
-                                const F4 S = ho[r * SW + sidx(t)];
-                                float S0, S1, S2, Sb;
-                                up2(S.lo, S0, S1); up2(S.hi, S2, Sb);
-                                const uint32_t g = cg[r];
-                                const float i0 = (float)(g & 0xffu) * s255, i1 = (float)((g >> 8) & 0xffu) * s255,
-                                            i2 = (float)((g >> 16) & 0xffu) * s255;
-                                float q = (Sb + S0 * i0 + S1 * i1 + S2 * i2) * (inv_nx * s_invny[v - 2 * R]);  // GuidedFilter.h:243
-                                if (P.with_check) {  // StereoEnergy.h:577-610
-                                    const float yb = __fmul_rn((float)yq, pl.b);
-                                    float ds = __fadd_rn(__fadd_rn(xa, yb), pl.c);
-                                    if (!(it.flags & 1)) ds = __fadd_rn(ds, vz);  // channelSum's 4th term (0 * v)
-                                    const float lo = P.min_disp, hi = P.max_disp;
-                                    const float dpp = __fadd_rn(__fadd_rn(ds, a5), b5), dpm = __fsub_rn(__fadd_rn(ds, a5), b5);
-                                    const float dmp = __fadd_rn(__fsub_rn(ds, a5), b5), dmm = __fsub_rn(__fsub_rn(ds, a5), b5);
-                                    const bool ok = ds >= lo && ds <= hi && dpp >= lo && dpp <= hi && dpm >= lo && dpm <= hi &&
-                                                    dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
-                                    if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
-                                }
-                                if (P.out_compact)
-                                    P.out[(size_t)it.compact_off + (size_t)(v - 4 * R) * it.compact_stride + t] = q;
-                                else
-                                    P.out[(size_t)yq * P.out_pitch + XE] = q;
+                    for (int r = 0; r < kCH; r++) {
+                        const int v = c * kCH + r;
+                        if (v >= vE0 && v < VHs) {
+                            const F4 S = ho[r * SW];
+                            float S0, S1, S2, Sb;
+                            up2(S.lo, S0, S1); up2(S.hi, S2, Sb);
+                            const uint32_t g = cg[r];
+                            const float i0 = __uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)) - 8388608.0f;
+                            const float i1 = __uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)) - 8388608.0f;
+                            const float i2 = __uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)) - 8388608.0f;
+                            const float dot = S0 * i0 + S1 * i1 + S2 * i2;
+                            float q = fmaf(dot, s255, Sb) * (inv_nx * s_invny[v - 2 * R]);  // GuidedFilter.h:243
+                            if (check) {  // StereoEnergy.h:577-610
+                                const int yq = ys + v - 2 * R;
+                                const float yb = __fmul_rn((float)yq, pl.b);
+                                float ds = __fadd_rn(__fadd_rn(xa, yb), pl.c);
+                                if (!(it.flags & 1)) ds = __fadd_rn(ds, vz);  // channelSum's 4th term (0 * v)
+                                const float lo = P.min_disp, hi = P.max_disp;
+                                const float dpp = __fadd_rn(__fadd_rn(ds, a5), b5), dpm = __fsub_rn(__fadd_rn(ds, a5), b5);
+                                const float dmp = __fadd_rn(__fsub_rn(ds, a5), b5), dmm = __fsub_rn(__fsub_rn(ds, a5), b5);
+                                const bool ok = ds >= lo && ds <= hi && dpp >= lo && dpp <= hi && dpm >= lo && dpm <= hi &&
+                                                dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
+                                if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
                             }
+                            *orow = q;
+                            orow += ostride;
                         }
                     }
                 }
@@ -469,6 +552,37 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict
     statA[p] = make_float4((float)m0, (float)m1, (float)m2, (float)(i00 / det));
     statB[p] = make_float4((float)(i01 / det), (float)(i02 / det), (float)(i11 / det), (float)(i12 / det));
     statC[p] = (float)(i22 / det);
+}
+
+// One-time re-layout of the cost volume (the input format float[D][H][W], README.md:85-91, is fixed
+// only at the API): dst[((y * Wb + x/4) * D + d) * 4 + x%4] = src[d][y][x].  All disparities of a 4-pixel
+// block are contiguous, so the two samples of a plane (d0, d0+1) of neighbouring pixels share sectors /
+// DRAM pages instead of being scattered over ndisp slices H*W*4 bytes apart.
+// grid = (ceil(W/32), H, ceil(D/32)), block = (32, 8)
+__global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb) {
+    __shared__ float tile[32][33];  // [d][x]
+    const int x0 = blockIdx.x * 32, y = blockIdx.y, d0 = blockIdx.z * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int d = d0 + i, x = x0 + threadIdx.x;
+        tile[i][threadIdx.x] = (d < D && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
+    }
+    __syncthreads();
+    // each thread writes one float: consecutive threads -> (x%4 fastest, then d)
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int lin = i * 32 + threadIdx.x;        // 0..1023 = [xb 8][d 32][q 4]
+        const int xb = lin >> 7, dd = (lin >> 2) & 31, q = lin & 3;
+        const int d = d0 + dd;
+        if (d < D && (x0 >> 2) + xb < Wb) dst[(((size_t)y * Wb + (x0 >> 2) + xb) * D + d) * 4 + q] = tile[dd][xb * 4 + q];
+    }
+}
+
+// upload-time scan: does the cost volume hold any NaN / Inf?  (the fast sampler multiplies by 0 weights)
+__global__ void lexp_scan_nonfinite(const float* __restrict__ vol, size_t n, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= !isfinite(vol[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
 // planar float[9][H][W] view of the statistics (lexp_get_stats)

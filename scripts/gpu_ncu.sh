@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+TAG=${1:-cur}
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lexp_fused -s 30 -c 1 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$TAG.log 2>&1
+tail -2 gpurun_out/ncu_$TAG.log | cut -c1-300
