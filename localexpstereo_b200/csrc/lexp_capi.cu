@@ -58,11 +58,16 @@ struct lexp_ctx {
     float4* d_statA[2] = {nullptr, nullptr};
     float4* d_statB[2] = {nullptr, nullptr};
     float* d_statC[2] = {nullptr, nullptr};
+    char* d_gs[2] = {nullptr, nullptr};   // backing allocation of guide + statistics
+    size_t gs_bytes = 0;
+    size_t persist_bytes = 0;             // L2 set-aside for persisting accesses (0: unsupported)
+    int persist_mode = -1;                // view whose window is currently installed on the stream
     float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[H][Wb][D][4] (owned)
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
     size_t smem_limit = 0;
+    size_t window_max = 0;
     bool smem_configured = false;
     bool own_stream = true;
     bool vol_finite[2] = {false, false};
@@ -105,6 +110,18 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
              int with_check) {
     if (mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "mode must be 0 or 1");
     if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
+    if (c->persist_bytes && c->persist_mode != mode) {
+        // keep the plane-independent inputs (statistics, guide) resident in L2 across the K steps of a group;
+        // the cost-volume gathers are issued with an evict-first policy by the kernel
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = c->d_gs[mode];
+        av.accessPolicyWindow.num_bytes = std::min(c->gs_bytes, c->window_max);
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->persist_bytes / (double)av.accessPolicyWindow.num_bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) c->persist_mode = mode;
+        else { cudaGetLastError(); c->persist_bytes = 0; }
+    }
     KParams kp{};
     kp.vol = c->d_vol[mode];
     kp.Wb = (c->p.width + 3) / 4;
@@ -171,6 +188,13 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->R = params->windR / 2;  // CostVolumeEnergy.h:30
     c->smem_limit = prop.sharedMemPerBlockOptin;
     c->tile_oh = std::max(8, env_int("LEXP_TILE_OH", 128));
+    if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            c->persist_bytes = want;
+            c->window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else cudaGetLastError();
+    }
     if (max_tile_ow(c->R) < 8) { delete c; return fail(LEXP_ERR_INVALID, "windR too large for the tile width"); }
     LEXP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out_ctx = c;
@@ -182,10 +206,7 @@ int lexp_destroy(lexp_ctx* c) {
     cudaSetDevice(c->p.device);
     cudaStreamSynchronize(c->stream);
     for (int m = 0; m < 2; m++) {
-        cudaFree(c->d_guide[m]);
-        cudaFree(c->d_statA[m]);
-        cudaFree(c->d_statB[m]);
-        cudaFree(c->d_statC[m]);
+        cudaFree(c->d_gs[m]);
         cudaFree(c->d_vol[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -204,11 +225,16 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
         const uint8_t* row = bgr + (ptrdiff_t)y * step;
         for (int x = 0; x < W; x++) tmp[(size_t)y * W + x] = make_uchar4(row[3 * x], row[3 * x + 1], row[3 * x + 2], 0);
     }
-    if (!c->d_guide[mode]) LEXP_CUDA(cudaMalloc(&c->d_guide[mode], HW * sizeof(uchar4)));
-    if (!c->d_statA[mode]) {
-        LEXP_CUDA(cudaMalloc(&c->d_statA[mode], HW * sizeof(float4)));
-        LEXP_CUDA(cudaMalloc(&c->d_statB[mode], HW * sizeof(float4)));
-        LEXP_CUDA(cudaMalloc(&c->d_statC[mode], HW * sizeof(float)));
+    if (!c->d_gs[mode]) {
+        // one allocation [statA | statC | guide | statB] so that a single L2 access-policy window can pin a prefix
+        const size_t HWp = (HW + 63) / 64 * 64;
+        LEXP_CUDA(cudaMalloc(&c->d_gs[mode], HWp * (16 + 4 + 4 + 16)));
+        char* b = c->d_gs[mode];
+        c->d_statA[mode] = reinterpret_cast<float4*>(b);
+        c->d_statC[mode] = reinterpret_cast<float*>(b + HWp * 16);
+        c->d_guide[mode] = reinterpret_cast<uchar4*>(b + HWp * 20);
+        c->d_statB[mode] = reinterpret_cast<float4*>(b + HWp * 24);
+        c->gs_bytes = HWp * 40;
     }
     LEXP_CUDA(cudaMemcpyAsync(c->d_guide[mode], tmp.data(), HW * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
     int* d_rs = nullptr;
@@ -447,6 +473,7 @@ int lexp_set_stream(lexp_ctx* c, void* s) {
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)s;
+    c->persist_mode = -1;
     return LEXP_OK;
 }
 int64_t lexp_launch_count(const lexp_ctx* c) { return c ? c->launches : 0; }

@@ -34,7 +34,7 @@ constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
 constexpr int kMaxOW = 32 * kWarpsE;   // output columns
 constexpr int kRun = 8;                // columns per H task
 constexpr int kCH = 2;                 // rows per pipeline chunk
-constexpr int kG = 8;                  // rows per gather batch of team A (one batch of loads in flight)
+constexpr int kG = 6;                  // rows per gather batch of team A (one batch of loads in flight)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
 
 struct __align__(16) Item {  // one CTA work item (64 B)
@@ -82,7 +82,7 @@ __host__ __device__ inline int srow_stride(int vw) {
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
-    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + (vh + 3) / 4) * 16;
+    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 2 * ((vh + 3) / 4)) * 16;
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
     F4* ho2 = hb2 + 2 * kCH * SW;          // [2][CH][SW] stage-2 box sums      (index: column - X0 - 2R)
     float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VHs] 1 / (#rows of the window inside filterRect)
+    float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
         const int total = K * VW + K * W2 + 8 * kCH * SW;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         for (int v = tid; v < VHs; v += kThreads) {
             const int y = ys + v;
             s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
+            s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);                   // CostVolumeEnergy.h:73
         }
     }
     __syncthreads();
@@ -180,14 +182,12 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         // Gather batches of kG rows.  Exactly ONE batch of loads is in flight at any time: the hardware
         // scoreboard cannot tell older from younger loads, so a deeper register pipeline would stall on the
         // youngest load.  Order per batch: wait(batch b) -> issue(batch b+1) -> process(batch b).
-        float lv0[kG], lv1[kG];
+        float lv0[kG], lv1[kG], lf1[kG];
         uint32_t lg[kG];
-        // weight f1 and slice indices of row y (recomputed at the consume point instead of being kept in registers)
+        // weight f1 and slice indices for plane disparity d
         //   fast: d < 0 -> V[0]; d >= D-1 -> (1-1) V[D-2] + 1 V[D-1] = V[D-1]; else lerp (:78-92)
-        //   generic: f1 in [0,1] lerp | 2: COST_FOR_INVALID | 3: C = V[d0]
-        auto weights = [&](int y, int& d0, int& d1) -> float {
-            const float d_base = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);  // :73
-            const float d = __fadd_rn(ax, d_base);                             // :76
+        //   generic: f1 in [0,1] lerp | 2: COST_FOR_INVALID | 3: C = V[d0] | -1: outside filterRect
+        auto weights = [&](float d, int& d0, int& d1) -> float {
             if (fast) {
                 const float dc = fminf(fmaxf(d, 0.f), maxd);
                 d0 = min(__float2int_rz(dc), P.D - 2);
@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         auto issue = [&]() {
 #pragma unroll
             for (int j = 0; j < kG; j++) {
-                lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u;  // outside filterRect: zero
+                lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u; lf1[j] = fast ? 0.f : -1.f;  // outside filterRect: zero
                 if (colA && vi < vReal) {
                     int d0, d1;
-                    weights(ys + vi, d0, d1);
+                    lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
                     lv0[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 16), pol);
                     lv1[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d1 * 16), pol);
                     lg[j] = __ldg(reinterpret_cast<const unsigned int*>(grow));
@@ -229,13 +229,22 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         issue();
         int c = 0;  // pipeline chunk
         while (c < nChunks) {
-            float wv0[kG], wv1[kG];
+            float wp[kG];
             uint32_t wg[kG];
 #pragma unroll
             for (int j = 0; j < kG; j++) {
                 // consume point of the batch: every load must have landed before the next batch is issued
                 asm volatile("" : "+f"(lv0[j]), "+f"(lv1[j]), "+r"(lg[j]) :: "memory");
-                wv0[j] = lv0[j]; wv1[j] = lv1[j]; wg[j] = lg[j];
+                const float f1 = lf1[j];
+                float C = __fadd_rn(__fmul_rn(1.0f - f1, lv0[j]), __fmul_rn(f1, lv1[j]));  // :92
+                if (!fast) {
+                    if (f1 > 2.5f) C = lv0[j];             // :78-79
+                    else if (f1 > 1.5f) C = kCostInvalid;  // :80,:89
+                }
+                float p = (th < C) ? th : C;               // std::min (:96); fast & outside: min(0, th) = 0
+                if (!fast && f1 < 0.f) p = 0.f;            // outside filterRect: zero padding
+                wp[j] = p;
+                wg[j] = lg[j];
             }
             issue();
 #pragma unroll
@@ -246,18 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
 #pragma unroll
                         for (int r = 0; r < kCH; r++) {
                             const int j = cc * kCH + r;
-                            const int v = c * kCH + r;
-                            float p = 0.f;  // outside filterRect: zero padding
-                            if (fast || (colA && v < vReal)) {
-                                int d0, d1;
-                                const float f1 = weights(ys + v, d0, d1);
-                                float C = __fadd_rn(__fmul_rn(1.0f - f1, wv0[j]), __fmul_rn(f1, wv1[j]));  // :92
-                                if (!fast) {
-                                    if (f1 > 2.5f) C = wv0[j];             // :78-79
-                                    else if (f1 > 1.5f) C = kCostInvalid;  // :80,:89
-                                }
-                                p = (th < C) ? th : C;                     // std::min (:96); fast & outside: min(0, th) = 0
-                            }
+                            const float p = wp[j];
                             const float ps = p * s255, nm = -8388608.0f * ps;
                             const uint32_t g = wg[j];
                             // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169)
