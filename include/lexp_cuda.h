@@ -122,6 +122,12 @@ LEXP_API int lexp_plan_eval_device_tiles(lexp_ctx* ctx, lexp_plan* plan, int mod
 LEXP_API int lexp_plan_eval_host(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
                                  float* cost_image, ptrdiff_t cost_step_bytes, int with_check);
 
+/* Page-lock and map a host buffer (e.g. the caller's cost image, cv::Mat::data) so that the batched host entry
+ * points write results straight into it from the kernel over PCIe (zero-copy) instead of staging through a
+ * pinned bounce buffer + CPU scatter.  Optional; unregister before freeing the buffer. */
+LEXP_API int lexp_host_register(void* ptr, size_t bytes);
+LEXP_API int lexp_host_unregister(void* ptr);
+
 LEXP_API int lexp_sync(lexp_ctx* ctx);
 /* cudaStream_t of the context (so a caller can order its own device work / events after ours). */
 LEXP_API void* lexp_stream(lexp_ctx* ctx);

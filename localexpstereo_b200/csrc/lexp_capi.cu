@@ -415,6 +415,18 @@ int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
     if (!c || !pl || !planes || !cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
+    {   // zero-copy path: the caller's image is page-locked + mapped (lexp_host_register)
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, cost_image, 0) == cudaSuccess && dptr) {
+            if (step_bytes % 4 != 0) return fail(LEXP_ERR_INVALID, "bad row pitch");
+            LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+            int rc = run_plan(c, pl, mode, pl->d_planes, reinterpret_cast<float*>(dptr), step_bytes / 4, 0, with_check);
+            if (rc) return rc;
+            LEXP_CUDA(cudaStreamSynchronize(c->stream));
+            return LEXP_OK;
+        }
+        cudaGetLastError();  // not a mapped buffer: staged path below
+    }
     const size_t nout = (size_t)pl->sum_s;
     if (!pl->d_compact) {
         LEXP_CUDA(cudaMalloc(&pl->d_compact, nout * sizeof(float)));
@@ -455,6 +467,18 @@ int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect
     // `costs` addresses element (filterRect.y, filterRect.x); rebase to image element (0,0)
     float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(costs) - (ptrdiff_t)filt->y * step_bytes) - filt->x;
     return lexp_eval_batch(c, mode, 1, filt, targ, plane, base, step_bytes, with_check);
+}
+
+int lexp_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(LEXP_ERR_INVALID, "bad argument");
+    LEXP_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return LEXP_OK;
+}
+
+int lexp_host_unregister(void* ptr) {
+    if (!ptr) return fail(LEXP_ERR_INVALID, "bad argument");
+    LEXP_CUDA(cudaHostUnregister(ptr));
+    return LEXP_OK;
 }
 
 int lexp_sync(lexp_ctx* c) {

@@ -125,6 +125,15 @@ class LayerManager:
         return self.layers[-1]
 
 
+def host_register(array: np.ndarray):
+    """Page-lock + map a numpy buffer (lexp_host_register): the host entry points then write into it zero-copy."""
+    check(lib().lexp_host_register(array.ctypes.data, array.nbytes))
+
+
+def host_unregister(array: np.ndarray):
+    check(lib().lexp_host_unregister(array.ctypes.data))
+
+
 class Plan:
     """Device-resident work list for a fixed list of (filterRect, targetRect) (see lexp_plan_create)."""
 

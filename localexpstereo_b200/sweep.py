@@ -22,6 +22,18 @@ def v3_layer_units(width):  # main.cpp:395-397
 V3_STEPS = [9, 3, 3]  # Exp(1)+Ransac(1)+Random(7) | Exp(2)+Ransac(1) | same (main.cpp:391-397)
 
 
+def shard_cells(cells, rank, world):
+    """Cell-shard rule: the cells of one disjoint group are dealt round-robin to ranks."""
+    return np.asarray(cells, dtype=np.int64)[rank::world]
+
+
+def tile_offsets(target_rects):
+    """Float offsets of the per-cell unary tiles inside a rank's contiguous tile buffer (the all-gather payload,
+    same rule as lexp_plan_eval_device_tiles): tile i starts at the sum of the areas of tiles 0..i-1."""
+    areas = np.array([r[2] * r[3] for r in target_rects], dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(areas)[:-1]]) if len(areas) else np.zeros(0, np.int64), int(areas.sum())
+
+
 @dataclass
 class GroupPlan:
     layer: int
@@ -50,7 +62,7 @@ class UnarySweep:
                 cells = np.asarray(cells, dtype=np.int64)
                 self.total_filter_px += K * sum(lay.filterRegions[r][2] * lay.filterRegions[r][3] for r in cells)
                 self.total_target_px += K * sum(lay.sharedRegions[r][2] * lay.sharedRegions[r][3] for r in cells)
-                mine = cells[rank::world]
+                mine = shard_cells(cells, rank, world)
                 if len(mine) == 0:
                     continue
                 plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])

@@ -1,0 +1,184 @@
+"""GPU parity against the committed golden vectors and, at BASELINE.json's full size, against the oracle on
+sampled cells plus size-independent properties of the operator."""
+import numpy as np
+import pytest
+
+from oracle import lexp_oracle as O
+from lexp_testlib import assert_costs_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_vectors_through_the_c_abi():
+    import lexp_golden
+    import localexpstereo_b200 as L
+    G = lexp_golden.load()
+    H, W = G["imL"].shape[:2]
+    prm = L.Parameters(windR=G["windR"], filterName="GF", filter_param1=G["eps"], th_col=G["th"])
+    E = L.CostVolumeEnergy(G["imL"], G["imR"], G["volL"], G["volR"], prm, G["D"] - 1)
+    s = E.stats(0)[:, ::8, ::8]
+    ref = G["stats0"]
+    assert np.abs(s[:3] - ref[:3]).max() < 2e-7
+    assert (np.abs(s[3:] - ref[3:]) / np.abs(ref[3:]).max(axis=0, keepdims=True)).max() < 1e-6
+    worst = 0.0
+    for i, c in enumerate(G["cases"]):
+        f, t = c["frect"], c["trect"]
+        img = np.full((H, W), -3.0, np.float32)
+        view = img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]]
+        (E.ComputeUnaryPotential if c["check"] else E.ComputeUnaryPotentialWithoutCheck)(f, t, view, c["plane"], None, c["mode"])
+        got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+        ref = c["ref"]
+        if np.isnan(ref).any():
+            assert np.array_equal(np.isnan(ref), np.isnan(got)), f"case {i}"
+            continue
+        worst = max(worst, assert_costs_close(got, ref, f"golden case {i}"))
+        img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]] = -3.0
+        assert (img == -3.0).all(), f"case {i} wrote outside targetRect"
+    print("golden worst rel err", worst)
+    E.close()
+
+
+@pytest.fixture(scope="module")
+def full():
+    """BASELINE.json configs[2]: 2048 x 1536 x 256, windR 20 (volume generated on the device)."""
+    import torch
+    import localexpstereo_b200 as L
+    from localexpstereo_b200 import synth
+    W, H, D, windR = 2048, 1536, 256, 20
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    vol = torch.rand((D, H, W), generator=g, device="cuda", dtype=torch.float32)
+    img = synth.synthetic_image(H, W, 42)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(img, None, vol, None, prm, D - 1)
+    yield dict(E=E, L=L, vol=vol, img=img, W=W, H=H, D=D, windR=windR, torch=torch)
+    E.close()
+
+
+def test_full_size_sampled_cells_vs_oracle(full):
+    L, E, D = full["L"], full["E"], full["D"]
+    W, H, windR = full["W"], full["H"], full["windR"]
+    from localexpstereo_b200 import synth
+    lm = L.LayerManager(W, H, windR)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    vol_h = None
+    for li, u in enumerate([20, 61, 184]):
+        lay = lm.addLayer(u)
+        g = lay.disjointRegionSets[int(rng.integers(len(lay.disjointRegionSets)))]
+        planes = synth.synthetic_planes(lay.unitRegions, 2, D, 11 + li)[1][g]
+        fr = [lay.filterRegions[r] for r in g]
+        tr = [lay.sharedRegions[r] for r in g]
+        img = np.zeros((H, W), np.float32)
+        E.ComputeUnaryPotentialBatch(fr, tr, img, planes)
+        pick = rng.choice(len(g), size=min(len(g), 6 if li == 0 else 2), replace=False)
+        for i in pick:
+            f, t, p = fr[i], tr[i], planes[i]
+            # the oracle only needs the filterRect columns of the volume: pull that slab from the device
+            slab = full["vol"][:, f[1]:f[1] + f[3], f[0]:f[0] + f[2]].cpu().numpy()
+            Or = O.CostVolumeEnergyOracle(full["img"][f[1]:f[1] + f[3], f[0]:f[0] + f[2]], None, slab, None, windR, 1e-4, 0.5, D - 1)
+            # statistics must come from the whole image (FastGuidedImageFilter reuses global statistics, GuidedFilter.h:301-326)
+            if "stats" not in full:
+                full["stats"] = O.GuidedFilterStats(full["img"], windR // 2, 1e-4)
+            S = full["stats"]
+            sl = (slice(f[1], f[1] + f[3]), slice(f[0], f[0] + f[2]))
+            Or.filter[0].I = [c[sl] for c in S.I]; Or.filter[0].mean = [c[sl] for c in S.mean]; Or.filter[0].inv = [c[sl] for c in S.inv]
+            pl = p.copy()
+            pl[2] = np.float32(pl[2])  # plane in image coordinates; shift the slab origin instead
+            fl, tl = (0, 0, f[2], f[3]), (t[0] - f[0], t[1] - f[1], t[2], t[3])
+            # d = a*x + b*y + c is evaluated in image coordinates by both sides: emulate by sampling with offsets
+            raw = O.sample_plane_cost(_OffsetVolume(slab, f[0], f[1]), f, pl, np.float32(0.5), 0.0, D - 1)
+            q = O.guided_filter_sub(Or.filter[0], fl, raw)[tl[1]:tl[1] + tl[3], tl[0]:tl[0] + tl[2]]
+            valid = O.is_valid_label(pl, t, 0.0, D - 1)
+            q = q.copy(); q[~valid] = O.COST_FOR_INVALID
+            worst = max(worst, assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], q, f"layer {li} cell {g[i]}"))
+    print("full-size worst rel err", worst)
+
+
+class _OffsetVolume:
+    """View of a [D][h][w] slab that is indexed with image coordinates (y, x) of the full volume."""
+
+    def __init__(self, slab, x0, y0):
+        self.slab, self.x0, self.y0 = slab, x0, y0
+        self.shape = slab.shape
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple) and len(idx) == 3:
+            d, Y, X = idx
+            return self.slab[d, Y - self.y0, X - self.x0]
+        return _OffsetPlane(self.slab[idx], self.x0, self.y0)
+
+
+class _OffsetPlane:
+    def __init__(self, pl, x0, y0):
+        self.pl, self.x0, self.y0 = pl, x0, y0
+
+    def __getitem__(self, idx):
+        Y, X = idx
+        return self.pl[Y - self.y0, X - self.x0]
+
+
+def test_full_size_constant_volume_is_a_fixed_point(full):
+    """Guided filter of a constant is that constant (a = 0, b = c): q == min(c, th) wherever the plane is valid."""
+    L, torch = full["L"], full["torch"]
+    W, H, D, windR = full["W"], full["H"], 8, full["windR"]
+    vol = torch.full((D, H, W), 0.3125, device="cuda")
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(full["img"], None, vol, None, prm, D - 1)
+    lay = L.LayerManager(W, H, windR).addLayer(61)
+    g = lay.disjointRegionSets[3]
+    planes = np.tile(np.array([[0.001, -0.002, 3.0, 0.0]], np.float32), (len(g), 1))
+    img = np.zeros((H, W), np.float32)
+    E.ComputeUnaryPotentialBatch([lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g], img, planes, with_check=False)
+    for r in g:
+        t = lay.sharedRegions[r]
+        tile = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+        assert np.abs(tile - 0.3125).max() < 0.3125 * 1e-4
+    E.close()
+
+
+def test_full_size_linearity_without_truncation(full):
+    """With th_col = +big the operator is linear in the volume: q(V1 + 2 V2) = q(V1) + 2 q(V2) for the same plane."""
+    L, torch = full["L"], full["torch"]
+    W, H, D, windR = full["W"], full["H"], 12, full["windR"]
+    g1 = torch.Generator(device="cuda").manual_seed(1)
+    V1 = torch.rand((D, H, W), generator=g1, device="cuda")
+    V2 = torch.rand((D, H, W), generator=g1, device="cuda")
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=1e9)
+    lay = L.LayerManager(W, H, windR).addLayer(184)
+    g = lay.disjointRegionSets[0]
+    from localexpstereo_b200 import synth
+    planes = synth.synthetic_planes(lay.unitRegions, 1, D, 3)[0][g]
+    outs = []
+    for V in (V1, V2, V1 + 2 * V2):
+        E = L.CostVolumeEnergy(full["img"], None, V, None, prm, D - 1)
+        img = np.zeros((H, W), np.float32)
+        E.ComputeUnaryPotentialBatch([lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g], img, planes, with_check=False)
+        outs.append(img)
+        E.close()
+    lin = outs[0] + 2 * outs[1]
+    m = np.zeros((H, W), bool)
+    for r in g:
+        t = lay.sharedRegions[r]
+        m[t[1]:t[1] + t[3], t[0]:t[0] + t[2]] = True
+    err = np.abs(outs[2] - lin)[m] / np.maximum(np.abs(lin[m]), 1e-3)
+    assert err.max() < 2e-4, err.max()
+
+
+def test_zero_copy_host_image_equals_staged_path(full):
+    L, E = full["L"], full["E"]
+    W, H, windR, D = full["W"], full["H"], full["windR"], full["D"]
+    from localexpstereo_b200 import synth
+    lay = L.LayerManager(W, H, windR).addLayer(20)
+    g = lay.disjointRegionSets[7]
+    planes = synth.synthetic_planes(lay.unitRegions, 1, D, 9)[0][g]
+    plan = E.make_plan([lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g])
+    a = np.zeros((H, W), np.float32)
+    b = np.zeros((H, W), np.float32)
+    plan.eval_host(planes, a)
+    L.host_register(b)
+    try:
+        plan.eval_host(planes, b)
+    finally:
+        L.host_unregister(b)
+    assert np.array_equal(a, b) and a.any()
+    plan.close()
