@@ -1,0 +1,84 @@
+// CudaCostVolumeEnergy.h -- the reference-side binding: a StereoEnergy subclass that a maintainer of
+// t-taniai/LocalExpStereo adds next to CostVolumeEnergy.h.  It keeps the virtual interface
+// (StereoEnergy.h:625-626), Plane (Plane.h) and LayerManager untouched and forwards the two unary-cost
+// virtuals to the C-ABI of lexp_cuda.h.  Install it exactly where the reference installs its CPU energy:
+//
+//     stereo.setStereoEnergyCPU(std::make_unique<CudaCostVolumeEnergy>(imL, imR, volL, volR, param, maxdisp));   // main.cpp:386
+//
+// Compile-checked in this repository against a minimal cv:: stub (tests/cxx/); it needs the real
+// <opencv2/opencv.hpp> and StereoEnergy.h of the reference to be used for real.
+#pragma once
+#include "lexp_cuda.h"
+#ifndef LEXP_ADAPTER_NO_REFERENCE_INCLUDES
+#include "StereoEnergy.h"
+#endif
+#include <stdexcept>
+#include <string>
+
+class CudaCostVolumeEnergy : public StereoEnergy {
+    lexp_ctx* ctx_ = nullptr;
+
+    static void check(int rc) {
+        if (rc != LEXP_OK) throw std::runtime_error(std::string("lexp_cuda: ") + lexp_last_error());
+    }
+    static lexp_rect toRect(const cv::Rect& r) { return lexp_rect{r.x, r.y, r.width, r.height}; }
+
+public:
+    // same argument list as CostVolumeEnergy::CostVolumeEnergy (CostVolumeEnergy.h:16)
+    CudaCostVolumeEnergy(const cv::Mat imL, const cv::Mat imR, const cv::Mat volL, const cv::Mat volR, Parameters params,
+                         float MAX_DISPARITY, float MIN_DISPARITY = 0, float MAX_VDISPARITY = 0, int device = 0)
+        : StereoEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY) {
+        if (params.filterName != "GF" && params.filterName != "GFfloat")
+            throw std::invalid_argument("CudaCostVolumeEnergy implements the guided-filter aggregation only");
+        lexp_params p{};
+        p.height = imL.rows; p.width = imL.cols; p.ndisp = volL.size.p[0];
+        p.windR = params.windR; p.eps = params.filter_param1; p.th_col = params.th_col;
+        p.min_disp = MIN_DISPARITY; p.max_disp = MAX_DISPARITY; p.device = device;
+        check(lexp_create(&p, &ctx_));
+        check(lexp_set_image(ctx_, 0, imL.data, (ptrdiff_t)imL.step));
+        check(lexp_set_image(ctx_, 1, imR.data, (ptrdiff_t)imR.step));
+        check(lexp_set_volume_host(ctx_, 0, volL.ptr<float>()));   // float[D][H][W], continuous (main.cpp:353-354)
+        check(lexp_set_volume_host(ctx_, 1, volR.ptr<float>()));
+    }
+    ~CudaCostVolumeEnergy() override { lexp_destroy(ctx_); }
+    CudaCostVolumeEnergy(const CudaCostVolumeEnergy&) = delete;
+    CudaCostVolumeEnergy& operator=(const CudaCostVolumeEnergy&) = delete;
+
+    // `costs` is proposalCost(filterRect) (FastGCStereo.h:49): costs.data addresses element (filterRect.y, filterRect.x).
+    // `reusable` is unused: the per-cell sub-filter it caches on the CPU (GuidedFilter.h:301-326) has no device state.
+    void ComputeUnaryPotentialWithoutCheck(const cv::Rect& filterRect, const cv::Rect& targetRect, const cv::Mat& costs,
+                                           const Plane& plane, Reusable& reusable = defaultReusable(), int mode = 0) const override {
+        (void)reusable;
+        const lexp_rect f = toRect(filterRect), t = toRect(targetRect);
+        const lexp_plane pl{plane.a, plane.b, plane.c, plane.v};
+        check(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 0));
+    }
+    void ComputeUnaryPotential(const cv::Rect& filterRect, const cv::Rect& targetRect, const cv::Mat& costs, const Plane& plane,
+                               Reusable& reusable = defaultReusable(), int mode = 0) const override {
+        (void)reusable;
+        const lexp_rect f = toRect(filterRect), t = toRect(targetRect);
+        const lexp_plane pl{plane.a, plane.b, plane.c, plane.v};
+        check(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 1));
+    }
+
+    // Batched form for a loop that has been restructured step-wise: one call per
+    // (layer, group, proposal step) instead of one per cell; proposalCost is the full H x W image (FastGCStereo.h:25).
+    void ComputeUnaryPotentialBatch(const std::vector<cv::Rect>& filterRects, const std::vector<cv::Rect>& targetRects,
+                                    cv::Mat& proposalCost, const std::vector<Plane>& planes, int mode = 0, bool check_valid = true) const {
+        std::vector<lexp_rect> f(filterRects.size()), t(targetRects.size());
+        for (size_t i = 0; i < f.size(); i++) { f[i] = toRect(filterRects[i]); t[i] = toRect(targetRects[i]); }
+        static_assert(sizeof(Plane) == sizeof(lexp_plane), "Plane must stay {a,b,c,v} floats (Plane.h:4-8)");
+        check(lexp_eval_batch(ctx_, mode, (int)f.size(), f.data(), t.data(), reinterpret_cast<const lexp_plane*>(planes.data()),
+                              reinterpret_cast<float*>(proposalCost.data), (ptrdiff_t)proposalCost.step, check_valid ? 1 : 0));
+    }
+
+    lexp_ctx* context() const { return ctx_; }
+
+private:
+    // The reference declares `Reusable& reusable = Reusable()` (an MSVC extension binding a temporary to a non-const
+    // reference); a conforming compiler needs an lvalue.
+    static Reusable& defaultReusable() {
+        static thread_local Reusable r;
+        return r;
+    }
+};

@@ -1,0 +1,19 @@
+// Compile-and-link check of include/CudaCostVolumeEnergy.h against the cv stub and liblexp_cuda.so.
+#define LEXP_ADAPTER_NO_REFERENCE_INCLUDES
+#include "cv_stub.h"
+#include "../../include/CudaCostVolumeEnergy.h"
+#include <cstdio>
+int main(int argc, char**) {
+    std::printf("lexp version %d\n", lexp_version());
+    if (argc > 100) {  // never executed: only instantiates the adapter so that every call is type-checked and linked
+        cv::Mat im, vol;
+        CudaCostVolumeEnergy e(im, im, vol, vol, Parameters(), 63.f);
+        cv::Rect r{0, 0, 1, 1};
+        StereoEnergy::Reusable ru;
+        e.ComputeUnaryPotential(r, r, im, Plane{0, 0, 0, 0}, ru, 0);
+        e.ComputeUnaryPotentialWithoutCheck(r, r, im, Plane{0, 0, 0, 0}, ru, 0);
+        std::vector<cv::Rect> rs; std::vector<Plane> ps;
+        e.ComputeUnaryPotentialBatch(rs, rs, im, ps);
+    }
+    return 0;
+}

@@ -138,3 +138,18 @@ def test_synthetic_planes_distribution():
     cx, cy = u[:, 0] + u[:, 2] / 2, u[:, 1] + u[:, 3] / 2
     z = P[0, :, 0] * cx + P[0, :, 1] * cy + P[0, :, 2]
     assert z.min() > -40 and z.max() < 127 + 40
+
+
+def test_reference_side_adapter_compiles_and_links(tmp_path):
+    """include/CudaCostVolumeEnergy.h (the StereoEnergy subclass a reference maintainer adds) against a cv:: stub."""
+    import subprocess
+    from localexpstereo_b200 import _capi, build
+    build.build()
+    exe = tmp_path / "adapter_check"
+    so_dir = os.path.dirname(_capi.SO_PATH)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "cxx"), os.path.join(ROOT, "tests", "cxx", "adapter_check.cpp"),
+           "-o", str(exe), "-L", so_dir, "-llexp_cuda", f"-Wl,-rpath,{so_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "lexp version" in out.stdout, out.stderr
