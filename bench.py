@@ -87,6 +87,28 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pick_threads(run_once):
+    """The CPU arm gets its best thread count: all hardware threads or one per core pair, whichever is faster here
+    (torchrun exports OMP_NUM_THREADS=1, so the count is always passed explicitly)."""
+    n = host_threads()
+    best, best_t = n, None
+    for cand in sorted({n, max(1, n // 2)}, reverse=True):
+        run_once(cand)  # warm
+        t0 = time.perf_counter()
+        run_once(cand)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = cand, dt
+    return best
+
+
 def make_inputs(W, H, D, need_right=False):
     from localexpstereo_b200 import synth
     imL = synth.synthetic_image(H, W, 42)
@@ -127,7 +149,7 @@ def run_reference(args, W, H, D, windR, rank, world):
             sample.append((fr, tr, pls[k]))
     evals = sum(sum(f[2] * f[3] for f in fr) for fr, _, _ in sample)
     out = np.zeros((H, W), np.float32)
-    nthr = max_threads()
+    nthr = pick_threads(lambda n: orc.unary_batch(0, sample[0][0], sample[0][1], sample[0][2], out, True, n))
 
     def step():
         for fr, tr, pl in sample:
@@ -284,8 +306,11 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
         orc.set_image(0, imL)
         orc.set_volume(0, vol_h)
-        nthr = max_threads()
         out = np.zeros((H, W), np.float32)
+        g0 = sweep.groups[0]
+        lay0 = sweep.layer(g0.layer)
+        nthr = pick_threads(lambda n: orc.unary_batch(0, [lay0.filterRegions[r] for r in g0.cells], [lay0.sharedRegions[r] for r in g0.cells],
+                                                      planes_h[0][0], out, True, n))
         tot_e, tot_t, used = 0, 0.0, []
         for gi, g in enumerate(sweep.groups):
             if g.group != 0:

@@ -66,6 +66,8 @@ struct lexp_ctx {
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
+    bool tile_oh_fixed = false;  // LEXP_TILE_OH given: no per-plan search
+    int num_sms = 148;
     size_t smem_limit = 0;
     size_t window_max = 0;
     bool smem_configured = false;
@@ -188,6 +190,8 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->R = params->windR / 2;  // CostVolumeEnergy.h:30
     c->smem_limit = prop.sharedMemPerBlockOptin;
     c->tile_oh = std::max(8, env_int("LEXP_TILE_OH", 128));
+    c->tile_oh_fixed = getenv("LEXP_TILE_OH") != nullptr;
+    c->num_sms = prop.multiProcessorCount;
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
@@ -303,7 +307,25 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int R = c->R;
     const int ow_max = max_tile_ow(R);
-    const int oh_max = c->tile_oh;
+    // Row segmentation: every segment re-streams 4R warm-up rows, but more items fill the 2 x #SM CTA slots better.
+    // Pick the segment height that minimises  waves x (rows streamed per item)  for this plan.
+    int oh_max = c->tile_oh;
+    if (!c->tile_oh_fixed) {
+        const int64_t slots = 2LL * c->num_sms;
+        double best = 1e300;
+        for (int cand = 24; cand <= 128; cand += 4) {
+            int64_t items = 0;
+            int max_rows = 0;
+            for (int i = 0; i < n; i++) {
+                const int ncol = (targ[i].width + ow_max - 1) / ow_max, nrow = (targ[i].height + cand - 1) / cand;
+                items += (int64_t)ncol * nrow;
+                max_rows = std::max(max_rows, (targ[i].height + nrow - 1) / nrow);
+            }
+            const double waves = (double)((items + slots - 1) / slots);
+            const double cost = waves * (max_rows + 4 * R + 12);
+            if (cost < best - 1e-9) { best = cost; oh_max = cand; }
+        }
+    }
     lexp_plan* pl = new lexp_plan();
     pl->ctx = c;
     pl->ncalls = n;

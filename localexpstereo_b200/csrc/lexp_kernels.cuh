@@ -296,14 +296,15 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
                 if (R_T > 0) {
                     F4 w[kRun - 1];
-                    F4 s = in[0];
-                    w[0] = s;
+                    F4 s = in[0], s2 = in[1];  // two partial sums: halves the dependent FADD2 chain
+                    w[0] = s; w[1] = s2;
 #pragma unroll
-                    for (int j = 1; j < 2 * R_T + 1; j++) {
+                    for (int j = 2; j < 2 * R_T + 1; j++) {
                         const F4 x = in[j + (j >> 3)];
                         if (j < kRun - 1) w[j] = x;
-                        s = f4add(s, x);
+                        if (j & 1) s2 = f4add(s2, x); else s = f4add(s, x);
                     }
+                    s = f4add(s, s2);
                     out[0] = s;
 #pragma unroll
                     for (int j = 1; j < kRun; j++) {
