@@ -100,6 +100,18 @@ __device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), ad
 __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
 
+// ---- named barriers: pairwise producer/consumer hand-off between warp teams ------------------------
+// link L (0: A->H1 via hb1, 1: H1->C via ho1, 2: C->H2 via hb2, 3: H2->E via ho2), buffer parity b:
+//   FULL  id = 4 L + b       producer bar.arrive after writing, consumer bar.sync before reading
+//   EMPTY id = 4 L + 2 + b   consumer bar.arrive after reading, producer bar.sync before overwriting (chunk >= 2)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void produce_begin(int link, int c, int nthreads) { if (c >= 2) bar_sync(4 * link + 2 + (c & 1), nthreads); }
+__device__ __forceinline__ void produce_end(int link, int c, int nthreads) { bar_arrive(4 * link + (c & 1), nthreads); }
+__device__ __forceinline__ void consume_begin(int link, int c, int nthreads) { bar_sync(4 * link + (c & 1), nthreads); }
+__device__ __forceinline__ void consume_end(int link, int c, int nChunks, int nthreads) { if (c + 2 < nChunks) bar_arrive(4 * link + 2 + (c & 1), nthreads); }
+constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 + 1), kLinkHE = 32 * (1 + 2);  // threads per link
+
 // cost-volume samples are used once: keep them from displacing the guide statistics in L2
 __device__ __forceinline__ u64 policy_evict_first() {
     u64 pol;
@@ -157,7 +169,6 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     __syncthreads();
 
     const int nChunks = (VHs + kCH - 1) / kCH;
-    const int nIter = nChunks + 4;
 
     if (warp < kWarpsA) {
         // =========================================================================== team A
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
 #pragma unroll
             for (int cc = 0; cc < kG / kCH; cc++) {
                 if (c < nChunks) {  // CTA-uniform
+                    produce_begin(0, c, kLinkAH);
                     if (t < VW) {
                         F4* hb = hb1 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
@@ -271,27 +283,27 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                             slot = (slot + 1 == K) ? 0 : slot + 1;
                         }
                     }
-                    __syncthreads();
+                    produce_end(0, c, kLinkAH);
                     c++;
                 }
             }
         }
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) __syncthreads();
     } else if (warp < kWarpsA + kWarpsH) {
         // =========================================================================== team H
         // out[i] = sum_{m=0}^{2R} in[i + m]: lane = (row r of the chunk, run k of 8 columns)
         const bool st2 = (warp == kWarpsA + 1);
         const int r = lane & (kCH - 1), k = lane / kCH;
         const int nruns = ((st2 ? it.ow : W2) + kRun - 1) / kRun;
-        const int lag = st2 ? 3 : 1;
+        const int lin = st2 ? 2 : 0, lout = st2 ? 3 : 1;                 // input / output link
+        const int nin = st2 ? kLinkCH : kLinkAH, nout = st2 ? kLinkHE : kLinkHC;
         const int vmin = st2 ? vE0 : vC0, vmax = st2 ? VHs : vC1;
         const F4* inb = st2 ? hb2 : hb1;
         F4* outb = st2 ? ho2 : ho1;
-        for (int itn = 0; itn < nIter; itn++) {
-            const int c = itn - lag;
+        for (int c = 0; c < nChunks; c++) {
             const int v = c * kCH + r;
-            if (c >= 0 && c < nChunks && k < nruns && v >= vmin && v < vmax) {
+            consume_begin(lin, c, nin);
+            produce_begin(lout, c, nout);
+            if (k < nruns && v >= vmin && v < vmax) {
                 const F4* in = inb + ((c & 1) * kCH + r) * SW + 9 * k;
                 F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
                 if (R_T > 0) {
@@ -322,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                     }
                 }
             }
-            __syncthreads();
+            consume_end(lin, c, nChunks, nin);
+            produce_end(lout, c, nout);
         }
     } else if (warp < kWarpsA + kWarpsH + kWarpsC) {
         // =========================================================================== team C
@@ -361,8 +374,6 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
             }
         };
         issue();
-        __syncthreads();
-        __syncthreads();
         for (int c = 0; c < nChunks; c++) {
             {
                 float4 ca[kCH], cb[kCH];
@@ -374,6 +385,8 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                     ca[r] = sa[r]; cb[r] = sb[r]; cc[r] = sc[r];
                 }
                 issue();
+                consume_begin(1, c, kLinkHC);
+                produce_begin(2, c, kLinkCH);
                 if (t < W2) {
                     const F4* ho = ho1 + (c & 1) * kCH * SW + sidx(t);
                     F4* hb = hb2 + (c & 1) * kCH * SW + sidx(t);
@@ -408,11 +421,10 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                         }
                     }
                 }
-                __syncthreads();
+                consume_end(1, c, nChunks, kLinkHC);
+                produce_end(2, c, kLinkCH);
             }
         }
-        __syncthreads();
-        __syncthreads();
     } else {
         // =========================================================================== team E
         const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);
@@ -453,8 +465,6 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
             }
         };
         issue();
-#pragma unroll 1
-        for (int i = 0; i < 4; i++) __syncthreads();
         float* orow;  // output pointer of row yq = ys + v - 2R at column XE
         long long ostride;
         if (P.out_compact) { orow = P.out + (size_t)it.compact_off + t; ostride = it.compact_stride; }
@@ -468,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                     cg[r] = gq[r];
                 }
                 issue();
+                consume_begin(3, c, kLinkHE);
                 if (colE) {
                     const F4* ho = ho2 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                         }
                     }
                 }
-                __syncthreads();
+                consume_end(3, c, nChunks, kLinkHE);
             }
         }
     }
