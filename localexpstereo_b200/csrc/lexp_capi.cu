@@ -198,6 +198,9 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
             c->persist_bytes = want;
             c->window_max = (size_t)prop.accessPolicyMaxWindowSize;
         } else cudaGetLastError();
+        if (env_int("LEXP_DEBUG", 0))
+            fprintf(stderr, "[lexp] L2 %d B, persisting max %d B, window max %d B, set-aside %zu B\n", prop.l2CacheSize,
+                    prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize, c->persist_bytes);
     }
     if (max_tile_ow(c->R) < 8) { delete c; return fail(LEXP_ERR_INVALID, "windR too large for the tile width"); }
     LEXP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
