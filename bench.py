@@ -30,6 +30,7 @@ WORKLOADS = {
     "adirondack_shape_1436x992x290_r20": (1436, 992, 290, 20),
     "synthetic_4k_3840x2160x512_r32": (3840, 2160, 512, 32),
     "tiny_450x375x64_r20": (450, 375, 64, 20),
+    "middv2_cones_shape_450x375x64_naive": (450, 375, 64, 20),   # configs[0]: NaiveStereoEnergy, layers 5/15/25 (main.cpp:304-306)
     "probe_2048x1536x16_r20": (2048, 1536, 16, 20),   # TLB / DRAM-locality probe (not a BASELINE config)
 }
 TH_COL, EPS = 0.5, 1e-4  # main.cpp:26,351 / main.cpp:73
@@ -190,11 +191,17 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
 
     imL, vol_h = make_inputs(W, H, D)
     vol_d = torch.from_numpy(vol_h).to(dev)
-    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS, th_col=TH_COL)
-    E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
+    naive = args.workload.endswith("_naive")
+    if naive:  # -mode MiddV2: image-based energy, th_col 10 / th_grad 2 / alpha 0.9 (StereoEnergy.h:26-37), layers 5/15/25
+        from localexpstereo_b200 import synth
+        prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS)
+        E = L.NaiveStereoEnergy(imL, synth.synthetic_image(H, W, 43), prm, D - 1, device=local_rank)
+    else:
+        prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS, th_col=TH_COL)
+        E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
     stream = torch.cuda.current_stream(dev)
     E.set_stream(stream.cuda_stream)
-    sweep = UnarySweep(E, rank=rank, world=world)
+    sweep = UnarySweep(E, unit_sizes=[5, 15, 25] if naive else None, rank=rank, world=world)
     planes_h = all_planes(sweep, D)
     planes_d = [torch.from_numpy(p).to(dev) for p in planes_h]
     cost_d = torch.zeros((H, W), dtype=torch.float32, device=dev)
@@ -301,7 +308,7 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
 
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on a bounded sample
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not naive:
         from oracle.c_oracle import COracle, max_threads
         orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
         orc.set_image(0, imL)

@@ -16,6 +16,7 @@
 #include <string>
 
 class CudaCostVolumeEnergy : public StereoEnergy {
+protected:
     lexp_ctx* ctx_ = nullptr;
 
     static void check(int rc) {
@@ -23,20 +24,27 @@ class CudaCostVolumeEnergy : public StereoEnergy {
     }
     static lexp_rect toRect(const cv::Rect& r) { return lexp_rect{r.x, r.y, r.width, r.height}; }
 
+    // shared by the two energies
+    CudaCostVolumeEnergy(const cv::Mat imL, const cv::Mat imR, Parameters params, float MAX_DISPARITY, float MIN_DISPARITY, float MAX_VDISPARITY,
+                         int device, int energy_kind, int ndisp)
+        : StereoEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY) {
+        if (params.filterName != "GF" && params.filterName != "GFfloat")
+            throw std::invalid_argument("the CUDA energies implement the guided-filter aggregation only");
+        lexp_params p{};
+        p.height = imL.rows; p.width = imL.cols; p.ndisp = ndisp;
+        p.windR = params.windR; p.eps = params.filter_param1; p.th_col = params.th_col;
+        p.min_disp = MIN_DISPARITY; p.max_disp = MAX_DISPARITY; p.device = device;
+        p.energy_kind = energy_kind; p.alpha = params.alpha; p.th_grad = params.th_grad;
+        check(lexp_create(&p, &ctx_));
+        check(lexp_set_image(ctx_, 0, imL.data, (ptrdiff_t)imL.step));
+        check(lexp_set_image(ctx_, 1, imR.data, (ptrdiff_t)imR.step));
+    }
+
 public:
     // same argument list as CostVolumeEnergy::CostVolumeEnergy (CostVolumeEnergy.h:16)
     CudaCostVolumeEnergy(const cv::Mat imL, const cv::Mat imR, const cv::Mat volL, const cv::Mat volR, Parameters params,
                          float MAX_DISPARITY, float MIN_DISPARITY = 0, float MAX_VDISPARITY = 0, int device = 0)
-        : StereoEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY) {
-        if (params.filterName != "GF" && params.filterName != "GFfloat")
-            throw std::invalid_argument("CudaCostVolumeEnergy implements the guided-filter aggregation only");
-        lexp_params p{};
-        p.height = imL.rows; p.width = imL.cols; p.ndisp = volL.size.p[0];
-        p.windR = params.windR; p.eps = params.filter_param1; p.th_col = params.th_col;
-        p.min_disp = MIN_DISPARITY; p.max_disp = MAX_DISPARITY; p.device = device;
-        check(lexp_create(&p, &ctx_));
-        check(lexp_set_image(ctx_, 0, imL.data, (ptrdiff_t)imL.step));
-        check(lexp_set_image(ctx_, 1, imR.data, (ptrdiff_t)imR.step));
+        : CudaCostVolumeEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY, device, 0, volL.size.p[0]) {
         check(lexp_set_volume_host(ctx_, 0, volL.ptr<float>()));   // float[D][H][W], continuous (main.cpp:353-354)
         check(lexp_set_volume_host(ctx_, 1, volR.ptr<float>()));
     }
@@ -81,4 +89,14 @@ private:
         static thread_local Reusable r;
         return r;
     }
+};
+
+// NaiveStereoEnergy (StereoEnergy.h:629-764) on the device: the image-based unary term of `-mode MiddV2`.  The reference builds it
+// inside the PMStereoBase constructor (PMStereoBase.h:37); replace it the same way as above:
+//     stereo.setStereoEnergyCPU(std::make_unique<CudaNaiveStereoEnergy>(imL, imR, param, maxdisp));
+class CudaNaiveStereoEnergy : public CudaCostVolumeEnergy {
+public:
+    CudaNaiveStereoEnergy(const cv::Mat imL, const cv::Mat imR, Parameters params, float MAX_DISPARITY, float MIN_DISPARITY = 0,
+                          float MAX_VDISPARITY = 0, int device = 0)
+        : CudaCostVolumeEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY, device, 1, (int)MAX_DISPARITY + 1) {}
 };

@@ -52,7 +52,10 @@ typedef struct lexp_params {
     float min_disp;     /* MIN_DISPARITY (0 in main.cpp)                                       */
     float max_disp;     /* MAX_DISPARITY (= ndisp-1 in main.cpp:385-386)                       */
     int device;         /* CUDA device ordinal                                                  */
-    int reserved[7];
+    int energy_kind;    /* 0: CostVolumeEnergy (CostVolumeEnergy.h:6-184); 1: NaiveStereoEnergy (StereoEnergy.h:629-764), no volume */
+    float alpha;        /* Parameters::alpha   (NaiveStereoEnergy only, StereoEnergy.h:659-664)   */
+    float th_grad;      /* Parameters::th_grad (NaiveStereoEnergy only)                            */
+    int reserved[4];
 } lexp_params;
 
 typedef struct lexp_ctx lexp_ctx;   /* replaces a CostVolumeEnergy instance (CostVolumeEnergy.h:6-184) */

@@ -59,6 +59,7 @@ struct lexp_ctx {
     float4* d_statB[2] = {nullptr, nullptr};
     float* d_statC[2] = {nullptr, nullptr};
     char* d_gs[2] = {nullptr, nullptr};   // backing allocation of guide + statistics
+    float4* d_exi[2] = {nullptr, nullptr}; // NaiveStereoEnergy: ExI planes
     size_t gs_bytes = 0;
     size_t persist_bytes = 0;             // L2 set-aside for persisting accesses (0: unsupported)
     int persist_mode = -1;                // view whose window is currently installed on the stream
@@ -77,9 +78,9 @@ struct lexp_ctx {
 
 namespace {
 
-template <int R_T>
+template <int R_T, bool NAIVE>
 int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
-    auto kern = lexp_fused_kernel<R_T>;
+    auto kern = lexp_fused_kernel<R_T, NAIVE>;
     if (!c->smem_configured) {  // one R instantiation per context
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
         c->smem_configured = true;
@@ -92,10 +93,16 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
 
 int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
     if (smem > c->smem_limit) return fail(LEXP_ERR_INVALID, "tile needs more shared memory than the device offers");
+    if (c->p.energy_kind == 1) {
+        switch (c->R) {
+            case 10: return launch_fused_t<10, true>(c, kp, nitems, smem);
+            default: return launch_fused_t<0, true>(c, kp, nitems, smem);
+        }
+    }
     switch (c->R) {
-        case 10: return launch_fused_t<10>(c, kp, nitems, smem);
-        case 16: return launch_fused_t<16>(c, kp, nitems, smem);
-        default: return launch_fused_t<0>(c, kp, nitems, smem);
+        case 10: return launch_fused_t<10, false>(c, kp, nitems, smem);
+        case 16: return launch_fused_t<16, false>(c, kp, nitems, smem);
+        default: return launch_fused_t<0, false>(c, kp, nitems, smem);
     }
 }
 
@@ -111,7 +118,9 @@ int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
 int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float* d_out, long long pitch, int compact,
              int with_check) {
     if (mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "mode must be 0 or 1");
-    if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
+    if (c->p.energy_kind == 1) {
+        if (!c->d_exi[0] || !c->d_exi[1]) return fail(LEXP_ERR_STATE, "NaiveStereoEnergy needs the images of both views");
+    } else if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
     if (c->persist_bytes && c->persist_mode != mode) {
         // keep the plane-independent inputs (statistics, guide) resident in L2 across the K steps of a group;
         // the cost-volume gathers are issued with an evict-first policy by the kernel
@@ -140,6 +149,11 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     kp.th_col = c->p.th_col; kp.min_disp = c->p.min_disp; kp.max_disp = c->p.max_disp;
     kp.with_check = with_check;
     kp.R = c->R;
+    kp.exi_own = c->d_exi[mode];
+    kp.exi_other = c->d_exi[1 - mode];
+    kp.thresh_color = c->p.th_col * (1.0f - c->p.alpha);    // StereoEnergy.h:663
+    kp.thresh_gradient = c->p.th_grad * c->p.alpha;          // StereoEnergy.h:664
+    kp.mode = mode;
     kp.fast_ok = (c->vol_finite[mode] && c->p.min_disp == 0.0f && c->p.max_disp == (float)(c->p.ndisp - 1) && c->p.th_col >= 0.0f) ? 1 : 0;
     return launch_fused(c, kp, pl->nitems, pl->smem);
 }
@@ -175,9 +189,10 @@ int lexp_version(void) { return 100; }
 
 int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     if (!params || !out_ctx) return fail(LEXP_ERR_INVALID, "null argument");
-    if (params->height <= 0 || params->width <= 0 || params->ndisp < 2) return fail(LEXP_ERR_INVALID, "bad H/W/D");
+    if (params->height <= 0 || params->width <= 0 || (params->ndisp < 2 && params->energy_kind == 0)) return fail(LEXP_ERR_INVALID, "bad H/W/D");
     if ((size_t)params->height * params->width >= (1ull << 30)) return fail(LEXP_ERR_INVALID, "image too large (H*W must be < 2^30)");
     if (params->windR < 2 || params->windR / 2 > 24) return fail(LEXP_ERR_INVALID, "windR/2 must be in [1, 24]");
+    if (params->energy_kind != 0 && params->energy_kind != 1) return fail(LEXP_ERR_INVALID, "energy_kind must be 0 or 1");
     int ndev = 0;
     LEXP_CUDA(cudaGetDeviceCount(&ndev));
     if (params->device < 0 || params->device >= ndev) return fail(LEXP_ERR_INVALID, "bad device ordinal");
@@ -214,6 +229,7 @@ int lexp_destroy(lexp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int m = 0; m < 2; m++) {
         cudaFree(c->d_gs[m]);
+        cudaFree(c->d_exi[m]);
         cudaFree(c->d_vol[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -250,6 +266,12 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     lexp_stats_rowsum<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], d_rs, H, W, c->R);
     lexp_stats_finish<<<grd, blk, 0, c->stream>>>(d_rs, c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], H, W, c->R, (double)c->p.eps);
     c->launches += 2;
+    if (c->p.energy_kind == 1) {
+        if (!c->d_exi[mode] && cudaMalloc(&c->d_exi[mode], HW * sizeof(float4)) != cudaSuccess) { cudaFree(d_rs); return fail(LEXP_ERR_NOMEM, "ExI allocation failed"); }
+        const float s_col = (float)(1.0 - (double)c->p.alpha);  // `I[m] * (1.0 - params.alpha)`, StereoEnergy.h:659
+        lexp_build_exi<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], c->d_exi[mode], H, W, s_col, c->p.alpha);
+        c->launches++;
+    }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_rs);

@@ -65,6 +65,11 @@ struct KParams {
     float th_col, min_disp, max_disp;
     int with_check;
     int R;                              // guided-filter box radius (windR / 2)
+    // NaiveStereoEnergy (StereoEnergy.h:629-764): image-based raw cost instead of the cost volume
+    const float4* __restrict__ exi_own;   // ExI[mode]      float4[H][W] = {c0,c1,c2 * (1-alpha), alpha * Sobel_x(gray)}
+    const float4* __restrict__ exi_other; // ExI[1 - mode]
+    float thresh_color, thresh_gradient;  // StereoEnergy.h:663-664
+    int mode;                             // 0: left reference view, 1: right
     int fast_ok;                        // MIN == 0, MAX == D-1, th_col >= 0 and the volume holds no NaN/Inf
 };
 
@@ -82,7 +87,7 @@ __host__ __device__ inline int srow_stride(int vw) {
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
-    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 2 * ((vh + 3) / 4)) * 16;
+    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 3 * ((vh + 3) / 4)) * 16;
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -112,6 +117,28 @@ __device__ __forceinline__ void consume_begin(int link, int c, int nthreads) { b
 __device__ __forceinline__ void consume_end(int link, int c, int nChunks, int nthreads) { if (c + 2 < nChunks) bar_arrive(4 * link + 2 + (c & 1), nthreads); }
 constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 + 1), kLinkHE = 32 * (1 + 2);  // threads per link
 
+// Inverse affine map (dst pixel of the filterRect -> source pixel of the other view) of NaiveStereoEnergy
+// (StereoEnergy.h:704-729): the three float corner correspondences, then the closed form of
+// cv::getAffineTransform + the inversion inside cv::warpAffine (see oracle affine_inverse_for_plane).
+__device__ __forceinline__ void naive_inverse_affine(const Item& it, const Plane4& pl, int mode, double* iM) {
+    const float sign = mode ? -1.0f : 1.0f;
+    const float x00 = (float)it.fx, y00 = (float)it.fy;
+    const float x11 = __fadd_rn(x00, (float)it.fw), y11 = __fadd_rn(y00, (float)it.fh);
+    auto gz = [&](float x, float y) { return __fadd_rn(__fadd_rn(__fmul_rn(pl.a, x), __fmul_rn(pl.b, y)), pl.c); };  // Plane.h:51-54
+    const float sx0 = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y00)));
+    const float sx1 = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y11)));
+    const float sx2 = __fsub_rn(x11, __fmul_rn(sign, gz(x11, y00)));
+    float sy0 = y00, sy1 = y11;
+    if (pl.v != 0.0f) { sy0 = __fadd_rn(sy0, pl.v); sy1 = __fadd_rn(sy1, pl.v); }
+    const double dw = (double)__fsub_rn(x11, x00), dh = (double)__fsub_rn(y11, y00);
+    iM[0] = __ddiv_rn(__dsub_rn((double)sx2, (double)sx0), dw);
+    iM[1] = __ddiv_rn(__dsub_rn((double)sx1, (double)sx0), dh);
+    iM[2] = (double)sx0;
+    iM[3] = 0.0;
+    iM[4] = __ddiv_rn(__dsub_rn((double)sy1, (double)sy0), dh);
+    iM[5] = (double)sy0;
+}
+
 // cost-volume samples are used once: keep them from displacing the guide statistics in L2
 __device__ __forceinline__ u64 policy_evict_first() {
     u64 pol;
@@ -124,7 +151,7 @@ __device__ __forceinline__ float ldg_stream(const float* p, u64 pol) {
     return v;
 }
 
-template <int R_T>
+template <int R_T, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
     const int K = 2 * R + 1;
@@ -155,7 +182,8 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
     F4* ho2 = hb2 + 2 * kCH * SW;          // [2][CH][SW] stage-2 box sums      (index: column - X0 - 2R)
     float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VHs] 1 / (#rows of the window inside filterRect)
-    float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane
+    float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
+    int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
         const int total = K * VW + K * W2 + 8 * kCH * SW;
@@ -163,7 +191,17 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         for (int v = tid; v < VHs; v += kThreads) {
             const int y = ys + v;
             s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
-            s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);                   // CostVolumeEnergy.h:73
+            if (!NAIVE) {
+                s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);               // CostVolumeEnergy.h:73
+            } else {
+                // cv::warpAffine fixed-point row terms (AB_BITS = 10, round_delta = 16) for the inverse affine map of
+                // StereoEnergy.h:704-729; closed form of getAffineTransform + inversion, same operation order as the oracle
+                double iM[6];
+                naive_inverse_affine(it, pl, P.mode, iM);
+                const double yr = (double)(y - it.fy);
+                reinterpret_cast<int*>(s_dbase)[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[1], yr), iM[2]), 1024.0)) + 16;
+                s_Y0[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[4], yr), iM[5]), 1024.0)) + 16;
+            }
         }
     }
     __syncthreads();
@@ -172,6 +210,69 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
 
     if (warp < kWarpsA) {
         // =========================================================================== team A
+        if (NAIVE) {
+            // NaiveStereoEnergy raw cost: bilinear sample of ExI[1-mode] at cv::warpAffine's fixed-point coordinates,
+            // truncated L1 colour + gradient difference (StereoEnergy.h:729-741).  Straightforward (one chunk of loads
+            // at a time): config 1 is the reference's small CPU-runnable case, not the throughput path.
+            const int t = tid;
+            const int XA = X0 + t;
+            const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
+            double iM[6];
+            naive_inverse_affine(it, pl, P.mode, iM);
+            const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(iM[0], (double)(XA - it.fx)), 1024.0));
+            const float s255 = 1.0f / 255.0f;
+            const int Wm1 = P.W - 1, Hm1 = P.H - 1;
+            F4 acc = f4zero();
+            int slot = 0;
+            for (int c = 0; c < nChunks; c++) {
+                F4 nwr[kCH];
+#pragma unroll
+                for (int r = 0; r < kCH; r++) {
+                    const int v = c * kCH + r;
+                    nwr[r] = f4zero();
+                    if (colA && v < vReal) {
+                        const int y = ys + v;
+                        const int X = (reinterpret_cast<const int*>(s_dbase)[v] + adelta) >> 5, Y = s_Y0[v] >> 5;  // bdelta = 0 (iM[3] = 0)
+                        const int sx = X >> 5, sy = Y >> 5;
+                        const float fxw = (float)(X & 31) * (1.0f / 32), fyw = (float)(Y & 31) * (1.0f / 32);
+                        const int x0c = min(max(sx, 0), Wm1), x1c = min(max(sx + 1, 0), Wm1);
+                        const int y0c = min(max(sy, 0), Hm1), y1c = min(max(sy + 1, 0), Hm1);
+                        const float4 S00 = __ldg(P.exi_other + (size_t)y0c * P.W + x0c), S01 = __ldg(P.exi_other + (size_t)y0c * P.W + x1c);
+                        const float4 S10 = __ldg(P.exi_other + (size_t)y1c * P.W + x0c), S11 = __ldg(P.exi_other + (size_t)y1c * P.W + x1c);
+                        const float4 L = __ldg(P.exi_own + (size_t)y * P.W + XA);
+                        const uint32_t g = __ldg(reinterpret_cast<const unsigned int*>(P.guide) + (size_t)y * P.W + XA);
+                        const float w00 = __fmul_rn(1.0f - fyw, 1.0f - fxw), w01 = __fmul_rn(1.0f - fyw, fxw);
+                        const float w10 = __fmul_rn(fyw, 1.0f - fxw), w11 = __fmul_rn(fyw, fxw);
+                        auto bil = [&](float a, float b, float cc, float d) {  // remapBilinear: ((S00 w00 + S01 w01) + S10 w10) + S11 w11
+                            return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, w00), __fmul_rn(b, w01)), __fmul_rn(cc, w10)), __fmul_rn(d, w11));
+                        };
+                        const float r0 = bil(S00.x, S01.x, S10.x, S11.x), r1 = bil(S00.y, S01.y, S10.y, S11.y);
+                        const float r2 = bil(S00.z, S01.z, S10.z, S11.z), r3 = bil(S00.w, S01.w, S10.w, S11.w);
+                        const float col = __fadd_rn(__fadd_rn(fabsf(__fsub_rn(L.x, r0)), fabsf(__fsub_rn(L.y, r1))), fabsf(__fsub_rn(L.z, r2)));
+                        const float p = __fadd_rn(fminf(P.thresh_color, col), fminf(P.thresh_gradient, fabsf(__fsub_rn(L.w, r3))));  // :737-740
+                        const float ps = p * s255, nm = -8388608.0f * ps;
+                        const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
+                        const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
+                        const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
+                        nwr[r] = F4{pk2(p, q0), pk2(q1, q2)};
+                    }
+                }
+                produce_begin(0, c, kLinkAH);
+                if (t < VW) {
+                    F4* hb = hb1 + (c & 1) * kCH * SW + sidx(t);
+#pragma unroll
+                    for (int r = 0; r < kCH; r++) {
+                        F4* sl = ring1 + slot * VW + t;
+                        const F4 old = *sl;
+                        *sl = nwr[r];
+                        acc = f4add(acc, f4sub(nwr[r], old));
+                        hb[r * SW] = acc;
+                        slot = (slot + 1 == K) ? 0 : slot + 1;
+                    }
+                }
+                produce_end(0, c, kLinkAH);
+            }
+        } else {
         const int t = tid;
         const int XA = X0 + t;
         const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
@@ -288,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 }
             }
         }
+        }  // !NAIVE
     } else if (warp < kWarpsA + kWarpsH) {
         // =========================================================================== team H
         // out[i] = sum_{m=0}^{2R} in[i + m]: lane = (row r of the chunk, run k of 8 columns)
@@ -584,6 +686,21 @@ __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __res
         const int d = d0 + dd;
         if (d < D && (x0 >> 2) + xb < Wb) dst[(((size_t)y * Wb + (x0 >> 2) + xb) * D + d) * 4 + q] = tile[dd][xb * 4 + q];
     }
+}
+
+// NaiveStereoEnergy constructor (StereoEnergy.h:647-662): ExI = merge(I * (1 - alpha), alpha * Sobel_x(gray)), with
+// cvtColor(BGR2GRAY) = (B*0.114f + G*0.587f) + R*0.299f and Sobel(dx=1, ksize=1, scale=0.5, BORDER_REPLICATE) in float.
+__global__ void lexp_build_exi(const uchar4* __restrict__ guide, float4* __restrict__ exi, int H, int W, float s_col, float alpha) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    auto gray = [&](int xx) {
+        const uchar4 g = guide[(size_t)y * W + min(max(xx, 0), W - 1)];
+        return __fadd_rn(__fadd_rn(__fmul_rn((float)g.x, 0.114f), __fmul_rn((float)g.y, 0.587f)), __fmul_rn((float)g.z, 0.299f));
+    };
+    const uchar4 g = guide[(size_t)y * W + x];
+    const float gx = __fmul_rn(__fsub_rn(gray(x + 1), gray(x - 1)), 0.5f);
+    exi[(size_t)y * W + x] = make_float4(__fmul_rn((float)g.x, s_col), __fmul_rn((float)g.y, s_col), __fmul_rn((float)g.z, s_col),
+                                         __fmul_rn(gx, alpha));
 }
 
 // upload-time scan: does the cost volume hold any NaN / Inf?  (the fast sampler multiplies by 0 weights)

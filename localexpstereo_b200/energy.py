@@ -199,6 +199,8 @@ class CostVolumeEnergy:
     integer device pointers (then no copy is made).  `params.filterName` must be "GF" or "GFfloat"
     (both run the same FP32 kernel, within the 1e-4 tolerance of the reference's double filter)."""
 
+    ENERGY_KIND = 0
+
     def __init__(self, imL, imR, volL, volR, params: Parameters, MAX_DISPARITY, MIN_DISPARITY=0.0, MAX_VDISPARITY=0.0,
                  device: int = 0):
         if params.filterName not in ("GF", "GFfloat"):
@@ -209,9 +211,10 @@ class CostVolumeEnergy:
         self.height, self.width = imL.shape[:2]
         self.params = params
         self.MAX_DISPARITY, self.MIN_DISPARITY = float(MAX_DISPARITY), float(MIN_DISPARITY)
-        D = self._ndisp(volL)
+        D = self._ndisp(volL) if volL is not None else int(MAX_DISPARITY) + 1
         p = _capi.Params(self.height, self.width, D, int(params.windR), float(params.filter_param1), float(params.th_col),
-                         float(MIN_DISPARITY), float(MAX_DISPARITY), int(device))
+                         float(MIN_DISPARITY), float(MAX_DISPARITY), int(device), int(self.ENERGY_KIND), float(params.alpha),
+                         float(params.th_grad))
         h = C.c_void_p()
         check(lib().lexp_create(C.byref(p), C.byref(h)))
         self._h = h
@@ -295,3 +298,15 @@ class CostVolumeEnergy:
             self.close()
         except Exception:
             pass
+
+
+class NaiveStereoEnergy(CostVolumeEnergy):
+    """NaiveStereoEnergy (StereoEnergy.h:629-764): the image-based unary term of `-mode MiddV2` (BASELINE.json
+    configs[0]) -- 4-channel ExI = [(1-alpha) BGR, alpha d/dx gray], other view warped with cv::warpAffine's fixed-point
+    bilinear sampling, truncated L1 colour + gradient cost, same guided-filter aggregation.  No cost volume."""
+    ENERGY_KIND = 1
+
+    def __init__(self, imL, imR, params: Parameters, MAX_DISPARITY, MIN_DISPARITY=0.0, MAX_VDISPARITY=0.0, device: int = 0):
+        if imL is None or imR is None:
+            raise LexpError("NaiveStereoEnergy needs both images")
+        super().__init__(imL, imR, None, None, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY, device)

@@ -489,3 +489,115 @@ def synthetic_planes(cells_unit, n_steps, D, seed):
         for s in range(1, n_steps):
             out[s, i] = random_proposal(rng, base, sx, sy, s - 1, 0.0, float(D - 1))
     return out
+
+
+# ----------------------------------------------------------------------------
+# NaiveStereoEnergy (StereoEnergy.h:629-764): image-based unary term of `-mode MiddV2`
+# (BASELINE.json configs[0]).  OpenCV calls restated: cvtColor(BGR2GRAY) on 32F, Sobel(ksize=1,
+# scale=0.5, BORDER_REPLICATE), getAffineTransform, warpAffine(INTER_LINEAR, BORDER_REPLICATE)
+# with its fixed-point coordinates (imgwarp.cpp: AB_BITS = 10, INTER_BITS = 5).
+# ----------------------------------------------------------------------------
+def build_exI(im8, alpha):
+    """ExI = merge(I*(1-alpha), alpha*Sobel_x(gray)) as float32[H][W][4]  (StereoEnergy.h:647-662)."""
+    I = np.asarray(im8).astype(np.float32)  # imL.convertTo(I[0], CV_32FC3) (StereoEnergy.h:96)
+    # cv::cvtColor(BGR2GRAY) on CV_32F: B*0.114f + G*0.587f + R*0.299f in float, left to right (OpenCV 3.1 scalar path)
+    gray = ((I[:, :, 0] * f32(0.114) + I[:, :, 1] * f32(0.587)).astype(np.float32) + I[:, :, 2] * f32(0.299)).astype(np.float32)
+    gp = np.pad(gray, ((0, 0), (1, 1)), mode="edge")
+    gx = ((gp[:, 2:] - gp[:, :-2]) * f32(0.5)).astype(np.float32)  # Sobel dx=1, ksize=1, scale 0.5, BORDER_REPLICATE (:654)
+    s_col = f32(1.0 - float(f32(alpha)))  # `I[m] * (1.0 - params.alpha)`: double scale, applied in float by cvtScale
+    ex = np.empty(I.shape[:2] + (4,), np.float32)
+    ex[:, :, :3] = (I * s_col).astype(np.float32)
+    ex[:, :, 3] = (gx * f32(alpha)).astype(np.float32)
+    return ex
+
+
+def _cv_round(x):
+    """saturate_cast<int>(double) = cvRound: round half to even."""
+    return np.rint(np.asarray(x, dtype=np.float64)).astype(np.int64)
+
+
+def affine_inverse_for_plane(filter_rect, plane, mode):
+    """The 2x3 double matrix cv::warpAffine uses (dst pixel -> source pixel) for the three float corner
+    correspondences of StereoEnergy.h:704-727.  The reference gets it from cv::getAffineTransform (6x6 LU solve in
+    double) followed by the inversion inside cv::warpAffine; because the destination corners are (0,0), (0,h), (w,0),
+    that inverse map is exactly the affine interpolation of the three source points, which is what is evaluated
+    here (closed form, double, fixed operation order -- the CUDA path repeats it bit for bit).  It equals OpenCV's
+    matrix to ~1e-16 relative; the 1/32-pixel coordinate rounding can therefore differ from cv2 only at exact
+    rounding ties (a handful of pixels per thousand calls, see tests/test_oracle.py)."""
+    x, y, w, h = filter_rect
+    sign = f32(-1.0) if mode else f32(1.0)
+    x00, y00 = f32(x), f32(y)
+    x11, y11 = f32(x00 + f32(w)), f32(y00 + f32(h))
+    gz = lambda xx, yy: plane_get_z(plane, xx, yy)
+    sx0 = f32(x00 - f32(sign * gz(x00, y00)))   # (:714-719) float arithmetic
+    sx1 = f32(x00 - f32(sign * gz(x00, y11)))
+    sx2 = f32(x11 - f32(sign * gz(x11, y00)))
+    sy0, sy1 = y00, y11
+    v = f32(plane[3])
+    if v != 0:                                     # (:720-725)
+        sy0, sy1 = f32(sy0 + v), f32(sy1 + v)
+    dw, dh = float(f32(x11 - x00)), float(f32(y11 - y00))
+    return np.array([(float(sx2) - float(sx0)) / dw, (float(sx1) - float(sx0)) / dh, float(sx0),
+                     0.0, (float(sy1) - float(sy0)) / dh, float(sy0)], dtype=np.float64)
+
+
+def warp_affine_linear_replicate(src, iM, w, h):
+    """cv::warpAffine(src, dst, M, Size(w,h), INTER_LINEAR, BORDER_REPLICATE) for a float image with `iM` the
+    already-inverted matrix: 10-bit fixed-point coordinates, 1/32-pixel bilinear weights."""
+    H, W = src.shape[:2]
+    xs = np.arange(w)
+    ys = np.arange(h)
+    adelta = _cv_round(iM[0] * xs * 1024.0)
+    bdelta = _cv_round(iM[3] * xs * 1024.0)
+    X0 = _cv_round((iM[1] * ys + iM[2]) * 1024.0) + 16
+    Y0 = _cv_round((iM[4] * ys + iM[5]) * 1024.0) + 16
+    X = (X0[:, None] + adelta[None, :]) >> 5
+    Y = (Y0[:, None] + bdelta[None, :]) >> 5
+    sx, sy = X >> 5, Y >> 5
+    fx = ((X & 31).astype(np.float32) * f32(1.0 / 32)).astype(np.float32)
+    fy = ((Y & 31).astype(np.float32) * f32(1.0 / 32)).astype(np.float32)
+    w00 = ((f32(1) - fy) * (f32(1) - fx)).astype(np.float32)
+    w01 = ((f32(1) - fy) * fx).astype(np.float32)
+    w10 = (fy * (f32(1) - fx)).astype(np.float32)
+    w11 = (fy * fx).astype(np.float32)
+    x0c, x1c = np.clip(sx, 0, W - 1), np.clip(sx + 1, 0, W - 1)
+    y0c, y1c = np.clip(sy, 0, H - 1), np.clip(sy + 1, 0, H - 1)
+    S = src.reshape(H, W, -1)
+    out = (S[y0c, x0c] * w00[..., None]).astype(np.float32)
+    out = (out + S[y0c, x1c] * w01[..., None]).astype(np.float32)
+    out = (out + S[y1c, x0c] * w10[..., None]).astype(np.float32)
+    out = (out + S[y1c, x1c] * w11[..., None]).astype(np.float32)
+    return out.reshape((h, w) + src.shape[2:])
+
+
+class NaiveStereoEnergyOracle:
+    """NaiveStereoEnergy (StereoEnergy.h:629-764), filterName "GF"."""
+
+    def __init__(self, imL, imR, windR, eps, th_col, th_grad, alpha, max_disp, min_disp=0.0, box=box_sum_fast):
+        self.im = [np.asarray(imL), np.asarray(imR)]
+        self.windR, self.MAX, self.MIN = int(windR), f32(max_disp), f32(min_disp)
+        self.ExI = [build_exI(self.im[0], alpha), build_exI(self.im[1], alpha)]
+        self.thresh_color = f32(f32(th_col) * f32(f32(1.0) - f32(alpha)))   # :663
+        self.thresh_gradient = f32(f32(th_grad) * f32(alpha))               # :664
+        self.filter = [GuidedFilterStats(self.im[m], self.windR // 2, eps, np.float64, box=box) for m in range(2)]  # :674-675
+
+    def raw(self, filter_rect, plane, mode=0):
+        x, y, w, h = filter_rect
+        iM = affine_inverse_for_plane(filter_rect, plane, mode)
+        pIR = warp_affine_linear_replicate(self.ExI[1 - mode], iM, w, h)  # :729
+        pIL = self.ExI[mode][y:y + h, x:x + w]
+        d = np.abs(pIL - pIR).astype(np.float32)
+        col = ((d[:, :, 0] + d[:, :, 1]).astype(np.float32) + d[:, :, 2]).astype(np.float32)
+        return (np.minimum(self.thresh_color, col) + np.minimum(self.thresh_gradient, d[:, :, 3])).astype(np.float32)  # :737-740
+
+    def compute_unary_potential_without_check(self, filter_rect, target_rect, plane, mode=0):
+        p = self.raw(filter_rect, plane, mode)
+        fx, fy, _, _ = filter_rect
+        tx, ty, tw, th = target_rect
+        q = guided_filter_sub(self.filter[mode], filter_rect, p)
+        return q[ty - fy:ty - fy + th, tx - fx:tx - fx + tw].copy()
+
+    def compute_unary_potential(self, filter_rect, target_rect, plane, mode=0):
+        out = self.compute_unary_potential_without_check(filter_rect, target_rect, plane, mode)
+        out[~is_valid_label(plane, target_rect, self.MIN, self.MAX)] = COST_FOR_INVALID  # :756-763
+        return out

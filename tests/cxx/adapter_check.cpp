@@ -14,6 +14,8 @@ int main(int argc, char**) {
         e.ComputeUnaryPotentialWithoutCheck(r, r, im, Plane{0, 0, 0, 0}, ru, 0);
         std::vector<cv::Rect> rs; std::vector<Plane> ps;
         e.ComputeUnaryPotentialBatch(rs, rs, im, ps);
+        CudaNaiveStereoEnergy n(im, im, Parameters(), 63.f);
+        n.ComputeUnaryPotential(r, r, im, Plane{0, 0, 0, 0}, ru, 1);
     }
     return 0;
 }

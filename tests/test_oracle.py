@@ -152,3 +152,40 @@ def test_plane_helpers_and_rng():
     assert all(2.0 <= x < 3.0 for x in u)
     pl = O.create_random_label(O.CvRNG(3), 10, 20, 0.0, 63.0)
     assert np.isfinite(pl).all() and 0 <= float(O.plane_get_z(pl, 10, 20)) < 63.0 + 1e-3
+
+
+def test_naive_energy_oracle_against_opencv_kernels():
+    """NaiveStereoEnergy restatement vs the OpenCV kernels the reference calls (StereoEnergy.h:651-654,727-729)."""
+    rng = np.random.default_rng(3)
+    im = O.synthetic_image(70, 90, 8)
+    ex = O.build_exI(im, 0.9)
+    I = im.astype(np.float32)
+    gray = cv2.cvtColor(I, cv2.COLOR_BGR2GRAY)
+    gx = cv2.Sobel(gray, cv2.CV_32F, 1, 0, ksize=1, scale=0.5, borderType=cv2.BORDER_REPLICATE)
+    ref = np.dstack([I * np.float32(1.0 - float(np.float32(0.9))), gx * np.float32(0.9)]).astype(np.float32)
+    assert np.abs(ex - ref).max() < 5e-5  # cv2 4.x evaluates the gray dot product with FMAs: <= 1 ulp of 255
+    # fixed-point warp: exact for a given inverse matrix
+    src = (rng.random((40, 60, 4)) * 100).astype(np.float32)
+    for a, tx in [(1.0, 0.3), (0.93, 2.11), (1.21, -5.6)]:
+        ref = cv2.warpAffine(src, np.array([[a, 0, tx], [0, 1, 0]]), (50, 30), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                             borderMode=cv2.BORDER_REPLICATE)
+        assert np.array_equal(O.warp_affine_linear_replicate(src, np.array([a, 0, tx, 0, 1, 0.0]), 50, 30), ref)
+    # end to end vs getAffineTransform + warpAffine: identical except at exact 1/32-pixel rounding ties
+    r2 = O.CvRNG(3)
+    nd = npx = 0
+    for _ in range(30):
+        fx, fy = r2.uniform_int(0, 40), r2.uniform_int(0, 20)
+        fr = (fx, fy, 45, 40)
+        pl = O.create_random_label(r2, fx + 20, fy + 20, 0, 31.0)
+        for mode in (0, 1):
+            sign = np.float32(-1.0 if mode else 1.0)
+            x00, y00 = np.float32(fx), np.float32(fy)
+            x11, y11 = np.float32(x00 + 45), np.float32(y00 + 40)
+            gz = lambda xx, yy: O.plane_get_z(pl, xx, yy)
+            s3 = np.array([[x00 - sign * gz(x00, y00), y00], [x00 - sign * gz(x00, y11), y11], [x11 - sign * gz(x11, y00), y00]], np.float32)
+            d3 = np.array([[0, 0], [0, y11 - y00], [x11 - x00, 0]], np.float32)
+            refw = cv2.warpAffine(ex, cv2.getAffineTransform(s3, d3), (45, 40), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+            mine = O.warp_affine_linear_replicate(ex, O.affine_inverse_for_plane(fr, pl, mode), 45, 40)
+            d = np.abs(mine - refw).max(axis=2)
+            nd += int((d > 1e-4).sum()); npx += d.size
+    assert nd / npx < 1e-3, (nd, npx)
