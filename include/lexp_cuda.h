@@ -134,7 +134,8 @@ LEXP_API int lexp_host_unregister(void* ptr);
 LEXP_API int lexp_sync(lexp_ctx* ctx);
 /* cudaStream_t of the context (so a caller can order its own device work / events after ours). */
 LEXP_API void* lexp_stream(lexp_ctx* ctx);
-/* Run all subsequent work of this context on the caller's stream (e.g. torch's current stream). */
+/* Run all subsequent work of this context on the caller's stream (e.g. torch's current stream, or a stream that is
+ * being captured into a CUDA graph: lexp_plan_eval_device* issue only graph-capturable work).  Does not synchronise. */
 LEXP_API int lexp_set_stream(lexp_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);

@@ -541,8 +541,9 @@ int lexp_set_stream(lexp_ctx* c, void* s) {
     if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
-    LEXP_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    // no synchronisation here (the call must be legal while the caller captures a CUDA graph): ordering between the
+    // old and the new stream is the caller's business
+    if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)s;
     c->persist_mode = -1;
     return LEXP_OK;
