@@ -380,11 +380,17 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        # A captured graph holds NCCL work: tearing the process group down underneath it can hang.  All results are
+        # printed; synchronise, then leave without running destructors.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    graph = None
     sweep.close()
     E.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 def main():
