@@ -63,7 +63,7 @@ struct lexp_ctx {
     size_t gs_bytes = 0;
     size_t persist_bytes = 0;             // L2 set-aside for persisting accesses (0: unsupported)
     int persist_mode = -1;                // view whose window is currently installed on the stream
-    float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[H][Wb][D][4] (owned)
+    float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[Hb][Wb][D][4][4] (owned)
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
@@ -161,14 +161,15 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
 // scan the caller's volume for NaN/Inf and re-lay it out into the context's blocked copy
 int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
     const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4;
-    const size_t nblk = (size_t)H * Wb * D * 4;
+    const int Hb = (H + 3) / 4;
+    const size_t nblk = (size_t)Hb * Wb * D * 16;
     if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], nblk * sizeof(float)));
     int* d_flag = nullptr;
     LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream);
     lexp_scan_nonfinite<<<148 * 8, 256, 0, c->stream>>>(d_src, (size_t)D * H * W, d_flag);
-    dim3 grd((W + 31) / 32, H, (D + 31) / 32), blk(32, 8);
-    lexp_relayout_volume<<<grd, blk, 0, c->stream>>>(d_src, c->d_vol[mode], D, H, W, Wb);
+    dim3 grd((W + 31) / 32, Hb, (D + 7) / 8);
+    lexp_relayout_volume<<<grd, 256, 0, c->stream>>>(d_src, c->d_vol[mode], D, H, W, Wb);
     c->launches += 2;
     int h = 1;
     cudaError_t e = cudaGetLastError();

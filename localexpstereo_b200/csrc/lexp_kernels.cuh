@@ -50,7 +50,7 @@ struct __align__(16) Item {  // one CTA work item (64 B)
 struct Plane4 { float a, b, c, v; };
 
 struct KParams {
-    const float* __restrict__ vol;      // blocked cost volume float[H][Wb][D][4], Wb = ceil(W/4) (see lexp_relayout_volume)
+    const float* __restrict__ vol;      // blocked cost volume float[Hb][Wb][D][4 rows][4 px], Hb = ceil(H/4), Wb = ceil(W/4) (lexp_relayout_volume)
     int Wb;
     const uchar4* __restrict__ guide;   // uchar4[H][W] = (c0,c1,c2,0), OpenCV BGR order
     const float4* __restrict__ statA;   // float4[H][W] = {mean0, mean1, mean2, inv00}
@@ -139,17 +139,9 @@ __device__ __forceinline__ void naive_inverse_affine(const Item& it, const Plane
     iM[5] = (double)sy0;
 }
 
-// cost-volume samples are used once: keep them from displacing the guide statistics in L2
-__device__ __forceinline__ u64 policy_evict_first() {
-    u64 pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ float ldg_stream(const float* p, u64 pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
+// Cost-volume samples: plain read-only loads.  Measured on B200 (profiles/r1_experiments.md): letting them allocate in
+// L1 (the d0 / d0+1 samples of a 4-pixel block share 128-byte lines) beats L1::no_allocate + L2 evict-first by 8 %.
+__device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
 
 template <int R_T, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
@@ -282,11 +274,11 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         // fast sampler: finite plane, MIN = 0, MAX = D-1, th >= 0, finite volume (checked at upload)
         const bool fast = P.fast_ok && isfinite(pl.a) && isfinite(pl.b) && isfinite(pl.c);
         const unsigned W4 = (unsigned)P.W * 4u;
-        const u64 pol = policy_evict_first();
         const int XAc = colA ? XA : it.fx;
-        // blocked volume: element (d, y, x) lives at ((y * Wb + x / 4) * D + d) * 4 + x % 4
-        const size_t vstride = (size_t)P.Wb * P.D * 16;  // bytes per image row
-        const char* vrow = reinterpret_cast<const char*>(P.vol) + (size_t)ys * vstride + ((size_t)(XAc >> 2) * P.D * 4 + (XAc & 3)) * 4;
+        // blocked volume: element (d, y, x) lives at ((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4:
+        // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
+        const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
+        const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
         const char* grow = reinterpret_cast<const char*>(P.guide) + ((size_t)ys * P.W + XAc) * 4;
         const float maxd = (float)(P.D - 1);
         F4 acc = f4zero();
@@ -328,12 +320,13 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 if (colA && vi < vReal) {
                     int d0, d1;
                     lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
-                    lv0[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 16), pol);
-                    lv1[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d1 * 16), pol);
+                    const int y = ys + vi;
+                    const char* vrow = vcol + (size_t)(y >> 2) * vblk + (y & 3) * 16;
+                    lv0[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 64));
+                    lv1[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d1 * 64));
                     lg[j] = __ldg(reinterpret_cast<const unsigned int*>(grow));
                 }
                 vi++;
-                vrow += vstride;
                 grow += W4;
             }
         };
@@ -666,25 +659,26 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict
     statC[p] = (float)(i22 / det);
 }
 
-// One-time re-layout of the cost volume (the input format float[D][H][W], README.md:85-91, is fixed
-// only at the API): dst[((y * Wb + x/4) * D + d) * 4 + x%4] = src[d][y][x].  All disparities of a 4-pixel
-// block are contiguous, so the two samples of a plane (d0, d0+1) of neighbouring pixels share sectors /
-// DRAM pages instead of being scattered over ndisp slices H*W*4 bytes apart.
-// grid = (ceil(W/32), H, ceil(D/32)), block = (32, 8)
+// One-time re-layout of the cost volume (the input format float[D][H][W], README.md:85-91, is fixed only at the API):
+// dst[((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4] = src[d][y][x].  All disparities of a 4x4 pixel block are
+// contiguous (64 B per disparity), so the two samples (d0, d0+1) of a pixel, of its neighbours in x AND of the next
+// rows of the streaming gather share 128-byte lines / DRAM pages instead of being scattered over ndisp slices
+// H*W*4 bytes apart.   grid = (ceil(W/32), ceil(H/4), ceil(D/8)), block = 256
 __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb) {
-    __shared__ float tile[32][33];  // [d][x]
-    const int x0 = blockIdx.x * 32, y = blockIdx.y, d0 = blockIdx.z * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int d = d0 + i, x = x0 + threadIdx.x;
-        tile[i][threadIdx.x] = (d < D && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
+    __shared__ float tile[8][4][33];  // [d][row][x]
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
+    for (int i = threadIdx.x; i < 8 * 4 * 32; i += 256) {
+        const int xx = i & 31, rr = (i >> 5) & 3, dd = i >> 7;
+        const int x = x0 + xx, y = y0 + rr, d = d0 + dd;
+        tile[dd][rr][xx] = (d < D && y < H && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
     }
     __syncthreads();
-    // each thread writes one float: consecutive threads -> (x%4 fastest, then d)
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int lin = i * 32 + threadIdx.x;        // 0..1023 = [xb 8][d 32][q 4]
-        const int xb = lin >> 7, dd = (lin >> 2) & 31, q = lin & 3;
+    // consecutive threads write consecutive floats of the destination: [xb 8][d 8][row 4][px 4]
+    for (int i = threadIdx.x; i < 8 * 8 * 16; i += 256) {
+        const int q = i & 3, rr = (i >> 2) & 3, dd = (i >> 4) & 7, xb = i >> 7;
         const int d = d0 + dd;
-        if (d < D && (x0 >> 2) + xb < Wb) dst[(((size_t)y * Wb + (x0 >> 2) + xb) * D + d) * 4 + q] = tile[dd][xb * 4 + q];
+        if (d < D && (x0 >> 2) + xb < Wb)
+            dst[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = tile[dd][rr][xb * 4 + q];
     }
 }
 
