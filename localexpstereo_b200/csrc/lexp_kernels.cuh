@@ -8,16 +8,17 @@
 //                       (StereoEnergy.h:577-610, CostVolumeEnergy.h:176-183).
 // File:line citations are relative to /root/reference/LocalExpansionStereo/.
 //
-// Design: one CTA = one output tile (<= 64 columns) of one (cell, plane)
-// call.  The CTA streams top-to-bottom over the rows of the tile's dependency cone
-// (tile +- 2R) in chunks of CH rows.  Five warp teams form a software pipeline, one CTA
-// barrier per chunk, all intermediates in shared memory / registers:
-//   A (4 warps, thread = column): gather p = min(lerp(V, plane), th) (register prefetch three
-//       chunks ahead), products {p, I0 p, I1 p, I2 p}, running column sums over 2R+1 rows
-//       (thread-private ring of the rows to subtract later)            -> hb1
-//   H (2 warps, thread = run of 8 columns): horizontal window sums of hb1 -> ho1, hb2 -> ho2
+// Design: one CTA = one output tile (<= 64 columns) of one (cell, plane) call.  The CTA streams
+// top-to-bottom over the rows of the tile's dependency cone (tile +- 2R) in chunks of kCH rows.  Four warp teams form a
+// producer/consumer pipeline; each hand-off is a double-buffered shared-memory row buffer guarded by a pair of named
+// barriers (bar.arrive / bar.sync), all intermediates stay in shared memory / registers:
+//   A (4 warps, thread = column): gather p = min(lerp(V, plane), th) from the blocked volume (register batch of kG rows,
+//       one batch of loads in flight), products {p, I0 p, I1 p, I2 p}, running column sums over 2R+1 rows
+//       (thread-private ring of the rows to subtract later)              -> hb1
+//       NAIVE: the raw cost comes from the warped other view instead (NaiveStereoEnergy, StereoEnergy.h:694-754)
+//   H (2 warps, thread = run of 8 columns): horizontal window sums: warp 0 hb1 -> ho1, warp 1 hb2 -> ho2
 //   C (3 warps, thread = column): (a, b) from the stage-1 box sums and the precomputed
-//       statistics, running column sums of {a0, a1, a2, b}              -> hb2
+//       statistics, running column sums of {a0, a1, a2, b}                -> hb2
 //   E (2 warps, thread = column): q = (Bb + Ba.I) / N, validity mask, store.
 // float4 quantities are held as two packed f32x2 registers and added with Blackwell's
 // FADD2 (add.rn.f32x2): two FP32 adds per issue slot.
