@@ -153,3 +153,17 @@ def test_reference_side_adapter_compiles_and_links(tmp_path):
     assert res.returncode == 0, res.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "lexp version" in out.stdout, out.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints one JSON line with the agreed keys."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny_450x375x64_r20",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads(res.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"].startswith("tiny")
