@@ -374,7 +374,11 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "lexp_fused_kernel", "peak_source": peak_src,
+                         # DRAM read+write of ONE layer-0 launch (500 cells, algorithmic 2.34e8 B) from the ncu --set full capture
+                         # summarised in profiles/r1_final_fused_ncu_L0.md; only known for the default workload at N = 1
+                         "traffic": (230713088 + 9571072) if (args.workload == "synthetic_2048x1536x256_r20" and world == 1) else None,
+                         "traffic_note": "per layer-0 launch of 500 cells (algorithmic 2.34e8 B); profiles/r1_final_fused_ncu_L0.md",
+                         "kernel": "lexp_fused_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_step": sweep.local_alg_bytes, "kernel_ms_per_step": kern_ms,
                          "ms_by_layer": {str(k): round(v[0], 4) for k, v in by_layer.items()}},
         }
