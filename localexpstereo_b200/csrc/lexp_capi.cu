@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -74,6 +76,10 @@ struct lexp_ctx {
     bool smem_configured = false;
     bool own_stream = true;
     bool vol_finite[2] = {false, false};
+    // single-cell plans of lexp_eval_cell, keyed by (filterRect, targetRect): the unchanged reference loop calls the
+    // virtual again and again with the same rects (LayerManager.h:14-24), so the tiling / device upload is done once
+    std::mutex cache_mu;
+    std::map<std::array<int, 8>, lexp_plan*> cell_plans;
 };
 
 namespace {
@@ -228,6 +234,8 @@ int lexp_destroy(lexp_ctx* c) {
     if (!c) return LEXP_OK;
     cudaSetDevice(c->p.device);
     cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->cell_plans) lexp_plan_destroy(kv.second);
+    c->cell_plans.clear();
     for (int m = 0; m < 2; m++) {
         cudaFree(c->d_gs[m]);
         cudaFree(c->d_exi[m]);
@@ -511,10 +519,34 @@ int lexp_eval_batch(lexp_ctx* c, int mode, int n, const lexp_rect* filt, const l
 
 int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect* targ, const lexp_plane* plane, float* costs,
                    ptrdiff_t step_bytes, int with_check) {
-    if (!filt || !targ || !plane || !costs) return fail(LEXP_ERR_INVALID, "null argument");
+    if (!c || !filt || !targ || !plane || !costs) return fail(LEXP_ERR_INVALID, "null argument");
     // `costs` addresses element (filterRect.y, filterRect.x); rebase to image element (0,0)
     float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(costs) - (ptrdiff_t)filt->y * step_bytes) - filt->x;
-    return lexp_eval_batch(c, mode, 1, filt, targ, plane, base, step_bytes, with_check);
+    const std::array<int, 8> key = {filt->x, filt->y, filt->width, filt->height, targ->x, targ->y, targ->width, targ->height};
+    lexp_plan* pl = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->cache_mu);
+        auto itp = c->cell_plans.find(key);
+        if (itp != c->cell_plans.end()) pl = itp->second;
+    }
+    if (!pl) {
+        int rc = lexp_plan_create(c, 1, filt, targ, &pl);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(c->cache_mu);
+        auto ins = c->cell_plans.emplace(key, pl);
+        if (!ins.second) {  // another thread created it meanwhile
+            lexp_plan_destroy(pl);
+            pl = ins.first->second;
+        } else if (c->cell_plans.size() > 200000) {  // unbounded callers (initCurrentFast with a labeling: one rect per pixel)
+            c->cell_plans.erase(ins.first);
+            int rc2 = lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
+            std::string keep = g_err;
+            lexp_plan_destroy(pl);
+            g_err = keep;
+            return rc2;
+        }
+    }
+    return lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
 }
 
 int lexp_host_register(void* ptr, size_t bytes) {

@@ -120,3 +120,27 @@ def test_errors_are_reported(scene):
         E.ComputeUnaryPotentialBatch([(0, 0, 50, 50)], [(40, 40, 20, 20)], img, np.zeros((1, 4), np.float32))  # target not inside filter
     with pytest.raises(L.LexpError):
         E.ComputeUnaryPotentialBatch([(-5, 0, 50, 50)], [(0, 0, 20, 20)], img, np.zeros((1, 4), np.float32))  # outside the image
+
+
+def test_concurrent_single_cell_calls_like_the_openmp_loop(scene):
+    """FastGCStereo.h:30-49: N host threads call the virtual concurrently, one cell each, K proposals per cell, all writing
+    disjoint targetRects of one proposalCost image.  Must equal the batched evaluation (and exercises the per-cell plan cache)."""
+    from concurrent.futures import ThreadPoolExecutor
+    L, E = scene["L"], scene["E"]
+    H, W, D = scene["H"], scene["W"], scene["D"]
+    lay = L.LayerManager(W, H, scene["windR"]).addLayer(12)
+    g = lay.disjointRegionSets[2]
+    rng = O.CvRNG(41)
+    for step in range(3):
+        planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+        ref = np.zeros((H, W), np.float32)
+        E.ComputeUnaryPotentialBatch([lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g], ref, planes)
+        img = np.zeros((H, W), np.float32)
+
+        def one(i):
+            f, t = lay.filterRegions[g[i]], lay.sharedRegions[g[i]]
+            E.ComputeUnaryPotential(f, t, img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], planes[i])
+
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            list(ex.map(one, range(len(g))))
+        assert np.array_equal(img, ref)
