@@ -144,3 +144,46 @@ def test_concurrent_single_cell_calls_like_the_openmp_loop(scene):
         with ThreadPoolExecutor(max_workers=8) as ex:
             list(ex.map(one, range(len(g))))
         assert np.array_equal(img, ref)
+
+
+@pytest.mark.parametrize("windR", [8, 13, 32])
+def test_other_filter_radii(windR):
+    """R = windR / 2 = 4 and 6 run the generic (runtime-R) kernel, R = 16 the second specialised one (config 5: windR 32)."""
+    import localexpstereo_b200 as L
+    H, W, D = 140, 190, 20
+    imL, imR, volL, volR = make_scene(H, W, D, seed=windR)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(imL, imR, volL, volR, prm, D - 1)
+    Or = O.CostVolumeEnergyOracle(imL, imR, volL, volR, windR, 1e-4, 0.5, D - 1)
+    lay = L.LayerManager(W, H, windR).addLayer(23)
+    rng = O.CvRNG(windR)
+    worst = 0.0
+    for mode, g in ((0, lay.disjointRegionSets[0]), (1, lay.disjointRegionSets[5]), (0, lay.disjointRegionSets[-1])):
+        planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+        fr = [lay.filterRegions[r] for r in g]
+        tr = [lay.sharedRegions[r] for r in g]
+        img = np.zeros((H, W), np.float32)
+        E.ComputeUnaryPotentialBatch(fr, tr, img, planes, mode=mode)
+        for f, t, p in zip(fr, tr, planes):
+            worst = max(worst, assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], Or.compute_unary_potential(f, t, p, mode), f"windR {windR} {f}"))
+    print("windR", windR, "worst rel err", worst)
+    E.close()
+
+
+def test_nonzero_min_disparity_and_odd_max(scene):
+    """MIN_DISPARITY != 0 / MAX_DISPARITY != D-1 take the generic sampler (D0 offset, CostVolumeEnergy.h:67,83)."""
+    import localexpstereo_b200 as L
+    H, W, D = 100, 130, 16
+    imL, imR, volL, volR = make_scene(H, W, D, seed=77)
+    prm = L.Parameters(windR=20, filterName="GF", filter_param1=1e-4, th_col=0.6)
+    for (mn, mx) in [(-4.0, 11.0), (0.0, 9.0)]:
+        E = L.CostVolumeEnergy(imL, imR, volL, volR, prm, mx, mn)
+        Or = O.CostVolumeEnergyOracle(imL, imR, volL, volR, 20, 1e-4, 0.6, mx, mn)
+        f, t = (10, 5, 110, 90), (30, 25, 70, 50)
+        for p in [(0.05, 0.02, 1.0, 0), (0.0, 0.0, -2.5, 0), (0.2, -0.1, 4.0, 0), (0.0, 0.0, 10.5, 0)]:
+            p = np.array(p, np.float32)
+            img = np.zeros((H, W), np.float32)
+            E.ComputeUnaryPotential(f, t, img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], p)
+            ref = Or.compute_unary_potential(f, t, p)
+            assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"min {mn} max {mx} plane {p}")
+        E.close()
