@@ -132,7 +132,10 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
         // the cost-volume gathers are issued with an evict-first policy by the kernel
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.base_ptr = c->d_gs[mode];
-        av.accessPolicyWindow.num_bytes = std::min(c->gs_bytes, c->window_max);
+        // default: pin a prefix [statA | statC | guide | ..] of exactly the set-aside size with hit ratio 1 (measured 1 %
+        // better than LEXP_L2_PERSIST=2: the whole allocation with a fractional hit ratio)
+        const bool prefix = env_int("LEXP_L2_PERSIST", 1) != 2;
+        av.accessPolicyWindow.num_bytes = prefix ? std::min(c->gs_bytes, c->persist_bytes) : std::min(c->gs_bytes, c->window_max);
         av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->persist_bytes / (double)av.accessPolicyWindow.num_bytes);
         av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
