@@ -307,6 +307,8 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     # ---- end to end through the host-buffer API: planes H2D + unary tiles D2H every evaluation
     cost_h = np.zeros((H, W), np.float32)
     L.host_register(cost_h)  # page-locked + mapped: unary tiles land in the host image without a bounce buffer
+    for ph in planes_h:
+        L.host_register(ph)  # the per-step inputs (plane hypotheses) are copied H2D from pinned memory
 
     def sweep_host():
         for gi, g in enumerate(sweep.groups):
@@ -325,6 +327,8 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = evals_per_step / float(dt.item())
     L.host_unregister(cost_h)
+    for ph in planes_h:
+        L.host_unregister(ph)
     h2d = sum(g.plan.num_calls * 16 * g.n_steps for g in sweep.groups)
     d2h = sweep.local_target_px * 4
 
