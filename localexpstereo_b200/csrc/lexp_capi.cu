@@ -129,7 +129,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     } else if (!c->d_guide[mode] || !c->d_vol[mode]) return fail(LEXP_ERR_STATE, "image / volume of this view not set");
     if (c->persist_bytes && c->persist_mode != mode) {
         // keep the plane-independent inputs (statistics, guide) resident in L2 across the K steps of a group;
-        // the cost-volume gathers are issued with an evict-first policy by the kernel
+        // (the cost-volume gathers are plain read-only loads; see profiles/r1_experiments.md)
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.base_ptr = c->d_gs[mode];
         // default: pin a prefix [statA | statC | guide | ..] of exactly the set-aside size with hit ratio 1 (measured 1 %
