@@ -204,7 +204,8 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
     stream = torch.cuda.current_stream(dev)
     E.set_stream(stream.cuda_stream)
-    sweep = UnarySweep(E, unit_sizes=[5, 15, 25] if naive else None, rank=rank, world=world)
+    shard_rank, shard_world = (0, 1) if args.replicas else (rank, world)
+    sweep = UnarySweep(E, unit_sizes=[5, 15, 25] if naive else None, rank=shard_rank, world=shard_world)
     planes_h = all_planes(sweep, D)
     planes_d = [torch.from_numpy(p).to(dev) for p in planes_h]
     cost_d = torch.zeros((H, W), dtype=torch.float32, device=dev)
@@ -212,7 +213,7 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
 
     # cell-shard exchange buffers: per group, every rank contributes its per-cell unary tiles (padded to the max)
     gather = None
-    if world > 1:
+    if world > 1 and not args.replicas:
         sizes = torch.tensor([g.plan.target_px for g in sweep.groups], device=dev)
         # groups are identical in count on all ranks only if every group has >= world cells; align by (layer, group) key
         keys = [(g.layer, g.group) for g in sweep.groups]
@@ -288,7 +289,7 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
-    evals_per_step = sweep.total_filter_px  # whole job, all ranks
+    evals_per_step = sweep.total_filter_px * (world if args.replicas else 1)  # whole job, all ranks
     value = evals_per_step / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (lexp_fused_kernel): algorithmic bytes / per-launch device time
@@ -365,13 +366,14 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.replicas else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "W": W, "H": H, "ndisp": D, "windR": windR, "th_col": TH_COL, "eps": EPS,
                        "layers_unit": sweep.unit_sizes, "steps_per_layer": sweep.steps,
                        "evals_per_step": evals_per_step, "target_px_per_step": sweep.total_target_px,
                        "batched_evaluations_per_step": sweep.launches_per_sweep,
-                       "parallelism": f"cell-shard x{world}" + (", all-gather of per-cell unary tiles per group" if world > 1 else ""),
+                       "parallelism": (f"replicas x{world} (one image pair per GPU)" if args.replicas else
+                                       f"cell-shard x{world}" + (", all-gather of per-cell unary tiles per group" if world > 1 else "")),
                        "cuda_graph": graph is not None,
                        "l2": "inputs larger than L2 (cost volume %.2f GB, random planes)" % (vol_h.nbytes / 1e9)},
             "clocks": clk,
@@ -410,6 +412,9 @@ def main():
     ap.add_argument("--workload", default="synthetic_2048x1536x256_r20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the sweep eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--replicas", action="store_true",
+                    help="BASELINE.json configs[3] style: every rank sweeps its OWN image pair (weak scaling, no data-path collective) "
+                         "instead of sharding the cells of one pair (default, strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     W, H, D, windR = WORKLOADS[args.workload]
