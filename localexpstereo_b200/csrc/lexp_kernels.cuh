@@ -88,7 +88,7 @@ __host__ __device__ inline int srow_stride(int vw) {
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
-    return (size_t)(K * vw + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 3 * ((vh + 3) / 4)) * 16;
+    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 3 * ((vh + 3) / 4)) * 16;
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     const int vC1 = min(VHs, fy1 + R - ys);                  // centre rows >= fy1 are zero rows
     const int vE0 = it.oy0 + 2 * R - ys;                     // first v whose stage-2 centre row (y - 2R) is an output row
 
-    F4* ring1 = smem;                      // [K][VW]
-    F4* ring2 = ring1 + K * VW;            // [K][W2]
+    uint2* ring1 = reinterpret_cast<uint2*>(smem);   // [K][VW] {p, packed guide}: the products are recomputed when a row leaves the window
+    F4* ring2 = smem + (K * VW + 1) / 2;              // [K][W2]
     F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
     F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW] stage-1 box sums      (index: column - X0 - R)
     F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
     int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
-        const int total = K * VW + K * W2 + 8 * kCH * SW;
+        const int total = (K * VW + 1) / 2 + K * W2 + 8 * kCH * SW;
         for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
         for (int v = tid; v < VHs; v += kThreads) {
             const int y = ys + v;
@@ -219,10 +219,12 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
             int slot = 0;
             for (int c = 0; c < nChunks; c++) {
                 F4 nwr[kCH];
+                float pr[kCH];
+                uint32_t gr[kCH];
 #pragma unroll
                 for (int r = 0; r < kCH; r++) {
                     const int v = c * kCH + r;
-                    nwr[r] = f4zero();
+                    nwr[r] = f4zero(); pr[r] = 0.f; gr[r] = 0u;
                     if (colA && v < vReal) {
                         const int y = ys + v;
                         const int X = (reinterpret_cast<const int*>(s_dbase)[v] + adelta) >> 5, Y = s_Y0[v] >> 5;  // bdelta = 0 (iM[3] = 0)
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                         const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
                         const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
                         const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
-                        nwr[r] = F4{pk2(p, q0), pk2(q1, q2)};
+                        nwr[r] = F4{pk2(p, q0), pk2(q1, q2)}; pr[r] = p; gr[r] = g;
                     }
                 }
                 produce_begin(0, c, kLinkAH);
@@ -255,10 +257,15 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                     F4* hb = hb1 + (c & 1) * kCH * SW + sidx(t);
 #pragma unroll
                     for (int r = 0; r < kCH; r++) {
-                        F4* sl = ring1 + slot * VW + t;
-                        const F4 old = *sl;
-                        *sl = nwr[r];
-                        acc = f4add(acc, f4sub(nwr[r], old));
+                        uint2* sl = ring1 + slot * VW + t;
+                        const uint2 oldpg = *sl;
+                        *sl = make_uint2(__float_as_uint(pr[r]), gr[r]);
+                        const float po = __uint_as_float(oldpg.x);
+                        const float pso = po * s255, nmo = -8388608.0f * pso;
+                        const float o0 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7440)), pso, nmo);
+                        const float o1 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7441)), pso, nmo);
+                        const float o2 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7442)), pso, nmo);
+                        acc = f4add(acc, f4sub(nwr[r], F4{pk2(po, o0), pk2(o1, o2)}));
                         hb[r * SW] = acc;
                         slot = (slot + 1 == K) ? 0 : slot + 1;
                     }
@@ -363,16 +370,23 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                         for (int r = 0; r < kCH; r++) {
                             const int j = cc * kCH + r;
                             const float p = wp[j];
-                            const float ps = p * s255, nm = -8388608.0f * ps;
                             const uint32_t g = wg[j];
-                            // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169)
+                            uint2* sl = ring1 + slot * VW + t;
+                            const uint2 oldpg = *sl;
+                            *sl = make_uint2(__float_as_uint(p), g);
+                            // (2^23 + byte) * ps - 2^23 * ps = byte/255 * p   (GuidedFilter.h:62-65,151-169), for the entering row
+                            // and again for the row that leaves the window (kept as {p, guide}: 8 instead of 16 bytes per pixel)
+                            const float ps = p * s255, nm = -8388608.0f * ps;
                             const float q0 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7440)), ps, nm);
                             const float q1 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7441)), ps, nm);
                             const float q2 = fmaf(__uint_as_float(__byte_perm(g, 0x4B000000u, 0x7442)), ps, nm);
+                            const float po = __uint_as_float(oldpg.x);
+                            const float pso = po * s255, nmo = -8388608.0f * pso;
+                            const float o0 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7440)), pso, nmo);
+                            const float o1 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7441)), pso, nmo);
+                            const float o2 = fmaf(__uint_as_float(__byte_perm(oldpg.y, 0x4B000000u, 0x7442)), pso, nmo);
                             const F4 nw = F4{pk2(p, q0), pk2(q1, q2)};
-                            F4* sl = ring1 + slot * VW + t;
-                            const F4 old = *sl;
-                            *sl = nw;
+                            const F4 old = F4{pk2(po, o0), pk2(o1, o2)};
                             acc = f4add(acc, f4sub(nw, old));
                             hb[r * SW] = acc;  // column sum centred on row y - R
                             slot = (slot + 1 == K) ? 0 : slot + 1;
