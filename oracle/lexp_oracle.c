@@ -39,21 +39,20 @@ typedef struct {
 /* cv::boxFilter(ksize 2R+1, normalize=false, BORDER_CONSTANT) on a w x h double
  * image with row stride `ss` (GuidedFilter.h:40-45): running row sums, then running
  * column sums.  `tmp` holds w*h doubles. */
-static void box_sum(const double* src, int ss, double* dst, int w, int h, int R, double* tmp) {
+static void box_sum(const double* src, int ss, double* dst, int w, int h, int R, double* tmp, double* acc) {
     for (int y = 0; y < h; y++) {
         const double* s = src + (size_t)y * ss;
         double* t = tmp + (size_t)y * w;
-        double acc = 0;
-        for (int x = 0; x < R && x < w; x++) acc += s[x];
+        double run = 0;
+        for (int x = 0; x < R && x < w; x++) run += s[x];
         for (int x = 0; x < w; x++) {
-            if (x + R < w) acc += s[x + R];
-            if (x - R - 1 >= 0) acc -= s[x - R - 1];
-            t[x] = acc;
+            if (x + R < w) run += s[x + R];
+            if (x - R - 1 >= 0) run -= s[x - R - 1];
+            t[x] = run;
         }
     }
-    for (int x = 0; x < w; x++) dst[x] = 0;
     /* column running sums, row-major friendly */
-    double* acc = (double*)calloc((size_t)w, sizeof(double));
+    for (int x = 0; x < w; x++) acc[x] = 0;
     for (int y = 0; y < R && y < h; y++)
         for (int x = 0; x < w; x++) acc[x] += tmp[(size_t)y * w + x];
     for (int y = 0; y < h; y++) {
@@ -63,7 +62,6 @@ static void box_sum(const double* src, int ss, double* dst, int w, int h, int R,
             for (int x = 0; x < w; x++) acc[x] -= tmp[(size_t)(y - R - 1) * w + x];
         memcpy(dst + (size_t)y * w, acc, (size_t)w * sizeof(double));
     }
-    free(acc);
 }
 
 void* oracle_create(int H, int W, int D, int windR, double eps, float th_col, float min_disp, float max_disp) {
@@ -90,7 +88,7 @@ void oracle_set_image(void* p, int mode, const uint8_t* bgr) {
     oracle_ctx* c = (oracle_ctx*)p;
     const int H = c->H, W = c->W, R = c->R;
     const size_t n = (size_t)H * W;
-    double *N = (double*)malloc(n * 8), *tmp = (double*)malloc(n * 8), *prod = (double*)malloc(n * 8);
+    double *N = (double*)malloc(n * 8), *tmp = (double*)malloc(n * 8), *prod = (double*)malloc(n * 8), *acc = (double*)malloc((size_t)W * 8);
     double* var[6];
     for (int k = 0; k < 3; k++) {
         free(c->I[mode][k]); free(c->mean[mode][k]);
@@ -99,9 +97,9 @@ void oracle_set_image(void* p, int mode, const uint8_t* bgr) {
         for (size_t i = 0; i < n; i++) c->I[mode][k][i] = (double)bgr[i * 3 + k] * (1.0 / 255); /* :62-65 */
     }
     for (size_t i = 0; i < n; i++) prod[i] = 1.0;
-    box_sum(prod, W, N, W, H, R, tmp); /* :69 */
+    box_sum(prod, W, N, W, H, R, tmp, acc); /* :69 */
     for (int k = 0; k < 3; k++) {
-        box_sum(c->I[mode][k], W, c->mean[mode][k], W, H, R, tmp);
+        box_sum(c->I[mode][k], W, c->mean[mode][k], W, H, R, tmp, acc);
         for (size_t i = 0; i < n; i++) c->mean[mode][k][i] /= N[i]; /* :70-72 */
     }
     static const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {0, 1, 2, 1, 2, 2}; /* rr rg rb gg gb bb */
@@ -110,7 +108,7 @@ void oracle_set_image(void* p, int mode, const uint8_t* bgr) {
         const double *A = c->I[mode][pa[k]], *B = c->I[mode][pb[k]];
         const double *mA = c->mean[mode][pa[k]], *mB = c->mean[mode][pb[k]];
         for (size_t i = 0; i < n; i++) prod[i] = A[i] * B[i];
-        box_sum(prod, W, var[k], W, H, R, tmp);
+        box_sum(prod, W, var[k], W, H, R, tmp, acc);
         const double e = (pa[k] == pb[k]) ? c->eps : 0.0;
         for (size_t i = 0; i < n; i++) var[k][i] = var[k][i] / N[i] - mA[i] * mB[i] + e; /* :79-84 */
     }
@@ -124,7 +122,7 @@ void oracle_set_image(void* p, int mode, const uint8_t* bgr) {
         c->inv[mode][3][i] = igg / det; c->inv[mode][4][i] = igb / det; c->inv[mode][5][i] = ibb / det;
     }
     for (int k = 0; k < 6; k++) free(var[k]);
-    free(N); free(tmp); free(prod);
+    free(N); free(tmp); free(prod); free(acc);
 }
 
 /* export the 9 float statistics planes [mean r,g,b, inv rr,rg,rb,gg,gb,bb] (for cross-checks) */
@@ -177,21 +175,35 @@ static inline int valid_ds(float ds, float a5, float b5, float MIN, float MAX) {
 }
 
 /* One call of ComputeUnaryPotential[WithoutCheck].  out = float[th][tw] (row stride out_stride floats). */
-void oracle_unary(void* p, int mode, const int* frect, const int* trect, const float* plane, float* out, int out_stride,
-                  int with_check) {
+/* scratch of one worker thread: reused across calls (a malloc/free per call serialises the OpenMP threads in the
+ * allocator and makes the baseline scale negatively) */
+typedef struct { size_t cap; float* raw; double* buf; } oracle_scratch;
+static void scratch_reserve(oracle_scratch* s, size_t n, size_t w) {
+    const size_t need = n + w;
+    if (need <= s->cap) return;
+    free(s->raw); free(s->buf);
+    s->raw = (float*)malloc(n * sizeof(float));
+    s->buf = (double*)malloc((n * 10 + w) * sizeof(double));
+    s->cap = need;
+}
+
+static void oracle_unary_s(void* p, int mode, const int* frect, const int* trect, const float* plane, float* out, int out_stride,
+                           int with_check, oracle_scratch* sc) {
     oracle_ctx* c = (oracle_ctx*)p;
     const int W = c->W, R = c->R;
     const int fx = frect[0], fy = frect[1], fw = frect[2], fh = frect[3];
     const int tx = trect[0], ty = trect[1], tw = trect[2], th = trect[3];
     const size_t n = (size_t)fw * fh;
-    float* raw = (float*)malloc(n * sizeof(float));
-    double* buf = (double*)malloc(n * 8 * 10);
+    scratch_reserve(sc, n, (size_t)fw);
+    float* raw = sc->raw;
+    double* buf = sc->buf;
+    double* acc = buf + n * 10;
     double *P = buf, *Br = buf + n, *Bg = buf + 2 * n, *Bb = buf + 3 * n, *Ar = buf + 4 * n, *Ag = buf + 5 * n,
            *Ab = buf + 6 * n, *Bq = buf + 7 * n, *tmp = buf + 8 * n, *N = buf + 9 * n;
     oracle_sample(p, mode, fx, fy, fw, fh, plane, raw);
     /* N = boxfilter(ones(rect.size()))  GuidedFilter.h:324 */
     for (size_t i = 0; i < n; i++) Bq[i] = 1.0;
-    box_sum(Bq, fw, N, fw, fh, R, tmp);
+    box_sum(Bq, fw, N, fw, fh, R, tmp, acc);
     const double *Ir = c->I[mode][0], *Ig = c->I[mode][1], *Ib = c->I[mode][2];
     for (int y = 0; y < fh; y++)
         for (int x = 0; x < fw; x++) { /* :151-169 */
@@ -199,10 +211,10 @@ void oracle_unary(void* p, int mode, const int* frect, const int* trect, const f
             const double vp = (double)raw[i];
             P[i] = vp; Br[i] = Ir[g] * vp; Bg[i] = Ig[g] * vp; Bb[i] = Ib[g] * vp;
         }
-    box_sum(P, fw, Bq, fw, fh, R, tmp); memcpy(P, Bq, n * 8);   /* :145 */
-    box_sum(Br, fw, Bq, fw, fh, R, tmp); memcpy(Br, Bq, n * 8); /* :170-172 */
-    box_sum(Bg, fw, Bq, fw, fh, R, tmp); memcpy(Bg, Bq, n * 8);
-    box_sum(Bb, fw, Bq, fw, fh, R, tmp); memcpy(Bb, Bq, n * 8);
+    box_sum(P, fw, Bq, fw, fh, R, tmp, acc); memcpy(P, Bq, n * 8);   /* :145 */
+    box_sum(Br, fw, Bq, fw, fh, R, tmp, acc); memcpy(Br, Bq, n * 8); /* :170-172 */
+    box_sum(Bg, fw, Bq, fw, fh, R, tmp, acc); memcpy(Bg, Bq, n * 8);
+    box_sum(Bb, fw, Bq, fw, fh, R, tmp, acc); memcpy(Bb, Bq, n * 8);
     for (int y = 0; y < fh; y++)
         for (int x = 0; x < fw; x++) { /* :180-222 */
             const size_t i = (size_t)y * fw + x, g = (size_t)(fy + y) * W + fx + x;
@@ -217,10 +229,10 @@ void oracle_unary(void* p, int mode, const int* frect, const int* trect, const f
             Ar[i] = ar; Ag[i] = ag; Ab[i] = ab;
             P[i] = mp - ar * mIr - ag * mIg - ab * mIb; /* b, :220 */
         }
-    box_sum(Ar, fw, Bq, fw, fh, R, tmp); memcpy(Ar, Bq, n * 8); /* :224-227 */
-    box_sum(Ag, fw, Bq, fw, fh, R, tmp); memcpy(Ag, Bq, n * 8);
-    box_sum(Ab, fw, Bq, fw, fh, R, tmp); memcpy(Ab, Bq, n * 8);
-    box_sum(P, fw, Bq, fw, fh, R, tmp);
+    box_sum(Ar, fw, Bq, fw, fh, R, tmp, acc); memcpy(Ar, Bq, n * 8); /* :224-227 */
+    box_sum(Ag, fw, Bq, fw, fh, R, tmp, acc); memcpy(Ag, Bq, n * 8);
+    box_sum(Ab, fw, Bq, fw, fh, R, tmp, acc); memcpy(Ab, Bq, n * 8);
+    box_sum(P, fw, Bq, fw, fh, R, tmp, acc);
     const float MIN = c->min_disp, MAX = c->max_disp;
     const float a = plane[0], b = plane[1], cc = plane[2], v = plane[3];
     const float a5 = a * 5, b5 = b * 5;
@@ -246,7 +258,13 @@ void oracle_unary(void* p, int mode, const int* frect, const int* trect, const f
             }
             out[(size_t)(y - ty) * out_stride + (x - tx)] = r;
         }
-    free(raw); free(buf);
+}
+
+void oracle_unary(void* p, int mode, const int* frect, const int* trect, const float* plane, float* out, int out_stride,
+                  int with_check) {
+    oracle_scratch sc = {0, NULL, NULL};
+    oracle_unary_s(p, mode, frect, trect, plane, out, out_stride, with_check, &sc);
+    free(sc.raw); free(sc.buf);
 }
 
 /* A batch = the cells of one (layer, group, step): one OpenMP thread per cell (FastGCStereo.h:30-49).
@@ -257,10 +275,15 @@ void oracle_unary_batch(void* p, int mode, int ncalls, const int* frects, const 
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int i = 0; i < ncalls; i++) {
-        const int* t = trects + 4 * i;
-        oracle_unary(p, mode, frects + 4 * i, t, planes + 4 * i, out_base + (size_t)t[1] * c->W + t[0], c->W, with_check);
+#pragma omp parallel
+    {
+        oracle_scratch sc = {0, NULL, NULL};
+#pragma omp for schedule(dynamic, 1)
+        for (int i = 0; i < ncalls; i++) {
+            const int* t = trects + 4 * i;
+            oracle_unary_s(p, mode, frects + 4 * i, t, planes + 4 * i, out_base + (size_t)t[1] * c->W + t[0], c->W, with_check, &sc);
+        }
+        free(sc.raw); free(sc.buf);
     }
 }
 
