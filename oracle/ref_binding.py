@@ -1,0 +1,245 @@
+"""TEST INFRASTRUCTURE ONLY.  ctypes view of oracle/_ref/liblexp_ref.so: the reference's own classes
+(CostVolumeEnergy, NaiveStereoEnergy, FastGuidedImageFilter<double>, LayerManager, RandomProposer) compiled from
+/root/reference by oracle/build_ref.py.  Used to pin the restated oracles and to generate tests/golden/ref_*.npz."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_ref
+
+_lib = None
+
+
+def available():
+    return build_ref.available()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build_ref.build()
+        if path is None or not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/liblexp_ref.so is absent and the reference sources are not here to build it")
+        L = C.CDLL(path)
+        vp, ip, fp, dp, u8p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_ubyte)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_max_threads.restype = C.c_int
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [C.c_int] * 4 + [u8p, u8p, fp, fp, C.c_int] + [C.c_float] * 6
+        L.ref_destroy.argtypes = [vp]
+        L.ref_unary.argtypes = [vp, ip, ip, fp, C.c_int, C.c_int, fp]
+        L.ref_unary_group.argtypes = [vp, C.c_int, ip, ip, fp, C.c_int, C.c_int, C.c_int, fp, C.c_int]
+        L.ref_stats.argtypes = [vp, C.c_int, dp]
+        L.ref_exi.argtypes = [vp, C.c_int, fp]
+        L.ref_valid_mask.argtypes = [vp, fp, ip, u8p]
+        L.ref_rng_seed.argtypes = [C.c_uint64]
+        L.ref_rng_state.restype = C.c_uint64
+        L.ref_create_random_label.argtypes = [vp, C.c_int, C.c_int, fp]
+        L.ref_random_proposals.argtypes = [fp, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_float, C.c_float, fp]
+        L.ref_plane_normal.argtypes = [fp, fp]
+        L.ref_create_plane.argtypes = [fp] + [C.c_float] * 4 + [fp]
+        L.ref_layer_create.restype = vp
+        L.ref_layer_create.argtypes = [C.c_int] * 4
+        L.ref_layer_destroy.argtypes = [vp]
+        L.ref_layer_counts.argtypes = [vp, ip]
+        L.ref_layer_rects.argtypes = [vp, ip, ip, ip]
+        L.ref_layer_group.argtypes = [vp, C.c_int, ip]
+        L.ref_layer_group.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _i4(r):
+    return np.ascontiguousarray(np.asarray(r, dtype=np.int32).reshape(-1))
+
+
+def _f(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class RefEnergy:
+    """kind 0 = CostVolumeEnergy(imL, imR, volL, volR, Parameters(windR, "GF", eps), MAX, MIN); kind 1 = NaiveStereoEnergy."""
+
+    def __init__(self, imL, imR, volL=None, volR=None, windR=20, eps=1e-4, th_col=0.5, th_grad=2.0, alpha=0.9, max_disp=None, min_disp=0.0, kind=0):
+        L = lib()
+        self.imL = np.ascontiguousarray(imL, dtype=np.uint8)
+        self.imR = np.ascontiguousarray(imR, dtype=np.uint8)
+        self.H, self.W = self.imL.shape[:2]
+        self.kind = kind
+        if kind == 0:
+            self.volL, self.volR = _f(volL), _f(volR)  # borrowed by the C++ side: kept alive here
+            self.D = self.volL.shape[0]
+            vl, vr = _p(self.volL, C.c_float), _p(self.volR, C.c_float)
+        else:
+            self.D, vl, vr = 0, None, None
+        self.h = L.ref_create(kind, self.H, self.W, self.D, _p(self.imL, C.c_ubyte), _p(self.imR, C.c_ubyte), vl, vr, int(windR),
+                              float(eps), float(th_col), float(th_grad), float(alpha), float(max_disp), float(min_disp))
+        if not self.h:
+            raise RuntimeError(L.ref_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ref_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def unary(self, filter_rect, target_rect, plane, mode=0, with_check=True, fill=np.nan):
+        """Returns the filterRect-sized cost view after the call (untouched pixels keep `fill`)."""
+        fr, tr, pl = _i4(filter_rect), _i4(target_rect), _f(plane)
+        out = np.full((fr[3], fr[2]), fill, np.float32)
+        if lib().ref_unary(self.h, _p(fr, C.c_int), _p(tr, C.c_int), _p(pl, C.c_float), int(mode), int(with_check), _p(out, C.c_float)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def unary_target(self, filter_rect, target_rect, plane, mode=0, with_check=True):
+        fx, fy = filter_rect[0], filter_rect[1]
+        tx, ty, tw, th = target_rect
+        return self.unary(filter_rect, target_rect, plane, mode, with_check)[ty - fy:ty - fy + th, tx - fx:tx - fx + tw].copy()
+
+    def unary_group(self, filter_rects, target_rects, planes, mode=0, with_check=True, cost_image=None, nthreads=0):
+        """planes: [n][K][4].  Returns the H x W cost image after the last proposal of every cell."""
+        fr, tr = _i4(filter_rects), _i4(target_rects)
+        pl = _f(planes)
+        n, K = pl.shape[0], pl.shape[1]
+        if cost_image is None:
+            cost_image = np.zeros((self.H, self.W), np.float32)
+        if lib().ref_unary_group(self.h, n, _p(fr, C.c_int), _p(tr, C.c_int), _p(pl, C.c_float), K, int(mode), int(with_check), _p(cost_image, C.c_float), int(nthreads)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return cost_image
+
+    def stats(self, mode=0):
+        out = np.empty((9, self.H, self.W), np.float64)
+        if lib().ref_stats(self.h, int(mode), _p(out, C.c_double)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def exi(self, mode=0):
+        out = np.empty((self.H, self.W, 4), np.float32)
+        if lib().ref_exi(self.h, int(mode), _p(out, C.c_float)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def valid_mask(self, plane, rect):
+        r, pl = _i4(rect), _f(plane)
+        out = np.empty((r[3], r[2]), np.uint8)
+        if lib().ref_valid_mask(self.h, _p(pl, C.c_float), _p(r, C.c_int), _p(out, C.c_ubyte)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def create_random_label(self, x, y):
+        out = np.empty(4, np.float32)
+        lib().ref_create_random_label(self.h, int(x), int(y), _p(out, C.c_float))
+        return out
+
+
+def rng_seed(s):
+    lib().ref_rng_seed(int(s))
+
+
+def rng_state():
+    return int(lib().ref_rng_state())
+
+
+def random_proposals(labeling, unit, outer_iter, K, max_disp, min_disp=0.0):
+    lab = _f(labeling)
+    H, W = lab.shape[:2]
+    out = np.empty((K, 4), np.float32)
+    u = _i4(unit)
+    n = lib().ref_random_proposals(_p(lab, C.c_float), H, W, _p(u, C.c_int), int(outer_iter), int(K), float(max_disp), float(min_disp), _p(out, C.c_float))
+    return out[:n]
+
+
+def plane_normal(plane):
+    out = np.empty(3, np.float32)
+    pl = _f(plane)
+    lib().ref_plane_normal(_p(pl, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def create_plane(n, z, x, y, v=0.0):
+    out = np.empty(4, np.float32)
+    nn = _f(n)
+    lib().ref_create_plane(_p(nn, C.c_float), float(z), float(x), float(y), float(v), _p(out, C.c_float))
+    return out
+
+
+def layer(W, H, windR, unit):
+    """LayerManager(W, H, windR, 0).addLayer(unit) -> the same dict shape as lexp_oracle.make_layer."""
+    L = lib()
+    h = L.ref_layer_create(int(W), int(H), int(windR), int(unit))
+    try:
+        cnt = np.zeros(4, np.int32)
+        L.ref_layer_counts(h, _p(cnt, C.c_int))
+        hb, wb, n, ng = (int(v) for v in cnt)
+        u, s, f = (np.zeros((n, 4), np.int32) for _ in range(3))
+        L.ref_layer_rects(h, _p(u, C.c_int), _p(s, C.c_int), _p(f, C.c_int))
+        groups = []
+        for g in range(ng):
+            m = L.ref_layer_group(h, g, None)
+            idx = np.zeros(m, np.int32)
+            L.ref_layer_group(h, g, _p(idx, C.c_int))
+            groups.append([int(i) for i in idx])
+        as_t = lambda a: [tuple(int(v) for v in r) for r in a]
+        return dict(heightBlocks=hb, widthBlocks=wb, unitSize=int(unit), unit=as_t(u), shared=as_t(s), filter=as_t(f), groups=groups)
+    finally:
+        L.ref_layer_destroy(h)
+
+
+# ---- the cv:: layer's own primitives (held against cv2 in tests/test_ref_pin.py) --------------------------------------
+def shim_box_sum(X, R):
+    X = np.ascontiguousarray(X)
+    assert X.dtype in (np.float32, np.float64) and X.ndim == 2
+    out = np.empty_like(X)
+    L = lib()
+    L.shim_box_sum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    if L.shim_box_sum(X.ctypes.data, int(X.dtype == np.float64), X.shape[0], X.shape[1], int(R), out.ctypes.data):
+        raise RuntimeError(L.ref_last_error().decode())
+    return out
+
+
+def shim_get_affine(src_pts, dst_pts):
+    s, d = _f(src_pts).reshape(-1), _f(dst_pts).reshape(-1)
+    M = np.empty(6, np.float64)
+    L = lib()
+    L.shim_get_affine.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    L.shim_get_affine(_p(s, C.c_float), _p(d, C.c_float), _p(M, C.c_double))
+    return M.reshape(2, 3)
+
+
+def shim_warp_affine(src, M, w, h):
+    src = _f(src)
+    H, W = src.shape[:2]
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    M = np.ascontiguousarray(np.asarray(M, np.float64).reshape(-1))
+    out = np.empty((h, w) + src.shape[2:], np.float32)
+    L = lib()
+    L.shim_warp_affine.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_float)]
+    if L.shim_warp_affine(_p(src, C.c_float), H, W, cn, _p(M, C.c_double), int(h), int(w), _p(out, C.c_float)):
+        raise RuntimeError(L.ref_last_error().decode())
+    return out
+
+
+def shim_bgr2gray(src):
+    src = _f(src)
+    out = np.empty(src.shape[:2], np.float32)
+    L = lib()
+    L.shim_bgr2gray.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float)]
+    if L.shim_bgr2gray(_p(src, C.c_float), src.shape[0], src.shape[1], _p(out, C.c_float)):
+        raise RuntimeError(L.ref_last_error().decode())
+    return out
+
+
+def shim_sobel_x(src, scale):
+    src = _f(src)
+    out = np.empty(src.shape, np.float32)
+    L = lib()
+    L.shim_sobel_x.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_float)]
+    if L.shim_sobel_x(_p(src, C.c_float), src.shape[0], src.shape[1], float(scale), _p(out, C.c_float)):
+        raise RuntimeError(L.ref_last_error().decode())
+    return out

@@ -1,0 +1,246 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the product path.
+//
+// C entry points around the reference's OWN classes, compiled from the reference's headers where they lie
+// (/root/reference/LocalExpansionStereo, read-only; see oracle/build_ref.py) over the mini cv:: layer in
+// oracle/cvshim/.  Nothing here restates the algorithm: every cost, mask, statistic, rectangle and random label
+// returned below is produced by CostVolumeEnergy / NaiveStereoEnergy / FastGuidedImageFilter<double> / LayerManager /
+// RandomProposer / StereoEnergy::createRandomLabel themselves.  The output, oracle/_ref/liblexp_ref.so, pins the
+// restated oracles (oracle/lexp_oracle.py, oracle/lexp_oracle.c) and generates tests/golden/ref_*.npz.
+#include <opencv2/opencv.hpp>
+#include "Utilities.hpp"
+#include "Plane.h"
+#include "StereoEnergy.h"
+#include "CostVolumeEnergy.h"
+#include "LayerManager.h"
+#include <omp.h>
+#include <malloc.h>
+
+namespace {
+
+struct ref_ctx {
+    std::unique_ptr<StereoEnergy> energy;
+    cv::Mat im[2];
+    int H, W, D, kind;
+};
+
+// protected members of the reference's classes, reached through pointers to members named via a derived class
+struct EnergyProbe : CostVolumeEnergy {
+    static const std::unique_ptr<IJointFilter>& filter_of(const CostVolumeEnergy& e, int m) { return (e.*(&EnergyProbe::filter))[m]; }
+};
+struct NaiveProbe : NaiveStereoEnergy {
+    static const std::unique_ptr<IJointFilter>& filter_of(const NaiveStereoEnergy& e, int m) { return (e.*(&NaiveProbe::filter))[m]; }
+    static const cv::Mat& exi_of(const NaiveStereoEnergy& e, int m) { return (e.*(&NaiveProbe::ExI))[m]; }
+};
+struct FilterProbe : FastGuidedImageFilter<double> {
+    typedef GuidedImageFilter<double> G;
+    static void planes(const G& f, const cv::Mat* out[9]) {
+        out[0] = &(f.*(&FilterProbe::mean_I_r)); out[1] = &(f.*(&FilterProbe::mean_I_g)); out[2] = &(f.*(&FilterProbe::mean_I_b));
+        out[3] = &(f.*(&FilterProbe::invrr)); out[4] = &(f.*(&FilterProbe::invrg)); out[5] = &(f.*(&FilterProbe::invrb));
+        out[6] = &(f.*(&FilterProbe::invgg)); out[7] = &(f.*(&FilterProbe::invgb)); out[8] = &(f.*(&FilterProbe::invbb));
+    }
+};
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+int ref_max_threads() { return omp_get_max_threads(); }
+
+// kind 0: CostVolumeEnergy (volumes [D][H][W] float, borrowed -- the caller keeps them alive); kind 1: NaiveStereoEnergy.
+// Images are 8-bit BGR [H][W][3].  filterName "GF" (FastGuidedImageFilter<double>), as main.cpp selects for both modes.
+void* ref_create(int kind, int H, int W, int D, const uchar* imL, const uchar* imR, float* volL, float* volR, int windR, float eps,
+                 float th_col, float th_grad, float alpha, float max_disp, float min_disp) {
+    try {
+        // every cv::Mat temporary of the filter is a malloc: keep large blocks in the per-thread arenas instead of mmap/munmap,
+        // which would serialise the OpenMP threads in the kernel
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        auto c = std::make_unique<ref_ctx>();
+        c->H = H; c->W = W; c->D = D; c->kind = kind;
+        c->im[0] = cv::Mat(H, W, CV_8UC3, (void*)imL).clone();
+        c->im[1] = cv::Mat(H, W, CV_8UC3, (void*)imR).clone();
+        Parameters params(20.f, windR, "GF", eps);
+        params.th_col = th_col; params.th_grad = th_grad; params.alpha = alpha;
+        if (kind == 0) {
+            int sz[3] = {D, H, W};
+            cv::Mat vL(3, sz, CV_32F, volL), vR(3, sz, CV_32F, volR);
+            c->energy = std::make_unique<CostVolumeEnergy>(c->im[0], c->im[1], vL, vR, params, max_disp, min_disp);
+        } else {
+            c->energy = std::make_unique<NaiveStereoEnergy>(c->im[0], c->im[1], params, max_disp, min_disp);
+        }
+        return c.release();
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void ref_destroy(void* h) { delete (ref_ctx*)h; }
+
+// One call of the virtual, exactly as FastGCStereo.h:47 issues it: `out` is the filterRect-sized view
+// proposalCost(filterRect) ([fh][fw] float, caller-initialised; only the target sub-rectangle is written).
+int ref_unary(void* h, const int frect[4], const int trect[4], const float plane[4], int mode, int with_check, float* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        cv::Rect fr(frect[0], frect[1], frect[2], frect[3]), tr(trect[0], trect[1], trect[2], trect[3]);
+        cv::Mat costs(fr.height, fr.width, CV_32F, out);
+        Plane p(plane[0], plane[1], plane[2], plane[3]);
+        StereoEnergy::Reusable reusable;
+        if (with_check) c->energy->ComputeUnaryPotential(fr, tr, costs, p, reusable, mode);
+        else c->energy->ComputeUnaryPotentialWithoutCheck(fr, tr, costs, p, reusable, mode);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// The reference's inner loop over one disjoint group (FastGCStereo.h:30-49) without the fusion step: cells in an
+// OpenMP parallel for, one Reusable per cell kept across its K proposals, each proposal evaluated into the shared
+// H x W `cost_image` through the view cost_image(filterRect).  planes: [n][K][4].
+int ref_unary_group(void* h, int n, const int* frects, const int* trects, const float* planes, int K, int mode, int with_check, float* cost_image, int nthreads) {
+    ref_ctx* c = (ref_ctx*)h;
+    cv::Mat proposalCost(c->H, c->W, CV_32F, cost_image);
+    int failed = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        try {
+            cv::Rect fr(frects[4 * i], frects[4 * i + 1], frects[4 * i + 2], frects[4 * i + 3]), tr(trects[4 * i], trects[4 * i + 1], trects[4 * i + 2], trects[4 * i + 3]);
+            StereoEnergy::Reusable reusable;
+            for (int k = 0; k < K; k++) {
+                const float* pl = planes + ((size_t)i * K + k) * 4;
+                Plane label(pl[0], pl[1], pl[2], pl[3]);
+                if (with_check) c->energy->ComputeUnaryPotential(fr, tr, proposalCost(fr), label, reusable, mode);
+                else c->energy->ComputeUnaryPotentialWithoutCheck(fr, tr, proposalCost(fr), label, reusable, mode);
+            }
+        } catch (const std::exception&) {
+#pragma omp atomic
+            failed++;
+        }
+    }
+    if (failed) g_err = "ref_unary_group: a cell threw";
+    return failed;
+}
+
+// guided-filter statistics of view `mode`: 9 planes [H][W] double: mean_I r,g,b then inv rr,rg,rb,gg,gb,bb
+int ref_stats(void* h, int mode, double* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        const IJointFilter* f = c->kind == 0 ? EnergyProbe::filter_of(*static_cast<CostVolumeEnergy*>(c->energy.get()), mode).get()
+                                             : NaiveProbe::filter_of(*static_cast<NaiveStereoEnergy*>(c->energy.get()), mode).get();
+        auto g = dynamic_cast<const GuidedImageFilter<double>*>(f);
+        if (!g) throw std::runtime_error("not a guided filter");
+        const cv::Mat* pl[9];
+        FilterProbe::planes(*g, pl);
+        for (int k = 0; k < 9; k++)
+            for (int y = 0; y < c->H; y++) std::memcpy(out + ((size_t)k * c->H + y) * c->W, pl[k]->ptr<double>(y), sizeof(double) * c->W);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+// NaiveStereoEnergy::ExI[mode] as [H][W][4] float
+int ref_exi(void* h, int mode, float* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        if (c->kind != 1) throw std::runtime_error("ExI exists for NaiveStereoEnergy only");
+        const cv::Mat& e = NaiveProbe::exi_of(*static_cast<NaiveStereoEnergy*>(c->energy.get()), mode);
+        for (int y = 0; y < c->H; y++) std::memcpy(out + (size_t)y * c->W * 4, e.ptr<float>(y), sizeof(float) * 4 * c->W);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+// StereoEnergy::IsValiLabel(plane, rect) -> [h][w] uchar (255 / 0)
+int ref_valid_mask(void* h, const float plane[4], const int rect[4], uchar* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        cv::Mat m = c->energy->IsValiLabel(Plane(plane[0], plane[1], plane[2], plane[3]), cv::Rect(rect[0], rect[1], rect[2], rect[3]));
+        for (int y = 0; y < m.rows; y++) std::memcpy(out + (size_t)y * m.cols, m.ptr<uchar>(y), m.cols);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// ---- cv::theRNG-driven label generation ----------------------------------------------------------------------------
+void ref_rng_seed(uint64_t s) { cv::theRNG().state = s; }
+uint64_t ref_rng_state() { return cv::theRNG().state; }
+void ref_create_random_label(void* h, int x, int y, float out[4]) {
+    Plane p = ((ref_ctx*)h)->energy->createRandomLabel(cv::Point(x, y));
+    out[0] = p.a; out[1] = p.b; out[2] = p.c; out[3] = p.v;
+}
+// RandomProposer over `unit` of the labeling [H][W][4] (Plane per pixel), FastGCStereo.h:39-46: returns the proposals
+// generated while isContinued(); out [K][4]
+int ref_random_proposals(float* labeling, int H, int W, const int unit[4], int outerIter, int K, float max_disp, float min_disp, float* out) {
+    cv::Mat lab(H, W, CV_32FC4, labeling);
+    RandomProposer proto(K, max_disp, min_disp);
+    IProposer* prop = proto.createInstance();
+    prop->startIterations(lab, cv::Rect(unit[0], unit[1], unit[2], unit[3]), outerIter);
+    int n = 0;
+    while (prop->isContinued()) {
+        Plane p = prop->getNextProposal();
+        out[4 * n] = p.a; out[4 * n + 1] = p.b; out[4 * n + 2] = p.c; out[4 * n + 3] = p.v;
+        n++;
+    }
+    delete prop;
+    return n;
+}
+void ref_plane_normal(const float plane[4], float out[3]) {
+    cv::Vec<float, 3> n = Plane(plane[0], plane[1], plane[2], plane[3]).GetNormal();
+    out[0] = n[0]; out[1] = n[1]; out[2] = n[2];
+}
+void ref_create_plane(const float n[3], float z, float x, float y, float v, float out[4]) {
+    Plane p = Plane::CreatePlane(n[0], n[1], n[2], z, x, y, v);
+    out[0] = p.a; out[1] = p.b; out[2] = p.c; out[3] = p.v;
+}
+
+// ---- LayerManager::addLayer ---------------------------------------------------------------------------------------------
+void* ref_layer_create(int W, int H, int windR, int unit) {
+    auto lm = new LayerManager(W, H, windR, 0);
+    lm->addLayer(unit);
+    return lm;
+}
+void ref_layer_destroy(void* h) { delete (LayerManager*)h; }
+void ref_layer_counts(void* h, int out[4]) {
+    auto& L = ((LayerManager*)h)->layers[0];
+    out[0] = L.heightBlocks; out[1] = L.widthBlocks; out[2] = (int)L.unitRegions.size(); out[3] = (int)L.disjointRegionSets.size();
+}
+void ref_layer_rects(void* h, int* unit, int* shared, int* filter) {
+    auto& L = ((LayerManager*)h)->layers[0];
+    for (size_t i = 0; i < L.unitRegions.size(); i++) {
+        const cv::Rect* r[3] = {&L.unitRegions[i], &L.sharedRegions[i], &L.filterRegions[i]};
+        int* o[3] = {unit, shared, filter};
+        for (int k = 0; k < 3; k++) { o[k][4 * i] = r[k]->x; o[k][4 * i + 1] = r[k]->y; o[k][4 * i + 2] = r[k]->width; o[k][4 * i + 3] = r[k]->height; }
+    }
+}
+int ref_layer_group(void* h, int g, int* idx) {
+    auto& S = ((LayerManager*)h)->layers[0].disjointRegionSets[g];
+    if (idx) for (size_t i = 0; i < S.size(); i++) idx[i] = S[i];
+    return (int)S.size();
+}
+
+// ---- the cv:: layer's own primitives, exported so that tests can hold them against the real OpenCV (cv2) ---------------
+int shim_box_sum(const void* src, int is_double, int h, int w, int R, void* dst) {
+    try {
+        int t = is_double ? CV_64FC1 : CV_32FC1;
+        cv::Mat s(h, w, t, (void*)src), d(h, w, t, dst);
+        cv::boxFilter(s, d, -1, cv::Size(2 * R + 1, 2 * R + 1), cv::Point(-1, -1), false, cv::BORDER_CONSTANT);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int shim_get_affine(const float src[6], const float dst[6], double M[6]) {
+    cv::Point2f s[3], d[3];
+    for (int i = 0; i < 3; i++) { s[i] = cv::Point2f(src[2 * i], src[2 * i + 1]); d[i] = cv::Point2f(dst[2 * i], dst[2 * i + 1]); }
+    cv::Mat m = cv::getAffineTransform(s, d);
+    for (int i = 0; i < 6; i++) M[i] = m.at<double>(i / 3, i % 3);
+    return 0;
+}
+int shim_warp_affine(float* src, int H, int W, int cn, double M[6], int h, int w, float* dst) {
+    try {
+        cv::Mat s(H, W, CV_MAKETYPE(CV_32F, cn), src), d(h, w, CV_MAKETYPE(CV_32F, cn), dst), m(2, 3, CV_64FC1, M);
+        cv::warpAffine(s, d, m, cv::Size(w, h), cv::INTER_LINEAR, cv::BORDER_REPLICATE);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int shim_bgr2gray(float* src, int H, int W, float* dst) {
+    try { cv::Mat s(H, W, CV_32FC3, src), d(H, W, CV_32FC1, dst); cv::cvtColor(s, d, cv::COLOR_BGR2GRAY); return 0; }
+    catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+int shim_sobel_x(float* src, int H, int W, double scale, float* dst) {
+    try { cv::Mat s(H, W, CV_32FC1, src), d(H, W, CV_32FC1, dst); cv::Sobel(s, d, CV_32F, 1, 0, 1, scale, 0, cv::BORDER_REPLICATE); return 0; }
+    catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+}  // extern "C"

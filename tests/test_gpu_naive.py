@@ -52,3 +52,25 @@ def test_naive_virtuals_and_edge_planes(scene):
             (E.ComputeUnaryPotential if chk else E.ComputeUnaryPotentialWithoutCheck)(f, t, view, p)
             ref = (Or.compute_unary_potential if chk else Or.compute_unary_potential_without_check)(f, t, p)
             assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"plane {p} chk={chk}")
+
+
+def test_naive_matches_reference_minted_vectors(scene):
+    """tests/golden/cones_crop_naive.npz: outputs of the reference's own NaiveStereoEnergy (compiled from its headers by
+    oracle/build_ref.py in the authoring container).  The CUDA path evaluates the inverse affine map in closed form where the
+    reference solves getAffineTransform by LU, so single source pixels may flip at exact 1/32-pixel rounding ties."""
+    import lexp_golden
+    G = lexp_golden.load_naive()
+    E, H, W = scene["E"], scene["H"], scene["W"]
+    assert G["D"] == scene["D"]
+    nbad = ntot = 0
+    for i, c in enumerate(G["cases"]):
+        f, t = c["frect"], c["trect"]
+        img = np.zeros((H, W), np.float32)
+        view = img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]]
+        (E.ComputeUnaryPotential if c["check"] else E.ComputeUnaryPotentialWithoutCheck)(f, t, view, c["plane"], mode=c["mode"])
+        got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+        inv = c["ref"] == O.COST_FOR_INVALID
+        assert np.array_equal(got == O.COST_FOR_INVALID, inv), f"case {i}: COST_FOR_INVALID mask"
+        err = np.abs(got[~inv].astype(np.float64) - c["ref"][~inv]) / np.maximum(np.abs(c["ref"][~inv]), 1e-3)
+        nbad += int((err > 1e-4).sum()); ntot += int((~inv).sum())
+    assert ntot > 20000 and nbad / ntot < 2e-3, (nbad, ntot)
