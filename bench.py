@@ -5,8 +5,10 @@ A *step* is one local-expansion sweep over one view: 3 layers x <=16 disjoint gr
 steps = 240 batched evaluations (FastGCStereo.h:22-72), on synthetic inputs of the shape
 BASELINE.json names.  `value` = filterRect-pixel evals of the whole job / device time, inputs
 resident in HBM.  `e2e` = same sweep through the host-buffer API (planes H2D, costs D2H).
-`--impl reference` times the CPU restatement of the reference (oracle/lexp_oracle.c; the reference
-itself cannot be compiled here) on the host cores.
+`--impl reference` times the reference's CPU implementation on the host cores: oracle/_ref (the reference's own
+CostVolumeEnergy / NaiveStereoEnergy classes compiled from its headers by oracle/build_ref.py, kind "reference",
+driven by the OpenMP loop of FastGCStereo.h:30-49) or the plain-C restatement oracle/lexp_oracle.c (kind "port"),
+whichever is faster on this host.
 """
 from __future__ import annotations
 
@@ -128,36 +130,97 @@ def all_planes(sweep, D):
 
 
 # ---------------------------------------------------------------------------------------------
+class CpuArm:
+    """The reference's CPU implementation of the path, for timing only (never on the product path).
+
+    kind "reference": oracle/_ref/liblexp_ref.so -- the reference's own classes compiled from its headers over the cv:: layer
+    of oracle/cvshim (its box filter is that layer's, not OpenCV's hand-vectorised one), cells of a group in an OpenMP
+    parallel for with one Reusable per cell across its K proposals, exactly the loop of FastGCStereo.h:30-49 minus fusion.
+    kind "port": oracle/lexp_oracle.c, the plain-C restatement (running-sum box filter, per-thread scratch).
+    Both are calibrated on one group and the faster one, at its better thread count, is used."""
+
+    def __init__(self, W, H, D, windR, imL, vol, naive=False, imR=None):
+        self.W, self.H, self.naive = W, H, naive
+        self.out = np.zeros((H, W), np.float32)
+        self.arms = {}
+        try:
+            from oracle import ref_binding
+            if ref_binding.available() or ref_binding.build_ref.reference_present():
+                if naive:
+                    self.arms["reference"] = ref_binding.RefEnergy(imL, imR if imR is not None else imL, windR=windR, eps=EPS, th_col=10.0, th_grad=2.0,
+                                                                   alpha=0.9, max_disp=D - 1, min_disp=0.0, kind=1)
+                else:
+                    self.arms["reference"] = ref_binding.RefEnergy(imL, imL, vol, vol, windR=windR, eps=EPS, th_col=TH_COL, max_disp=D - 1, min_disp=0.0, kind=0)
+        except Exception as e:  # the prebuilt library is optional on the GPU box
+            print(f"[bench] oracle/_ref unavailable ({e}); CPU arm = port", file=sys.stderr)
+        if not naive:
+            from oracle.c_oracle import COracle
+            orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
+            orc.set_image(0, imL)
+            orc.set_volume(0, vol)
+            self.arms["port"] = orc
+        if not self.arms:
+            raise RuntimeError("no CPU implementation available for this workload")
+        self.kind, self.nthr, self.calib = None, None, {}
+
+    def run_group(self, kind, fr, tr, planes_kn4, nthr):
+        """planes_kn4: [K][n][4] -- all K proposal steps of one disjoint group."""
+        if kind == "reference":
+            self.arms[kind].unary_group(fr, tr, np.ascontiguousarray(np.transpose(planes_kn4, (1, 0, 2))), 0, True, self.out, nthr)
+        else:
+            for k in range(planes_kn4.shape[0]):
+                self.arms[kind].unary_batch(0, fr, tr, planes_kn4[k], self.out, True, nthr)
+
+    def calibrate(self, fr, tr, planes_kn4):
+        evals = sum(f[2] * f[3] for f in fr) * planes_kn4.shape[0]
+        best = None
+        for kind in self.arms:
+            nthr = pick_threads(lambda n: self.run_group(kind, fr, tr, planes_kn4, n))
+            t0 = time.perf_counter()
+            self.run_group(kind, fr, tr, planes_kn4, nthr)
+            rate = evals / (time.perf_counter() - t0)
+            self.calib[kind] = {"evals_per_s": rate, "threads": nthr}
+            if best is None or rate > best[0]:
+                best = (rate, kind, nthr)
+        _, self.kind, self.nthr = best
+        return self.kind, self.nthr
+
+    def run(self, fr, tr, planes_kn4):
+        self.run_group(self.kind, fr, tr, planes_kn4, self.nthr)
+
+    def calib_note(self):
+        return "; ".join(f"{k}: {v['evals_per_s']:.3g} evals/s @ {v['threads']} thr" for k, v in self.calib.items())
+
+    def close(self):
+        for a in self.arms.values():
+            a.close()
+
+
 def run_reference(args, W, H, D, windR, rank, world):
-    """CPU arm: oracle/lexp_oracle.c (kind "port") with all host threads, on a bounded sample of the sweep."""
+    """CPU arm with all host threads, on a bounded sample of the sweep (group 0 of every layer, all proposal steps)."""
     if rank != 0:
         return
-    from oracle.c_oracle import COracle, max_threads
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import V3_STEPS, v3_layer_units
     from localexpstereo_b200 import synth
+    naive = args.workload.endswith("_naive")
     imL, vol = make_inputs(W, H, D)
-    orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
-    orc.set_image(0, imL)
-    orc.set_volume(0, vol)
+    imR = synth.synthetic_image(H, W, 43) if naive else None
+    arm = CpuArm(W, H, D, windR, imL, None if naive else vol, naive=naive, imR=imR)
     lm = L.LayerManager(W, H, windR)
-    units = v3_layer_units(W)
-    sample = []  # (layer, group 0, step k) for every layer: 15 of the 240 batched evaluations
+    units = [5, 15, 25] if naive else v3_layer_units(W)
+    sample = []  # (filter rects, target rects, planes [K][n][4]) of group 0 of every layer: 15 of the 240 batched evaluations
     for li, u in enumerate(units):
         lay = lm.addLayer(u)
         cells = lay.disjointRegionSets[0]
-        pls = synth.synthetic_planes(lay.unitRegions, V3_STEPS[li], D, 7 + li)[:, cells, :]
-        fr = [lay.filterRegions[r] for r in cells]
-        tr = [lay.sharedRegions[r] for r in cells]
-        for k in range(V3_STEPS[li]):
-            sample.append((fr, tr, pls[k]))
-    evals = sum(sum(f[2] * f[3] for f in fr) for fr, _, _ in sample)
-    out = np.zeros((H, W), np.float32)
-    nthr = pick_threads(lambda n: orc.unary_batch(0, sample[0][0], sample[0][1], sample[0][2], out, True, n))
+        pls = np.ascontiguousarray(synth.synthetic_planes(lay.unitRegions, V3_STEPS[li], D, 7 + li)[:, cells, :])
+        sample.append(([lay.filterRegions[r] for r in cells], [lay.sharedRegions[r] for r in cells], pls))
+    evals = sum(sum(f[2] * f[3] for f in fr) * pls.shape[0] for fr, _, pls in sample)
+    kind, nthr = arm.calibrate(*sample[0])
 
     def step():
-        for fr, tr, pl in sample:
-            orc.unary_batch(0, fr, tr, pl, out, True, nthr)
+        for fr, tr, pls in sample:
+            arm.run(fr, tr, pls)
 
     for _ in range(args.warmup):
         step()
@@ -166,15 +229,18 @@ def run_reference(args, W, H, D, windR, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = evals / dt
-    desc = f"group 0 of each of the 3 layers, all K=9/3/3 steps ({len(sample)} of 240 batched evaluations, {evals} evals per step)"
+    nb = sum(p.shape[0] for _, _, p in sample)
+    desc = (f"group 0 of each of the 3 layers, all K=9/3/3 steps ({nb} of 240 batched evaluations, {evals} evals per step); "
+            f"calibration on layer 0: {arm.calib_note()}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 guided filter / f32 sampling", "data": "synthetic",
         "config": {"workload": args.workload, "W": W, "H": H, "ndisp": D, "windR": windR, "sample": desc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+    arm.close()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -198,7 +264,8 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     if naive:  # -mode MiddV2: image-based energy, th_col 10 / th_grad 2 / alpha 0.9 (StereoEnergy.h:26-37), layers 5/15/25
         from localexpstereo_b200 import synth
         prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS)
-        E = L.NaiveStereoEnergy(imL, synth.synthetic_image(H, W, 43), prm, D - 1, device=local_rank)
+        imR_h = synth.synthetic_image(H, W, 43)
+        E = L.NaiveStereoEnergy(imL, imR_h, prm, D - 1, device=local_rank)
     else:
         prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS, th_col=TH_COL)
         E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
@@ -333,18 +400,11 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     h2d = sum(g.plan.num_calls * 16 * g.n_steps for g in sweep.groups)
     d2h = sweep.local_target_px * 4
 
-    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on a bounded sample
+    # ---- CPU baseline beside it (rank 0, N = 1): the reference's CPU implementation on a bounded sample
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and not naive:
-        from oracle.c_oracle import COracle, max_threads
-        orc = COracle(H, W, D, windR, EPS, TH_COL, D - 1)
-        orc.set_image(0, imL)
-        orc.set_volume(0, vol_h)
-        out = np.zeros((H, W), np.float32)
-        g0 = sweep.groups[0]
-        lay0 = sweep.layer(g0.layer)
-        nthr = pick_threads(lambda n: orc.unary_batch(0, [lay0.filterRegions[r] for r in g0.cells], [lay0.sharedRegions[r] for r in g0.cells],
-                                                      planes_h[0][0], out, True, n))
+    if world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(W, H, D, windR, imL, None if naive else vol_h, naive=naive, imR=imR_h if naive else None)
+        first = True
         tot_e, tot_t, used = 0, 0.0, []
         for gi, g in enumerate(sweep.groups):
             if g.group != 0:
@@ -352,16 +412,18 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
             lay = sweep.layer(g.layer)
             fr = [lay.filterRegions[r] for r in g.cells]
             tr = [lay.sharedRegions[r] for r in g.cells]
-            orc.unary_batch(0, fr, tr, planes_h[gi][0], out, True, nthr)  # warm
+            pls = np.ascontiguousarray(planes_h[gi])  # [K][n][4]
+            if first:
+                arm.calibrate(fr, tr, pls)  # also warms
+                first = False
             t0 = time.perf_counter()
-            for k in range(g.n_steps):
-                orc.unary_batch(0, fr, tr, planes_h[gi][k], out, True, nthr)
+            arm.run(fr, tr, pls)
             tot_t += time.perf_counter() - t0
             tot_e += g.plan.filter_px * g.n_steps
             used.append(f"L{g.layer}g0x{g.n_steps}")
-        cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": nthr, "kind": "port",
-               "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s)"}
-        orc.close()
+        cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": arm.nthr, "kind": arm.kind,
+               "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s); calibration: {arm.calib_note()}"}
+        arm.close()
 
     if rank == 0:
         out = {

@@ -277,13 +277,14 @@ void oracle_unary_batch(void* p, int mode, int ncalls, const int* frects, const 
 #endif
 #pragma omp parallel
     {
-        oracle_scratch sc = {0, NULL, NULL};
+        /* the scratch outlives the call (libgomp keeps its worker threads): allocating ~1 MB per thread per call means an
+         * mmap/munmap pair each, whose TLB shootdowns serialise the threads -- measured as NEGATIVE scaling in a VM */
+        static __thread oracle_scratch sc = {0, NULL, NULL};
 #pragma omp for schedule(dynamic, 1)
         for (int i = 0; i < ncalls; i++) {
             const int* t = trects + 4 * i;
             oracle_unary_s(p, mode, frects + 4 * i, t, planes + 4 * i, out_base + (size_t)t[1] * c->W + t[0], c->W, with_check, &sc);
         }
-        free(sc.raw); free(sc.buf);
     }
 }
 
