@@ -188,6 +188,14 @@ class CpuArm:
     def run(self, fr, tr, planes_kn4):
         self.run_group(self.kind, fr, tr, planes_kn4, self.nthr)
 
+    def time_sample(self, sample):
+        """sample: [(filter rects, target rects, planes [K][n][4])].  Returns (evals, seconds) of one pass."""
+        evals = sum(sum(f[2] * f[3] for f in fr) * pls.shape[0] for fr, _, pls in sample)
+        t0 = time.perf_counter()
+        for fr, tr, pls in sample:
+            self.run(fr, tr, pls)
+        return evals, time.perf_counter() - t0
+
     def calib_note(self):
         return "; ".join(f"{k}: {v['evals_per_s']:.3g} evals/s @ {v['threads']} thr" for k, v in self.calib.items())
 
@@ -215,19 +223,14 @@ def run_reference(args, W, H, D, windR, rank, world):
         cells = lay.disjointRegionSets[0]
         pls = np.ascontiguousarray(synth.synthetic_planes(lay.unitRegions, V3_STEPS[li], D, 7 + li)[:, cells, :])
         sample.append(([lay.filterRegions[r] for r in cells], [lay.sharedRegions[r] for r in cells], pls))
-    evals = sum(sum(f[2] * f[3] for f in fr) * pls.shape[0] for fr, _, pls in sample)
     kind, nthr = arm.calibrate(*sample[0])
-
-    def step():
-        for fr, tr, pls in sample:
-            arm.run(fr, tr, pls)
-
     for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
+        arm.time_sample(sample)
+    evals, dt = 0, 0.0
     for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
+        e, t = arm.time_sample(sample)
+        evals, dt = e, dt + t
+    dt /= args.steps
     val = evals / dt
     nb = sum(p.shape[0] for _, _, p in sample)
     desc = (f"group 0 of each of the 3 layers, all K=9/3/3 steps ({nb} of 240 batched evaluations, {evals} evals per step); "
@@ -404,23 +407,15 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(W, H, D, windR, imL, None if naive else vol_h, naive=naive, imR=imR_h if naive else None)
-        first = True
-        tot_e, tot_t, used = 0, 0.0, []
+        sample, used = [], []
         for gi, g in enumerate(sweep.groups):
             if g.group != 0:
                 continue
             lay = sweep.layer(g.layer)
-            fr = [lay.filterRegions[r] for r in g.cells]
-            tr = [lay.sharedRegions[r] for r in g.cells]
-            pls = np.ascontiguousarray(planes_h[gi])  # [K][n][4]
-            if first:
-                arm.calibrate(fr, tr, pls)  # also warms
-                first = False
-            t0 = time.perf_counter()
-            arm.run(fr, tr, pls)
-            tot_t += time.perf_counter() - t0
-            tot_e += g.plan.filter_px * g.n_steps
+            sample.append(([lay.filterRegions[r] for r in g.cells], [lay.sharedRegions[r] for r in g.cells], np.ascontiguousarray(planes_h[gi])))
             used.append(f"L{g.layer}g0x{g.n_steps}")
+        arm.calibrate(*sample[0])  # also warms
+        tot_e, tot_t = arm.time_sample(sample)
         cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": arm.nthr, "kind": arm.kind,
                "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s); calibration: {arm.calib_note()}"}
         arm.close()
