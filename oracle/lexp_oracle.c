@@ -9,12 +9,12 @@
  *   StereoEnergy::IsValiLabel                               StereoEnergy.h:560-610
  * (paths relative to /root/reference/LocalExpansionStereo/).
  *
- * PARITY STATUS: parity unpinned by the reference (it has no tests / golden
- * vectors and does not compile here); this file is cross-checked against the
- * numpy oracle (oracle/lexp_oracle.py), which in turn is checked against the
- * cv2 kernels the reference calls.  It is also the timed CPU baseline ("port")
- * of bench.py: one OpenMP thread per cell of a batch, like the reference's
- * `#pragma omp parallel for` over the cells of a disjoint group (FastGCStereo.h:30).
+ * PARITY STATUS: pinned by the reference's own code -- tests/test_ref_pin.py holds this file (and the numpy oracle)
+ * against oracle/_ref/liblexp_ref.so, the reference's CostVolumeEnergy / FastGuidedImageFilter<double> classes compiled
+ * from its headers (oracle/build_ref.py), and against the reference-minted tests/golden/ vectors.  It is also one of the
+ * two timed CPU baselines of bench.py (kind "port"; the other is the compiled reference itself, kind "reference"): one
+ * OpenMP thread per cell of a batch, like the reference's `#pragma omp parallel for` over the cells of a disjoint group
+ * (FastGCStereo.h:30).
  */
 #include <math.h>
 #include <stdint.h>

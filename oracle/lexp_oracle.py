@@ -6,16 +6,27 @@ directory).  It is the *checker* for the CUDA path: only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
 legs may import it.  Nothing under `localexpstereo_b200/` imports it.
 
-PARITY STATUS: **parity unpinned by the reference** -- the reference ships no
+PARITY STATUS: **pinned by the reference's own code.**  The reference ships no
 tests, golden vectors or known-answer values for this path (SURVEY.md section 4
-and 8c) and cannot be compiled in this container (MSVC dialect, OpenCV C++ 3.1.0
-headers absent).  What pins this restatement instead:
-  * `tests/test_oracle_cv2.py` checks the box filter / reduce order / warpAffine
-    emulation against the OpenCV kernels the reference calls (`cv2` 4.13 Python
-    wheel, the only OpenCV in the image),
-  * `oracle/lexp_oracle.c` is an independent plain-C restatement cross-checked
-    against this file,
-  * `tests/golden/*.npz` are vectors minted by `tests/golden/make_golden.py`.
+and 8c), and its own build (Visual Studio + NuGet OpenCV 3.1) cannot run here; but
+the classes on the path -- CostVolumeEnergy, NaiveStereoEnergy,
+FastGuidedImageFilter<double>, LayerManager, RandomProposer -- compile with g++
+from the headers where they lie (`oracle/build_ref.py` -> `oracle/_ref/`, over the
+small cv:: layer of `oracle/cvshim/`).  What pins this restatement:
+  * `tests/test_ref_pin.py`: costs (every cell class, both views, with and
+    without the validity check, NaN / out-of-range / steep planes, MIN != 0),
+    validity masks, guided-filter statistics, cell geometry, Plane helpers and
+    cv::RNG-driven labels are compared with the compiled reference: costs agree
+    bit for bit on synthetic scenes and to 1 float ulp on a natural image,
+  * the cv:: layer's primitives (box filter, warpAffine, getAffineTransform,
+    cvtColor, Sobel) and this file's own (`tests/test_oracle.py`) are checked
+    against the real OpenCV kernels (`cv2` 4.13 wheel, the only OpenCV in the image),
+  * `tests/golden/*.npz` are OUTPUTS OF THE COMPILED REFERENCE
+    (`tests/golden/make_golden.py`); they travel to the GPU box, which has no
+    /root/reference,
+  * `oracle/lexp_oracle.c` is an independent plain-C restatement held to both.
+Residual freedom: the cv:: layer is this repository's reading of OpenCV 3.1's
+documented behaviour (checked on 4.13), not OpenCV 3.1 itself.
 
 Conventions: rect = (x, y, w, h) in image coordinates (cv::Rect); plane =
 (a, b, c, v) float32 (Plane.h:4-8); volume = float32[D][H][W] (main.cpp:353-354);
