@@ -24,8 +24,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.environ.get("LEXP_REFERENCE_DIR", "/root/reference/LocalExpansionStereo")
 OUT_DIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "liblexp_ref.so")
+DROPIN = os.path.join(OUT_DIR, "dropin_check")  # the reference's loop + include/CudaCostVolumeEnergy.h, linked to liblexp_cuda.so
 CXX = os.environ.get("LEXP_REF_CXX", "/usr/bin/g++")
-SOURCES = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(HERE, "cvshim", "opencv2", "opencv.hpp"), os.path.abspath(__file__)]
+ROOT = os.path.dirname(HERE)
+SOURCES = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(HERE, "dropin_check.cpp"), os.path.join(HERE, "cvshim", "opencv2", "opencv.hpp"),
+           os.path.join(ROOT, "include", "CudaCostVolumeEnergy.h"), os.path.join(ROOT, "include", "lexp_cuda.h"), os.path.abspath(__file__)]
 
 
 def _dialect_fixed_guided_filter(text):
@@ -56,9 +59,11 @@ def build(force=False, verbose=False):
     """Returns the path of liblexp_ref.so, or None when it neither exists nor can be built."""
     if not reference_present():
         return LIB if available() else None
+    cuda_dir = os.path.join(ROOT, "localexpstereo_b200")
+    have_cuda_lib = os.path.exists(os.path.join(cuda_dir, "liblexp_cuda.so"))
     if available() and not force:
         newest = max(os.path.getmtime(p) for p in SOURCES)
-        if os.path.getmtime(LIB) >= newest:
+        if os.path.getmtime(LIB) >= newest and (not have_cuda_lib or (os.path.exists(DROPIN) and os.path.getmtime(DROPIN) >= newest)):
             return LIB
     gen = os.path.join(OUT_DIR, "gen")
     os.makedirs(gen, exist_ok=True)
@@ -78,6 +83,17 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("building oracle/_ref failed:\n" + r.stderr[-6000:])
         os.replace(LIB + ".tmp", LIB)
+        if have_cuda_lib:  # the drop-in harness needs the product library to link against (it is run on the GPU box only)
+            cmd = [CXX, "-std=c++14", "-O2", "-fopenmp", "-ffp-contract=off", "-fpermissive", "-w",
+                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
+                   os.path.join(HERE, "dropin_check.cpp"), "-o", DROPIN + ".tmp", "-L", cuda_dir, "-llexp_cuda",
+                   "-Wl,-rpath,$ORIGIN/../../localexpstereo_b200"]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("building oracle/_ref/dropin_check failed:\n" + r.stderr[-6000:])
+            os.replace(DROPIN + ".tmp", DROPIN)
     finally:
         shutil.rmtree(gen, ignore_errors=True)
     return LIB

@@ -1,0 +1,180 @@
+// TEST INFRASTRUCTURE ONLY -- never part of the product path.
+//
+// The drop-in, end to end, in the reference's own types: this program is compiled from the reference's headers
+// (StereoEnergy.h, CostVolumeEnergy.h, LayerManager.h, Proposer.h -- where they lie, see oracle/build_ref.py) plus
+// include/CudaCostVolumeEnergy.h, the adapter a maintainer would add.  It drives the loop of
+// FastGCStereo::localExpansionMovesForLayer_CPU (FastGCStereo.h:22-72, the doGC == false branch, cells visited
+// sequentially so that cv::theRNG is deterministic) and, for EVERY proposal, evaluates the unary costs twice through the
+// StereoEnergy virtual interface: once with the reference's CPU energy (CostVolumeEnergy / NaiveStereoEnergy) and once
+// with the CUDA energy behind the adapter; cv::Mat views, Plane, Reusable and LayerManager rectangles are the
+// reference's.  The fusion step then continues with the CPU costs, so both energies always see the same proposals.
+//
+//   dropin_check [--naive] [--cpu-self-check | --cpu-float-check] [--W n --H n --D n --K n]
+// --cpu-self-check replaces the CUDA energy by a second CPU instance (validates this harness without a GPU);
+// --cpu-float-check by the reference's own single-precision variant (filterName "GFfloat", FastGuidedImageFilter<float>):
+// the size of its deviation from the double filter shows how well conditioned the scene is for any FP32 implementation.
+// Prints one JSON line; exit code 0 iff every call agreed (1e-4 relative, COST_FOR_INVALID masks identical).
+#include <opencv2/opencv.hpp>
+#include "Utilities.hpp"
+#include "Plane.h"
+#include "StereoEnergy.h"
+#include "CostVolumeEnergy.h"
+#include "LayerManager.h"
+#include "CudaCostVolumeEnergy.h"
+#include <cstring>
+
+namespace {
+
+struct Tally {
+    long calls = 0, px = 0, bad = 0, mask_mismatch = 0;
+    double worst = 0;  // max |a-b| / (1e-4 * max(|a|, 1e-3))
+};
+
+void compare(const cv::Mat& a, const cv::Mat& b, const cv::Rect& r, Tally& t) {
+    t.calls++;
+    for (int y = r.y; y < r.y + r.height; y++) {
+        const float* pa = a.ptr<float>(y);
+        const float* pb = b.ptr<float>(y);
+        for (int x = r.x; x < r.x + r.width; x++) {
+            t.px++;
+            const bool ia = pa[x] == (float)StereoEnergy::COST_FOR_INVALID, ib = pb[x] == (float)StereoEnergy::COST_FOR_INVALID;
+            if (ia != ib) { t.mask_mismatch++; continue; }
+            if (ia) continue;
+            if (std::isnan(pa[x]) && std::isnan(pb[x])) continue;
+            double e = std::fabs((double)pa[x] - pb[x]) / (1e-4 * std::max(std::fabs((double)pa[x]), 1e-3));
+            if (!(e <= 1.0)) t.bad++;
+            if (e > t.worst || std::isnan(e)) t.worst = e;
+        }
+    }
+}
+
+cv::Mat synthetic_image(int H, int W, uint64_t seed) {
+    cv::RNG rng(seed);
+    cv::Mat im(H, W, CV_8UC3);
+    // smooth blobs + texture, so that the guided filter sees edges
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            double s = 0.5 + 0.5 * std::sin(0.11 * x + 0.07 * y) * std::cos(0.05 * x - 0.13 * y);
+            int edge = ((x / 23 + y / 17) & 1) ? 60 : 0;
+            for (int c = 0; c < 3; c++) {
+                int v = (int)(40 + 120 * s + edge + (c * 17) + rng.uniform(0, 30));
+                im.at<cv::Vec3b>(y, x)[c] = (uchar)std::min(255, std::max(0, v));
+            }
+        }
+    return im;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    int W = 160, H = 120, D = 16, K = 3, windR = 20;
+    bool naive = false, self = false, selff = false;
+    for (int i = 1; i < argc; i++) {
+        if (!std::strcmp(argv[i], "--naive")) naive = true;
+        else if (!std::strcmp(argv[i], "--cpu-self-check")) self = true;
+        else if (!std::strcmp(argv[i], "--cpu-float-check")) self = selff = true;
+        else if (i + 1 < argc && !std::strcmp(argv[i], "--W")) W = std::atoi(argv[++i]);
+        else if (i + 1 < argc && !std::strcmp(argv[i], "--H")) H = std::atoi(argv[++i]);
+        else if (i + 1 < argc && !std::strcmp(argv[i], "--D")) D = std::atoi(argv[++i]);
+        else if (i + 1 < argc && !std::strcmp(argv[i], "--K")) K = std::atoi(argv[++i]);
+        else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
+    }
+    try {
+        const float maxdisp = (float)D - 1;
+        cv::Mat imL = synthetic_image(H, W, 11), imR = synthetic_image(H, W, 12);
+        std::vector<float> vL((size_t)D * H * W), vR((size_t)D * H * W);
+        cv::RNG vr(99);
+        for (auto& v : vL) v = (float)vr;
+        for (auto& v : vR) v = (float)vr;
+        int sizes[3] = {D, H, W};
+        cv::Mat volL(3, sizes, CV_32F, vL.data()), volR(3, sizes, CV_32F, vR.data());
+
+        Parameters param(1.0f, windR, "GF", 0.0001f);  // paramsGF, main.cpp:73
+        if (!naive) param.th_col = 0.5f;                // main.cpp:26,351
+
+        Parameters paramB = param;
+        if (selff) paramB.filterName = "GFfloat";
+        std::unique_ptr<StereoEnergy> A, B;  // A: the reference's CPU energy; B: the energy under test
+        if (naive) {
+            A = std::make_unique<NaiveStereoEnergy>(imL, imR, param, maxdisp);
+            if (self) B = std::make_unique<NaiveStereoEnergy>(imL, imR, paramB, maxdisp);
+            else B = std::make_unique<CudaNaiveStereoEnergy>(imL, imR, param, maxdisp);
+        } else {
+            A = std::make_unique<CostVolumeEnergy>(imL, imR, volL, volR, param, maxdisp);
+            if (self) B = std::make_unique<CostVolumeEnergy>(imL, imR, volL, volR, paramB, maxdisp);
+            else B = std::make_unique<CudaCostVolumeEnergy>(imL, imR, volL, volR, param, maxdisp);  // main.cpp:386, with the adapter
+        }
+
+        LayerManager layermng(W, H, windR, 0);
+        const int units[3] = {5, 15, 25};  // main.cpp:304-306
+        for (int u : units) layermng.addLayer(u);
+        const cv::Rect imageDomain(0, 0, W, H);
+        Tally init, moves;
+
+        for (int mode = 0; mode < 2; mode++) {
+            cv::theRNG().state = 1234 + mode;
+            cv::Mat currentCost(H, W, CV_32F, cv::Scalar(INFINITY));
+            cv::Mat currentLabeling(H, W, CV_32FC4, cv::Scalar::all(0));
+            cv::Mat costB(H, W, CV_32F, cv::Scalar(INFINITY));
+            // initCurrentFast (FastGCStereo.h:95-116): a random label per unit region of layer 0
+            auto& layer0 = layermng.layers[0];
+            for (size_t j = 0; j < layer0.unitRegions.size(); j++) {
+                cv::Rect unit = layer0.unitRegions[j];
+                int n = cv::theRNG().uniform(0, unit.height * unit.width);
+                cv::Point pnt(unit.x + n % unit.width, unit.y + n / unit.width);
+                Plane label = A->createRandomLabel(pnt);
+                currentLabeling(unit) = label.toScalar();
+                cv::Rect filterRegion = cv::Rect(unit.x - windR, unit.y - windR, unit.width + windR * 2, unit.height + windR * 2) & imageDomain;
+                StereoEnergy::Reusable ra, rb;
+                A->ComputeUnaryPotential(filterRegion, unit, currentCost(filterRegion), label, ra, mode);
+                B->ComputeUnaryPotential(filterRegion, unit, costB(filterRegion), label, rb, mode);
+                compare(currentCost, costB, unit, init);
+            }
+            // local expansion moves (FastGCStereo.h:22-72), doGC == false
+            for (int iteration = 0; iteration < 2; iteration++)
+                for (auto& layer : layermng.layers) {
+                    cv::Mat proposalCost(H, W, CV_32F), proposalCostB(H, W, CV_32F);
+                    for (size_t j = 0; j < layer.disjointRegionSets.size(); j++)
+                        for (size_t n = 0; n < layer.disjointRegionSets[j].size(); n++) {
+                            int r = layer.disjointRegionSets[j][n];
+                            auto& sharedRegion = layer.sharedRegions[r];
+                            auto& unitRegion = layer.unitRegions[r];
+                            cv::Mat subCurrentCost = currentCost(sharedRegion);
+                            cv::Mat subProposalCost = proposalCost(sharedRegion);
+                            cv::Mat subCurrentLabeling = currentLabeling(sharedRegion);
+                            StereoEnergy::Reusable reusable, reusableB;
+                            ExpansionProposer p1(1);
+                            RandomProposer p2(K, maxdisp);
+                            IProposer* protos[2] = {&p1, &p2};
+                            for (IProposer* proto : protos) {
+                                IProposer* prop = proto->createInstance();
+                                prop->startIterations(currentLabeling, unitRegion, iteration);
+                                while (prop->isContinued()) {
+                                    Plane label = prop->getNextProposal();
+                                    A->ComputeUnaryPotential(layer.filterRegions[r], sharedRegion, proposalCost(layer.filterRegions[r]), label, reusable, mode);
+                                    B->ComputeUnaryPotential(layer.filterRegions[r], sharedRegion, proposalCostB(layer.filterRegions[r]), label, reusableB, mode);
+                                    compare(proposalCost, proposalCostB, sharedRegion, moves);
+                                    cv::Mat updateMask = subCurrentCost > subProposalCost;
+                                    subProposalCost.copyTo(subCurrentCost, updateMask);
+                                    subCurrentLabeling.setTo(label.toScalar(), updateMask);
+                                }
+                                delete prop;
+                            }
+                        }
+                }
+        }
+        const long px = init.px + moves.px, bad = init.bad + moves.bad, mm = init.mask_mismatch + moves.mask_mismatch;
+        const double worst = std::max(init.worst, moves.worst);
+        // NaiveStereoEnergy: the CUDA path evaluates the inverse affine map in closed form, the reference by LU; single source
+        // pixels may flip at exact 1/32-pixel rounding ties, which the 21x21 filter spreads: allow a 2e-3 fraction there
+        const bool ok = mm == 0 && (naive ? bad <= px * 2e-3 : bad == 0);
+        std::printf("{\"energy\": \"%s\", \"under_test\": \"%s\", \"W\": %d, \"H\": %d, \"D\": %d, \"init_calls\": %ld, \"move_calls\": %ld, "
+                    "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"ok\": %s}\n",
+                    naive ? "NaiveStereoEnergy" : "CostVolumeEnergy", selff ? "cpu GFfloat" : self ? "cpu-self-check" : "CudaCostVolumeEnergy adapter", W, H, D,
+                    init.calls, moves.calls, px, bad, mm, worst, ok ? "true" : "false");
+        return ok ? 0 : 1;
+    } catch (const std::exception& e) {
+        std::printf("{\"error\": \"%s\"}\n", e.what());
+        return 3;
+    }
+}

@@ -304,3 +304,19 @@ def test_random_labels_and_proposals_equal_the_reference(cv_pair):
         # plane normals go through sqrt/sin/cos in double and a float division: allow 2 ulp on a, b and the c they feed
         assert np.allclose(got, want, rtol=3e-6, atol=1e-6), (outer, np.abs(got - want).max())
         assert R.rng_state() == rng.state
+
+
+def test_adapter_compiles_against_the_reference_headers_and_harness_self_check():
+    """oracle/_ref/dropin_check = the reference's FastGCStereo loop + include/CudaCostVolumeEnergy.h compiled against the REAL
+    StereoEnergy.h (not the stub of tests/cxx) and linked with liblexp_cuda.so.  Without a GPU only its CPU self-check can run:
+    the reference's CPU energy on both sides, which validates the harness the GPU test relies on."""
+    import json
+    import os
+    import subprocess
+    assert build_ref.build() is not None
+    if not os.path.exists(build_ref.DROPIN):
+        pytest.skip("liblexp_cuda.so is not built yet")
+    for extra in ([], ["--naive"]):
+        res = subprocess.run([build_ref.DROPIN, "--cpu-self-check", "--W", "96", "--H", "80"] + extra, capture_output=True, text=True, timeout=600)
+        d = json.loads(res.stdout.strip().splitlines()[-1])
+        assert res.returncode == 0 and d["ok"] is True and d["out_of_tolerance"] == 0 and d["move_calls"] > 1000, d
