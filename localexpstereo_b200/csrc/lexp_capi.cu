@@ -25,6 +25,14 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+// kernel launch: CUDA's <<<>>> for nvcc; the same call goes to the fiber scheduler of tests/emu/ when the file is compiled
+// with g++ -DLEXP_EMU into the CPU test emulator (test infrastructure only, never part of liblexp_cuda.so)
+#ifndef LEXP_EMU
+#define LEXP_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#else
+#define LEXP_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch(kern, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#endif
+
 #define LEXP_CUDA(expr)                                                                                  \
     do {                                                                                                 \
         cudaError_t e__ = (expr);                                                                        \
@@ -91,7 +99,7 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
         c->smem_configured = true;
     }
-    kern<<<nitems, kThreads, smem, c->stream>>>(kp);
+    LEXP_LAUNCH(kern, nitems, kThreads, smem, c->stream, kp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
     return LEXP_OK;
@@ -176,9 +184,9 @@ int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
     int* d_flag = nullptr;
     LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream);
-    lexp_scan_nonfinite<<<148 * 8, 256, 0, c->stream>>>(d_src, (size_t)D * H * W, d_flag);
+    LEXP_LAUNCH(lexp_scan_nonfinite, 148 * 8, 256, 0, c->stream, d_src, (size_t)D * H * W, d_flag);
     dim3 grd((W + 31) / 32, Hb, (D + 7) / 8);
-    lexp_relayout_volume<<<grd, 256, 0, c->stream>>>(d_src, c->d_vol[mode], D, H, W, Wb);
+    LEXP_LAUNCH(lexp_relayout_volume, grd, 256, 0, c->stream, d_src, c->d_vol[mode], D, H, W, Wb);
     c->launches += 2;
     int h = 1;
     cudaError_t e = cudaGetLastError();
@@ -275,13 +283,13 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     int* d_rs = nullptr;
     LEXP_CUDA(cudaMalloc(&d_rs, 9 * HW * sizeof(int)));
     dim3 blk(128), grd((W + 127) / 128, H);
-    lexp_stats_rowsum<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], d_rs, H, W, c->R);
-    lexp_stats_finish<<<grd, blk, 0, c->stream>>>(d_rs, c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], H, W, c->R, (double)c->p.eps);
+    LEXP_LAUNCH(lexp_stats_rowsum, grd, blk, 0, c->stream, c->d_guide[mode], d_rs, H, W, c->R);
+    LEXP_LAUNCH(lexp_stats_finish, grd, blk, 0, c->stream, d_rs, c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], H, W, c->R, (double)c->p.eps);
     c->launches += 2;
     if (c->p.energy_kind == 1) {
         if (!c->d_exi[mode] && cudaMalloc(&c->d_exi[mode], HW * sizeof(float4)) != cudaSuccess) { cudaFree(d_rs); return fail(LEXP_ERR_NOMEM, "ExI allocation failed"); }
         const float s_col = (float)(1.0 - (double)c->p.alpha);  // `I[m] * (1.0 - params.alpha)`, StereoEnergy.h:659
-        lexp_build_exi<<<grd, blk, 0, c->stream>>>(c->d_guide[mode], c->d_exi[mode], H, W, s_col, c->p.alpha);
+        LEXP_LAUNCH(lexp_build_exi, grd, blk, 0, c->stream, c->d_guide[mode], c->d_exi[mode], H, W, s_col, c->p.alpha);
         c->launches++;
     }
     cudaError_t e = cudaGetLastError();
@@ -325,7 +333,7 @@ int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {
     const size_t HW = (size_t)c->p.height * c->p.width;
     float* d9 = nullptr;
     LEXP_CUDA(cudaMalloc(&d9, 9 * HW * sizeof(float)));
-    lexp_stats_unpack<<<(unsigned)((HW + 255) / 256), 256, 0, c->stream>>>(c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], d9, HW);
+    LEXP_LAUNCH(lexp_stats_unpack, (unsigned)((HW + 255) / 256), 256, 0, c->stream, c->d_statA[mode], c->d_statB[mode], c->d_statC[mode], d9, HW);
     c->launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(out9, d9, 9 * HW * sizeof(float), cudaMemcpyDeviceToHost);

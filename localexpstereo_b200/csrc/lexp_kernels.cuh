@@ -94,6 +94,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
 typedef unsigned long long u64;
 struct __align__(16) F4 { u64 lo, hi; };  // lo = (x, y), hi = (z, w)
+#ifndef LEXP_EMU
 __device__ __forceinline__ u64 pk2(float a, float b) {
     u64 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
@@ -102,6 +103,16 @@ __device__ __forceinline__ u64 pk2(float a, float b) {
 __device__ __forceinline__ void up2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#define LEXP_LOADS_LANDED(...) asm volatile("" : __VA_ARGS__ :: "memory")
+#define LEXP_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else  // host emulation of the same operations (tests/emu/, test infrastructure only)
+inline u64 pk2(float a, float b) { return (u64)__float_as_uint(a) | ((u64)__float_as_uint(b) << 32); }
+inline void up2(u64 v, float& a, float& b) { a = __uint_as_float((unsigned)v); b = __uint_as_float((unsigned)(v >> 32)); }
+inline u64 add2(u64 a, u64 b) { float a0, a1, b0, b1; up2(a, a0, a1); up2(b, b0, b1); return pk2(__fadd_rn(a0, b0), __fadd_rn(a1, b1)); }
+inline u64 sub2(u64 a, u64 b) { float a0, a1, b0, b1; up2(a, a0, a1); up2(b, b0, b1); return pk2(__fsub_rn(a0, b0), __fsub_rn(a1, b1)); }
+#define LEXP_LOADS_LANDED(...) ((void)0)
+#define LEXP_DYNAMIC_SMEM(name) unsigned char* name = emu::dyn_smem()
+#endif
 __device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
@@ -110,8 +121,13 @@ __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
 // link L (0: A->H1 via hb1, 1: H1->C via ho1, 2: C->H2 via hb2, 3: H2->E via ho2), buffer parity b:
 //   FULL  id = 4 L + b       producer bar.arrive after writing, consumer bar.sync before reading
 //   EMPTY id = 4 L + 2 + b   consumer bar.arrive after reading, producer bar.sync before overwriting (chunk >= 2)
+#ifndef LEXP_EMU
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#else
+inline void bar_sync(int id, int nthreads) { emu::barrier(id, nthreads, true); }
+inline void bar_arrive(int id, int nthreads) { emu::barrier(id, nthreads, false); }
+#endif
 __device__ __forceinline__ void produce_begin(int link, int c, int nthreads) { if (c >= 2) bar_sync(4 * link + 2 + (c & 1), nthreads); }
 __device__ __forceinline__ void produce_end(int link, int c, int nthreads) { bar_arrive(4 * link + (c & 1), nthreads); }
 __device__ __forceinline__ void consume_begin(int link, int c, int nthreads) { bar_sync(4 * link + (c & 1), nthreads); }
@@ -148,7 +164,7 @@ template <int R_T, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
     const int K = 2 * R + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LEXP_DYNAMIC_SMEM(smem_raw);
     F4* smem = reinterpret_cast<F4*>(smem_raw);
 
     const Item it = P.items[blockIdx.x];
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
 #pragma unroll
             for (int j = 0; j < kG; j++) {
                 // consume point of the batch: every load must have landed before the next batch is issued
-                asm volatile("" : "+f"(lv0[j]), "+f"(lv1[j]), "+r"(lg[j]) :: "memory");
+                LEXP_LOADS_LANDED("+f"(lv0[j]), "+f"(lv1[j]), "+r"(lg[j]));
                 const float f1 = lf1[j];
                 float C = __fadd_rn(__fmul_rn(1.0f - f1, lv0[j]), __fmul_rn(f1, lv1[j]));  // :92
                 if (!fast) {
@@ -490,8 +506,8 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 float cc[kCH];
 #pragma unroll
                 for (int r = 0; r < kCH; r++) {
-                    asm volatile("" : "+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
-                                 "+f"(sb[r].z), "+f"(sb[r].w), "+f"(sc[r]) :: "memory");
+                    LEXP_LOADS_LANDED("+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
+                                      "+f"(sb[r].z), "+f"(sb[r].w), "+f"(sc[r]));
                     ca[r] = sa[r]; cb[r] = sb[r]; cc[r] = sc[r];
                 }
                 issue();
@@ -584,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 uint32_t cg[kCH];
 #pragma unroll
                 for (int r = 0; r < kCH; r++) {
-                    asm volatile("" : "+r"(gq[r]) :: "memory");
+                    LEXP_LOADS_LANDED("+r"(gq[r]));
                     cg[r] = gq[r];
                 }
                 issue();
@@ -718,7 +734,11 @@ __global__ void lexp_scan_nonfinite(const float* __restrict__ vol, size_t n, int
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     bool bad = false;
     for (; i < n; i += stride) bad |= !isfinite(vol[i]);
+#ifndef LEXP_EMU
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+#else
+    if (bad) atomicOr(flag, 1);  // emulated threads do not run in warp lock-step
+#endif
 }
 
 // planar float[9][H][W] view of the statistics (lexp_get_stats)

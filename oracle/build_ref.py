@@ -25,6 +25,7 @@ REF_DIR = os.environ.get("LEXP_REFERENCE_DIR", "/root/reference/LocalExpansionSt
 OUT_DIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(OUT_DIR, "liblexp_ref.so")
 DROPIN = os.path.join(OUT_DIR, "dropin_check")  # the reference's loop + include/CudaCostVolumeEnergy.h, linked to liblexp_cuda.so
+DROPIN_EMU = os.path.join(OUT_DIR, "dropin_check_emu")  # same program linked to tests/emu/liblexp_emu.so (kernel source on CPU fibers)
 CXX = os.environ.get("LEXP_REF_CXX", "/usr/bin/g++")
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(HERE, "dropin_check.cpp"), os.path.join(HERE, "cvshim", "opencv2", "opencv.hpp"),
@@ -63,7 +64,9 @@ def build(force=False, verbose=False):
     have_cuda_lib = os.path.exists(os.path.join(cuda_dir, "liblexp_cuda.so"))
     if available() and not force:
         newest = max(os.path.getmtime(p) for p in SOURCES)
-        if os.path.getmtime(LIB) >= newest and (not have_cuda_lib or (os.path.exists(DROPIN) and os.path.getmtime(DROPIN) >= newest)):
+        emu_so = os.path.join(ROOT, "tests", "emu", "liblexp_emu.so")
+        emu_ok = not os.path.exists(emu_so) or (os.path.exists(DROPIN_EMU) and os.path.getmtime(DROPIN_EMU) >= max(newest, os.path.getmtime(emu_so)))
+        if os.path.getmtime(LIB) >= newest and (not have_cuda_lib or (os.path.exists(DROPIN) and os.path.getmtime(DROPIN) >= newest)) and emu_ok:
             return LIB
     gen = os.path.join(OUT_DIR, "gen")
     os.makedirs(gen, exist_ok=True)
@@ -94,6 +97,16 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("building oracle/_ref/dropin_check failed:\n" + r.stderr[-6000:])
             os.replace(DROPIN + ".tmp", DROPIN)
+        emu_dir = os.path.join(ROOT, "tests", "emu")
+        if os.path.exists(os.path.join(emu_dir, "liblexp_emu.so")):  # CPU twin: the adapter + the kernel source, no GPU
+            cmd = [CXX, "-std=c++14", "-O2", "-fopenmp", "-ffp-contract=off", "-fpermissive", "-w",
+                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
+                   os.path.join(HERE, "dropin_check.cpp"), "-o", DROPIN_EMU + ".tmp", "-L", emu_dir, "-llexp_emu",
+                   "-Wl,-rpath,$ORIGIN/../../tests/emu"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("building oracle/_ref/dropin_check_emu failed:\n" + r.stderr[-6000:])
+            os.replace(DROPIN_EMU + ".tmp", DROPIN_EMU)
     finally:
         shutil.rmtree(gen, ignore_errors=True)
     return LIB

@@ -1,0 +1,30 @@
+"""TEST INFRASTRUCTURE ONLY.  Builds tests/emu/liblexp_emu.so: the product's own sources (csrc/lexp_capi.cu + lexp_kernels.cuh)
+compiled by g++ with -DLEXP_EMU against tests/emu/cuda_runtime.h, a host emulation of the CUDA execution model (fibers +
+named barriers).  Same C-ABI as liblexp_cuda.so; loaded only by tests/test_emu_*.py, never by the package."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_capi.cu")
+DEPS = [SRC, os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_kernels.cuh"), os.path.join(ROOT, "include", "lexp_cuda.h"),
+        os.path.join(HERE, "cuda_runtime.h"), os.path.abspath(__file__)]
+SO = os.path.join(HERE, "liblexp_emu.so")
+
+
+def build(force=False):
+    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in DEPS):
+        return SO
+    # -ffp-contract=fast + -mfma: let the host compiler fuse a*b+c like nvcc does by default (the exact choices still differ)
+    fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=fast"] + fma + [
+        "-I", HERE, "-x", "c++", SRC, "-o", SO + ".tmp"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building the emulator failed:\n" + r.stderr[-8000:])
+    os.replace(SO + ".tmp", SO)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True))

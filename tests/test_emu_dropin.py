@@ -1,0 +1,32 @@
+"""The reference's own FastGCStereo loop, compiled from its headers with include/CudaCostVolumeEnergy.h installed as the
+StereoEnergy, running against the KERNEL SOURCE on the CPU emulator (oracle/_ref/dropin_check_emu = oracle/dropin_check.cpp
+linked to tests/emu/liblexp_emu.so): every proposal's costs are compared with the reference's CPU energy.  The same program
+linked to liblexp_cuda.so is the GPU test tests/test_gpu_zz_dropin.py."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from oracle import build_ref
+
+if not (build_ref.available() or build_ref.reference_present()):
+    pytest.skip("oracle/_ref is not built and the reference sources are not on this machine", allow_module_level=True)
+
+
+@pytest.mark.parametrize("energy", ["CostVolumeEnergy", "NaiveStereoEnergy"])
+def test_reference_loop_through_the_adapter_on_the_emulator(energy):
+    from emu import emu_lib
+    emu_lib.load()           # builds tests/emu/liblexp_emu.so if needed
+    assert build_ref.build() is not None
+    if not os.path.exists(build_ref.DROPIN_EMU):
+        pytest.skip("dropin_check_emu was not built")
+    cmd = [build_ref.DROPIN_EMU, "--W", "80", "--H", "64", "--K", "1"] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    d = json.loads(res.stdout.strip().splitlines()[-1])
+    print(d)
+    assert "error" not in d, d
+    assert d["under_test"].startswith("CudaCostVolumeEnergy") and d["move_calls"] > 1000
+    assert d["mask_mismatch"] == 0 and d["ok"] is True and res.returncode == 0, d
+    if energy == "CostVolumeEnergy":
+        assert d["out_of_tolerance"] == 0 and d["worst_err_over_tol"] < 0.5, d

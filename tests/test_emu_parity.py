@@ -1,0 +1,57 @@
+"""The GPU parity tests, run on the CPU against the kernel source itself.
+
+tests/emu/liblexp_emu.so is localexpstereo_b200/csrc (lexp_capi.cu + lexp_kernels.cuh, unmodified) compiled with
+g++ -DLEXP_EMU against tests/emu/cuda_runtime.h: every CUDA thread is a fiber, named barriers follow the PTX semantics, a
+deadlock or an unbalanced barrier is an error.  The tests below are the very functions of tests/test_gpu_parity.py,
+tests/test_gpu_naive.py and the golden-vector test, executed through the same Python binding and C-ABI with the emulator
+swapped in as the library.  They check the kernel's logic (indices, pipeline protocol, planner) without a GPU; the `-m gpu`
+suite remains the parity gate for the real device."""
+import pytest
+
+from emu import emu_lib
+
+# the test functions and their fixtures, imported under new names so that pytest collects them here without the gpu mark
+import test_gpu_parity as _p
+import test_gpu_golden as _g
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _use_emulator():
+    with emu_lib.emulated():
+        yield
+
+
+scene = _p.scene
+
+test_emu_stats_match_oracle = _p.test_stats_match_oracle
+test_emu_cells_of_a_layer = _p.test_cells_of_a_layer
+test_emu_single_cell_virtuals = _p.test_single_cell_virtuals
+test_emu_branches_of_the_sampler = _p.test_branches_of_the_sampler
+test_emu_filter_rect_smaller_than_dependency_cone = _p.test_filter_rect_smaller_than_dependency_cone
+test_emu_errors_are_reported = _p.test_errors_are_reported
+test_emu_concurrent_single_cell_calls = _p.test_concurrent_single_cell_calls_like_the_openmp_loop
+test_emu_other_filter_radii = _p.test_other_filter_radii
+test_emu_nonzero_min_disparity_and_odd_max = _p.test_nonzero_min_disparity_and_odd_max
+test_emu_golden_vectors_through_the_c_abi = _g.test_golden_vectors_through_the_c_abi
+
+
+def test_emu_result_does_not_depend_on_the_thread_schedule(scene):
+    """A missing or misplaced barrier in lexp_fused_kernel would make the result depend on the order in which the emulated
+    threads run between barriers: forward, reverse and reshuffled-every-pass schedules must agree bit for bit."""
+    import numpy as np
+    from oracle import lexp_oracle as O
+    L, E, H, W, D = (scene[k] for k in "L E H W D".split())
+    lay = L.LayerManager(W, H, 20).addLayer(10)
+    rng = O.CvRNG(5)
+    outs = []
+    for order in (0, 1, 2):
+        with emu_lib.emulated(order=order):
+            res = []
+            for g in lay.disjointRegionSets[:3]:
+                rng_g = O.CvRNG(5 + len(res))
+                planes = np.stack([O.create_random_label(rng_g, *lay.unitRegions[r][:2], 0.0, D - 1.0) for r in g])
+                img = np.full((H, W), -7.0, np.float32)
+                E.ComputeUnaryPotentialBatch([lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g], img, planes, mode=0)
+                res.append(img)
+            outs.append(np.stack(res))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])

@@ -167,3 +167,15 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["unit"] == "evals/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"].startswith("tiny")
+
+
+def test_emulation_hooks_never_reach_the_product_library():
+    """csrc carries `#ifdef LEXP_EMU` hooks for the CPU emulator of tests/emu (test infrastructure).  The product build must not
+    define it, and the built library must not contain the emulator."""
+    import subprocess
+    from localexpstereo_b200 import build, _capi
+    assert not any("LEXP_EMU" in f for f in build.NVCC_FLAGS)
+    build.build()
+    syms = subprocess.run(["nm", "-C", _capi.SO_PATH], capture_output=True, text=True).stdout
+    assert "emu::" not in syms and "run_block" not in syms
+    assert "lexp_fused_kernel" in syms  # the device kernels are what the library carries
