@@ -24,10 +24,18 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    # LEXP_NVCC_DEFS: extra -D flags for build-time kernel variants (experiments only, e.g. "-DLEXP_OCC3"); a variant build is
+    # always forced and the next plain build() restores the default kernel because the .so is older than this marker
+    extra = os.environ.get("LEXP_NVCC_DEFS", "").split()
+    marker = SO + ".variant"
+    if extra:
+        force = True
+    elif os.path.exists(marker):
+        force = True
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + SRCS
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + SRCS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -35,6 +43,11 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building liblexp_cuda.so")
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(res.stdout + res.stderr)
+    if extra:
+        with open(marker, "w") as f:
+            f.write(" ".join(extra))
+    elif os.path.exists(marker):
+        os.remove(marker)
     return SO
 
 

@@ -79,6 +79,9 @@ struct lexp_ctx {
     int tile_oh = 128;    // max output rows per work item
     bool tile_oh_fixed = false;  // LEXP_TILE_OH given: no per-plan search
     int num_sms = 148;
+    int ctas_per_sm = kMinCtas;  // CTA slots per SM the planner fills (LEXP_CTAS_PER_SM)
+    bool pdl = false;            // launch with programmatic stream serialization (builds with -DLEXP_PDL=1; LEXP_PDL_OFF=1 disables)
+    size_t smem_cap = 0;         // upper bound on a work item's dynamic shared memory, 0: none (LEXP_SMEM_CAP)
     size_t smem_limit = 0;
     size_t window_max = 0;
     bool smem_configured = false;
@@ -99,6 +102,17 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
         c->smem_configured = true;
     }
+#if LEXP_PDL && !defined(LEXP_EMU)
+    if (c->pdl) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)nitems); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LEXP_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+    } else
+#endif
     LEXP_LAUNCH(kern, nitems, kThreads, smem, c->stream, kp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
@@ -225,6 +239,11 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->tile_oh = std::max(8, env_int("LEXP_TILE_OH", 128));
     c->tile_oh_fixed = getenv("LEXP_TILE_OH") != nullptr;
     c->num_sms = prop.multiProcessorCount;
+    // kMinCtas CTAs must fit next to each other: 1 KB of every CTA's shared memory is reserved by the system.  With the
+    // default build (2 CTAs) no cap is needed: the widest tile needs ~93 KB.
+    c->ctas_per_sm = env_int("LEXP_CTAS_PER_SM", kMinCtas);
+    c->pdl = LEXP_PDL && !env_int("LEXP_PDL_OFF", 0);
+    c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", kMinCtas > 2 ? (int)(233472 / kMinCtas - 1024) : 0);
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
@@ -351,12 +370,14 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int R = c->R;
-    const int ow_max = max_tile_ow(R);
+    int ow_max = max_tile_ow(R);
+    if (c->smem_cap)  // narrower tiles so that every work item fits the per-CTA shared-memory budget of the build
+        while (ow_max > 8 && fused_smem_bytes(ow_max + 4 * R, 128, R) > c->smem_cap) ow_max -= 4;
     // Row segmentation: every segment re-streams 4R warm-up rows, but more items fill the 2 x #SM CTA slots better.
     // Pick the segment height that minimises  waves x (rows streamed per item)  for this plan.
     int oh_max = c->tile_oh;
     if (!c->tile_oh_fixed) {
-        const int64_t slots = 2LL * c->num_sms;
+        const int64_t slots = (int64_t)c->ctas_per_sm * c->num_sms;
         double best = 1e300;
         for (int cand = 24; cand <= 128; cand += 4) {
             int64_t items = 0;

@@ -35,7 +35,40 @@ constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
 constexpr int kMaxOW = 32 * kWarpsE;   // output columns
 constexpr int kRun = 8;                // columns per H task
 constexpr int kCH = 2;                 // rows per pipeline chunk
-constexpr int kG = 6;                  // rows per gather batch of team A (one batch of loads in flight)
+// ---- build-time variants (default: the round-1 kernel; nothing below changes its code) --------------------------------
+// LEXP_OCC3: the "three CTAs per SM" register diet measured only at compile time so far (ptxas: 56 registers, no spills):
+//   gather batches of 4 rows instead of 6, team C re-loads each statistics row as soon as it has been consumed (one
+//   register set instead of two), team H re-reads the elements that leave the window from shared memory instead of
+//   holding them in 28 registers; the planner then caps a work item's shared memory at 75 KB (lexp_capi.cu).
+#ifdef LEXP_OCC3
+#define LEXP_MIN_CTAS 3
+#define LEXP_KG 4
+#define LEXP_C_ROLLING 1
+#define LEXP_H_REREAD 1
+#endif
+// LEXP_PDL: programmatic dependent launch.  Every thread signals `griddepcontrol.launch_dependents` at the top of the kernel, so
+//   the NEXT batched evaluation of the stream (launched with the programmatic-stream-serialization attribute, lexp_capi.cu) may
+//   occupy CTA slots as soon as all CTAs of this one are resident: it fills the partly empty last wave and hides the launch gap
+//   and its own prologue + 4R warm-up rows.  Consecutive launches write overlapping parts of the same cost image (the steps of a
+//   group), so team E executes `griddepcontrol.wait` (previous grids complete, their writes visible) before its first store;
+//   nothing else written by a previous launch is read.  Not yet run on a GPU.
+#ifndef LEXP_PDL
+#define LEXP_PDL 0
+#endif
+#ifndef LEXP_MIN_CTAS
+#define LEXP_MIN_CTAS 2
+#endif
+#ifndef LEXP_KG
+#define LEXP_KG 6
+#endif
+#ifndef LEXP_C_ROLLING
+#define LEXP_C_ROLLING 0
+#endif
+#ifndef LEXP_H_REREAD
+#define LEXP_H_REREAD 0
+#endif
+constexpr int kMinCtas = LEXP_MIN_CTAS;  // resident CTAs per SM the kernel is compiled for (register cap 65536 / (kMinCtas * 352))
+constexpr int kG = LEXP_KG;            // rows per gather batch of team A (one batch of loads in flight)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
 
 struct __align__(16) Item {  // one CTA work item (64 B)
@@ -161,12 +194,15 @@ __device__ __forceinline__ void naive_inverse_affine(const Item& it, const Plane
 __device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
 
 template <int R_T, bool NAIVE>
-__global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
     const int K = 2 * R + 1;
     LEXP_DYNAMIC_SMEM(smem_raw);
     F4* smem = reinterpret_cast<F4*>(smem_raw);
 
+#if LEXP_PDL && !defined(LEXP_EMU)
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     const Item it = P.items[blockIdx.x];
     const Plane4 pl = P.planes[it.call];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -433,6 +469,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 const F4* in = inb + ((c & 1) * kCH + r) * SW + 9 * k;
                 F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
                 if (R_T > 0) {
+#if !LEXP_H_REREAD
                     F4 w[kRun - 1];
                     F4 s = in[0], s2 = in[1];  // two partial sums: halves the dependent FADD2 chain
                     w[0] = s; w[1] = s2;
@@ -450,6 +487,22 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                         s = f4add(s, f4sub(in[jn + (jn >> 3)], w[j - 1]));
                         out[j] = s;
                     }
+#else   // same sums in the same order; the 7 elements that leave the window are read again instead of kept in registers
+                    F4 s = in[0], s2 = in[1];
+#pragma unroll
+                    for (int j = 2; j < 2 * R_T + 1; j++) {
+                        const F4 x = in[j + (j >> 3)];
+                        if (j & 1) s2 = f4add(s2, x); else s = f4add(s, x);
+                    }
+                    s = f4add(s, s2);
+                    out[0] = s;
+#pragma unroll
+                    for (int j = 1; j < kRun; j++) {
+                        const int jn = 2 * R_T + j;
+                        s = f4add(s, f4sub(in[jn + (jn >> 3)], in[j - 1]));
+                        out[j] = s;
+                    }
+#endif
                 } else {
                     F4 s = in[0];
                     for (int j = 1; j < K; j++) s = f4add(s, in[sidx(j)]);
@@ -481,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         const float4* pa = P.statA + pix0;
         const float4* pb = P.statB + pix0;
         const float* pc = P.statC + pix0;
+#if !LEXP_C_ROLLING
         auto issue = [&]() {
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
@@ -551,6 +605,66 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                 produce_end(2, c, kLinkCH);
             }
         }
+#else
+        // LEXP_C_ROLLING: each statistics row is re-loaded (for the next chunk) right after it has been copied out, so only one
+        // register set + one row is live instead of two sets; the loads of chunk c + 1 are issued while chunk c is processed
+        unsigned pix = (unsigned)pix0;  // one 32-bit pixel index instead of three 64-bit row pointers (H * W < 2^32)
+        auto issue_row = [&](int r) {
+            sa[r] = make_float4(0.f, 0.f, 0.f, 0.f); sb[r] = sa[r]; sc[r] = 0.f;
+            if (colC && vi >= vC0 && vi < vC1) {
+                sa[r] = __ldg(P.statA + pix);
+                sb[r] = __ldg(P.statB + pix);
+                sc[r] = __ldg(P.statC + pix);
+            }
+            vi++;
+            pix += (unsigned)P.W;
+        };
+#pragma unroll
+        for (int r = 0; r < kCH; r++) issue_row(r);
+        for (int c = 0; c < nChunks; c++) {
+            consume_begin(1, c, kLinkHC);
+            produce_begin(2, c, kLinkCH);
+            const F4* ho = ho1 + (c & 1) * kCH * SW + sidx(t < W2 ? t : 0);
+            F4* hb = hb2 + (c & 1) * kCH * SW + sidx(t < W2 ? t : 0);
+#pragma unroll
+            for (int r = 0; r < kCH; r++) {
+                LEXP_LOADS_LANDED("+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
+                                  "+f"(sb[r].z), "+f"(sb[r].w), "+f"(sc[r]));
+                const float4 ca = sa[r], cb = sb[r];
+                const float cc = sc[r];
+                issue_row(r);
+                const int v = c * kCH + r;
+                if (t < W2 && v >= vC0 && v < VHs) {
+                    F4 ab = f4zero();
+                    if (colC && v < vC1) {
+                        const float invN = inv_nx * s_invny[v - R];
+                        const F4 B = ho[r * SW];
+                        float Bp, B0, B1, B2;
+                        up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
+                        const float m0 = ca.x, m1 = ca.y, m2 = ca.z, i00 = ca.w;
+                        const float i01 = cb.x, i02 = cb.y, i11 = cb.z, i12 = cb.w, i22 = cc;
+                        const float mp = Bp * invN;                      // GuidedFilter.h:206
+                        const float c0 = fmaf(B0, invN, -m0 * mp);       // :212-214
+                        const float c1 = fmaf(B1, invN, -m1 * mp);
+                        const float c2 = fmaf(B2, invN, -m2 * mp);
+                        const float a0 = i00 * c0 + i01 * c1 + i02 * c2;  // :216-218
+                        const float a1 = i01 * c0 + i11 * c1 + i12 * c2;
+                        const float a2 = i02 * c0 + i12 * c1 + i22 * c2;
+                        const float bb = mp - a0 * m0 - a1 * m1 - a2 * m2;  // :220
+                        ab = F4{pk2(a0, a1), pk2(a2, bb)};
+                    }
+                    F4* sl = ring2 + slot * W2 + t;
+                    const F4 old = *sl;
+                    *sl = ab;
+                    acc = f4add(acc, f4sub(ab, old));
+                    hb[r * SW] = acc;  // column sum centred on row y - 2R
+                    slot = (slot + 1 == K) ? 0 : slot + 1;
+                }
+            }
+            consume_end(1, c, nChunks, kLinkHC);
+            produce_end(2, c, kLinkCH);
+        }
+#endif
     } else {
         // =========================================================================== team E
         const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);
@@ -595,6 +709,9 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
         long long ostride;
         if (P.out_compact) { orow = P.out + (size_t)it.compact_off + t; ostride = it.compact_stride; }
         else { orow = P.out + (size_t)it.oy0 * P.out_pitch + XE; ostride = P.out_pitch; }
+#if LEXP_PDL
+        bool prior_grids_done = false;
+#endif
         for (int c = 0; c < nChunks; c++) {
             {
                 uint32_t cg[kCH];
@@ -632,6 +749,14 @@ __global__ void __launch_bounds__(kThreads, 2) lexp_fused_kernel(const KParams P
                                                 dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
                                 if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
                             }
+#if LEXP_PDL
+                            if (!prior_grids_done) {  // write-after-write order against the previous launch of the stream
+#ifndef LEXP_EMU
+                                asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+                                prior_grids_done = true;
+                            }
+#endif
                             *orow = q;
                             orow += ostride;
                         }

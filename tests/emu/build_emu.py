@@ -12,12 +12,20 @@ DEPS = [SRC, os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_kernels.cuh
 SO = os.path.join(HERE, "liblexp_emu.so")
 
 
-def build(force=False):
-    if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in DEPS):
-        return SO
-    # -ffp-contract=fast + -mfma: let the host compiler fuse a*b+c like nvcc does by default (the exact choices still differ)
+def build(force=False, defs=(), tag=""):
+    """`defs`: extra -D flags selecting a build-time kernel variant (e.g. ("-DLEXP_OCC3",)), `tag` names its library."""
+    so = SO if not tag else os.path.join(HERE, f"liblexp_emu_{tag}.so")
+    if not force and os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(d) for d in DEPS):
+        return so
+    return _compile(so, list(defs))
+
+
+def _compile(SO, defs):
+    # -ffp-contract=off: only the explicit fmaf() calls fuse.  nvcc also contracts plain a*b+c expressions, so the emulated
+    # results differ from the GPU's in the last bits, but they are identical across build-time variants of the kernel, which is
+    # what the A/B equivalence tests need.  -mfma only makes fmaf() a single instruction.
     fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=fast"] + fma + [
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=off"] + defs + fma + [
         "-I", HERE, "-x", "c++", SRC, "-o", SO + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -10,28 +10,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 if HERE not in sys.path:
     sys.path.insert(0, HERE)
 
-_emu = None
+_emu = {}
+
+VARIANTS = {"": (), "occ3": ("-DLEXP_OCC3",), "pdl": ("-DLEXP_PDL=1",), "occ3pdl": ("-DLEXP_OCC3", "-DLEXP_PDL=1")}  # build-time kernel variants (lexp_kernels.cuh), "" = the shipped kernel
 
 
-def load():
-    global _emu
-    if _emu is None:
+def load(variant=""):
+    if variant not in _emu:
         import build_emu
         from localexpstereo_b200 import _capi
-        L = C.CDLL(build_emu.build())
+        L = C.CDLL(build_emu.build(defs=VARIANTS[variant], tag=variant))
         for name, (res, args) in _capi.SYMBOLS.items():
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        _emu = L
-    return _emu
+        _emu[variant] = L
+    return _emu[variant]
 
 
 @contextlib.contextmanager
-def emulated(order=None):
+def emulated(order=None, variant=""):
     """`order`: LEXP_EMU_ORDER for the fiber scheduler (0 forward, 1 reverse, 2 shuffled every pass)."""
     from localexpstereo_b200 import _capi
     prev_lib, prev_env = _capi._lib, os.environ.get("LEXP_EMU_ORDER")
-    _capi._lib = load()
+    _capi._lib = load(variant)
     if order is not None:
         os.environ["LEXP_EMU_ORDER"] = str(order)
     try:
