@@ -25,7 +25,8 @@ def _compile(SO, defs):
     # results differ from the GPU's in the last bits, but they are identical across build-time variants of the kernel, which is
     # what the A/B equivalence tests need.  -mfma only makes fmaf() a single instruction.
     fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read() else []
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=off"] + defs + fma + [
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=off",
+           "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-fno-gnu-unique"] + defs + fma + [
         "-I", HERE, "-x", "c++", SRC, "-o", SO + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -243,16 +243,25 @@ struct cudaDeviceProp {
 };
 
 namespace emu {
+inline std::string& reported_error();
 inline std::map<void*, size_t>& registered() { static std::map<void*, size_t> s; return s; }
 inline std::mutex& reg_mu() { static std::mutex m; return m; }
 }  // namespace emu
 
 static inline const char* cudaGetErrorString(cudaError_t e) {
     static thread_local std::string s;
-    s = e == cudaSuccess ? "no error" : ("emulated CUDA error " + std::to_string(e) + (emu::last_launch_error().empty() ? "" : ": " + emu::last_launch_error()));
+    const std::string& why = emu::last_launch_error().empty() ? emu::reported_error() : emu::last_launch_error();
+    s = e == cudaSuccess ? "no error" : ("emulated CUDA error " + std::to_string(e) + (why.empty() ? "" : ": " + why));
     return s.c_str();
 }
-static inline cudaError_t cudaGetLastError() { if (!emu::last_launch_error().empty()) { return cudaErrorLaunchFailure; } return cudaSuccess; }
+// like CUDA: returns the pending launch error and resets it (the message stays readable through cudaGetErrorString)
+inline std::string& emu::reported_error() { static thread_local std::string e; return e; }
+static inline cudaError_t cudaGetLastError() {
+    if (emu::last_launch_error().empty()) return cudaSuccess;
+    emu::reported_error() = emu::last_launch_error();
+    emu::last_launch_error().clear();
+    return cudaErrorLaunchFailure;
+}
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {

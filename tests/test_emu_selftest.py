@@ -13,7 +13,7 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 @pytest.fixture(scope="module")
 def st(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "libemu_selftest.so")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-DLEXP_EMU", "-fPIC", "-shared", "-I", HERE, os.path.join(HERE, "selftest.cpp"), "-o", so])
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-DLEXP_EMU", "-fPIC", "-shared", "-fvisibility-inlines-hidden", "-fno-gnu-unique", "-I", HERE, os.path.join(HERE, "selftest.cpp"), "-o", so])
     L = C.CDLL(so)
     L.emu_selftest_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
 
