@@ -139,6 +139,11 @@ LEXP_API void* lexp_stream(lexp_ctx* ctx);
 LEXP_API int lexp_set_stream(lexp_ctx* ctx, void* cuda_stream);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);
+/* Concurrent lexp_eval_cell calls (the OpenMP loop of FastGCStereo.h:30-49, one blocking call per cell and thread) are
+ * combined: calls that arrive while the device is busy are evaluated together in one batched launch.  Returns how many
+ * such launches there were and how many calls they served (calls that found the device idle are not counted).
+ * LEXP_COMBINE=0 in the environment at lexp_create disables the combining. */
+LEXP_API int lexp_combine_stats(const lexp_ctx* ctx, int64_t* batches, int64_t* calls);
 
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */

@@ -56,6 +56,7 @@ SYMBOLS = {
     "lexp_stream": (_P, [_P]),
     "lexp_set_stream": (C.c_int, [_P, _P]),
     "lexp_launch_count": (C.c_int64, [_P]),
+    "lexp_combine_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lexp_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, _P, _P]),
 }
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <array>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <string>
@@ -55,6 +56,7 @@ struct lexp_plan {
     std::vector<int> compact_off;  // per call
     int64_t sum_f = 0, sum_s = 0, alg_bytes = 0;
     Item* d_items = nullptr;
+    std::vector<Item> h_items;    // host copy (the combiner of concurrent lexp_eval_cell calls concatenates them)
     Plane4* d_planes = nullptr;   // staging for host planes
     float* d_compact = nullptr;   // lazily allocated compact output (host path)
     float* h_compact = nullptr;   // pinned
@@ -91,6 +93,31 @@ struct lexp_ctx {
     // virtual again and again with the same rects (LayerManager.h:14-24), so the tiling / device upload is done once
     std::mutex cache_mu;
     std::map<std::array<int, 8>, lexp_plan*> cell_plans;
+    // Combining of CONCURRENT lexp_eval_cell calls.  The unchanged reference loop issues one blocking call per cell from an OpenMP
+    // `parallel for` over the cells of a disjoint group (FastGCStereo.h:30-49): while one call owns the device, the calls of the
+    // other threads queue up here and are then evaluated together as ONE batched launch (same work items, same results).
+    // A call that finds the device idle and the queue empty takes the plain single-cell path.
+    struct CellReq {
+        int mode, with_check;
+        lexp_plan* pl;
+        lexp_plane plane;
+        float* base;
+        ptrdiff_t step_bytes;
+        int status = LEXP_OK;
+        std::string err;
+        bool done = false;
+    };
+    std::mutex comb_mu;
+    std::condition_variable comb_cv;
+    std::vector<CellReq*> comb_q;
+    bool comb_busy = false;
+    bool combine = true;           // LEXP_COMBINE=0: every call on its own (the round-1 behaviour)
+    Item* cb_items = nullptr;      // reusable buffers of the combined launches
+    Plane4* cb_planes = nullptr;
+    float* cb_dout = nullptr;
+    float* cb_hout = nullptr;      // pinned
+    size_t cb_items_cap = 0, cb_planes_cap = 0, cb_out_cap = 0;
+    int64_t combined_batches = 0, combined_calls = 0;
 };
 
 namespace {
@@ -243,6 +270,7 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     // default build (2 CTAs) no cap is needed: the widest tile needs ~93 KB.
     c->ctas_per_sm = env_int("LEXP_CTAS_PER_SM", kMinCtas);
     c->pdl = LEXP_PDL && !env_int("LEXP_PDL_OFF", 0);
+    c->combine = env_int("LEXP_COMBINE", 1) != 0;
     c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", kMinCtas > 2 ? (int)(233472 / kMinCtas - 1024) : 0);
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
@@ -266,6 +294,8 @@ int lexp_destroy(lexp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->cell_plans) lexp_plan_destroy(kv.second);
     c->cell_plans.clear();
+    cudaFree(c->cb_items); cudaFree(c->cb_planes); cudaFree(c->cb_dout);
+    if (c->cb_hout) cudaFreeHost(c->cb_hout);
     for (int m = 0; m < 2; m++) {
         cudaFree(c->d_gs[m]);
         cudaFree(c->d_exi[m]);
@@ -436,6 +466,7 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
         return (int64_t)(a.ow + 4 * R) * (a.oh + 4 * R) > (int64_t)(b.ow + 4 * R) * (b.oh + 4 * R);
     });
     pl->nitems = (int)items.size();
+    pl->h_items = items;
     cudaError_t e = cudaMalloc(&pl->d_items, items.size() * sizeof(Item));
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_planes, (size_t)n * sizeof(Plane4));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice);
@@ -549,6 +580,81 @@ int lexp_eval_batch(lexp_ctx* c, int mode, int n, const lexp_rect* filt, const l
     return rc;
 }
 
+namespace {
+
+// One batched launch for the queued single-cell requests of one (mode, with_check): the work items of the cached per-cell
+// plans are concatenated (call index = position in the batch, compact outputs back to back), evaluated like the staged path
+// of lexp_plan_eval_host, and every tile is copied into its caller's image.
+int run_combined(lexp_ctx* c, const std::vector<lexp_ctx::CellReq*>& reqs) {
+    std::vector<Item> items;
+    std::vector<Plane4> planes(reqs.size());
+    std::vector<size_t> off(reqs.size());
+    size_t nout = 0, smem = 0;
+    for (size_t i = 0; i < reqs.size(); i++) {
+        const lexp_plan* pl = reqs[i]->pl;
+        off[i] = nout;
+        for (Item it : pl->h_items) {
+            it.call = (int)i;
+            it.compact_off += (int)nout;  // the plan's own call starts at offset 0
+            items.push_back(it);
+        }
+        nout += (size_t)pl->sum_s;
+        smem = std::max(smem, pl->smem);
+        const lexp_plane& p = reqs[i]->plane;
+        planes[i] = Plane4{p.a, p.b, p.c, p.v};
+    }
+    if (nout > 0x7fffffffULL) return fail(LEXP_ERR_INVALID, "combined output too large");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    if (items.size() > c->cb_items_cap || planes.size() > c->cb_planes_cap || nout > c->cb_out_cap) {
+        LEXP_CUDA(cudaStreamSynchronize(c->stream));
+        if (items.size() > c->cb_items_cap) {
+            cudaFree(c->cb_items); c->cb_items = nullptr; c->cb_items_cap = 0;
+            LEXP_CUDA(cudaMalloc(&c->cb_items, 2 * items.size() * sizeof(Item)));
+            c->cb_items_cap = 2 * items.size();
+        }
+        if (planes.size() > c->cb_planes_cap) {
+            cudaFree(c->cb_planes); c->cb_planes = nullptr; c->cb_planes_cap = 0;
+            LEXP_CUDA(cudaMalloc(&c->cb_planes, 2 * planes.size() * sizeof(Plane4)));
+            c->cb_planes_cap = 2 * planes.size();
+        }
+        if (nout > c->cb_out_cap) {
+            cudaFree(c->cb_dout); c->cb_dout = nullptr;
+            if (c->cb_hout) { cudaFreeHost(c->cb_hout); c->cb_hout = nullptr; }
+            c->cb_out_cap = 0;
+            LEXP_CUDA(cudaMalloc(&c->cb_dout, 2 * nout * sizeof(float)));
+            LEXP_CUDA(cudaHostAlloc(&c->cb_hout, 2 * nout * sizeof(float), cudaHostAllocDefault));
+            c->cb_out_cap = 2 * nout;
+        }
+    }
+    LEXP_CUDA(cudaMemcpyAsync(c->cb_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, c->stream));
+    LEXP_CUDA(cudaMemcpyAsync(c->cb_planes, planes.data(), planes.size() * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+    lexp_plan batch;  // a view: nothing in it is owned
+    batch.ctx = c;
+    batch.ncalls = (int)reqs.size();
+    batch.nitems = (int)items.size();
+    batch.smem = smem;
+    batch.d_items = c->cb_items;
+    int rc = run_plan(c, &batch, reqs[0]->mode, c->cb_planes, c->cb_dout, 0, 1, reqs[0]->with_check);
+    batch.d_items = nullptr;
+    if (rc) return rc;
+    LEXP_CUDA(cudaMemcpyAsync(c->cb_hout, c->cb_dout, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < reqs.size(); i++) {  // costs(targetRect) only (CostVolumeEnergy.h:169-171)
+        const lexp_rect& t = reqs[i]->pl->targ[0];
+        const float* src = c->cb_hout + off[i];
+        for (int y = 0; y < t.height; y++) {
+            float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(reqs[i]->base) + (ptrdiff_t)(t.y + y) * reqs[i]->step_bytes) + t.x;
+            memcpy(dst, src + (size_t)y * t.width, (size_t)t.width * sizeof(float));
+        }
+    }
+    c->combined_batches++;
+    c->combined_calls += (int64_t)reqs.size();
+    return LEXP_OK;
+}
+
+}  // namespace
+
 int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect* targ, const lexp_plane* plane, float* costs,
                    ptrdiff_t step_bytes, int with_check) {
     if (!c || !filt || !targ || !plane || !costs) return fail(LEXP_ERR_INVALID, "null argument");
@@ -578,7 +684,54 @@ int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect
             return rc2;
         }
     }
-    return lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
+    if (!c->combine || mode < 0 || mode > 1) return lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
+
+    std::unique_lock<std::mutex> lk(c->comb_mu);
+    if (!c->comb_busy && c->comb_q.empty()) {  // nobody else is calling: the plain single-cell path
+        c->comb_busy = true;
+        lk.unlock();
+        const int rc = lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
+        lk.lock();
+        c->comb_busy = false;
+        if (!c->comb_q.empty()) c->comb_cv.notify_all();  // calls that arrived meanwhile: one of them becomes the leader
+        return rc;
+    }
+    lexp_ctx::CellReq req;
+    req.mode = mode; req.with_check = with_check; req.pl = pl; req.plane = *plane; req.base = base; req.step_bytes = step_bytes;
+    c->comb_q.push_back(&req);
+    for (;;) {
+        c->comb_cv.wait(lk, [&] { return req.done || !c->comb_busy; });
+        if (req.done) break;
+        // the device is free and this request is still queued: lead one batch
+        c->comb_busy = true;
+        std::vector<lexp_ctx::CellReq*> all;
+        all.swap(c->comb_q);
+        lk.unlock();
+        // one launch per (mode, with_check) present in the queue (the reference's loop uses a single combination at a time)
+        while (!all.empty()) {
+            std::vector<lexp_ctx::CellReq*> grp, rest;
+            for (auto* r : all) (r->mode == all[0]->mode && r->with_check == all[0]->with_check ? grp : rest).push_back(r);
+            const int rc = run_combined(c, grp);
+            for (auto* r : grp) { r->status = rc; if (rc) r->err = g_err; }
+            all.swap(rest);
+            lk.lock();
+            for (auto* r : grp) r->done = true;
+            lk.unlock();
+        }
+        lk.lock();
+        c->comb_busy = false;
+        c->comb_cv.notify_all();
+        if (req.done) break;
+    }
+    if (req.status) g_err = req.err;
+    return req.status;
+}
+
+int lexp_combine_stats(const lexp_ctx* c, int64_t* batches, int64_t* calls) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    if (batches) *batches = c->combined_batches;
+    if (calls) *calls = c->combined_calls;
+    return LEXP_OK;
 }
 
 int lexp_host_register(void* ptr, size_t bytes) {

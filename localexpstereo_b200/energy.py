@@ -288,6 +288,13 @@ class CostVolumeEnergy:
     def launch_count(self) -> int:
         return int(lib().lexp_launch_count(self._h))
 
+    @property
+    def combine_stats(self):
+        """(batched launches that served concurrent single-cell calls, number of calls they served)."""
+        b, n = C.c_int64(0), C.c_int64(0)
+        check(lib().lexp_combine_stats(self._h, C.byref(b), C.byref(n)))
+        return int(b.value), int(n.value)
+
     def close(self):
         if getattr(self, "_h", None):
             lib().lexp_destroy(self._h)

@@ -9,7 +9,10 @@
 // with the CUDA energy behind the adapter; cv::Mat views, Plane, Reusable and LayerManager rectangles are the
 // reference's.  The fusion step then continues with the CPU costs, so both energies always see the same proposals.
 //
-//   dropin_check [--naive] [--cpu-self-check | --cpu-float-check] [--W n --H n --D n --K n]
+//   dropin_check [--naive] [--cpu-self-check | --cpu-float-check] [--threads T] [--W n --H n --D n --K n]
+// --threads T > 1 runs the cells of a disjoint group in an OpenMP `parallel for`, as the reference does (FastGCStereo.h:30):
+// the virtuals are then called concurrently (cv::theRNG is per thread, so the proposals differ from run to run, but every
+// call is still compared with the CPU energy on the same proposal).
 // --cpu-self-check replaces the CUDA energy by a second CPU instance (validates this harness without a GPU);
 // --cpu-float-check by the reference's own single-precision variant (filterName "GFfloat", FastGuidedImageFilter<float>):
 // the size of its deviation from the double filter shows how well conditioned the scene is for any FP32 implementation.
@@ -22,6 +25,7 @@
 #include "LayerManager.h"
 #include "CudaCostVolumeEnergy.h"
 #include <cstring>
+#include <omp.h>
 
 namespace {
 
@@ -67,7 +71,7 @@ cv::Mat synthetic_image(int H, int W, uint64_t seed) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    int W = 160, H = 120, D = 16, K = 3, windR = 20;
+    int W = 160, H = 120, D = 16, K = 3, windR = 20, threads = 1;
     bool naive = false, self = false, selff = false;
     for (int i = 1; i < argc; i++) {
         if (!std::strcmp(argv[i], "--naive")) naive = true;
@@ -77,6 +81,7 @@ int main(int argc, char** argv) {
         else if (i + 1 < argc && !std::strcmp(argv[i], "--H")) H = std::atoi(argv[++i]);
         else if (i + 1 < argc && !std::strcmp(argv[i], "--D")) D = std::atoi(argv[++i]);
         else if (i + 1 < argc && !std::strcmp(argv[i], "--K")) K = std::atoi(argv[++i]);
+        else if (i + 1 < argc && !std::strcmp(argv[i], "--threads")) threads = std::max(1, std::atoi(argv[++i]));
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     try {
@@ -134,8 +139,11 @@ int main(int argc, char** argv) {
             for (int iteration = 0; iteration < 2; iteration++)
                 for (auto& layer : layermng.layers) {
                     cv::Mat proposalCost(H, W, CV_32F), proposalCostB(H, W, CV_32F);
-                    for (size_t j = 0; j < layer.disjointRegionSets.size(); j++)
-                        for (size_t n = 0; n < layer.disjointRegionSets[j].size(); n++) {
+                    for (size_t j = 0; j < layer.disjointRegionSets.size(); j++) {
+                        std::vector<Tally> part(threads);
+#pragma omp parallel for num_threads(threads) if (threads > 1)
+                        for (int n = 0; n < (int)layer.disjointRegionSets[j].size(); n++) {
+                            Tally& moves = part[omp_get_thread_num()];
                             int r = layer.disjointRegionSets[j][n];
                             auto& sharedRegion = layer.sharedRegions[r];
                             auto& unitRegion = layer.unitRegions[r];
@@ -161,6 +169,11 @@ int main(int argc, char** argv) {
                                 delete prop;
                             }
                         }
+                        for (const Tally& t : part) {
+                            moves.calls += t.calls; moves.px += t.px; moves.bad += t.bad; moves.mask_mismatch += t.mask_mismatch;
+                            if (t.worst > moves.worst || std::isnan(t.worst)) moves.worst = t.worst;
+                        }
+                    }
                 }
         }
         const long px = init.px + moves.px, bad = init.bad + moves.bad, mm = init.mask_mismatch + moves.mask_mismatch;
@@ -168,10 +181,16 @@ int main(int argc, char** argv) {
         // NaiveStereoEnergy: the CUDA path evaluates the inverse affine map in closed form, the reference by LU; single source
         // pixels may flip at exact 1/32-pixel rounding ties, which the 21x21 filter spreads: allow a 2e-3 fraction there
         const bool ok = mm == 0 && (naive ? bad <= px * 2e-3 : bad == 0);
+        char extra[128] = "";
+        if (!self) {  // how many of the concurrent calls the library served with combined launches
+            int64_t batches = 0, calls = 0;
+            lexp_combine_stats(static_cast<CudaCostVolumeEnergy*>(B.get())->context(), &batches, &calls);
+            std::snprintf(extra, sizeof extra, "\"combined_launches\": %lld, \"combined_calls\": %lld, ", (long long)batches, (long long)calls);
+        }
         std::printf("{\"energy\": \"%s\", \"under_test\": \"%s\", \"W\": %d, \"H\": %d, \"D\": %d, \"init_calls\": %ld, \"move_calls\": %ld, "
-                    "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"ok\": %s}\n",
+                    "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"threads\": %d, %s\"ok\": %s}\n",
                     naive ? "NaiveStereoEnergy" : "CostVolumeEnergy", selff ? "cpu GFfloat" : self ? "cpu-self-check" : "CudaCostVolumeEnergy adapter", W, H, D,
-                    init.calls, moves.calls, px, bad, mm, worst, ok ? "true" : "false");
+                    init.calls, moves.calls, px, bad, mm, worst, threads, extra, ok ? "true" : "false");
         return ok ? 0 : 1;
     } catch (const std::exception& e) {
         std::printf("{\"error\": \"%s\"}\n", e.what());

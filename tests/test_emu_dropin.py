@@ -14,14 +14,14 @@ if not (build_ref.available() or build_ref.reference_present()):
     pytest.skip("oracle/_ref is not built and the reference sources are not on this machine", allow_module_level=True)
 
 
-@pytest.mark.parametrize("energy", ["CostVolumeEnergy", "NaiveStereoEnergy"])
-def test_reference_loop_through_the_adapter_on_the_emulator(energy):
+@pytest.mark.parametrize("energy,threads", [("CostVolumeEnergy", 1), ("NaiveStereoEnergy", 1), ("CostVolumeEnergy", 6)])
+def test_reference_loop_through_the_adapter_on_the_emulator(energy, threads):
     from emu import emu_lib
     emu_lib.load()           # builds tests/emu/liblexp_emu.so if needed
     assert build_ref.build() is not None
     if not os.path.exists(build_ref.DROPIN_EMU):
         pytest.skip("dropin_check_emu was not built")
-    cmd = [build_ref.DROPIN_EMU, "--W", "80", "--H", "64", "--K", "1"] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
+    cmd = [build_ref.DROPIN_EMU, "--W", "80", "--H", "64", "--K", "1", "--threads", str(threads)] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     d = json.loads(res.stdout.strip().splitlines()[-1])
     print(d)
@@ -30,3 +30,5 @@ def test_reference_loop_through_the_adapter_on_the_emulator(energy):
     assert d["mask_mismatch"] == 0 and d["ok"] is True and res.returncode == 0, d
     if energy == "CostVolumeEnergy":
         assert d["out_of_tolerance"] == 0 and d["worst_err_over_tol"] < 0.5, d
+    if threads > 1:  # the reference's OpenMP loop: concurrent calls of the virtual are served by combined launches
+        assert d["combined_calls"] > d["move_calls"] // 4 and d["combined_launches"] < d["combined_calls"], d

@@ -55,3 +55,52 @@ def test_emu_result_does_not_depend_on_the_thread_schedule(scene):
                 res.append(img)
             outs.append(np.stack(res))
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_emu_concurrent_calls_are_combined_into_batched_launches(scene, monkeypatch):
+    """lexp_eval_cell from many threads at once (the reference's unchanged OpenMP loop): calls that arrive while the device is
+    busy must be served together by one launch, with exactly the results of one-call-at-a-time evaluation."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import lexp_oracle as O
+    L, H, W, D = (scene[k] for k in "L H W D".split())
+    imL, imR, volL, volR = _p.make_scene(H, W, D)
+    prm = L.Parameters(windR=20, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    lay = L.LayerManager(W, H, 20).addLayer(7)
+    cells = [r for g in lay.disjointRegionSets[:2] for r in g]
+    rng = O.CvRNG(9)
+    planes = [np.stack([O.create_random_label(rng, *lay.unitRegions[r][:2], 0.0, D - 1.0) for r in cells]) for _ in range(3)]
+
+    def sweep(E, workers):
+        outs = []
+        for k in range(3):
+            img = np.full((H, W), -7.0, np.float32)
+
+            def one(i, k=k, img=img):
+                f, t = lay.filterRegions[cells[i]], lay.sharedRegions[cells[i]]
+                # cells of different groups overlap: give every call its own image, as they would race otherwise
+                own = np.full((H, W), -7.0, np.float32)
+                E.ComputeUnaryPotential(f, t, own[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], planes[k][i], mode=k & 1)
+                return own[t[1]:t[1] + t[3], t[0]:t[0] + t[2]].copy()
+
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                outs.append(list(ex.map(one, range(len(cells)))))
+        return outs
+
+    monkeypatch.setenv("LEXP_COMBINE", "0")
+    E0 = L.CostVolumeEnergy(imL, imR, volL, volR, prm, D - 1)
+    ref = sweep(E0, 1)
+    assert E0.combine_stats == (0, 0)
+    E0.close()
+    monkeypatch.delenv("LEXP_COMBINE")
+    E1 = L.CostVolumeEnergy(imL, imR, volL, volR, prm, D - 1)
+    got = sweep(E1, 12)
+    batches, calls = E1.combine_stats
+    launches = E1.launch_count
+    E1.close()
+    for a, b in zip(ref, got):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    n = 3 * len(cells)
+    assert calls > n // 2 and batches < calls / 2, (batches, calls, n)   # most calls were served in groups
+    print(f"{n} calls: {calls} combined into {batches} launches, {launches} kernel launches in total")

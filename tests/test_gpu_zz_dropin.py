@@ -17,11 +17,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "dropin_check")
 
 
-@pytest.mark.parametrize("energy", ["CostVolumeEnergy", "NaiveStereoEnergy"])
-def test_reference_loop_through_the_adapter(energy):
+@pytest.mark.parametrize("energy,threads", [("CostVolumeEnergy", 1), ("NaiveStereoEnergy", 1), ("CostVolumeEnergy", 8)])
+def test_reference_loop_through_the_adapter(energy, threads):
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/dropin_check was not built (needs the reference sources at build time)")
-    cmd = [EXE] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
+    # threads > 1: the cells of a group in an OpenMP parallel for, as FastGCStereo.h:30 -- concurrent calls of the virtual,
+    # which the library combines into batched launches (lexp_combine_stats)
+    cmd = [EXE, "--threads", str(threads)] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     line = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else ""
     assert line.startswith("{"), (res.returncode, res.stdout[-500:], res.stderr[-2000:])
@@ -32,3 +34,5 @@ def test_reference_loop_through_the_adapter(energy):
     assert d["init_calls"] > 1000 and d["move_calls"] > 10000
     assert d["mask_mismatch"] == 0, d
     assert d["ok"] is True and res.returncode == 0, d
+    if threads > 1:
+        assert d["combined_calls"] > 0 and d["combined_launches"] <= d["combined_calls"], d
