@@ -31,4 +31,4 @@ def test_reference_loop_through_the_adapter_on_the_emulator(energy, threads):
     if energy == "CostVolumeEnergy":
         assert d["out_of_tolerance"] == 0 and d["worst_err_over_tol"] < 0.5, d
     if threads > 1:  # the reference's OpenMP loop: concurrent calls of the virtual are served by combined launches
-        assert d["combined_calls"] > d["move_calls"] // 4 and d["combined_launches"] < d["combined_calls"], d
+        assert d["combined_calls"] > d["move_calls"] // 10 and d["combined_launches"] < d["combined_calls"], d
