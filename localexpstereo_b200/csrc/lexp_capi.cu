@@ -118,12 +118,60 @@ struct lexp_ctx {
     float* cb_hout = nullptr;      // pinned
     size_t cb_items_cap = 0, cb_planes_cap = 0, cb_out_cap = 0;
     int64_t combined_batches = 0, combined_calls = 0;
+#if LEXP_TRACE
+    long long* d_trace = nullptr;
+    size_t trace_cap = 0;
+#endif
 };
 
 namespace {
 
+#if LEXP_TRACE
+// diagnosis build: per-team averages of {total cycles, waiting for input, waiting for an output buffer} of one launch
+void report_trace(lexp_ctx* c, int nitems) {
+    constexpr int NW = kThreads / 32;
+    std::vector<long long> h((size_t)nitems * NW * 4);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return;
+    if (cudaMemcpy(h.data(), c->d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    const char* names[5] = {"A", "H1", "H2", "C", "E"};
+    const int first[6] = {0, kWarpsA, kWarpsA + 1, kWarpsA + kWarpsH, kWarpsA + kWarpsH + kWarpsC, NW};
+    const char* path = getenv("LEXP_TRACE_FILE");
+    FILE* f = path ? fopen(path, "a") : stderr;
+    if (!f) return;
+    double chunks = 0;
+    for (int i = 0; i < nitems; i++) chunks += (double)h[(size_t)i * NW * 4 + 3];
+    fprintf(f, "launch items=%d chunks/item=%.1f", nitems, chunks / nitems);
+    for (int t = 0; t < 5; t++) {
+        double tot = 0, win = 0, wout = 0;
+        long long n = 0;
+        for (int i = 0; i < nitems; i++)
+            for (int w = first[t]; w < first[t + 1]; w++) {
+                const long long* o = &h[((size_t)i * NW + w) * 4];
+                tot += (double)o[0]; win += (double)o[1]; wout += (double)o[2]; n++;
+            }
+        fprintf(f, " | %s total %.0f wait_in %.0f wait_out %.0f busy %.0f (cycles/chunk %.0f)", names[t], tot / n, win / n, wout / n,
+                (tot - win - wout) / n, (tot - win - wout) / n / (chunks / nitems));
+    }
+    fprintf(f, "\n");
+    if (path) fclose(f);
+}
+#endif
+
 template <int R_T, bool NAIVE>
-int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
+int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem) {
+    KParams kp = kp_in;
+#if LEXP_TRACE
+    {
+        const size_t need = (size_t)nitems * (kThreads / 32) * 4;
+        if (need > c->trace_cap) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(c->d_trace); c->d_trace = nullptr; c->trace_cap = 0;
+            LEXP_CUDA(cudaMalloc(&c->d_trace, 2 * need * sizeof(long long)));
+            c->trace_cap = 2 * need;
+        }
+        kp.trace = c->d_trace;
+    }
+#endif
     auto kern = lexp_fused_kernel<R_T, NAIVE>;
     if (!c->smem_configured) {  // one R instantiation per context
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
@@ -143,6 +191,9 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
     LEXP_LAUNCH(kern, nitems, kThreads, smem, c->stream, kp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
+#if LEXP_TRACE
+    report_trace(c, nitems);
+#endif
     return LEXP_OK;
 }
 

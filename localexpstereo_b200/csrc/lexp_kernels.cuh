@@ -55,6 +55,12 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_PDL
 #define LEXP_PDL 0
 #endif
+// LEXP_TRACE: diagnosis build.  Every warp accumulates the clock cycles it spends waiting for its input link (consume_begin) and
+//   for a free output buffer (produce_begin) and writes {total, wait_in, wait_out, chunks} at the end; lexp_capi.cu averages
+//   them per team after every launch (LEXP_TRACE_FILE).  Shows directly which team the pipeline waits for.  Not a product build.
+#ifndef LEXP_TRACE
+#define LEXP_TRACE 0
+#endif
 #ifndef LEXP_MIN_CTAS
 #define LEXP_MIN_CTAS 2
 #endif
@@ -105,6 +111,9 @@ struct KParams {
     float thresh_color, thresh_gradient;  // StereoEnergy.h:663-664
     int mode;                             // 0: left reference view, 1: right
     int fast_ok;                        // MIN == 0, MAX == D-1, th_col >= 0 and the volume holds no NaN/Inf
+#if LEXP_TRACE
+    long long* trace;                   // [items][kThreads / 32][4]
+#endif
 };
 
 // largest output-tile width the team sizes allow for box radius R
@@ -165,6 +174,10 @@ __device__ __forceinline__ void produce_begin(int link, int c, int nthreads) { i
 __device__ __forceinline__ void produce_end(int link, int c, int nthreads) { bar_arrive(4 * link + (c & 1), nthreads); }
 __device__ __forceinline__ void consume_begin(int link, int c, int nthreads) { bar_sync(4 * link + (c & 1), nthreads); }
 __device__ __forceinline__ void consume_end(int link, int c, int nChunks, int nthreads) { if (c + 2 < nChunks) bar_arrive(4 * link + 2 + (c & 1), nthreads); }
+#if LEXP_TRACE  // timed versions: `(name)(...)` calls the function, not the macro
+#define consume_begin(link, c, n) do { const unsigned t__ = (unsigned)clock64(); (consume_begin)(link, c, n); tr_wait_in += (unsigned)clock64() - t__; } while (0)
+#define produce_begin(link, c, n) do { const unsigned t__ = (unsigned)clock64(); (produce_begin)(link, c, n); tr_wait_out += (unsigned)clock64() - t__; } while (0)
+#endif
 constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 + 1), kLinkHE = 32 * (1 + 2);  // threads per link
 
 // Inverse affine map (dst pixel of the filterRect -> source pixel of the other view) of NaiveStereoEnergy
@@ -202,6 +215,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 
 #if LEXP_PDL && !defined(LEXP_EMU)
     asm volatile("griddepcontrol.launch_dependents;");
+#endif
+#if LEXP_TRACE
+    unsigned tr_wait_in = 0, tr_wait_out = 0;  // 32-bit cycle counts: a work item runs for ~1e5 cycles
+    const unsigned tr_t0 = (unsigned)clock64();
 #endif
     const Item it = P.items[blockIdx.x];
     const Plane4 pl = P.planes[it.call];
@@ -766,6 +783,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             }
         }
     }
+#if LEXP_TRACE
+    if (lane == 0 && P.trace) {
+        long long* o = P.trace + ((size_t)blockIdx.x * (kThreads / 32) + warp) * 4;
+        o[0] = (unsigned)clock64() - tr_t0; o[1] = tr_wait_in; o[2] = tr_wait_out; o[3] = nChunks;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

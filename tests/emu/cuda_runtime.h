@@ -212,6 +212,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     return r;
 }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
+static inline long long clock64() { return (long long)__builtin_ia32_rdtsc(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }

@@ -8,9 +8,10 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["pdl", "occ3pdl"])
-def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch):
+@pytest.mark.parametrize("variant", ["pdl", "occ3pdl", "trace"])
+def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
+    monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it
     import localexpstereo_b200 as L
     from oracle import lexp_oracle as O
     with emu_lib.emulated(variant=variant):
@@ -34,3 +35,6 @@ def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monke
             E.close()
             outs.append(img)
     assert np.array_equal(outs[0], outs[1])
+    if variant == "trace":
+        lines = open(tmp_path / "trace.txt").read().strip().splitlines()
+        assert len(lines) >= 3 and all(" | A total " in l and " | E total " in l for l in lines)
