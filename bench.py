@@ -204,6 +204,25 @@ class CpuArm:
             a.close()
 
 
+def cpu_baseline_beside(W, H, D, windR, imL, vol_h, naive, imR_h, groups, layer_of, planes_h):
+    """`cpu_baseline` of our arm: group 0 of every layer, all its proposal steps, on the host cores.  `groups[i]` has .layer,
+    .group, .cells, .n_steps; `layer_of(l)` gives the rectangles; `planes_h[i]` is [K][n][4]."""
+    arm = CpuArm(W, H, D, windR, imL, vol_h, naive=naive, imR=imR_h)
+    sample, used = [], []
+    for gi, g in enumerate(groups):
+        if g.group != 0:
+            continue
+        lay = layer_of(g.layer)
+        sample.append(([lay.filterRegions[r] for r in g.cells], [lay.sharedRegions[r] for r in g.cells], np.ascontiguousarray(planes_h[gi])))
+        used.append(f"L{g.layer}g0x{g.n_steps}")
+    arm.calibrate(*sample[0])  # also warms
+    tot_e, tot_t = arm.time_sample(sample)
+    cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": arm.nthr, "kind": arm.kind,
+           "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s); calibration: {arm.calib_note()}"}
+    arm.close()
+    return cpu
+
+
 def run_reference(args, W, H, D, windR, rank, world):
     """CPU arm with all host threads, on a bounded sample of the sweep (group 0 of every layer, all proposal steps)."""
     if rank != 0:
@@ -406,19 +425,7 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     # ---- CPU baseline beside it (rank 0, N = 1): the reference's CPU implementation on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm(W, H, D, windR, imL, None if naive else vol_h, naive=naive, imR=imR_h if naive else None)
-        sample, used = [], []
-        for gi, g in enumerate(sweep.groups):
-            if g.group != 0:
-                continue
-            lay = sweep.layer(g.layer)
-            sample.append(([lay.filterRegions[r] for r in g.cells], [lay.sharedRegions[r] for r in g.cells], np.ascontiguousarray(planes_h[gi])))
-            used.append(f"L{g.layer}g0x{g.n_steps}")
-        arm.calibrate(*sample[0])  # also warms
-        tot_e, tot_t = arm.time_sample(sample)
-        cpu = {"value": tot_e / tot_t, "unit": UNIT, "cores": arm.nthr, "kind": arm.kind,
-               "sample": f"group 0 of each layer, all steps ({'+'.join(used)}; {tot_e} evals in {tot_t:.2f} s); calibration: {arm.calib_note()}"}
-        arm.close()
+        cpu = cpu_baseline_beside(W, H, D, windR, imL, None if naive else vol_h, naive, imR_h if naive else None, sweep.groups, sweep.layer, planes_h)
 
     if rank == 0:
         out = {

@@ -179,3 +179,29 @@ def test_emulation_hooks_never_reach_the_product_library():
     syms = subprocess.run(["nm", "-C", _capi.SO_PATH], capture_output=True, text=True).stdout
     assert "emu::" not in syms and "run_block" not in syms
     assert "lexp_fused_kernel" in syms  # the device kernels are what the library carries
+
+
+def test_bench_cpu_baseline_block_of_the_gpu_arm():
+    """bench.py's `cpu_baseline` (computed beside the GPU number at N = 1) with a stand-in for the sweep object: same
+    attributes as sweep.UnarySweep's groups; runs the reference's CPU implementation on group 0 of every layer."""
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, ROOT)
+    import bench
+    import localexpstereo_b200 as L
+    from localexpstereo_b200 import synth
+    W, H, D, windR = 200, 150, 16, 20
+    imL, vol = bench.make_inputs(W, H, D)
+    lm = L.LayerManager(W, H, windR)
+    layers = [lm.addLayer(u) for u in (5, 15)]
+    groups, planes = [], []
+    for li, lay in enumerate(layers):
+        for gj, cells in enumerate(lay.disjointRegionSets[:2]):
+            K = 3 - li
+            groups.append(SimpleNamespace(layer=li, group=gj, cells=list(cells), n_steps=K))
+            planes.append(np.ascontiguousarray(synth.synthetic_planes(lay.unitRegions, K, D, 7 + li)[:, cells, :]))
+    cpu = bench.cpu_baseline_beside(W, H, D, windR, imL, vol, False, None, groups, lambda l: layers[l], planes)
+    assert cpu["value"] > 0 and cpu["kind"] in ("reference", "port") and cpu["cores"] >= 1 and "L0g0x3+L1g0x2" in cpu["sample"]
+    imR = synth.synthetic_image(H, W, 43)
+    cpu = bench.cpu_baseline_beside(W, H, D, windR, imL, None, True, imR, groups, lambda l: layers[l], planes)
+    assert cpu["value"] > 0 and cpu["kind"] == "reference"
