@@ -45,6 +45,13 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #define LEXP_KG 4
 #define LEXP_C_ROLLING 1
 #define LEXP_H_REREAD 1
+#define LEXP_LINK_STRIDES 1
+#endif
+// LEXP_LINK_STRIDES: the row buffers of the four links get the stride their own width needs (hb1: VW columns, ho1 / hb2:
+//   VW - 2R, ho2: VW - 4R) instead of all using the widest: 5.5 KB less shared memory for a 60-column tile (76.8 -> 71.3 KB at
+//   R = 10), which is what lets three CTAs of the typical layer-0 tile share an SM.
+#ifndef LEXP_LINK_STRIDES
+#define LEXP_LINK_STRIDES 0
 #endif
 // LEXP_PDL: programmatic dependent launch.  Every thread signals `griddepcontrol.launch_dependents` at the top of the kernel, so
 //   the NEXT batched evaluation of the stream (launched with the programmatic-stream-serialization attribute, lexp_capi.cu) may
@@ -130,7 +137,12 @@ __host__ __device__ inline int srow_stride(int vw) {
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
-    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + 8 * kCH * srow_stride(vw) + 3 * ((vh + 3) / 4)) * 16;
+#if LEXP_LINK_STRIDES
+    const int rows = 2 * kCH * (srow_stride(vw) + 2 * srow_stride(vw - 2 * R) + srow_stride(vw - 4 * R));
+#else
+    const int rows = 8 * kCH * srow_stride(vw);
+#endif
+    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4)) * 16;
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -226,7 +238,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     const int VW = it.ow + 4 * R;
     const int X0 = it.ox0 - 2 * R;
     const int W2 = VW - 2 * R;
-    const int SW = srow_stride(VW);
+    const int SW = srow_stride(VW);   // row stride of hb1 (stage-1 column sums, VW columns)
+#if LEXP_LINK_STRIDES
+    const int SW2 = srow_stride(W2), SW3 = srow_stride(it.ow);  // ho1 / hb2 hold W2 columns, ho2 the ow output columns
+#else
+    const int SW2 = SW, SW3 = SW;
+#endif
     const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
     // streamed rows y = ys + v, v in [0, VHs): the dependency cone of the tile, minus leading rows above
     // the filterRect (they are zero padding).  Rows >= fy1 are zero rows that flush the running sums.
@@ -240,15 +257,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     uint2* ring1 = reinterpret_cast<uint2*>(smem);   // [K][VW] {p, packed guide}: the products are recomputed when a row leaves the window
     F4* ring2 = smem + (K * VW + 1) / 2;              // [K][W2]
     F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
-    F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW] stage-1 box sums      (index: column - X0 - R)
-    F4* hb2 = ho1 + 2 * kCH * SW;          // [2][CH][SW] stage-2 column sums   (index: column - X0 - R)
-    F4* ho2 = hb2 + 2 * kCH * SW;          // [2][CH][SW] stage-2 box sums      (index: column - X0 - 2R)
-    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW);  // [VHs] 1 / (#rows of the window inside filterRect)
+    F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW2] stage-1 box sums     (index: column - X0 - R)
+    F4* hb2 = ho1 + 2 * kCH * SW2;         // [2][CH][SW2] stage-2 column sums  (index: column - X0 - R)
+    F4* ho2 = hb2 + 2 * kCH * SW2;         // [2][CH][SW3] stage-2 box sums     (index: column - X0 - 2R)
+    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW3);  // [VHs] 1 / (#rows of the window inside filterRect)
     float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
     int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
-        const int total = (K * VW + 1) / 2 + K * W2 + 8 * kCH * SW;
+        const int total = (K * VW + 1) / 2 + K * W2 + 2 * kCH * (SW + 2 * SW2 + SW3);
         for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
         for (int v = tid; v < VHs; v += kThreads) {
             const int y = ys + v;
@@ -483,8 +500,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             consume_begin(lin, c, nin);
             produce_begin(lout, c, nout);
             if (k < nruns && v >= vmin && v < vmax) {
-                const F4* in = inb + ((c & 1) * kCH + r) * SW + 9 * k;
-                F4* out = outb + ((c & 1) * kCH + r) * SW + 9 * k;
+                const F4* in = inb + ((c & 1) * kCH + r) * (st2 ? SW2 : SW) + 9 * k;
+                F4* out = outb + ((c & 1) * kCH + r) * (st2 ? SW3 : SW2) + 9 * k;
                 if (R_T > 0) {
 #if !LEXP_H_REREAD
                     F4 w[kRun - 1];
@@ -585,8 +602,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 consume_begin(1, c, kLinkHC);
                 produce_begin(2, c, kLinkCH);
                 if (t < W2) {
-                    const F4* ho = ho1 + (c & 1) * kCH * SW + sidx(t);
-                    F4* hb = hb2 + (c & 1) * kCH * SW + sidx(t);
+                    const F4* ho = ho1 + (c & 1) * kCH * SW2 + sidx(t);
+                    F4* hb = hb2 + (c & 1) * kCH * SW2 + sidx(t);
 #pragma unroll
                     for (int r = 0; r < kCH; r++) {
                         const int v = c * kCH + r;
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                             F4 ab = f4zero();
                             if (colC && v < vC1) {
                                 const float invN = inv_nx * s_invny[v - R];
-                                const F4 B = ho[r * SW];
+                                const F4 B = ho[r * SW2];
                                 float Bp, B0, B1, B2;
                                 up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
                                 const float m0 = ca[r].x, m1 = ca[r].y, m2 = ca[r].z, i00 = ca[r].w;
@@ -613,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                             const F4 old = *sl;
                             *sl = ab;
                             acc = f4add(acc, f4sub(ab, old));
-                            hb[r * SW] = acc;  // column sum centred on row y - 2R
+                            hb[r * SW2] = acc;  // column sum centred on row y - 2R
                             slot = (slot + 1 == K) ? 0 : slot + 1;
                         }
                     }
@@ -641,8 +658,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         for (int c = 0; c < nChunks; c++) {
             consume_begin(1, c, kLinkHC);
             produce_begin(2, c, kLinkCH);
-            const F4* ho = ho1 + (c & 1) * kCH * SW + sidx(t < W2 ? t : 0);
-            F4* hb = hb2 + (c & 1) * kCH * SW + sidx(t < W2 ? t : 0);
+            const F4* ho = ho1 + (c & 1) * kCH * SW2 + sidx(t < W2 ? t : 0);
+            F4* hb = hb2 + (c & 1) * kCH * SW2 + sidx(t < W2 ? t : 0);
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
                 LEXP_LOADS_LANDED("+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
@@ -655,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                     F4 ab = f4zero();
                     if (colC && v < vC1) {
                         const float invN = inv_nx * s_invny[v - R];
-                        const F4 B = ho[r * SW];
+                        const F4 B = ho[r * SW2];
                         float Bp, B0, B1, B2;
                         up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
                         const float m0 = ca.x, m1 = ca.y, m2 = ca.z, i00 = ca.w;
@@ -674,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                     const F4 old = *sl;
                     *sl = ab;
                     acc = f4add(acc, f4sub(ab, old));
-                    hb[r * SW] = acc;  // column sum centred on row y - 2R
+                    hb[r * SW2] = acc;  // column sum centred on row y - 2R
                     slot = (slot + 1 == K) ? 0 : slot + 1;
                 }
             }
@@ -740,12 +757,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 issue();
                 consume_begin(3, c, kLinkHE);
                 if (colE) {
-                    const F4* ho = ho2 + (c & 1) * kCH * SW + sidx(t);
+                    const F4* ho = ho2 + (c & 1) * kCH * SW3 + sidx(t);
 #pragma unroll
                     for (int r = 0; r < kCH; r++) {
                         const int v = c * kCH + r;
                         if (v >= vE0 && v < VHs) {
-                            const F4 S = ho[r * SW];
+                            const F4 S = ho[r * SW3];
                             float S0, S1, S2, Sb;
                             up2(S.lo, S0, S1); up2(S.hi, S2, Sb);
                             const uint32_t g = cg[r];

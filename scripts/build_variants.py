@@ -18,6 +18,7 @@ VARIANTS = {
     "kg4": ["-DLEXP_KG=4"],                         # single knobs of occ3 at 2 CTAs / SM (register relief only)
     "crolling": ["-DLEXP_C_ROLLING=1"],
     "hreread": ["-DLEXP_H_REREAD=1"],
+    "linkstr": ["-DLEXP_LINK_STRIDES=1"],           # per-link row-buffer strides at 2 CTAs / SM: 5.5 KB less shared memory, more L1
     "trace": ["-DLEXP_TRACE=1"],                    # diagnosis: per-team wait / busy cycles of every launch (scripts/gpu_trace.sh)
     "occ3trace": ["-DLEXP_OCC3", "-DLEXP_TRACE=1"],
 }

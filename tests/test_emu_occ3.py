@@ -71,3 +71,11 @@ def naive_scene():
 
 def test_occ3_naive_matches_reference_minted_vectors(naive_scene):
     _n.test_naive_matches_reference_minted_vectors(naive_scene)
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_occ3_fuzz(seed):
+    """A slice of tests/test_emu_fuzz.py on this variant (random rects, radii, planes; the per-link buffer strides and the
+    75 KB tiling are what differ from the shipped kernel)."""
+    import test_emu_fuzz as _f
+    _f.test_random_rects_and_planes_match_the_oracle(seed)
