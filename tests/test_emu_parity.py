@@ -23,6 +23,35 @@ def _use_emulator():
 
 scene = _p.scene
 
+
+class _HostAsDeviceMemory:
+    """On the emulator device memory is host memory: numpy arrays stand in for the device buffers."""
+
+    @staticmethod
+    def zeros(shape, fill=0.0):
+        import numpy as np
+        return np.full(shape, fill, np.float32)
+
+    @staticmethod
+    def upload(a):
+        import numpy as np
+        return np.ascontiguousarray(a)
+
+    @staticmethod
+    def ptr(t):
+        return t.ctypes.data
+
+    @staticmethod
+    def download(t):
+        return t
+
+
+@pytest.fixture(scope="module")
+def devmem():
+    return _HostAsDeviceMemory()
+
+
+test_emu_device_image_and_tile_outputs = _p.test_device_image_and_tile_outputs
 test_emu_stats_match_oracle = _p.test_stats_match_oracle
 test_emu_cells_of_a_layer = _p.test_cells_of_a_layer
 test_emu_single_cell_virtuals = _p.test_single_cell_virtuals

@@ -187,3 +187,76 @@ def test_nonzero_min_disparity_and_odd_max(scene):
             ref = Or.compute_unary_potential(f, t, p)
             assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"min {mn} max {mx} plane {p}")
         E.close()
+
+
+class _TorchDeviceMemory:
+    """Device buffers for the device-output entry points: torch CUDA tensors on the GPU."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+
+    # the context launches on its own non-blocking stream: buffers must be complete before their pointers are handed over
+    def zeros(self, shape, fill=0.0):
+        t = self.torch.full(shape, fill, dtype=self.torch.float32, device="cuda")
+        self.torch.cuda.synchronize()
+        return t
+
+    def upload(self, a):
+        t = self.torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        self.torch.cuda.synchronize()
+        return t
+
+    @staticmethod
+    def ptr(t):
+        return t.data_ptr()
+
+    def download(self, t):
+        self.torch.cuda.synchronize()
+        return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def devmem():
+    return _TorchDeviceMemory()
+
+
+def test_device_image_and_tile_outputs(scene, devmem):
+    """lexp_plan_eval_device (H x W cost image in device memory, host or device planes) and lexp_plan_eval_device_tiles
+    (per-call contiguous tiles = the all-gather payload of the cell shard, sweep.tile_offsets) against the host path."""
+    from localexpstereo_b200.sweep import tile_offsets
+    L, E = scene["L"], scene["E"]
+    H, W, D = scene["H"], scene["W"], scene["D"]
+    lay = L.LayerManager(W, H, scene["windR"]).addLayer(14)
+    g = lay.disjointRegionSets[1]
+    fr = [lay.filterRegions[r] for r in g]
+    tr = [lay.sharedRegions[r] for r in g]
+    plan = E.make_plan(fr, tr)
+    rng = O.CvRNG(77)
+    offs, total = tile_offsets(tr)
+    for mode in (0, 1):
+        planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+        ref = np.full((H, W), -7.0, np.float32)
+        plan.eval_host(planes, ref, True, mode)
+        # device image, host planes; padded pitch
+        pitch = (W + 13) * 4
+        d_img = devmem.zeros((H, W + 13), -7.0)
+        plan.eval_device(planes, devmem.ptr(d_img), pitch, True, mode)
+        E.sync()
+        got = devmem.download(d_img)
+        assert np.array_equal(got[:, :W], ref) and (got[:, W:] == -7.0).all()
+        # device image, device planes
+        d_pl = devmem.upload(np.asarray(planes, np.float32))
+        d_img2 = devmem.zeros((H, W), -7.0)
+        plan.eval_device(devmem.ptr(d_pl), devmem.ptr(d_img2), W * 4, True, mode, planes_on_device=True)
+        E.sync()
+        assert np.array_equal(devmem.download(d_img2), ref)
+        # tiles
+        d_tiles = devmem.zeros((total + 5,), -9.0)
+        plan.eval_device_tiles(planes, devmem.ptr(d_tiles), True, mode)
+        E.sync()
+        tiles = devmem.download(d_tiles)
+        assert (tiles[total:] == -9.0).all()
+        for (x, y, w, h), o in zip(tr, offs):
+            assert np.array_equal(tiles[o:o + w * h].reshape(h, w), ref[y:y + h, x:x + w])
+    plan.close()
