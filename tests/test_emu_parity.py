@@ -133,3 +133,34 @@ def test_emu_concurrent_calls_are_combined_into_batched_launches(scene, monkeypa
     n = 3 * len(cells)
     assert calls > n // 4 and batches < calls, (batches, calls, n)   # calls were served in groups (typically ~280 of 288 in ~45 launches)
     print(f"{n} calls: {calls} combined into {batches} launches, {launches} kernel launches in total")
+
+
+def test_emu_zero_copy_and_staged_host_paths_agree(scene):
+    """lexp_plan_eval_host writes straight into a registered (mapped) cost image, and through a compact device buffer + host
+    scatter otherwise: same pixels, and only costs(targetRect) is touched in both."""
+    import numpy as np
+    from oracle import lexp_oracle as O
+    L, E, H, W, D = (scene[k] for k in "L E H W D".split())
+    lay = L.LayerManager(W, H, 20).addLayer(18)
+    g = lay.disjointRegionSets[0]
+    fr = [lay.filterRegions[r] for r in g]
+    tr = [lay.sharedRegions[r] for r in g]
+    plan = E.make_plan(fr, tr)
+    rng = O.CvRNG(31)
+    planes = np.stack([O.create_random_label(rng, *lay.unitRegions[r][:2], 0.0, D - 1.0) for r in g])
+    staged = np.full((H, W), -7.0, np.float32)
+    plan.eval_host(planes, staged, True, 0)
+    mapped = np.full((H, W), -7.0, np.float32)
+    L.host_register(mapped)
+    try:
+        plan.eval_host(planes, mapped, True, 0)
+    finally:
+        L.host_unregister(mapped)
+    assert np.array_equal(staged, mapped)
+    mask = np.zeros((H, W), bool)
+    for x, y, w, h in tr:
+        mask[y:y + h, x:x + w] = True
+    assert (staged[~mask] == -7.0).all() and (staged[mask] != -7.0).all()
+    with pytest.raises(L.LexpError):
+        L.host_unregister(mapped)  # not registered any more
+    plan.close()
