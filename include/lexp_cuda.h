@@ -9,7 +9,8 @@
  * evaluation runs hand-written sm_100a kernels, or fails.
  *
  * Threading: a context may be used from several host threads (the reference calls the
- * virtuals from OpenMP threads, FastGCStereo.h:30-49); calls are serialised internally.
+ * virtuals from OpenMP threads, FastGCStereo.h:30-49).  Device work is serialised internally;
+ * concurrent lexp_eval_cell calls are combined into batched launches (lexp_combine_stats).
  */
 #ifndef LEXP_CUDA_H_
 #define LEXP_CUDA_H_

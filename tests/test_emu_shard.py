@@ -78,13 +78,17 @@ def test_cell_shard_with_the_emulated_engine_world2_gloo():
     import torch.multiprocessing as mp
     from emu import emu_lib
     emu_lib.load()  # build the emulator library once, before the workers race for it
+    os.environ["LEXP_EMU_NO_REBUILD"] = "1"  # inherited by the spawned workers: they load what the parent built
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=400) for _ in procs]
+    try:
+        res = [q.get(timeout=400) for _ in procs]
+    finally:
+        os.environ.pop("LEXP_EMU_NO_REBUILD", None)
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
