@@ -21,7 +21,7 @@ def test_reference_loop_through_the_adapter_on_the_emulator(energy, threads):
     assert build_ref.build() is not None
     if not os.path.exists(build_ref.DROPIN_EMU):
         pytest.skip("dropin_check_emu was not built")
-    cmd = [build_ref.DROPIN_EMU, "--W", "80", "--H", "64", "--K", "1", "--threads", str(threads)] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
+    cmd = [build_ref.DROPIN_EMU, "--W", "64", "--H", "56", "--K", "1", "--threads", str(threads)] + (["--naive"] if energy == "NaiveStereoEnergy" else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     d = json.loads(res.stdout.strip().splitlines()[-1])
     print(d)
