@@ -139,18 +139,18 @@ void report_trace(lexp_ctx* c, int nitems) {
     FILE* f = path ? fopen(path, "a") : stderr;
     if (!f) return;
     double chunks = 0;
-    for (int i = 0; i < nitems; i++) chunks += (double)h[(size_t)i * NW * 4 + 3];
+    for (int i = 0; i < nitems; i++) chunks += (double)(h[(size_t)i * NW * 4 + 3] & 0xffffffffLL);
     fprintf(f, "launch items=%d chunks/item=%.1f", nitems, chunks / nitems);
     for (int t = 0; t < 5; t++) {
-        double tot = 0, win = 0, wout = 0;
+        double tot = 0, win = 0, wout = 0, wld = 0;
         long long n = 0;
         for (int i = 0; i < nitems; i++)
             for (int w = first[t]; w < first[t + 1]; w++) {
                 const long long* o = &h[((size_t)i * NW + w) * 4];
-                tot += (double)o[0]; win += (double)o[1]; wout += (double)o[2]; n++;
+                tot += (double)o[0]; win += (double)o[1]; wout += (double)o[2]; wld += (double)((unsigned long long)o[3] >> 32); n++;
             }
-        fprintf(f, " | %s total %.0f wait_in %.0f wait_out %.0f busy %.0f (cycles/chunk %.0f)", names[t], tot / n, win / n, wout / n,
-                (tot - win - wout) / n, (tot - win - wout) / n / (chunks / nitems));
+        fprintf(f, " | %s total %.0f wait_in %.0f wait_out %.0f busy %.0f wait_ld %.0f", names[t], tot / n, win / n, wout / n,
+                (tot - win - wout) / n, wld / n);
     }
     fprintf(f, "\n");
     if (path) fclose(f);

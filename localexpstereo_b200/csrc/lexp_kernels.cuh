@@ -189,6 +189,15 @@ __device__ __forceinline__ void consume_end(int link, int c, int nChunks, int nt
 #if LEXP_TRACE  // timed versions: `(name)(...)` calls the function, not the macro
 #define consume_begin(link, c, n) do { const unsigned t__ = (unsigned)clock64(); (consume_begin)(link, c, n); tr_wait_in += (unsigned)clock64() - t__; } while (0)
 #define produce_begin(link, c, n) do { const unsigned t__ = (unsigned)clock64(); (produce_begin)(link, c, n); tr_wait_out += (unsigned)clock64() - t__; } while (0)
+// cycles until a register filled by an earlier global load is readable (the MOV stalls on the scoreboard)
+#ifndef LEXP_EMU
+#define LEXP_TRACE_LOAD_WAIT(reg32) do { const unsigned t__ = (unsigned)clock64(); unsigned d__; asm volatile("mov.b32 %0, %1;" : "=r"(d__) : "r"(reg32)); \
+                                         tr_wait_ld += (unsigned)clock64() - t__; } while (0)
+#else
+#define LEXP_TRACE_LOAD_WAIT(reg32) do { tr_wait_ld += 0u * (unsigned)(reg32); } while (0)
+#endif
+#else
+#define LEXP_TRACE_LOAD_WAIT(reg32) ((void)0)
 #endif
 constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 + 1), kLinkHE = 32 * (1 + 2);  // threads per link
 
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
 #if LEXP_TRACE
-    unsigned tr_wait_in = 0, tr_wait_out = 0;  // 32-bit cycle counts: a work item runs for ~1e5 cycles
+    unsigned tr_wait_in = 0, tr_wait_out = 0, tr_wait_ld = 0;  // 32-bit cycle counts: a work item runs for ~1e5 cycles
     const unsigned tr_t0 = (unsigned)clock64();
 #endif
     const Item it = P.items[blockIdx.x];
@@ -428,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         issue();
         int c = 0;  // pipeline chunk
         while (c < nChunks) {
+            LEXP_TRACE_LOAD_WAIT(lg[kG - 1]);  // the youngest load of the batch in flight
             float wp[kG];
             uint32_t wg[kG];
 #pragma unroll
@@ -590,6 +600,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         issue();
         for (int c = 0; c < nChunks; c++) {
             {
+                LEXP_TRACE_LOAD_WAIT(__float_as_uint(sc[kCH - 1]));
                 float4 ca[kCH], cb[kCH];
                 float cc[kCH];
 #pragma unroll
@@ -748,6 +759,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #endif
         for (int c = 0; c < nChunks; c++) {
             {
+                LEXP_TRACE_LOAD_WAIT(gq[kCH - 1]);
                 uint32_t cg[kCH];
 #pragma unroll
                 for (int r = 0; r < kCH; r++) {
@@ -803,7 +815,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #if LEXP_TRACE
     if (lane == 0 && P.trace) {
         long long* o = P.trace + ((size_t)blockIdx.x * (kThreads / 32) + warp) * 4;
-        o[0] = (unsigned)clock64() - tr_t0; o[1] = tr_wait_in; o[2] = tr_wait_out; o[3] = nChunks;
+        o[0] = (unsigned)clock64() - tr_t0; o[1] = tr_wait_in; o[2] = tr_wait_out; o[3] = nChunks | ((long long)tr_wait_ld << 32);
     }
 #endif
 }
