@@ -32,6 +32,7 @@ namespace {
 struct Tally {
     long calls = 0, px = 0, bad = 0, mask_mismatch = 0;
     double worst = 0;  // max |a-b| / (1e-4 * max(|a|, 1e-3))
+    double t_ref = 0, t_test = 0;  // seconds this thread spent inside the reference CPU energy / the energy under test
 };
 
 void compare(const cv::Mat& a, const cv::Mat& b, const cv::Rect& r, Tally& t) {
@@ -159,8 +160,11 @@ int main(int argc, char** argv) {
                                 prop->startIterations(currentLabeling, unitRegion, iteration);
                                 while (prop->isContinued()) {
                                     Plane label = prop->getNextProposal();
+                                    const double t0 = omp_get_wtime();
                                     A->ComputeUnaryPotential(layer.filterRegions[r], sharedRegion, proposalCost(layer.filterRegions[r]), label, reusable, mode);
+                                    const double t1 = omp_get_wtime();
                                     B->ComputeUnaryPotential(layer.filterRegions[r], sharedRegion, proposalCostB(layer.filterRegions[r]), label, reusableB, mode);
+                                    moves.t_ref += t1 - t0; moves.t_test += omp_get_wtime() - t1;
                                     compare(proposalCost, proposalCostB, sharedRegion, moves);
                                     cv::Mat updateMask = subCurrentCost > subProposalCost;
                                     subProposalCost.copyTo(subCurrentCost, updateMask);
@@ -171,6 +175,7 @@ int main(int argc, char** argv) {
                         }
                         for (const Tally& t : part) {
                             moves.calls += t.calls; moves.px += t.px; moves.bad += t.bad; moves.mask_mismatch += t.mask_mismatch;
+                            moves.t_ref += t.t_ref; moves.t_test += t.t_test;
                             if (t.worst > moves.worst || std::isnan(t.worst)) moves.worst = t.worst;
                         }
                     }
@@ -181,6 +186,10 @@ int main(int argc, char** argv) {
         // NaiveStereoEnergy: the CUDA path evaluates the inverse affine map in closed form, the reference by LU; single source
         // pixels may flip at exact 1/32-pixel rounding ties, which the 21x21 filter spreads: allow a 2e-3 fraction there
         const bool ok = mm == 0 && (naive ? bad <= px * 2e-3 : bad == 0);
+        // thread-seconds inside the two energies during the expansion moves (same calls, same threads): how much faster the
+        // unchanged loop gets its unary costs through the adapter
+        char timing[160];
+        std::snprintf(timing, sizeof timing, "\"thread_seconds_reference_energy\": %.3f, \"thread_seconds_energy_under_test\": %.3f, ", moves.t_ref, moves.t_test);
         char extra[128] = "";
         if (!self) {  // how many of the concurrent calls the library served with combined launches
             int64_t batches = 0, calls = 0;
@@ -188,9 +197,9 @@ int main(int argc, char** argv) {
             std::snprintf(extra, sizeof extra, "\"combined_launches\": %lld, \"combined_calls\": %lld, ", (long long)batches, (long long)calls);
         }
         std::printf("{\"energy\": \"%s\", \"under_test\": \"%s\", \"W\": %d, \"H\": %d, \"D\": %d, \"init_calls\": %ld, \"move_calls\": %ld, "
-                    "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"threads\": %d, %s\"ok\": %s}\n",
+                    "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"threads\": %d, %s%s\"ok\": %s}\n",
                     naive ? "NaiveStereoEnergy" : "CostVolumeEnergy", selff ? "cpu GFfloat" : self ? "cpu-self-check" : "CudaCostVolumeEnergy adapter", W, H, D,
-                    init.calls, moves.calls, px, bad, mm, worst, threads, extra, ok ? "true" : "false");
+                    init.calls, moves.calls, px, bad, mm, worst, threads, extra, timing, ok ? "true" : "false");
         return ok ? 0 : 1;
     } catch (const std::exception& e) {
         std::printf("{\"error\": \"%s\"}\n", e.what());
