@@ -416,6 +416,27 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = evals_per_step / float(dt.item())
+    e2e_tiles = None
+    if args.e2e_tiles:  # optional: the same end-to-end sweep with per-cell contiguous tiles as the host output (lexp_plan_eval_host_tiles)
+        tiles_h = np.zeros(max(g.plan.target_px for g in sweep.groups), np.float32)
+        L.host_register(tiles_h)
+
+        def sweep_host_tiles():
+            for gi, g in enumerate(sweep.groups):
+                for k in range(g.n_steps):
+                    g.plan.eval_host_tiles(planes_h[gi][k], tiles_h, True, 0)
+
+        sweep_host_tiles()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            sweep_host_tiles()
+        torch.cuda.synchronize(dev)
+        dtt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
+        e2e_tiles = evals_per_step / float(dtt.item())
+        L.host_unregister(tiles_h)
     L.host_unregister(cost_h)
     for ph in planes_h:
         L.host_unregister(ph)
@@ -454,6 +475,8 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if e2e_tiles is not None:
+            out["e2e_tiles"] = {"value": e2e_tiles, "unit": UNIT, "note": "host output as per-cell contiguous tiles (lexp_plan_eval_host_tiles), zero-copy"}
         print(json.dumps(out), flush=True)
     if dist is not None:
         # A captured graph holds NCCL work: tearing the process group down underneath it can hang.  All results are
@@ -476,6 +499,7 @@ def main():
     ap.add_argument("--workload", default="synthetic_2048x1536x256_r20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the sweep eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--e2e-tiles", action="store_true", help="also time the end-to-end sweep with per-cell tile output (adds `e2e_tiles`)")
     ap.add_argument("--replicas", action="store_true",
                     help="BASELINE.json configs[3] style: every rank sweeps its OWN image pair (weak scaling, no data-path collective) "
                          "instead of sharding the cells of one pair (default, strong scaling)")

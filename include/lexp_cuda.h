@@ -122,6 +122,11 @@ LEXP_API int lexp_plan_eval_device(lexp_ctx* ctx, lexp_plan* plan, int mode, con
  * all-gathered between GPUs on the cell-shard path). */
 LEXP_API int lexp_plan_eval_device_tiles(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
                                          int planes_on_device, float* d_tiles, int with_check);
+/* Host planes in, the per-call contiguous tiles of lexp_plan_eval_device_tiles out into HOST memory (sum of the targetRect
+ * areas floats); blocking.  Zero-copy when `tiles` lies in a buffer registered with lexp_host_register, else one contiguous
+ * D2H copy.  For a loop restructured step-wise: the fusion of cell i (FastGCStereo.h:52-60) wraps tile i in a cv::Mat header. */
+LEXP_API int lexp_plan_eval_host_tiles(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes, float* tiles,
+                                       int with_check);
 /* Same, host in / host out (planes H2D, compact tiles D2H, scattered into cost_image); blocking. */
 LEXP_API int lexp_plan_eval_host(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes,
                                  float* cost_image, ptrdiff_t cost_step_bytes, int with_check);

@@ -50,6 +50,7 @@ SYMBOLS = {
     "lexp_plan_eval_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_ssize_t, C.c_int]),
     "lexp_plan_eval_device_tiles": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int]),
     "lexp_plan_eval_host": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_ssize_t, C.c_int]),
+    "lexp_plan_eval_host_tiles": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int]),
     "lexp_host_register": (C.c_int, [_P, C.c_size_t]),
     "lexp_host_unregister": (C.c_int, [_P]),
     "lexp_sync": (C.c_int, [_P]),

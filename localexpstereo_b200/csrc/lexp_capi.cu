@@ -580,6 +580,35 @@ int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp
     return run_plan(c, pl, mode, dp, d_tiles, 0, 1, with_check);
 }
 
+// Host planes in, per-call contiguous tiles out into HOST memory; blocking.  For the step-wise restructured loop
+// (INTEGRATION.md section 3): the fusion of cell i reads its proposal costs from a cv::Mat header over tile i
+// (cv::Mat(h, w, CV_32F, tiles + offset_i)), so nothing has to be scattered into an H x W image, and consecutive rows of a
+// tile are contiguous in memory (full-line PCIe writes on the zero-copy path).
+int lexp_plan_eval_host_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, float* tiles, int with_check) {
+    if (!c || !pl || !planes || !tiles || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, tiles, 0) == cudaSuccess && dptr) {  // registered (mapped) buffer: the kernel writes it directly
+        int rc = run_plan(c, pl, mode, pl->d_planes, reinterpret_cast<float*>(dptr), 0, 1, with_check);
+        if (rc) return rc;
+        LEXP_CUDA(cudaStreamSynchronize(c->stream));
+        return LEXP_OK;
+    }
+    cudaGetLastError();  // not a mapped buffer: compact device buffer, then one contiguous copy
+    const size_t nout = (size_t)pl->sum_s;
+    if (!pl->d_compact) {
+        LEXP_CUDA(cudaMalloc(&pl->d_compact, nout * sizeof(float)));
+        LEXP_CUDA(cudaHostAlloc(&pl->h_compact, nout * sizeof(float), cudaHostAllocDefault));
+    }
+    int rc = run_plan(c, pl, mode, pl->d_planes, pl->d_compact, 0, 1, with_check);
+    if (rc) return rc;
+    LEXP_CUDA(cudaMemcpyAsync(tiles, pl->d_compact, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    return LEXP_OK;
+}
+
 int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, float* cost_image,
                         ptrdiff_t step_bytes, int with_check) {
     if (!c || !pl || !planes || !cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");

@@ -159,6 +159,14 @@ class Plan:
                                         cost_image.strides[0], int(with_check)))
         return cost_image
 
+    def eval_host_tiles(self, planes, tiles: np.ndarray, with_check=True, mode=0):
+        """Per-call contiguous tiles into a host float32 array of target_px elements (tile i at sweep.tile_offsets)."""
+        pl = _plane_array(planes)
+        assert len(pl) == self.num_calls
+        assert tiles.dtype == np.float32 and tiles.ndim == 1 and tiles.size >= self.target_px and tiles.strides[0] == 4
+        check(lib().lexp_plan_eval_host_tiles(self.energy._h, self._h, mode, pl.ctypes.data, tiles.ctypes.data, int(with_check)))
+        return tiles
+
     def eval_device(self, planes, d_cost_ptr: int, step_bytes: int, with_check=True, mode=0, planes_on_device=False):
         """planes: numpy [n][4] (host) or an int device pointer when planes_on_device."""
         if planes_on_device:

@@ -260,3 +260,35 @@ def test_device_image_and_tile_outputs(scene, devmem):
         for (x, y, w, h), o in zip(tr, offs):
             assert np.array_equal(tiles[o:o + w * h].reshape(h, w), ref[y:y + h, x:x + w])
     plan.close()
+
+
+def test_host_tile_output(scene):
+    """lexp_plan_eval_host_tiles: per-call contiguous tiles in host memory, zero-copy (registered buffer) and staged, against
+    the H x W image path; a cv::Mat-style header over tile i is what the restructured fusion loop reads (INTEGRATION.md 3)."""
+    from localexpstereo_b200.sweep import tile_offsets
+    L, E = scene["L"], scene["E"]
+    H, W, D = scene["H"], scene["W"], scene["D"]
+    lay = L.LayerManager(W, H, scene["windR"]).addLayer(11)
+    g = lay.disjointRegionSets[3]
+    fr = [lay.filterRegions[r] for r in g]
+    tr = [lay.sharedRegions[r] for r in g]
+    plan = E.make_plan(fr, tr)
+    offs, total = tile_offsets(tr)
+    assert total == plan.target_px
+    rng = O.CvRNG(55)
+    for mode in (0, 1):
+        planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+        ref = np.full((H, W), -7.0, np.float32)
+        plan.eval_host(planes, ref, True, mode)
+        staged = np.full(total + 3, -9.0, np.float32)
+        plan.eval_host_tiles(planes, staged, True, mode)
+        mapped = np.full(total + 3, -9.0, np.float32)
+        L.host_register(mapped)
+        try:
+            plan.eval_host_tiles(planes, mapped, True, mode)
+        finally:
+            L.host_unregister(mapped)
+        assert np.array_equal(staged, mapped) and (staged[total:] == -9.0).all()
+        for (x, y, w, h), o in zip(tr, offs):
+            assert np.array_equal(staged[o:o + w * h].reshape(h, w), ref[y:y + h, x:x + w])
+    plan.close()
