@@ -82,6 +82,55 @@ public:
 
     lexp_ctx* context() const { return ctx_; }
 
+    // The cells of one disjoint group with their work list resident on the device.  Build it once per (layer, group) -- the
+    // rectangles never change (LayerManager.h:14-24) -- and evaluate it once per proposal step: this is the fast path of
+    // INTEGRATION.md section 3 (one launch for all cells of the group instead of one call per cell).
+    class GroupPlan {
+        lexp_ctx* ctx_;
+        lexp_plan* plan_ = nullptr;
+        std::vector<cv::Rect> targets_;
+        std::vector<size_t> offsets_;  // float offset of cell i's tile: sum of the targetRect areas of cells 0..i-1
+        size_t total_ = 0;
+
+    public:
+        GroupPlan(const CudaCostVolumeEnergy& e, const std::vector<cv::Rect>& filterRects, const std::vector<cv::Rect>& targetRects)
+            : ctx_(e.context()), targets_(targetRects), offsets_(targetRects.size()) {
+            if (filterRects.size() != targetRects.size()) throw std::invalid_argument("GroupPlan: one filterRect per targetRect");
+            std::vector<lexp_rect> f(filterRects.size()), t(targetRects.size());
+            for (size_t i = 0; i < f.size(); i++) {
+                f[i] = toRect(filterRects[i]); t[i] = toRect(targetRects[i]);
+                offsets_[i] = total_;
+                total_ += (size_t)targetRects[i].width * targetRects[i].height;
+            }
+            check(lexp_plan_create(ctx_, (int)f.size(), f.data(), t.data(), &plan_));
+        }
+        ~GroupPlan() { lexp_plan_destroy(plan_); }
+        GroupPlan(const GroupPlan&) = delete;
+        GroupPlan& operator=(const GroupPlan&) = delete;
+
+        size_t cells() const { return targets_.size(); }
+        size_t tileFloats() const { return total_; }
+        size_t tileOffset(size_t i) const { return offsets_[i]; }
+
+        // one proposal step: the costs of planes[i] for cell i go to proposalCost(targetRects[i]) of the H x W image
+        // (FastGCStereo.h:25,49); host memory, blocking; zero-copy if the image was registered with lexp_host_register
+        void evaluate(const std::vector<Plane>& planes, cv::Mat& proposalCost, int mode = 0, bool check_valid = true) const {
+            if (planes.size() != targets_.size()) throw std::invalid_argument("GroupPlan: one plane per cell");
+            static_assert(sizeof(Plane) == sizeof(lexp_plane), "Plane must stay {a,b,c,v} floats (Plane.h:4-8)");
+            check(lexp_plan_eval_host(ctx_, plan_, mode, reinterpret_cast<const lexp_plane*>(planes.data()),
+                                      reinterpret_cast<float*>(proposalCost.data), (ptrdiff_t)proposalCost.step, check_valid ? 1 : 0));
+        }
+        // the same costs as contiguous tiles: cell i at tiles + tileOffset(i), row pitch targetRects[i].width
+        void evaluateTiles(const std::vector<Plane>& planes, float* tiles, int mode = 0, bool check_valid = true) const {
+            if (planes.size() != targets_.size()) throw std::invalid_argument("GroupPlan: one plane per cell");
+            check(lexp_plan_eval_host_tiles(ctx_, plan_, mode, reinterpret_cast<const lexp_plane*>(planes.data()), tiles, check_valid ? 1 : 0));
+        }
+#ifndef LEXP_ADAPTER_NO_REFERENCE_INCLUDES
+        // cv::Mat header over cell i's tile: what the fusion step reads as `subProposalCost` (FastGCStereo.h:37,52-58)
+        cv::Mat tile(float* tiles, size_t i) const { return cv::Mat(targets_[i].height, targets_[i].width, CV_32F, tiles + offsets_[i]); }
+#endif
+    };
+
 private:
     // The reference declares `Reusable& reusable = Reusable()` (an MSVC extension binding a temporary to a non-const
     // reference); a conforming compiler needs an lvalue.

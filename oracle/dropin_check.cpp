@@ -16,6 +16,9 @@
 // --cpu-self-check replaces the CUDA energy by a second CPU instance (validates this harness without a GPU);
 // --cpu-float-check by the reference's own single-precision variant (filterName "GFfloat", FastGuidedImageFilter<float>):
 // the size of its deviation from the double filter shows how well conditioned the scene is for any FP32 implementation.
+// --batched runs the loop as INTEGRATION.md section 3 restructures it: per (layer, group) one CudaCostVolumeEnergy::GroupPlan,
+// per proposal step ONE evaluation of all cells of the group (image-shaped output on even steps, per-cell tiles wrapped in
+// cv::Mat headers on odd steps), then the unchanged per-cell fusion; the reference energy still checks every cell.
 // Prints one JSON line; exit code 0 iff every call agreed (1e-4 relative, COST_FOR_INVALID masks identical).
 #include <opencv2/opencv.hpp>
 #include "Utilities.hpp"
@@ -73,11 +76,12 @@ cv::Mat synthetic_image(int H, int W, uint64_t seed) {
 
 int main(int argc, char** argv) {
     int W = 160, H = 120, D = 16, K = 3, windR = 20, threads = 1;
-    bool naive = false, self = false, selff = false;
+    bool naive = false, self = false, selff = false, batched = false;
     for (int i = 1; i < argc; i++) {
         if (!std::strcmp(argv[i], "--naive")) naive = true;
         else if (!std::strcmp(argv[i], "--cpu-self-check")) self = true;
         else if (!std::strcmp(argv[i], "--cpu-float-check")) self = selff = true;
+        else if (!std::strcmp(argv[i], "--batched")) batched = true;
         else if (i + 1 < argc && !std::strcmp(argv[i], "--W")) W = std::atoi(argv[++i]);
         else if (i + 1 < argc && !std::strcmp(argv[i], "--H")) H = std::atoi(argv[++i]);
         else if (i + 1 < argc && !std::strcmp(argv[i], "--D")) D = std::atoi(argv[++i]);
@@ -140,7 +144,48 @@ int main(int argc, char** argv) {
             for (int iteration = 0; iteration < 2; iteration++)
                 for (auto& layer : layermng.layers) {
                     cv::Mat proposalCost(H, W, CV_32F), proposalCostB(H, W, CV_32F);
-                    for (size_t j = 0; j < layer.disjointRegionSets.size(); j++) {
+                    for (size_t j = 0; j < layer.disjointRegionSets.size() && batched && !self; j++) {
+                        // ---- one evaluation per proposal step for all cells of the group -----------------
+                        const std::vector<int>& cells = layer.disjointRegionSets[j];
+                        const int nc = (int)cells.size();
+                        std::vector<cv::Rect> fr(nc), tr(nc);
+                        for (int n = 0; n < nc; n++) { fr[n] = layer.filterRegions[cells[n]]; tr[n] = layer.sharedRegions[cells[n]]; }
+                        CudaCostVolumeEnergy::GroupPlan plan(*static_cast<CudaCostVolumeEnergy*>(B.get()), fr, tr);  // once per (layer, group) in a real run
+                        std::vector<float> tiles(plan.tileFloats());
+                        std::vector<StereoEnergy::Reusable> reus(nc);
+                        ExpansionProposer p1(1);
+                        RandomProposer p2(K, maxdisp);
+                        IProposer* protos[2] = {&p1, &p2};
+                        int step = 0;
+                        for (IProposer* proto : protos) {
+                            std::vector<IProposer*> prop(nc);
+                            for (int n = 0; n < nc; n++) { prop[n] = proto->createInstance(); prop[n]->startIterations(currentLabeling, layer.unitRegions[cells[n]], iteration); }
+                            while (prop[0]->isContinued()) {  // all cells of a group run the same number of steps (same K, same outerIter)
+                                std::vector<Plane> labels(nc);
+                                for (int n = 0; n < nc; n++) labels[n] = prop[n]->getNextProposal();
+                                const bool as_tiles = (step++ & 1) != 0;
+                                const double t1 = omp_get_wtime();
+                                if (as_tiles) plan.evaluateTiles(labels, tiles.data(), mode, true);
+                                else plan.evaluate(labels, proposalCostB, mode, true);
+                                moves.t_test += omp_get_wtime() - t1;
+                                for (int n = 0; n < nc; n++) {  // reference energy per cell + the unchanged fusion
+                                    const cv::Rect& sharedRegion = tr[n];
+                                    const double t0 = omp_get_wtime();
+                                    A->ComputeUnaryPotential(fr[n], sharedRegion, proposalCost(fr[n]), labels[n], reus[n], mode);
+                                    moves.t_ref += omp_get_wtime() - t0;
+                                    if (as_tiles) plan.tile(tiles.data(), n).copyTo(proposalCostB(sharedRegion));
+                                    compare(proposalCost, proposalCostB, sharedRegion, moves);
+                                    cv::Mat subCurrentCost = currentCost(sharedRegion), subProposalCost = proposalCost(sharedRegion);
+                                    cv::Mat subCurrentLabeling = currentLabeling(sharedRegion);
+                                    cv::Mat updateMask = subCurrentCost > subProposalCost;
+                                    subProposalCost.copyTo(subCurrentCost, updateMask);
+                                    subCurrentLabeling.setTo(labels[n].toScalar(), updateMask);
+                                }
+                            }
+                            for (IProposer* p : prop) delete p;
+                        }
+                    }
+                    for (size_t j = 0; j < layer.disjointRegionSets.size() && !(batched && !self); j++) {
                         std::vector<Tally> part(threads);
 #pragma omp parallel for num_threads(threads) if (threads > 1)
                         for (int n = 0; n < (int)layer.disjointRegionSets[j].size(); n++) {
@@ -198,7 +243,7 @@ int main(int argc, char** argv) {
         }
         std::printf("{\"energy\": \"%s\", \"under_test\": \"%s\", \"W\": %d, \"H\": %d, \"D\": %d, \"init_calls\": %ld, \"move_calls\": %ld, "
                     "\"pixels\": %ld, \"out_of_tolerance\": %ld, \"mask_mismatch\": %ld, \"worst_err_over_tol\": %.4g, \"threads\": %d, %s%s\"ok\": %s}\n",
-                    naive ? "NaiveStereoEnergy" : "CostVolumeEnergy", selff ? "cpu GFfloat" : self ? "cpu-self-check" : "CudaCostVolumeEnergy adapter", W, H, D,
+                    naive ? "NaiveStereoEnergy" : "CostVolumeEnergy", selff ? "cpu GFfloat" : self ? "cpu-self-check" : batched ? "CudaCostVolumeEnergy::GroupPlan (batched loop)" : "CudaCostVolumeEnergy adapter", W, H, D,
                     init.calls, moves.calls, px, bad, mm, worst, threads, extra, timing, ok ? "true" : "false");
         return ok ? 0 : 1;
     } catch (const std::exception& e) {

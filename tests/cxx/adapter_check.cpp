@@ -14,6 +14,10 @@ int main(int argc, char**) {
         e.ComputeUnaryPotentialWithoutCheck(r, r, im, Plane{0, 0, 0, 0}, ru, 0);
         std::vector<cv::Rect> rs; std::vector<Plane> ps;
         e.ComputeUnaryPotentialBatch(rs, rs, im, ps);
+        CudaCostVolumeEnergy::GroupPlan gp(e, rs, rs);
+        gp.evaluate(ps, im, 0, true);
+        gp.evaluateTiles(ps, nullptr, 1, false);
+        (void)gp.cells(); (void)gp.tileFloats();
         CudaNaiveStereoEnergy n(im, im, Parameters(), 63.f);
         n.ComputeUnaryPotential(r, r, im, Plane{0, 0, 0, 0}, ru, 1);
     }
