@@ -125,3 +125,31 @@ def test_random_batches_with_forced_tilings(seed, monkeypatch):
                     assert_costs_close(got, ref, f"batch f={f} t={t}")
     finally:
         E.close()
+
+
+def test_one_large_cell_is_cut_into_many_work_items():
+    """A layer-2-like cell (target 300 x 200): several column tiles x row segments, each with its own 2R warm-up, must
+    reassemble to the oracle's result without seams."""
+    import localexpstereo_b200 as L
+    H, W, D, windR = 250, 350, 20, 20
+    imL, imR, volL, volR = make_scene(H, W, D, seed=77)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(imL, imR, volL, volR, prm, D - 1)
+    Or = O.CostVolumeEnergyOracle(imL, imR, volL, volR, windR, 1e-4, 0.5, D - 1)
+    try:
+        f, t = (5, 5, 340, 240), (25, 25, 300, 200)
+        plan = E.make_plan([f], [t])
+        assert plan.num_items >= 8
+        p = np.array([0.031, -0.022, 8.5, 0], np.float32)
+        img = np.full((H, W), -7.0, np.float32)
+        plan.eval_host(p[None, :], img, True, 0)
+        plan.close()
+        ref = Or.compute_unary_potential(f, t, p, 0)
+        got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+        worst = assert_costs_close(got, ref, "large cell")
+        # seams: the error must not concentrate at tile borders (it would if a warm-up row or halo column were missing)
+        err = np.abs(got.astype(np.float64) - ref) / np.maximum(np.abs(ref), 1e-3)
+        assert err.max() < 3e-5, err.max()
+        print("items", "worst rel err", worst)
+    finally:
+        E.close()
