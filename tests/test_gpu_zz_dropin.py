@@ -22,6 +22,11 @@ EXE = os.path.join(ROOT, "oracle", "_ref", "dropin_check")
 def test_reference_loop_through_the_adapter(energy, threads):
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/dropin_check was not built (needs the reference sources at build time)")
+    if not os.access(EXE, os.X_OK):  # the snapshot that carried the file here may have dropped the mode bits
+        try:
+            os.chmod(EXE, 0o755)
+        except OSError:
+            pytest.skip("oracle/_ref/dropin_check is not executable on this machine")
     # threads > 1: the cells of a group in an OpenMP parallel for, as FastGCStereo.h:30 -- concurrent calls of the virtual,
     # which the library combines into batched launches (lexp_combine_stats)
     # "batched": the loop as INTEGRATION.md section 3 restructures it (CudaCostVolumeEnergy::GroupPlan: one evaluation of all cells
