@@ -53,6 +53,12 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_LINK_STRIDES
 #define LEXP_LINK_STRIDES 0
 #endif
+// LEXP_A_ROWTAB: the byte offset of a volume row inside the blocked layout, (y / 4) * block-row pitch + (y % 4) * 16, is looked up
+//   in a per-tile shared-memory table (16-byte units, filled in the prologue next to the plane's b*y + c) instead of being
+//   recomputed with 64-bit multiplies for every row of every column: ~19 -> ~5 address instructions per gathered row in team A.
+#ifndef LEXP_A_ROWTAB
+#define LEXP_A_ROWTAB 0
+#endif
 // LEXP_PDL: programmatic dependent launch.  Every thread signals `griddepcontrol.launch_dependents` at the top of the kernel, so
 //   the NEXT batched evaluation of the stream (launched with the programmatic-stream-serialization attribute, lexp_capi.cu) may
 //   occupy CTA slots as soon as all CTAs of this one are resident: it fills the partly empty last wave and hides the launch gap
@@ -281,6 +287,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
             if (!NAIVE) {
                 s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);               // CostVolumeEnergy.h:73
+#if LEXP_A_ROWTAB
+                // row offset in the blocked volume, in 16-byte units (the s_Y0 slot is unused by the cost-volume energy)
+                reinterpret_cast<unsigned*>(s_Y0)[v] = (unsigned)(y >> 2) * ((unsigned)P.Wb * (unsigned)P.D * 4u) + (unsigned)(y & 3);
+#endif
             } else {
                 // cv::warpAffine fixed-point row terms (AB_BITS = 10, round_delta = 16) for the inverse affine map of
                 // StereoEnergy.h:704-729; closed form of getAffineTransform + inversion, same operation order as the oracle
@@ -382,6 +392,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
         const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
         const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
+#if LEXP_A_ROWTAB && !defined(LEXP_EMU)
+        asm volatile("" : "+l"(vcol));  // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row)
+#endif
         const char* grow = reinterpret_cast<const char*>(P.guide) + ((size_t)ys * P.W + XAc) * 4;
         const float maxd = (float)(P.D - 1);
         F4 acc = f4zero();
@@ -422,11 +435,26 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u; lf1[j] = fast ? 0.f : -1.f;  // outside filterRect: zero
                 if (colA && vi < vReal) {
                     int d0, d1;
+#if LEXP_A_ROWTAB
+                    const char* vrow = vcol + (size_t)reinterpret_cast<const unsigned*>(s_Y0)[vi] * 16;
+                    if (fast) {  // the second sample is always the next disparity: 64 bytes further in the blocked layout
+                        lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
+                        const float* p0 = reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 64);
+                        lv0[j] = ldg_stream(p0);
+                        lv1[j] = ldg_stream(p0 + 16);
+                    } else {
+                        lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);
+                        const float* p0 = reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 64);
+                        lv0[j] = ldg_stream(p0);
+                        lv1[j] = ldg_stream(p0 + ((d1 - d0) << 4));  // d1 - d0 is 1, or 0 when the sampler clamps at D - 1
+                    }
+#else
                     lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
                     const int y = ys + vi;
                     const char* vrow = vcol + (size_t)(y >> 2) * vblk + (y & 3) * 16;
                     lv0[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d0 * 64));
                     lv1[j] = ldg_stream(reinterpret_cast<const float*>(vrow + (size_t)(unsigned)d1 * 64));
+#endif
                     lg[j] = __ldg(reinterpret_cast<const unsigned int*>(grow));
                 }
                 vi++;

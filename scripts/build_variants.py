@@ -19,6 +19,8 @@ VARIANTS = {
     "crolling": ["-DLEXP_C_ROLLING=1"],
     "hreread": ["-DLEXP_H_REREAD=1"],
     "linkstr": ["-DLEXP_LINK_STRIDES=1"],           # per-link row-buffer strides at 2 CTAs / SM: 5.5 KB less shared memory, more L1
+    "rowtab": ["-DLEXP_A_ROWTAB=1"],                # team A: row-offset table instead of 64-bit address arithmetic per gathered row
+    "occ3rowtab": ["-DLEXP_OCC3", "-DLEXP_A_ROWTAB=1"],
     "trace": ["-DLEXP_TRACE=1"],                    # diagnosis: per-team wait / busy cycles of every launch (scripts/gpu_trace.sh)
     "occ3trace": ["-DLEXP_OCC3", "-DLEXP_TRACE=1"],
 }

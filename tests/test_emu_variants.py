@@ -8,7 +8,7 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["pdl", "occ3pdl", "trace", "linkstr"])
+@pytest.mark.parametrize("variant", ["pdl", "occ3pdl", "trace", "linkstr", "rowtab", "occ3rowtab"])
 def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
     monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it
@@ -38,3 +38,12 @@ def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monke
     if variant == "trace":
         lines = open(tmp_path / "trace.txt").read().strip().splitlines()
         assert len(lines) >= 3 and all(" | A total " in l and " | E total " in l for l in lines)
+
+
+@pytest.mark.parametrize("seed", [5, 17])
+def test_rowtab_variant_fuzz(seed):
+    """LEXP_A_ROWTAB changes team A's address arithmetic (row-offset table, fixed +64 B second sample in the fast sampler):
+    random rects / planes incl. the generic sampler (MIN != 0, non-finite planes) against the oracle."""
+    import test_emu_fuzz as _f
+    with emu_lib.emulated(variant="rowtab"):
+        _f.test_random_rects_and_planes_match_the_oracle(seed)
