@@ -392,8 +392,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
         const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
         const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
-#if LEXP_A_ROWTAB && !defined(LEXP_EMU)
-        asm volatile("" : "+l"(vcol));  // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row)
+#if LEXP_A_ROWTAB && LEXP_MIN_CTAS <= 2 && !defined(LEXP_EMU)
+        // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row); not with the 56-register
+        // diet, where the extra live register pair spills
+        asm volatile("" : "+l"(vcol));
 #endif
         const char* grow = reinterpret_cast<const char*>(P.guide) + ((size_t)ys * P.W + XAc) * 4;
         const float maxd = (float)(P.D - 1);
