@@ -8,7 +8,7 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["pdl", "occ3pdl", "trace", "linkstr", "rowtab", "occ3rowtab"])
+@pytest.mark.parametrize("variant", ["pdl", "trace", "rowtab", "occ3rowtab"])  # occ3 (incl. link strides): tests/test_emu_occ3.py
 def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
     monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it
