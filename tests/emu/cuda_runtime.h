@@ -169,7 +169,11 @@ inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, A
     State& s = S();
     s.gdim = grid; s.bdim = block;
     s.error.clear();
+#ifdef __SANITIZE_ADDRESS__
+    s.dyn.assign(smem, 0xCD);       // exact size (malloc is 16-byte aligned): overruns of the dynamic shared memory are flagged
+#else
     s.dyn.assign(smem + 64, 0xCD);  // poison: the kernel must initialise what it reads
+#endif
     s.entry = [=]() { kern(args...); };
     const unsigned nthreads = block.x * block.y * block.z;
     for (unsigned bz = 0; bz < grid.z; bz++)
@@ -275,7 +279,11 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 }
 static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) {
+#ifdef __SANITIZE_ADDRESS__
+    *p = (T*)malloc(bytes);  // exact size: AddressSanitizer then flags the first byte read or written past a "device" buffer
+#else
     *p = (T*)aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+#endif
     if (!*p) return cudaErrorMemoryAllocation;
     memset((void*)*p, 0xCD, bytes);  // poison
     return cudaSuccess;
