@@ -4,6 +4,7 @@ builds the emulator library with AddressSanitizer -- "device" buffers and the dy
 blocks, so the first byte the kernel reads or writes out of bounds is reported -- and drives the fuzz tests through it.
 
     python tests/emu/asan_fuzz.py [first_seed last_seed]       (re-executes itself with libasan preloaded)
+    LEXP_ASAN_DEFS="-DLEXP_OCC3 -DLEXP_A_ROWTAB=1" python tests/emu/asan_fuzz.py 0 40      (a build-time kernel variant)
 """
 import ctypes as C
 import os
@@ -19,7 +20,7 @@ def build():
     src = os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_capi.cu")
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-DLEXP_EMU", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
            "-fvisibility-inlines-hidden", "-fno-gnu-unique", "-mfma", "-fsanitize=address", "-fno-omit-frame-pointer",
-           "-I", HERE, "-x", "c++", src, "-o", SO]
+           "-I", HERE, "-x", "c++", src, "-o", SO] + os.environ.get("LEXP_ASAN_DEFS", "").split()
     subprocess.check_call(cmd)
 
 
