@@ -7,8 +7,8 @@ BASELINE.json names.  `value` = filterRect-pixel evals of the whole job / device
 resident in HBM.  `e2e` = same sweep through the host-buffer API (planes H2D, costs D2H).
 `--impl reference` times the reference's CPU implementation on the host cores: oracle/_ref (the reference's own
 CostVolumeEnergy / NaiveStereoEnergy classes compiled from its headers by oracle/build_ref.py, kind "reference",
-driven by the OpenMP loop of FastGCStereo.h:30-49) or the plain-C restatement oracle/lexp_oracle.c (kind "port"),
-whichever is faster on this host.
+driven by the OpenMP loop of FastGCStereo.h:30-49); the plain-C restatement oracle/lexp_oracle.c (kind "port") stands in
+when oracle/_ref is absent, and its rate is reported next to the reference's in the `sample` note.
 """
 from __future__ import annotations
 
@@ -137,7 +137,8 @@ class CpuArm:
     of oracle/cvshim (its box filter is that layer's, not OpenCV's hand-vectorised one), cells of a group in an OpenMP
     parallel for with one Reusable per cell across its K proposals, exactly the loop of FastGCStereo.h:30-49 minus fusion.
     kind "port": oracle/lexp_oracle.c, the plain-C restatement (running-sum box filter, per-thread scratch).
-    Both are calibrated on one group and the faster one, at its better thread count, is used."""
+    Both are calibrated on one group (rates in the `sample` note); the compiled reference is the one timed whenever it is
+    available, at its better thread count; the port stands in when oracle/_ref is absent."""
 
     def __init__(self, W, H, D, windR, imL, vol, naive=False, imR=None):
         self.W, self.H, self.naive = W, H, naive
@@ -182,7 +183,12 @@ class CpuArm:
             self.calib[kind] = {"evals_per_s": rate, "threads": nthr}
             if best is None or rate > best[0]:
                 best = (rate, kind, nthr)
-        _, self.kind, self.nthr = best
+        # the reference's own code is the baseline whenever it is available (its calibration rate and the port's are both
+        # reported in the `sample` note); the port only stands in when oracle/_ref is absent
+        if "reference" in self.calib:
+            self.kind, self.nthr = "reference", self.calib["reference"]["threads"]
+        else:
+            _, self.kind, self.nthr = best
         return self.kind, self.nthr
 
     def run(self, fr, tr, planes_kn4):
