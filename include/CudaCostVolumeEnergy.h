@@ -12,6 +12,8 @@
 #ifndef LEXP_ADAPTER_NO_REFERENCE_INCLUDES
 #include "StereoEnergy.h"
 #endif
+#include <atomic>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -23,6 +25,26 @@ protected:
         if (rc != LEXP_OK) throw std::runtime_error(std::string("lexp_cuda: ") + lexp_last_error());
     }
     static lexp_rect toRect(const cv::Rect& r) { return lexp_rect{r.x, r.y, r.width, r.height}; }
+
+    // The two virtuals are called inside `#pragma omp parallel for` (FastGCStereo.h:30-49): an exception must not leave that
+    // region (std::terminate).  A failing call records the first error, marks the whole targetRect COST_FOR_INVALID (1e6,
+    // StereoEnergy.h:45 -- the fusion then never accepts the proposal there) and returns; the caller asks failed() /
+    // throwIfFailed() after the parallel region.
+    mutable std::mutex err_mu_;
+    mutable std::string err_;
+    mutable std::atomic<bool> failed_{false};
+    void guard(int rc, const cv::Rect& filterRect, const cv::Rect& targetRect, const cv::Mat& costs) const {
+        if (rc == LEXP_OK) return;
+        {
+            std::lock_guard<std::mutex> lk(err_mu_);
+            if (err_.empty()) err_ = std::string("lexp_cuda: ") + lexp_last_error();
+        }
+        failed_.store(true);
+        for (int y = 0; y < targetRect.height; y++) {
+            float* row = reinterpret_cast<float*>(costs.data + (ptrdiff_t)(targetRect.y - filterRect.y + y) * (ptrdiff_t)costs.step) + (targetRect.x - filterRect.x);
+            for (int x = 0; x < targetRect.width; x++) row[x] = 1000000.0f;
+        }
+    }
 
     // shared by the two energies
     CudaCostVolumeEnergy(const cv::Mat imL, const cv::Mat imR, Parameters params, float MAX_DISPARITY, float MIN_DISPARITY, float MAX_VDISPARITY,
@@ -59,14 +81,14 @@ public:
         (void)reusable;
         const lexp_rect f = toRect(filterRect), t = toRect(targetRect);
         const lexp_plane pl{plane.a, plane.b, plane.c, plane.v};
-        check(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 0));
+        guard(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 0), filterRect, targetRect, costs);
     }
     void ComputeUnaryPotential(const cv::Rect& filterRect, const cv::Rect& targetRect, const cv::Mat& costs, const Plane& plane,
                                Reusable& reusable = defaultReusable(), int mode = 0) const override {
         (void)reusable;
         const lexp_rect f = toRect(filterRect), t = toRect(targetRect);
         const lexp_plane pl{plane.a, plane.b, plane.c, plane.v};
-        check(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 1));
+        guard(lexp_eval_cell(ctx_, mode, &f, &t, &pl, reinterpret_cast<float*>(costs.data), (ptrdiff_t)costs.step, 1), filterRect, targetRect, costs);
     }
 
     // Batched form for a loop that has been restructured step-wise: one call per
@@ -81,6 +103,13 @@ public:
     }
 
     lexp_ctx* context() const { return ctx_; }
+    // error state of the per-cell virtuals (they never throw, see guard()): check after the OpenMP region
+    bool failed() const { return failed_.load(); }
+    void throwIfFailed() const {
+        if (!failed_.load()) return;
+        std::lock_guard<std::mutex> lk(err_mu_);
+        throw std::runtime_error(err_);
+    }
 
     // The cells of one disjoint group with their work list resident on the device.  Build it once per (layer, group) -- the
     // rectangles never change (LayerManager.h:14-24) -- and evaluate it once per proposal step: this is the fast path of

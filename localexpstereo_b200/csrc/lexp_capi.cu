@@ -11,6 +11,7 @@
 #include <array>
 #include <condition_variable>
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -93,6 +94,10 @@ struct lexp_ctx {
     // virtual again and again with the same rects (LayerManager.h:14-24), so the tiling / device upload is done once
     std::mutex cache_mu;
     std::map<std::array<int, 8>, lexp_plan*> cell_plans;
+    // every live plan of this context (user plans and cached cell plans): lexp_destroy releases their device memory and
+    // orphans them (ctx = nullptr), so that a plan handle that outlives its context stays safe to destroy
+    std::mutex plans_mu;
+    std::set<lexp_plan*> live_plans;
     // Combining of CONCURRENT lexp_eval_cell calls.  The unchanged reference loop issues one blocking call per cell from an OpenMP
     // `parallel for` over the cells of a disjoint group (FastGCStereo.h:30-49): while one call owns the device, the calls of the
     // other threads queue up here and are then evaluated together as ONE batched launch (same work items, same results).
@@ -210,6 +215,28 @@ int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
         case 16: return launch_fused_t<16, false>(c, kp, nitems, smem);
         default: return launch_fused_t<0, false>(c, kp, nitems, smem);
     }
+}
+
+void release_plan_memory(lexp_plan* pl) {
+    cudaFree(pl->d_items); pl->d_items = nullptr;
+    cudaFree(pl->d_planes); pl->d_planes = nullptr;
+    cudaFree(pl->d_compact); pl->d_compact = nullptr;
+    if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
+}
+
+// compact device buffer + pinned host mirror of the staged host paths: both or neither
+int ensure_compact(lexp_plan* pl, size_t nout) {
+    if (pl->d_compact && pl->h_compact) return LEXP_OK;
+    cudaFree(pl->d_compact); pl->d_compact = nullptr;
+    if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
+    cudaError_t e = cudaMalloc(&pl->d_compact, nout * sizeof(float));
+    if (e == cudaSuccess) e = cudaHostAlloc(&pl->h_compact, nout * sizeof(float), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaFree(pl->d_compact); pl->d_compact = nullptr; pl->h_compact = nullptr;
+        cudaGetLastError();
+        return fail(LEXP_ERR_NOMEM, std::string("staging buffers of the host path: ") + cudaGetErrorString(e));
+    }
+    return LEXP_OK;
 }
 
 int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
@@ -345,6 +372,11 @@ int lexp_destroy(lexp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->cell_plans) lexp_plan_destroy(kv.second);
     c->cell_plans.clear();
+    for (lexp_plan* pl : c->live_plans) {  // user plans that outlive the context: orphaned, lexp_plan_destroy then only deletes
+        release_plan_memory(pl);
+        pl->ctx = nullptr;
+    }
+    c->live_plans.clear();
     cudaFree(c->cb_items); cudaFree(c->cb_planes); cudaFree(c->cb_dout);
     if (c->cb_hout) cudaFreeHost(c->cb_hout);
     for (int m = 0; m < 2; m++) {
@@ -526,18 +558,23 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
         delete pl;
         return fail(LEXP_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e));
     }
+    {
+        std::lock_guard<std::mutex> lk2(c->plans_mu);
+        c->live_plans.insert(pl);
+    }
     *out_plan = pl;
     return LEXP_OK;
 }
 
 int lexp_plan_destroy(lexp_plan* pl) {
     if (!pl) return LEXP_OK;
-    cudaSetDevice(pl->ctx->p.device);
-    cudaStreamSynchronize(pl->ctx->stream);
-    cudaFree(pl->d_items);
-    cudaFree(pl->d_planes);
-    cudaFree(pl->d_compact);
-    if (pl->h_compact) cudaFreeHost(pl->h_compact);
+    if (lexp_ctx* c = pl->ctx) {  // nullptr: the context was destroyed first and has already released the plan's memory
+        cudaSetDevice(c->p.device);
+        cudaStreamSynchronize(c->stream);
+        release_plan_memory(pl);
+        std::lock_guard<std::mutex> lk(c->plans_mu);
+        c->live_plans.erase(pl);
+    }
     delete pl;
     return LEXP_OK;
 }
@@ -598,10 +635,7 @@ int lexp_plan_eval_host_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_p
     }
     cudaGetLastError();  // not a mapped buffer: compact device buffer, then one contiguous copy
     const size_t nout = (size_t)pl->sum_s;
-    if (!pl->d_compact) {
-        LEXP_CUDA(cudaMalloc(&pl->d_compact, nout * sizeof(float)));
-        LEXP_CUDA(cudaHostAlloc(&pl->h_compact, nout * sizeof(float), cudaHostAllocDefault));
-    }
+    { int rc0 = ensure_compact(pl, nout); if (rc0) return rc0; }
     int rc = run_plan(c, pl, mode, pl->d_planes, pl->d_compact, 0, 1, with_check);
     if (rc) return rc;
     LEXP_CUDA(cudaMemcpyAsync(tiles, pl->d_compact, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -627,10 +661,7 @@ int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
         cudaGetLastError();  // not a mapped buffer: staged path below
     }
     const size_t nout = (size_t)pl->sum_s;
-    if (!pl->d_compact) {
-        LEXP_CUDA(cudaMalloc(&pl->d_compact, nout * sizeof(float)));
-        LEXP_CUDA(cudaHostAlloc(&pl->h_compact, nout * sizeof(float), cudaHostAllocDefault));
-    }
+    { int rc0 = ensure_compact(pl, nout); if (rc0) return rc0; }
     LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
     int rc = run_plan(c, pl, mode, pl->d_planes, pl->d_compact, 0, 1, with_check);
     if (rc) return rc;

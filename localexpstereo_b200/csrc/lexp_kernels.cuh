@@ -148,7 +148,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
 #else
     const int rows = 8 * kCH * srow_stride(vw);
 #endif
-    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4)) * 16;
+    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 3) * 16;  // + 6 doubles (NAIVE: inverse affine map)
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -208,25 +208,53 @@ __device__ __forceinline__ void consume_end(int link, int c, int nChunks, int nt
 constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 + 1), kLinkHE = 32 * (1 + 2);  // threads per link
 
 // Inverse affine map (dst pixel of the filterRect -> source pixel of the other view) of NaiveStereoEnergy
-// (StereoEnergy.h:704-729): the three float corner correspondences, then the closed form of
-// cv::getAffineTransform + the inversion inside cv::warpAffine (see oracle affine_inverse_for_plane).
-__device__ __forceinline__ void naive_inverse_affine(const Item& it, const Plane4& pl, int mode, double* iM) {
+// (StereoEnergy.h:704-729), computed the way the reference does: the three float corner correspondences, then
+// cv::getAffineTransform (6x6 system, Gaussian elimination with partial pivoting in double) and the inversion at the top of
+// cv::warpAffine -- same operations in the same order as oracle/_ref, every product and sum rounded separately (no FMA
+// contraction), so the 10-bit fixed-point source coordinates are bit-identical to the reference's.  One thread per CTA.
+__device__ inline void naive_inverse_affine(const Item& it, const Plane4& pl, int mode, double* iM) {
     const float sign = mode ? -1.0f : 1.0f;
     const float x00 = (float)it.fx, y00 = (float)it.fy;
     const float x11 = __fadd_rn(x00, (float)it.fw), y11 = __fadd_rn(y00, (float)it.fh);
     auto gz = [&](float x, float y) { return __fadd_rn(__fadd_rn(__fmul_rn(pl.a, x), __fmul_rn(pl.b, y)), pl.c); };  // Plane.h:51-54
-    const float sx0 = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y00)));
-    const float sx1 = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y11)));
-    const float sx2 = __fsub_rn(x11, __fmul_rn(sign, gz(x11, y00)));
-    float sy0 = y00, sy1 = y11;
-    if (pl.v != 0.0f) { sy0 = __fadd_rn(sy0, pl.v); sy1 = __fadd_rn(sy1, pl.v); }
-    const double dw = (double)__fsub_rn(x11, x00), dh = (double)__fsub_rn(y11, y00);
-    iM[0] = __ddiv_rn(__dsub_rn((double)sx2, (double)sx0), dw);
-    iM[1] = __ddiv_rn(__dsub_rn((double)sx1, (double)sx0), dh);
-    iM[2] = (double)sx0;
-    iM[3] = 0.0;
-    iM[4] = __ddiv_rn(__dsub_rn((double)sy1, (double)sy0), dh);
-    iM[5] = (double)sy0;
+    float sx[3], sy[3];
+    sx[0] = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y00))); sy[0] = y00;   // :714-719
+    sx[1] = __fsub_rn(x00, __fmul_rn(sign, gz(x00, y11))); sy[1] = y11;
+    sx[2] = __fsub_rn(x11, __fmul_rn(sign, gz(x11, y00))); sy[2] = y00;
+    if (pl.v != 0.0f) { sy[0] = __fadd_rn(sy[0], pl.v); sy[1] = __fadd_rn(sy[1], pl.v); sy[2] = __fadd_rn(sy[2], pl.v); }  // :720-725
+    const double dx[3] = {0.0, 0.0, (double)__fsub_rn(x11, x00)}, dy[3] = {0.0, (double)__fsub_rn(y11, y00), 0.0};   // :711-713
+    double a[6][7];
+    for (int i = 0; i < 3; i++) {
+        a[i][0] = sx[i]; a[i][1] = sy[i]; a[i][2] = 1.0; a[i][3] = 0.0; a[i][4] = 0.0; a[i][5] = 0.0; a[i][6] = dx[i];
+        a[i + 3][0] = 0.0; a[i + 3][1] = 0.0; a[i + 3][2] = 0.0; a[i + 3][3] = sx[i]; a[i + 3][4] = sy[i]; a[i + 3][5] = 1.0; a[i + 3][6] = dy[i];
+    }
+    double M[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    bool singular = false;
+    for (int c = 0; c < 6 && !singular; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 6; r++) if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+        if (fabs(a[piv][c]) < 2.220446049250313e-16) { singular = true; break; }
+        if (piv != c) for (int k = 0; k < 7; k++) { const double t = a[c][k]; a[c][k] = a[piv][k]; a[piv][k] = t; }
+        const double d = __ddiv_rn(-1.0, a[c][c]);
+        for (int r = c + 1; r < 6; r++) {
+            const double f = __dmul_rn(a[r][c], d);
+            for (int k = c + 1; k < 7; k++) a[r][k] = __dadd_rn(a[r][k], __dmul_rn(f, a[c][k]));
+        }
+    }
+    if (!singular) {
+        for (int r = 5; r >= 0; r--) {
+            double s = a[r][6];
+            for (int k = r + 1; k < 6; k++) s = __dsub_rn(s, __dmul_rn(a[r][k], M[k]));
+            M[r] = __ddiv_rn(s, a[r][r]);
+        }
+    }
+    // cv::warpAffine without WARP_INVERSE_MAP inverts M in double
+    double D = __dsub_rn(__dmul_rn(M[0], M[4]), __dmul_rn(M[1], M[3]));
+    D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(M[4], D), A22 = __dmul_rn(M[0], D);
+    iM[0] = A11; iM[1] = __dmul_rn(M[1], -D); iM[3] = __dmul_rn(M[3], -D); iM[4] = A22;
+    iM[2] = __dsub_rn(__dmul_rn(-iM[0], M[2]), __dmul_rn(iM[1], M[5]));
+    iM[5] = __dsub_rn(__dmul_rn(-iM[3], M[2]), __dmul_rn(iM[4], M[5]));
 }
 
 // Cost-volume samples: plain read-only loads.  Measured on B200 (profiles/r1_experiments.md): letting them allocate in
@@ -278,6 +306,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW3);  // [VHs] 1 / (#rows of the window inside filterRect)
     float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
     int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
+    double* s_iM = reinterpret_cast<double*>(s_Y0 + 4 * ((it.oh + 4 * R + 3) / 4));  // [6] NAIVE: inverse affine map of the call
+
+    if (NAIVE) {
+        if (tid == 0) naive_inverse_affine(it, pl, P.mode, s_iM);
+        __syncthreads();
+    }
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
         const int total = (K * VW + 1) / 2 + K * W2 + 2 * kCH * (SW + 2 * SW2 + SW3);
@@ -293,12 +327,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #endif
             } else {
                 // cv::warpAffine fixed-point row terms (AB_BITS = 10, round_delta = 16) for the inverse affine map of
-                // StereoEnergy.h:704-729; closed form of getAffineTransform + inversion, same operation order as the oracle
-                double iM[6];
-                naive_inverse_affine(it, pl, P.mode, iM);
+                // StereoEnergy.h:704-729
                 const double yr = (double)(y - it.fy);
-                reinterpret_cast<int*>(s_dbase)[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[1], yr), iM[2]), 1024.0)) + 16;
-                s_Y0[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(iM[4], yr), iM[5]), 1024.0)) + 16;
+                reinterpret_cast<int*>(s_dbase)[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_iM[1], yr), s_iM[2]), 1024.0)) + 16;
+                s_Y0[v] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_iM[4], yr), s_iM[5]), 1024.0)) + 16;
             }
         }
     }
@@ -315,9 +347,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             const int t = tid;
             const int XA = X0 + t;
             const bool colA = (t < VW) && XA >= it.fx && XA < fx1;
-            double iM[6];
-            naive_inverse_affine(it, pl, P.mode, iM);
-            const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(iM[0], (double)(XA - it.fx)), 1024.0));
+            const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(s_iM[0], (double)(XA - it.fx)), 1024.0));
+            const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_iM[3], (double)(XA - it.fx)), 1024.0));
             const float s255 = 1.0f / 255.0f;
             const int Wm1 = P.W - 1, Hm1 = P.H - 1;
             F4 acc = f4zero();
@@ -332,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                     nwr[r] = f4zero(); pr[r] = 0.f; gr[r] = 0u;
                     if (colA && v < vReal) {
                         const int y = ys + v;
-                        const int X = (reinterpret_cast<const int*>(s_dbase)[v] + adelta) >> 5, Y = s_Y0[v] >> 5;  // bdelta = 0 (iM[3] = 0)
+                        const int X = (reinterpret_cast<const int*>(s_dbase)[v] + adelta) >> 5, Y = (s_Y0[v] + bdelta) >> 5;
                         const int sx = X >> 5, sy = Y >> 5;
                         const float fxw = (float)(X & 31) * (1.0f / 32), fyw = (float)(Y & 31) * (1.0f / 32);
                         const int x0c = min(max(sx, 0), Wm1), x1c = min(max(sx + 1, 0), Wm1);
@@ -385,7 +416,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const float th = P.th_col;
         const float s255 = 1.0f / 255.0f;
         // fast sampler: finite plane, MIN = 0, MAX = D-1, th >= 0, finite volume (checked at upload)
-        const bool fast = P.fast_ok && isfinite(pl.a) && isfinite(pl.b) && isfinite(pl.c);
+        // (finite bound on |a| W + |b| H + |c|: then a*x, b*y + c and their sum are finite for every pixel, so d is never NaN --
+        //  an overflowing a*x = +inf against b*y + c = -inf would be, and the reference then returns COST_FOR_INVALID, :80)
+        const bool fast = P.fast_ok && isfinite(fabsf(pl.a) * (float)P.W + fabsf(pl.b) * (float)P.H + fabsf(pl.c));
         const unsigned W4 = (unsigned)P.W * 4u;
         const int XAc = colA ? XA : it.fx;
         // blocked volume: element (d, y, x) lives at ((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4:

@@ -529,27 +529,57 @@ def _cv_round(x):
 
 def affine_inverse_for_plane(filter_rect, plane, mode):
     """The 2x3 double matrix cv::warpAffine uses (dst pixel -> source pixel) for the three float corner
-    correspondences of StereoEnergy.h:704-727.  The reference gets it from cv::getAffineTransform (6x6 LU solve in
-    double) followed by the inversion inside cv::warpAffine; because the destination corners are (0,0), (0,h), (w,0),
-    that inverse map is exactly the affine interpolation of the three source points, which is what is evaluated
-    here (closed form, double, fixed operation order -- the CUDA path repeats it bit for bit).  It equals OpenCV's
-    matrix to ~1e-16 relative; the 1/32-pixel coordinate rounding can therefore differ from cv2 only at exact
-    rounding ties (a handful of pixels per thousand calls, see tests/test_oracle.py)."""
+    correspondences of StereoEnergy.h:704-727, computed the way the reference does: cv::getAffineTransform (6x6 system,
+    Gaussian elimination with partial pivoting in double -- cv::solve DECOMP_LU) followed by the inversion at the top of
+    cv::warpAffine.  Python floats are IEEE doubles and every operation below is a single rounded one, in the order of
+    oracle/cvshim (the cv:: layer oracle/_ref is compiled over), so the matrix -- and with it every 1/32-pixel source
+    coordinate -- is bit-identical to the compiled reference's; the CUDA path repeats the same sequence."""
     x, y, w, h = filter_rect
     sign = f32(-1.0) if mode else f32(1.0)
     x00, y00 = f32(x), f32(y)
     x11, y11 = f32(x00 + f32(w)), f32(y00 + f32(h))
     gz = lambda xx, yy: plane_get_z(plane, xx, yy)
-    sx0 = f32(x00 - f32(sign * gz(x00, y00)))   # (:714-719) float arithmetic
-    sx1 = f32(x00 - f32(sign * gz(x00, y11)))
-    sx2 = f32(x11 - f32(sign * gz(x11, y00)))
-    sy0, sy1 = y00, y11
+    sx = [f32(x00 - f32(sign * gz(x00, y00))), f32(x00 - f32(sign * gz(x00, y11))), f32(x11 - f32(sign * gz(x11, y00)))]  # :714-719
+    sy = [y00, y11, y00]
     v = f32(plane[3])
     if v != 0:                                     # (:720-725)
-        sy0, sy1 = f32(sy0 + v), f32(sy1 + v)
-    dw, dh = float(f32(x11 - x00)), float(f32(y11 - y00))
-    return np.array([(float(sx2) - float(sx0)) / dw, (float(sx1) - float(sx0)) / dh, float(sx0),
-                     0.0, (float(sy1) - float(sy0)) / dh, float(sy0)], dtype=np.float64)
+        sy = [f32(t + v) for t in sy]
+    dx = [0.0, 0.0, float(f32(x11 - x00))]         # dst_pnt (:711-713)
+    dy = [0.0, float(f32(y11 - y00)), 0.0]
+    a = [[0.0] * 7 for _ in range(6)]
+    for i in range(3):
+        a[i] = [float(sx[i]), float(sy[i]), 1.0, 0.0, 0.0, 0.0, dx[i]]
+        a[i + 3] = [0.0, 0.0, 0.0, float(sx[i]), float(sy[i]), 1.0, dy[i]]
+    M = [0.0] * 6
+    singular = False
+    for c in range(6):
+        piv = c
+        for r in range(c + 1, 6):
+            if abs(a[r][c]) > abs(a[piv][c]):
+                piv = r
+        if abs(a[piv][c]) < 2.220446049250313e-16:
+            singular = True
+            break
+        if piv != c:
+            a[c], a[piv] = a[piv], a[c]
+        d = -1.0 / a[c][c]
+        for r in range(c + 1, 6):
+            f = a[r][c] * d
+            for k in range(c + 1, 7):
+                a[r][k] = a[r][k] + f * a[c][k]
+    if not singular:
+        for r in range(5, -1, -1):
+            s = a[r][6]
+            for k in range(r + 1, 6):
+                s = s - a[r][k] * M[k]
+            M[r] = s / a[r][r]
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    i0, i1, i3, i4 = A11, M[1] * (-D), M[3] * (-D), A22
+    i2 = (-i0) * M[2] - i1 * M[5]
+    i5 = (-i3) * M[2] - i4 * M[5]
+    return np.array([i0, i1, i2, i3, i4, i5], dtype=np.float64)
 
 
 def warp_affine_linear_replicate(src, iM, w, h):

@@ -63,6 +63,8 @@ test_emu_concurrent_single_cell_calls = _p.test_concurrent_single_cell_calls_lik
 test_emu_other_filter_radii = _p.test_other_filter_radii
 test_emu_nonzero_min_disparity_and_odd_max = _p.test_nonzero_min_disparity_and_odd_max
 test_emu_golden_vectors_through_the_c_abi = _g.test_golden_vectors_through_the_c_abi
+test_emu_textureless_guides = _p.test_textureless_guides
+test_emu_plan_outlives_its_energy = _p.test_plan_outlives_its_energy
 
 
 def test_emu_result_does_not_depend_on_the_thread_schedule(scene):

@@ -292,3 +292,54 @@ def test_host_tile_output(scene):
         for (x, y, w, h), o in zip(tr, offs):
             assert np.array_equal(staged[o:o + w * h].reshape(h, w), ref[y:y + h, x:x + w])
     plan.close()
+
+
+def _textureless_guides(H, W):
+    """Guides on which the 3x3 covariance is (nearly) singular: the FP32 hazard SURVEY.md section 7 names."""
+    const = np.full((H, W, 3), 128, np.uint8)
+    two = np.full((H, W, 3), 40, np.uint8); two[:, W // 2:] = 200                      # one vertical step edge
+    ramp = np.zeros((H, W, 3), np.uint8); ramp[:] = (np.arange(W) * 255 // (W - 1)).astype(np.uint8)[None, :, None]
+    sat = np.full((H, W, 3), 255, np.uint8); sat[H // 3:2 * H // 3, W // 4:W // 2] = 0  # saturated black / white blocks
+    chan = np.zeros((H, W, 3), np.uint8); chan[..., 0] = 255; chan[::2, :, 1] = 7       # one constant channel, one 2-level
+    return {"constant": const, "two_level": two, "ramp": ramp, "saturated": sat, "channel": chan}
+
+
+@pytest.mark.parametrize("name", ["constant", "two_level", "ramp", "saturated", "channel"])
+def test_textureless_guides(name):
+    """Constant / two-level / saturated guide images: the covariance is eps*I (or rank 1 + eps*I), inv-covariance entries
+    reach 1/eps = 1e4 and the (a, b) coefficients are differences of nearly equal numbers -- FP32 filter vs the FP64 oracle."""
+    import localexpstereo_b200 as L
+    H, W, D, windR = 120, 150, 16, 20
+    g = _textureless_guides(H, W)[name]
+    volL = O.synthetic_volume(D, H, W, 77)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    E = L.CostVolumeEnergy(g, None, volL, None, prm, D - 1)
+    try:
+        Or = O.CostVolumeEnergyOracle(g, None, volL, None, windR, 1e-4, 0.5, D - 1)
+        rng = O.CvRNG(5)
+        worst = 0.0
+        for (f, t) in [((0, 0, 100, 90), (0, 0, 60, 50)), ((30, 20, 120, 100), (50, 40, 80, 60)), ((60, 40, 90, 80), (80, 60, 50, 40))]:
+            for _ in range(3):
+                p = O.create_random_label(rng, t[0] + 5, t[1] + 5, 0, D - 1)
+                img = np.zeros((H, W), np.float32)
+                E.ComputeUnaryPotential(f, t, img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], p)
+                ref = Or.compute_unary_potential(f, t, p)
+                worst = max(worst, assert_costs_close(img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]], ref, f"{name} {f} {t}"))
+        print(name, "worst rel err", worst)
+    finally:
+        E.close()
+
+
+def test_plan_outlives_its_energy():
+    """lexp_destroy orphans the plans that are still alive: closing the energy first must stay safe."""
+    import localexpstereo_b200 as L
+    H, W, D = 64, 80, 8
+    imL, _, volL, _ = make_scene(H, W, D)
+    E = L.CostVolumeEnergy(imL, None, volL, None, L.Parameters(windR=8, filterName="GF", filter_param1=1e-4, th_col=0.5), D - 1)
+    plan = E.make_plan([(0, 0, 40, 40)], [(8, 8, 20, 20)])
+    img = np.zeros((H, W), np.float32)
+    plan.eval_host(np.array([[0, 0, 3.0, 0]], np.float32), img, True, 0)
+    E.close()
+    with pytest.raises(L.LexpError):
+        plan.eval_host(np.array([[0, 0, 3.0, 0]], np.float32), img, True, 0)   # the context is gone: an error, not a crash
+    plan.close()
