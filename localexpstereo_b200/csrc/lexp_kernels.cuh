@@ -56,17 +56,19 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 // LEXP_A_ROWTAB: the byte offset of a volume row inside the blocked layout, (y / 4) * block-row pitch + (y % 4) * 16, is looked up
 //   in a per-tile shared-memory table (16-byte units, filled in the prologue next to the plane's b*y + c) instead of being
 //   recomputed with 64-bit multiplies for every row of every column: ~19 -> ~5 address instructions per gathered row in team A.
+// Measured on B200 (profiles/r2_variants.md): 17.56 -> 17.26 ms per sweep; default since round 2.
 #ifndef LEXP_A_ROWTAB
-#define LEXP_A_ROWTAB 0
+#define LEXP_A_ROWTAB 1
 #endif
 // LEXP_PDL: programmatic dependent launch.  Every thread signals `griddepcontrol.launch_dependents` at the top of the kernel, so
 //   the NEXT batched evaluation of the stream (launched with the programmatic-stream-serialization attribute, lexp_capi.cu) may
 //   occupy CTA slots as soon as all CTAs of this one are resident: it fills the partly empty last wave and hides the launch gap
 //   and its own prologue + 4R warm-up rows.  Consecutive launches write overlapping parts of the same cost image (the steps of a
 //   group), so team E executes `griddepcontrol.wait` (previous grids complete, their writes visible) before its first store;
-//   nothing else written by a previous launch is read.  Not yet run on a GPU.
+//   nothing else written by a previous launch is read.  Measured on B200 (profiles/r2_variants.md): 17.56 -> 15.49 ms per
+//   sweep (the 240 launches of a sweep replayed as one CUDA graph); default since round 2.  LEXP_PDL_OFF=1 disables it at run time.
 #ifndef LEXP_PDL
-#define LEXP_PDL 0
+#define LEXP_PDL 1
 #endif
 // LEXP_TRACE: diagnosis build.  Every warp accumulates the clock cycles it spends waiting for its input link (consume_begin) and
 //   for a free output buffer (produce_begin) and writes {total, wait_in, wait_out, chunks} at the end; lexp_capi.cu averages

@@ -12,6 +12,9 @@ sys.path.insert(0, ROOT)
 from localexpstereo_b200 import build as B  # noqa: E402
 
 VARIANTS = {
+    "nopdl": ["-DLEXP_PDL=0"],                      # the round-2 defaults switched off one at a time (PDL and ROWTAB are on by default)
+    "norowtab": ["-DLEXP_A_ROWTAB=0"],
+    "r1": ["-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"],    # the round-1 kernel
     "occ3": ["-DLEXP_OCC3"],                        # 3 CTAs / SM: 56 registers, 75 KB shared-memory cap
     "pdl": ["-DLEXP_PDL=1"],                        # programmatic dependent launch between batched evaluations
     "occ3pdl": ["-DLEXP_OCC3", "-DLEXP_PDL=1"],

@@ -8,7 +8,7 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["pdl", "trace", "rowtab", "occ3rowtab"])  # occ3 (incl. link strides): tests/test_emu_occ3.py
+@pytest.mark.parametrize("variant", ["r1", "trace", "occ3rowtab"])  # r1 = PDL and ROWTAB (round-2 defaults) off; occ3 (incl. link strides): tests/test_emu_occ3.py
 def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
     monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it
@@ -45,5 +45,5 @@ def test_rowtab_variant_fuzz(seed):
     """LEXP_A_ROWTAB changes team A's address arithmetic (row-offset table, fixed +64 B second sample in the fast sampler):
     random rects / planes incl. the generic sampler (MIN != 0, non-finite planes) against the oracle."""
     import test_emu_fuzz as _f
-    with emu_lib.emulated(variant="rowtab"):
+    with emu_lib.emulated(variant="r1"):   # the row-offset table is the default since round 2: fuzz the other path too
         _f.test_random_rects_and_planes_match_the_oracle(seed)
