@@ -151,6 +151,35 @@ LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);
  * LEXP_COMBINE=0 in the environment at lexp_create disables the combining. */
 LEXP_API int lexp_combine_stats(const lexp_ctx* ctx, int64_t* batches, int64_t* calls);
 
+/* ---- PatchMatch phase on the device: FastGCStereo::run's `pmInit` iterations (FastGCStereo.h:143-157), i.e.
+ * localExpansionMovesForLayer_CPU with doGC == false (FastGCStereo.h:22-72): per cell and proposal
+ *     label = proposer->getNextProposal();  ComputeUnaryPotential(...);  mask = currentCost > proposalCost;
+ *     proposalCost.copyTo(currentCost, mask);  currentLabeling.setTo(label, mask);                     (:45-60)
+ * with currentCost_[mode] / currentLabeling_[mode] (PMStereoBase.h) resident in HBM, the proposal drawn on the device
+ * (ExpansionProposer Proposer.h:69-75, RandomProposer :120-148; cv::RNG-compatible streams, one per cell and step) and the
+ * update fused into the epilogue of the unary-cost kernel: nothing crosses PCIe between steps.  The proposal steps of a
+ * cell are ordered by per-cell completion counters, so consecutive launches overlap on the device. */
+#define LEXP_PROP_LIST 0       /* planes supplied by the caller (host list replay; the RansacProposer slot) */
+#define LEXP_PROP_EXPANSION 1  /* ExpansionProposer::getNextProposal */
+#define LEXP_PROP_RANDOM 2     /* RandomProposer::getNextProposal, m = outerIter + iter */
+#define LEXP_PM_INIT 1         /* flags: unconditional write of cost and label (initCurrentFast, FastGCStereo.h:105-113) */
+/* (Re)start the state of view `mode`: currentCost = cost (NULL: +INFINITY, FastGCStereo.h:137), currentLabeling = labeling
+ * (NULL: zeros); host arrays float[H][W] / lexp_plane[H][W]. */
+LEXP_API int lexp_pm_begin(lexp_ctx* ctx, int mode, const float* cost_host, const lexp_plane* labeling_host);
+/* Copy the state back (either pointer may be NULL); blocking. */
+LEXP_API int lexp_pm_get(lexp_ctx* ctx, int mode, float* cost_host, lexp_plane* labeling_host);
+/* Device pointers of the state (for callers that keep working on the device: multi-GPU exchange, disparity maps). */
+LEXP_API int lexp_pm_device_state(lexp_ctx* ctx, int mode, float** d_cost, lexp_plane** d_labeling);
+/* unitRegion of every call of the plan (where its proposers draw, LayerManager.h:117-121) and a global id per cell (seeds
+ * the cell's random streams; NULL: 0..n-1).  Required before lexp_plan_pm_step. */
+LEXP_API int lexp_plan_set_units(lexp_plan* plan, const lexp_rect* unit_rects, const int* cell_ids);
+/* One proposal step for all cells of the plan (asynchronous, on the context stream).  step_index = 0, 1, ... within the
+ * group (0 resets the group's completion counters; the steps of a group must be issued in order).  kind / m: LEXP_PROP_*;
+ * seed: random stream of this (view, iteration, layer, group, step).  planes: LEXP_PROP_LIST only.  d_planes_out: optional
+ * device array [ncalls] receiving the plane every call evaluated.  Always with the validity check (ComputeUnaryPotential). */
+LEXP_API int lexp_plan_pm_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int step_index, int kind, int m, uint64_t seed,
+                               const lexp_plane* planes, int planes_on_device, lexp_plane* d_planes_out, int flags);
+
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
 LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,

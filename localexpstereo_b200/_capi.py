@@ -58,6 +58,11 @@ SYMBOLS = {
     "lexp_set_stream": (C.c_int, [_P, _P]),
     "lexp_launch_count": (C.c_int64, [_P]),
     "lexp_combine_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lexp_pm_begin": (C.c_int, [_P, C.c_int, _P, _P]),
+    "lexp_pm_get": (C.c_int, [_P, C.c_int, _P, _P]),
+    "lexp_pm_device_state": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "lexp_plan_set_units": (C.c_int, [_P, _P, _P]),
+    "lexp_plan_pm_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, C.c_int]),
     "lexp_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, _P, _P]),
 }
 

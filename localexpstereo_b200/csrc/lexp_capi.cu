@@ -61,6 +61,10 @@ struct lexp_plan {
     Plane4* d_planes = nullptr;   // staging for host planes
     float* d_compact = nullptr;   // lazily allocated compact output (host path)
     float* h_compact = nullptr;   // pinned
+    // PatchMatch phase (lexp_plan_set_units / lexp_plan_pm_step)
+    CallInfo* d_calls = nullptr;  // [ncalls] unitRegion, signals per step, cell id
+    int* d_cell_done = nullptr;   // [ncalls] completion counters of the group
+    std::vector<int> items_per_call;
 };
 
 struct lexp_ctx {
@@ -77,6 +81,8 @@ struct lexp_ctx {
     size_t persist_bytes = 0;             // L2 set-aside for persisting accesses (0: unsupported)
     int persist_mode = -1;                // view whose window is currently installed on the stream
     float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[Hb][Wb][D][4][4] (owned)
+    float* d_cur_cost[2] = {nullptr, nullptr};     // PatchMatch phase: currentCost_[mode]   float [H][W]
+    float4* d_cur_label[2] = {nullptr, nullptr};   //                   currentLabeling_[mode] Plane[H][W]
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
@@ -163,7 +169,7 @@ void report_trace(lexp_ctx* c, int nitems) {
 #endif
 
 template <int R_T, bool NAIVE>
-int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem) {
+int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem, bool allow_pdl) {
     KParams kp = kp_in;
 #if LEXP_TRACE
     {
@@ -183,7 +189,7 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem) {
         c->smem_configured = true;
     }
 #if LEXP_PDL && !defined(LEXP_EMU)
-    if (c->pdl) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
+    if (c->pdl && allow_pdl) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)nitems); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
@@ -202,18 +208,18 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem) {
     return LEXP_OK;
 }
 
-int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem) {
+int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem, bool allow_pdl = true) {
     if (smem > c->smem_limit) return fail(LEXP_ERR_INVALID, "tile needs more shared memory than the device offers");
     if (c->p.energy_kind == 1) {
         switch (c->R) {
-            case 10: return launch_fused_t<10, true>(c, kp, nitems, smem);
-            default: return launch_fused_t<0, true>(c, kp, nitems, smem);
+            case 10: return launch_fused_t<10, true>(c, kp, nitems, smem, allow_pdl);
+            default: return launch_fused_t<0, true>(c, kp, nitems, smem, allow_pdl);
         }
     }
     switch (c->R) {
-        case 10: return launch_fused_t<10, false>(c, kp, nitems, smem);
-        case 16: return launch_fused_t<16, false>(c, kp, nitems, smem);
-        default: return launch_fused_t<0, false>(c, kp, nitems, smem);
+        case 10: return launch_fused_t<10, false>(c, kp, nitems, smem, allow_pdl);
+        case 16: return launch_fused_t<16, false>(c, kp, nitems, smem, allow_pdl);
+        default: return launch_fused_t<0, false>(c, kp, nitems, smem, allow_pdl);
     }
 }
 
@@ -222,6 +228,8 @@ void release_plan_memory(lexp_plan* pl) {
     cudaFree(pl->d_planes); pl->d_planes = nullptr;
     cudaFree(pl->d_compact); pl->d_compact = nullptr;
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
+    cudaFree(pl->d_calls); pl->d_calls = nullptr;
+    cudaFree(pl->d_cell_done); pl->d_cell_done = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -248,8 +256,14 @@ int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
     return LEXP_OK;
 }
 
+struct PmArgs {   // PatchMatch phase (lexp_plan_pm_step); nullptr = plain unary evaluation
+    int pm_mode, prop_kind, prop_m, step_index;
+    unsigned long long seed;
+    Plane4* planes_out;
+};
+
 int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float* d_out, long long pitch, int compact,
-             int with_check) {
+             int with_check, const PmArgs* pm = nullptr) {
     if (mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "mode must be 0 or 1");
     if (c->p.energy_kind == 1) {
         if (!c->d_exi[0] || !c->d_exi[1]) return fail(LEXP_ERR_STATE, "NaiveStereoEnergy needs the images of both views");
@@ -291,7 +305,15 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     kp.thresh_gradient = c->p.th_grad * c->p.alpha;          // StereoEnergy.h:664
     kp.mode = mode;
     kp.fast_ok = (c->vol_finite[mode] && c->p.min_disp == 0.0f && c->p.max_disp == (float)(c->p.ndisp - 1) && c->p.th_col >= 0.0f) ? 1 : 0;
-    return launch_fused(c, kp, pl->nitems, pl->smem);
+    if (pm) {
+        kp.pm_mode = pm->pm_mode; kp.prop_kind = pm->prop_kind; kp.prop_m = pm->prop_m; kp.step_index = pm->step_index;
+        kp.seed = pm->seed; kp.planes_out = pm->planes_out;
+        kp.cur_cost = c->d_cur_cost[mode]; kp.cur_label = c->d_cur_label[mode];
+        kp.calls = pl->d_calls; kp.cell_done = pl->d_cell_done;
+    }
+    // the first step of a group is ordered after everything before it (its cells overlap the previous group's); the later
+    // steps of the group may start early (programmatic dependent launch): per-cell counters order them
+    return launch_fused(c, kp, pl->nitems, pl->smem, !(pm && pm->step_index == 0));
 }
 
 // scan the caller's volume for NaN/Inf and re-lay it out into the context's blocked copy
@@ -383,6 +405,8 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_gs[m]);
         cudaFree(c->d_exi[m]);
         cudaFree(c->d_vol[m]);
+        cudaFree(c->d_cur_cost[m]);
+        cudaFree(c->d_cur_label[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -511,6 +535,7 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
     pl->filt.assign(filt, filt + n);
     pl->targ.assign(targ, targ + n);
     pl->compact_off.resize(n);
+    pl->items_per_call.assign(n, 0);
     std::vector<Item> items;
     int64_t coff = 0;
     for (int i = 0; i < n; i++) {
@@ -529,6 +554,7 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
                 it.compact_stride = t.width;
                 it.flags = (t.width == 1 && t.height == 1) ? 1 : 0;
                 items.push_back(it);
+                pl->items_per_call[i]++;
                 pl->max_vw = std::max(pl->max_vw, it.ow + 4 * R);
                 pl->smem = std::max(pl->smem, fused_smem_bytes(it.ow + 4 * R, it.oh, R));
             }
@@ -878,6 +904,92 @@ int lexp_set_stream(lexp_ctx* c, void* s) {
     return LEXP_OK;
 }
 int64_t lexp_launch_count(const lexp_ctx* c) { return c ? c->launches : 0; }
+
+// ---- PatchMatch phase on the device (FastGCStereo.h:94-157 with doGC == false) ---------------------------------------------
+int lexp_pm_begin(lexp_ctx* c, int mode, const float* cost, const lexp_plane* labeling) {
+    if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const size_t HW = (size_t)c->p.height * c->p.width;
+    if (!c->d_cur_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_cur_cost[mode], HW * sizeof(float)));
+    if (!c->d_cur_label[mode]) LEXP_CUDA(cudaMalloc(&c->d_cur_label[mode], HW * sizeof(float4)));
+    if (cost) LEXP_CUDA(cudaMemcpyAsync(c->d_cur_cost[mode], cost, HW * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    else {
+        LEXP_LAUNCH(lexp_fill_f32, 148 * 4, 256, 0, c->stream, c->d_cur_cost[mode], HW, __builtin_inff());   // currentCost_ = INFINITY (:137)
+        LEXP_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    if (labeling) LEXP_CUDA(cudaMemcpyAsync(c->d_cur_label[mode], labeling, HW * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    else LEXP_CUDA(cudaMemsetAsync(c->d_cur_label[mode], 0, HW * sizeof(float4), c->stream));
+    if (cost || labeling) LEXP_CUDA(cudaStreamSynchronize(c->stream));  // the host buffers may be pageable
+    return LEXP_OK;
+}
+
+int lexp_pm_get(lexp_ctx* c, int mode, float* cost, lexp_plane* labeling) {
+    if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const size_t HW = (size_t)c->p.height * c->p.width;
+    if (cost) LEXP_CUDA(cudaMemcpyAsync(cost, c->d_cur_cost[mode], HW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (labeling) LEXP_CUDA(cudaMemcpyAsync(labeling, c->d_cur_label[mode], HW * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    return LEXP_OK;
+}
+
+int lexp_pm_device_state(lexp_ctx* c, int mode, float** d_cost, lexp_plane** d_labeling) {
+    if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    if (d_cost) *d_cost = c->d_cur_cost[mode];
+    if (d_labeling) *d_labeling = reinterpret_cast<lexp_plane*>(c->d_cur_label[mode]);
+    return LEXP_OK;
+}
+
+int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_ids) {
+    if (!pl || !units) return fail(LEXP_ERR_INVALID, "bad argument");
+    lexp_ctx* c = pl->ctx;
+    if (!c) return fail(LEXP_ERR_STATE, "the plan's context has been destroyed");
+    const int H = c->p.height, W = c->p.width;
+    std::vector<CallInfo> h(pl->ncalls);
+    for (int i = 0; i < pl->ncalls; i++) {
+        const lexp_rect& u = units[i];
+        if (u.width <= 0 || u.height <= 0 || u.x < 0 || u.y < 0 || u.x + u.width > W || u.y + u.height > H)
+            return fail(LEXP_ERR_INVALID, "unitRegion outside the image");
+        h[i] = CallInfo{u.x, u.y, u.width, u.height, pl->items_per_call[i] * kWarpsE, cell_ids ? cell_ids[i] : i, {0, 0}};
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
+    if (!pl->d_cell_done) LEXP_CUDA(cudaMalloc(&pl->d_cell_done, (size_t)pl->ncalls * sizeof(int)));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    LEXP_CUDA(cudaMemcpy(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice));
+    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_done, 0, (size_t)pl->ncalls * sizeof(int), c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    return LEXP_OK;
+}
+
+int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes,
+                      int planes_on_device, lexp_plane* d_planes_out, int flags) {
+    if (!c || !pl || pl->ctx != c || mode < 0 || mode > 1 || step_index < 0) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (kind < LEXP_PROP_LIST || kind > LEXP_PROP_RANDOM || m < 0 || m > 120) return fail(LEXP_ERR_INVALID, "bad proposer kind / m");
+    if (kind == LEXP_PROP_LIST && !planes) return fail(LEXP_ERR_INVALID, "LEXP_PROP_LIST needs planes");
+    if (!pl->d_calls) return fail(LEXP_ERR_STATE, "lexp_plan_set_units has not been called for this plan");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    if (c->p.energy_kind != 0) return fail(LEXP_ERR_INVALID, "the device PatchMatch phase is implemented for the cost-volume energy");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const Plane4* dp = nullptr;
+    if (kind == LEXP_PROP_LIST) {
+        dp = reinterpret_cast<const Plane4*>(planes);
+        if (!planes_on_device) {
+            LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+            dp = pl->d_planes;
+        }
+    }
+    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_done, 0, (size_t)pl->ncalls * sizeof(int), c->stream));
+    PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out)};
+    return run_plan(c, pl, mode, dp, nullptr, 0, 0, 1, &pm);
+}
 
 // LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).
 int lexp_layer_geometry(int width, int height, int windR, int u, int* hb_out, int* wb_out, lexp_rect* unit, lexp_rect* shared,

@@ -104,6 +104,14 @@ struct __align__(16) Item {  // one CTA work item (64 B)
 
 struct Plane4 { float a, b, c, v; };
 
+// per-call (= per cell) data of the device-side PatchMatch phase (FastGCStereo.h:22-72 with doGC == false)
+struct __align__(16) CallInfo {
+    int ux, uy, uw, uh;      // unitRegion of the cell: where the proposers draw their source pixel (Proposer.h:38-45,69-75)
+    int n_done_per_step;     // completion signals one proposal step of this cell produces (its work items x kWarpsE)
+    int cell_id;             // global id of the cell (seeds its random stream; independent of how cells are sharded over GPUs)
+    int pad[2];
+};
+
 struct KParams {
     const float* __restrict__ vol;      // blocked cost volume float[Hb][Wb][D][4 rows][4 px], Hb = ceil(H/4), Wb = ceil(W/4) (lexp_relayout_volume)
     int Wb;
@@ -126,6 +134,18 @@ struct KParams {
     float thresh_color, thresh_gradient;  // StereoEnergy.h:663-664
     int mode;                             // 0: left reference view, 1: right
     int fast_ok;                        // MIN == 0, MAX == D-1, th_col >= 0 and the volume holds no NaN/Inf
+    // ---- device-side PatchMatch phase (pm_mode != 0): proposal -> unary cost -> `mask = cur > prop; copy; setTo`
+    // (FastGCStereo.h:34-60 with doGC == false) without leaving the device
+    int pm_mode;                        // 0: unary costs only (out); 1: fused update of cur_cost / cur_label; 2: initialisation (unconditional write, :105-113)
+    int prop_kind;                      // 0: planes[call] (host list / RANSAC slot), 1: ExpansionProposer, 2: RandomProposer
+    int prop_m;                         // RandomProposer: m = outerIter + iter (Proposer.h:124)
+    int step_index;                     // proposal step within the group: the cell's previous steps must have completed
+    unsigned long long seed;            // random stream of this (view, iteration, layer, group, step); hashed with the cell id
+    float* __restrict__ cur_cost;       // float [H][W]   currentCost_[mode]
+    float4* __restrict__ cur_label;     // float4[H][W]   currentLabeling_[mode] (Plane = 4 floats, Plane.h:4-8)
+    const CallInfo* __restrict__ calls; // [ncalls]
+    int* cell_done;                     // [ncalls] completion counters of the group (zeroed before its first step)
+    Plane4* planes_out;                 // [ncalls] the plane each call evaluated in this step (optional: replay / logging)
 #if LEXP_TRACE
     long long* trace;                   // [items][kThreads / 32][4]
 #endif
@@ -167,6 +187,7 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 #define LEXP_LOADS_LANDED(...) asm volatile("" : __VA_ARGS__ :: "memory")
 #define LEXP_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define LEXP_NOINLINE __noinline__
 #else  // host emulation of the same operations (tests/emu/, test infrastructure only)
 inline u64 pk2(float a, float b) { return (u64)__float_as_uint(a) | ((u64)__float_as_uint(b) << 32); }
 inline void up2(u64 v, float& a, float& b) { a = __uint_as_float((unsigned)v); b = __uint_as_float((unsigned)(v >> 32)); }
@@ -174,6 +195,7 @@ inline u64 add2(u64 a, u64 b) { float a0, a1, b0, b1; up2(a, a0, a1); up2(b, b0,
 inline u64 sub2(u64 a, u64 b) { float a0, a1, b0, b1; up2(a, a0, a1); up2(b, b0, b1); return pk2(__fsub_rn(a0, b0), __fsub_rn(a1, b1)); }
 #define LEXP_LOADS_LANDED(...) ((void)0)
 #define LEXP_DYNAMIC_SMEM(name) unsigned char* name = emu::dyn_smem()
+#define LEXP_NOINLINE
 #endif
 __device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
@@ -259,6 +281,89 @@ __device__ inline void naive_inverse_affine(const Item& it, const Plane4& pl, in
     iM[5] = __dsub_rn(__dmul_rn(-iM[3], M[2]), __dmul_rn(iM[4], M[5]));
 }
 
+// ---- device-side proposers of the PatchMatch phase ------------------------------------------------------------------------
+// cv::RNG (OpenCV core: multiply-with-carry, 64-bit state) -- the generator behind cv::theRNG() that the reference's proposers
+// draw from (Proposer.h:40,132,147; Utilities.hpp:254-261).  Same integer recurrence and the same float / double conversions,
+// every floating-point operation rounded separately, so a stream started from the same state yields the same proposals.
+struct CvRng {
+    u64 state;
+    __device__ unsigned next() {
+        state = (u64)(unsigned)state * 4164903690ull + (u64)(unsigned)(state >> 32);
+        return (unsigned)state;
+    }
+    __device__ int uniform_int(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + (unsigned)a); }
+    __device__ float uniform_float(float a, float b) {
+        const float r = __fmul_rn((float)next(), 2.32830643653869629E-10f);
+        return __fadd_rn(__fmul_rn(r, __fsub_rn(b, a)), a);
+    }
+    __device__ double uniform_double(double a, double b) {
+        const unsigned t = next();
+        const u64 w = ((u64)t << 32) | (u64)next();
+        const double r = __dmul_rn(__ull2double_rn(w), 5.4210108624275221700372640043497e-20);
+        return __dadd_rn(__dmul_rn(r, __dsub_rn(b, a)), a);
+    }
+};
+// Start state of the random stream of one (cell, proposal step): the reference draws from a per-thread cv::theRNG() whose
+// assignment to cells is arbitrary; here every (launch seed, cell id) pair gets its own stream (splitmix64 finaliser), so the
+// result does not depend on scheduling or on how cells are sharded over GPUs.  Restated by oracle.pm_rng_state.
+__host__ __device__ inline u64 pm_rng_state(u64 seed, int cell_id) {
+    u64 z = seed + 0x9E3779B97F4A7C15ull * (u64)(unsigned)(cell_id + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return z ? z : 0xffffffffull;   // cv::RNG(0) starts from 0xffffffff
+}
+// One proposal of ExpansionProposer (Proposer.h:69-75: the current label of a random pixel of the unitRegion) or of
+// RandomProposer (Proposer.h:120-148: that label with its disparity at the pixel and its normal perturbed), MAX_VDISPARITY = 0.
+// Executed by one thread of the CTA; kept out of line so that it does not weigh on the register allocation of the pipeline.
+struct ProposeArgs {   // by value: a reference to the kernel parameters would force them into a stack frame
+    u64 seed; const float4* cur_label; int W, prop_kind, prop_m; float min_disp, max_disp;
+};
+__device__ LEXP_NOINLINE float4 pm_propose(const ProposeArgs P, const int ux, const int uy, const int uw, const int uh, const int cell_id) {
+    CvRng rng{pm_rng_state(P.seed, cell_id)};
+    const int n = rng.uniform_int(0, uw * uh);                          // selectRandomPixelInRect (:38-45)
+    const int sx = ux + n % uw, sy = uy + n / uw;
+    const float4 in4 = __ldcg(P.cur_label + (size_t)sy * P.W + sx);   // L2: written by other SMs, possibly by a launch still running
+    const Plane4 in{in4.x, in4.y, in4.z, in4.w};
+    if (P.prop_kind == 1) return in4;                                    // ExpansionProposer (:69-75)
+    const float fx = (float)sx, fy = (float)sy;
+    float zs = __fadd_rn(__fadd_rn(__fmul_rn(in.a, fx), __fmul_rn(in.b, fy)), in.c);   // Plane::GetZ (Plane.h:51-54)
+    const float scale = exp2f(-(float)(P.prop_m + 1));                                 // pow(0.5f, m + 1): exact
+    const float dz = __fmul_rn(__fsub_rn(P.max_disp, P.min_disp), scale);              // :107-110
+    const float minz = fmaxf(P.min_disp, __fsub_rn(zs, dz)), maxz = fminf(P.max_disp, __fadd_rn(zs, dz));
+    zs = rng.uniform_float(minz, maxz);                                                 // :132
+    const float nr = exp2f(-(float)P.prop_m);                                           // randomNmax * pow(0.5f, m) (:143)
+    const double theta = rng.uniform_double(0.0, 3.14159265358979323846);               // getRandomUnitVector (Utilities.hpp:254-261)
+    const double phi = rng.uniform_double(0.0, __dmul_rn(3.14159265358979323846, 2.0));
+    const double cT = cos(theta), sT = sin(theta), cP = cos(phi), sP = sin(phi);
+    const float r0 = (float)__dmul_rn(sT, cP), r1 = (float)__dmul_rn(sT, sP), r2 = (float)cT;
+    // Plane::GetNormal (Plane.h:42-50): sqrt in double, then cast to float
+    const float gnz = (float)__ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(1.0, (double)__fmul_rn(in.a, in.a)), (double)__fmul_rn(in.b, in.b))));
+    const float gnx = __fmul_rn(-in.a, gnz), gny = __fmul_rn(-in.b, gnz);
+    const float v0 = __fadd_rn(gnx, __fmul_rn(r0, nr)), v1 = __fadd_rn(gny, __fmul_rn(r1, nr)), v2 = __fadd_rn(gnz, __fmul_rn(r2, nr));  // :144
+    double dd = __dmul_rn((double)v0, (double)v0);                                      // nv.ddot(nv), then nv / sqrt(.) = nv * (1 / sqrt(.))  (:146)
+    dd = __dadd_rn(dd, __dmul_rn((double)v1, (double)v1));
+    dd = __dadd_rn(dd, __dmul_rn((double)v2, (double)v2));
+    const double inv = __ddiv_rn(1.0, sqrt(dd));
+    const float nx = (float)__dmul_rn((double)v0, inv), ny = (float)__dmul_rn((double)v1, inv), nz = (float)__dmul_rn((double)v2, inv);
+    float4 out;                                                                         // Plane::CreatePlane (Plane.h:23-31)
+    out.x = __fdiv_rn(-nx, nz);
+    out.y = __fdiv_rn(-ny, nz);
+    out.z = __fsub_rn(__fsub_rn(zs, __fmul_rn(out.x, fx)), __fmul_rn(out.y, fy));
+    out.w = in.v;
+    return out;
+}
+// acquire load / polling of a completion counter written by CTAs of earlier launches that may still be running (PDL)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+#ifndef LEXP_EMU
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *reinterpret_cast<const volatile int*>(p);
+#endif
+}
+
 // Cost-volume samples: plain read-only loads.  Measured on B200 (profiles/r1_experiments.md): letting them allocate in
 // L1 (the d0 / d0+1 samples of a 4-pixel block share 128-byte lines) beats L1::no_allocate + L2 evict-first by 8 %.
 __device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
@@ -278,8 +383,34 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     const unsigned tr_t0 = (unsigned)clock64();
 #endif
     const Item it = P.items[blockIdx.x];
-    const Plane4 pl = P.planes[it.call];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Plane4 pl;
+    if (!P.pm_mode) pl = P.planes[it.call];
+    else {
+        // PatchMatch phase: this cell's previous proposal steps (all their work items) must have updated cur_cost / cur_label
+        // before the proposer reads a label and before this step's own update (FastGCStereo.h:41-60 is sequential per cell).
+        // The counters are written by CTAs of earlier launches of the stream, which may still be running (PDL): poll.
+        __shared__ Plane4 s_pl;
+        if (tid == 0) {
+            const CallInfo ci = P.calls[it.call];
+            const int need = P.step_index * ci.n_done_per_step;
+            while (ld_acquire(P.cell_done + it.call) < need) {
+#ifndef LEXP_EMU
+                __nanosleep(100);
+#endif
+            }
+            Plane4 q;
+            if (P.prop_kind) {
+                const float4 g = pm_propose(ProposeArgs{P.seed, P.cur_label, P.W, P.prop_kind, P.prop_m, P.min_disp, P.max_disp},
+                                            ci.ux, ci.uy, ci.uw, ci.uh, ci.cell_id);
+                q = Plane4{g.x, g.y, g.z, g.w};
+            } else q = P.planes[it.call];
+            s_pl = q;
+            if (P.planes_out) P.planes_out[it.call] = q;   // every work item of the call writes the same value
+        }
+        __syncthreads();
+        pl = s_pl;
+    }
     const int VW = it.ow + 4 * R;
     const int X0 = it.ox0 - 2 * R;
     const int W2 = VW - 2 * R;
@@ -425,7 +556,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const int XAc = colA ? XA : it.fx;
         // blocked volume: element (d, y, x) lives at ((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4:
         // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
+#if !LEXP_A_ROWTAB
         const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
+#endif
         const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
 #if LEXP_A_ROWTAB && LEXP_MIN_CTAS <= 2 && !defined(LEXP_EMU)
         // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row); not with the 56-register
@@ -799,22 +932,28 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             if (axl + byl + pl.c - ext - margin >= P.min_disp && axh + byh + pl.c + ext + margin <= P.max_disp) check = false;
         }
         uint32_t gq[kCH];
+        float cq[kCH];   // PatchMatch phase: the pixel's current cost, prefetched with the guide (L2 only: other SMs wrote it)
+        const bool pm_update = P.pm_mode == 1;
         int vi = 0;
         const unsigned int* pg = reinterpret_cast<const unsigned int*>(P.guide) + (size_t)(ys - 2 * R) * P.W + (colE ? XE : it.ox0);
         auto issue = [&]() {
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
-                gq[r] = 0u;
+                gq[r] = 0u; cq[r] = 0.f;
 #ifdef LEXP_X_NOGUIDE_E
                 if (colE && vi >= vE0 && vi < VHs) gq[r] = 0x00808080u;
 #else
-                if (colE && vi >= vE0 && vi < VHs) gq[r] = __ldg(pg);
+                if (colE && vi >= vE0 && vi < VHs) {
+                    gq[r] = __ldg(pg);
+                    if (pm_update) cq[r] = __ldcg(P.cur_cost + (pg - reinterpret_cast<const unsigned int*>(P.guide)));
+                }
 #endif
                 vi++;
                 pg += P.W;
             }
         };
         issue();
+        size_t cpix = (size_t)it.oy0 * P.W + XE;   // PatchMatch phase: pixel index of the next output row in cur_cost / cur_label
         float* orow;  // output pointer of row yq = ys + v - 2R at column XE
         long long ostride;
         if (P.out_compact) { orow = P.out + (size_t)it.compact_off + t; ostride = it.compact_stride; }
@@ -826,10 +965,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             {
                 LEXP_TRACE_LOAD_WAIT(gq[kCH - 1]);
                 uint32_t cg[kCH];
+                float cc[kCH];
 #pragma unroll
                 for (int r = 0; r < kCH; r++) {
-                    LEXP_LOADS_LANDED("+r"(gq[r]));
-                    cg[r] = gq[r];
+                    LEXP_LOADS_LANDED("+r"(gq[r]), "+f"(cq[r]));
+                    cg[r] = gq[r]; cc[r] = cq[r];
                 }
                 issue();
                 consume_begin(3, c, kLinkHE);
@@ -860,6 +1000,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                                                 dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
                                 if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
                             }
+                            if (P.pm_mode) {
+                                // `updateMask = subCurrentCost > subProposalCost; copyTo; setTo` (FastGCStereo.h:56-60); NaN never
+                                // updates.  Initialisation (pm_mode 2, :105-113) writes unconditionally.  Ordering against the cell's
+                                // previous steps is by its completion counter (prologue), not by griddepcontrol.wait.
+                                if (P.pm_mode == 2 || cc[r] > q) {
+                                    P.cur_cost[cpix] = q;
+                                    P.cur_label[cpix] = make_float4(pl.a, pl.b, pl.c, pl.v);
+                                }
+                                cpix += (size_t)P.W;
+                            } else {
 #if LEXP_PDL
                             if (!prior_grids_done) {  // write-after-write order against the previous launch of the stream
 #ifndef LEXP_EMU
@@ -870,11 +1020,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #endif
                             *orow = q;
                             orow += ostride;
+                            }
                         }
                     }
                 }
                 consume_end(3, c, nChunks, kLinkHE);
             }
+        }
+        if (P.pm_mode) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.cell_done + it.call, 1);
         }
     }
 #if LEXP_TRACE
@@ -981,6 +1137,12 @@ __global__ void lexp_scan_nonfinite(const float* __restrict__ vol, size_t n, int
 #else
     if (bad) atomicOr(flag, 1);  // emulated threads do not run in warp lock-step
 #endif
+}
+
+__global__ void lexp_fill_f32(float* __restrict__ dst, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = v;
 }
 
 // planar float[9][H][W] view of the statistics (lexp_get_stats)

@@ -134,6 +134,9 @@ def host_unregister(array: np.ndarray):
     check(lib().lexp_host_unregister(array.ctypes.data))
 
 
+PROP_LIST, PROP_EXPANSION, PROP_RANDOM = 0, 1, 2   # LEXP_PROP_* of include/lexp_cuda.h
+
+
 class Plan:
     """Device-resident work list for a fixed list of (filterRect, targetRect) (see lexp_plan_create)."""
 
@@ -187,6 +190,28 @@ class Plan:
             ptr = self._pl_keep.ctypes.data
         check(lib().lexp_plan_eval_device_tiles(self.energy._h, self._h, mode, ptr, int(planes_on_device), int(d_tiles_ptr),
                                                 int(with_check)))
+
+    # --- PatchMatch phase on the device (lexp_plan_set_units / lexp_plan_pm_step) -------------------------------------
+    def set_units(self, unit_rects, cell_ids=None):
+        """unitRegion of every call (LayerManager.h:117-121) and a global id per cell (seeds its random streams)."""
+        u = _rect_array(unit_rects)
+        assert len(u) == self.num_calls
+        ids = None if cell_ids is None else np.ascontiguousarray(cell_ids, dtype=np.int32)
+        check(lib().lexp_plan_set_units(self._h, u.ctypes.data, None if ids is None else ids.ctypes.data))
+
+    def pm_step(self, step_index, kind, m=0, seed=0, planes=None, planes_on_device=False, d_planes_out=0, init=False, mode=0):
+        """One proposal step of FastGCStereo.h:41-60 (doGC == false) for all cells of the plan, asynchronous:
+        kind = PROP_LIST (planes: numpy [n][4] or a device pointer) | PROP_EXPANSION | PROP_RANDOM (m = outerIter + iter)."""
+        ptr = None
+        if kind == PROP_LIST:
+            if planes_on_device:
+                ptr = int(planes)
+            else:
+                self._pl_keep = _plane_array(planes)
+                assert len(self._pl_keep) == self.num_calls
+                ptr = self._pl_keep.ctypes.data
+        check(lib().lexp_plan_pm_step(self.energy._h, self._h, mode, int(step_index), int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                      ptr, int(planes_on_device), int(d_planes_out) or None, 1 if init else 0))
 
     def close(self):
         if self._h:
@@ -280,6 +305,27 @@ class CostVolumeEnergy:
         out = np.empty((9, self.height, self.width), dtype=np.float32)
         check(lib().lexp_get_stats(self._h, mode, out.ctypes.data))
         return out
+
+    # --- PatchMatch phase state: currentCost_[mode] / currentLabeling_[mode] resident on the device ------------------------
+    def pm_begin(self, mode=0, cost=None, labeling=None):
+        """FastGCStereo::run, :137: currentCost_ = INFINITY (or `cost`), currentLabeling_ = `labeling` (or zeros)."""
+        c = None if cost is None else np.ascontiguousarray(cost, dtype=np.float32)
+        l = None if labeling is None else np.ascontiguousarray(labeling, dtype=np.float32)
+        assert c is None or c.shape == (self.height, self.width)
+        assert l is None or l.shape == (self.height, self.width, 4)
+        check(lib().lexp_pm_begin(self._h, mode, None if c is None else c.ctypes.data, None if l is None else l.ctypes.data))
+
+    def pm_get(self, mode=0, want_cost=True, want_labeling=True):
+        cost = np.empty((self.height, self.width), np.float32) if want_cost else None
+        lab = np.empty((self.height, self.width, 4), np.float32) if want_labeling else None
+        check(lib().lexp_pm_get(self._h, mode, None if cost is None else cost.ctypes.data, None if lab is None else lab.ctypes.data))
+        return cost, lab
+
+    def pm_device_state(self, mode=0):
+        """(device pointer of currentCost float[H][W], device pointer of currentLabeling Plane[H][W])."""
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib().lexp_pm_device_state(self._h, mode, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def sync(self):
         check(lib().lexp_sync(self._h))

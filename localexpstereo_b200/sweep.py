@@ -79,3 +79,105 @@ class UnarySweep:
         for g in self.groups:
             g.plan.close()
         self.groups = []
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PatchMatch phase on the device: FastGCStereo::run's pmInit iterations (FastGCStereo.h:143-157), i.e. the same call
+# schedule with doGC == false, proposals drawn and currentCost_/currentLabeling_ updated on the device (lexp_plan_pm_step).
+# ---------------------------------------------------------------------------------------------------------------------
+from .energy import PROP_EXPANSION, PROP_LIST, PROP_RANDOM  # noqa: E402
+
+# the reference's proposer lists (main.cpp:391-397: {Expansion(1), Ransac(1), Random(7)} / {Expansion(2), Ransac(1)} x 2).  The
+# RansacProposer slot (cv::solve SVD + std::random_shuffle on the host) has no device counterpart yet: schedules below give it to
+# the caller (PROP_LIST: planes supplied per step) or, for device-only sweeps, fill it with one more RandomProposer draw so that
+# the number of evaluations per cell stays K = 9 / 3 / 3.
+V3_PROPOSERS_DEVICE = [[(PROP_EXPANSION, 1), (PROP_RANDOM, 8)], [(PROP_EXPANSION, 2), (PROP_RANDOM, 1)], [(PROP_EXPANSION, 2), (PROP_RANDOM, 1)]]
+
+
+def pm_seed(base, mode, iteration, layer, group, step):
+    """Random stream of one launch = one (view, iteration, layer, group, proposal step); the kernel hashes it with the cell id."""
+    M = 0xFFFFFFFFFFFFFFFF
+    z = (int(base) * 0x9E3779B97F4A7C15 + (mode + 1) * 0xD1B54A32D192ED03 + (iteration + 1) * 0x8CB92BA72F3D8DD7
+         + (layer + 1) * 0xABC98388FB8FAC03 + (group + 1) * 0x2545F4914F6CDD1D + (step + 1) * 0xDA942042E4DD58B5) & M
+    z = ((z ^ (z >> 33)) * 0xFF51AFD7ED558CCD) & M
+    return z ^ (z >> 29)
+
+
+def expand_proposers(proposers, outer_iter, max_disp, min_disp=0.0):
+    """[(kind, K)] -> the proposal steps [(kind, m)] of one cell visit, as the `while (prop->isContinued())` loops of
+    FastGCStereo.h:41-46 produce them; RandomProposer stops early when its disparity perturbation width falls below 0.1
+    (Proposer.h:149-152) and uses m = outerIter + iter (:124)."""
+    steps = []
+    for kind, K in proposers:
+        for it in range(K):
+            if kind == PROP_RANDOM and np.float32(max_disp - min_disp) * np.float32(0.5) ** (outer_iter + it + 1) < 0.1:
+                break
+            steps.append((kind, outer_iter + it if kind == PROP_RANDOM else 0))
+    return steps
+
+
+class PMSweep:
+    """Device-resident PatchMatch phase of one view: state (currentCost_, currentLabeling_) in HBM, one plan per (layer, group),
+    one launch per proposal step; nothing crosses PCIe between `begin` / `init` and `get`."""
+
+    def __init__(self, energy: CostVolumeEnergy, unit_sizes=None, proposers=None, rank=0, world=1, mode=0):
+        self.energy, self.mode = energy, mode
+        self.unit_sizes = unit_sizes or v3_layer_units(energy.width)
+        self.proposers = proposers or V3_PROPOSERS_DEVICE
+        self.lm = LayerManager(energy.width, energy.height, energy.params.windR)
+        self.groups: List[GroupPlan] = []
+        self.evals_per_iteration = None
+        cell_base = 0
+        for li, u in enumerate(self.unit_sizes):
+            lay = self.lm.addLayer(u)
+            for gi, cells in enumerate(lay.disjointRegionSets):
+                mine = shard_cells(cells, rank, world)
+                if len(mine) == 0:
+                    continue
+                plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])
+                plan.set_units([lay.unitRegions[r] for r in mine], cell_base + mine)
+                self.groups.append(GroupPlan(li, gi, mine, plan, 0))
+            cell_base += len(lay.unitRegions)
+        # initCurrentFast (FastGCStereo.h:101-113): every unit region of layer 0 with filterRegion = unit +- windR
+        lay0 = self.lm.layers[0]
+        R, W, H = energy.params.windR, energy.width, energy.height
+        self.init_units = [lay0.unitRegions[r] for r in range(len(lay0.unitRegions))][rank::world]
+        fr = []
+        for (x, y, w, h) in self.init_units:
+            x0, y0, x1, y1 = max(x - R, 0), max(y - R, 0), min(x + w + R, W), min(y + h + R, H)
+            fr.append((x0, y0, x1 - x0, y1 - y0))
+        self.init_plan = energy.make_plan(fr, self.init_units)
+        self.init_plan.set_units(self.init_units, np.arange(len(lay0.unitRegions))[rank::world])
+
+    def begin(self, cost=None, labeling=None):
+        self.energy.pm_begin(self.mode, cost, labeling)
+
+    def init(self, labels):
+        """labels [n units of layer 0][4]: `currentLabeling(unit) = label; ComputeUnaryPotential(unit +- R, unit, ...)` (:107-111)."""
+        self.init_plan.pm_step(0, PROP_LIST, planes=labels, init=True, mode=self.mode)
+
+    def iteration(self, iteration, seed, list_planes=None, planes_out=None):
+        """One pm iteration over all layers (FastGCStereo.h:153-157).  list_planes: {(layer, group): [list steps][n][4]} for PROP_LIST
+        slots; planes_out: optional {(layer, group): device pointer of [steps][n] planes}.  Returns the number of launches."""
+        n_launch = 0
+        E = self.energy
+        for g in self.groups:
+            steps = expand_proposers(self.proposers[g.layer], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY)
+            li_at = 0
+            for k, (kind, m) in enumerate(steps):
+                pl = None
+                if kind == PROP_LIST:
+                    pl = list_planes[(g.layer, g.group)][li_at]; li_at += 1
+                out = 0 if planes_out is None else planes_out[(g.layer, g.group)] + k * g.plan.num_calls * 16
+                g.plan.pm_step(k, kind, m, pm_seed(seed, self.mode, iteration, g.layer, g.group, k), planes=pl, d_planes_out=out, mode=self.mode)
+                n_launch += 1
+        return n_launch
+
+    def get(self):
+        return self.energy.pm_get(self.mode)
+
+    def close(self):
+        for g in self.groups:
+            g.plan.close()
+        self.init_plan.close()
+        self.groups = []

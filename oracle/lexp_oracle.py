@@ -133,7 +133,7 @@ def random_proposal(rng: CvRNG, plane_in, sx, sy, m, min_disp, max_disp):
     nv = plane_normal(plane_in) + rv * nr
     nv = nv.astype(np.float32)
     nrm = np.sqrt(float(nv[0]) * float(nv[0]) + float(nv[1]) * float(nv[1]) + float(nv[2]) * float(nv[2]))
-    nv = (nv.astype(np.float64) / nrm).astype(np.float32)
+    nv = (nv.astype(np.float64) * (1.0 / nrm)).astype(np.float32)   # cv::Vec / double = Vec * (1. / alpha)  (matx.hpp)
     return create_plane(nv[0], nv[1], nv[2], zs, f32(sx), f32(sy), plane_in[3])
 
 
@@ -642,3 +642,48 @@ class NaiveStereoEnergyOracle:
         out = self.compute_unary_potential_without_check(filter_rect, target_rect, plane, mode)
         out[~is_valid_label(plane, target_rect, self.MIN, self.MAX)] = COST_FOR_INVALID  # :756-763
         return out
+
+
+# ----------------------------------------------------------------------------
+# PatchMatch phase: FastGCStereo::run's pmInit iterations = localExpansionMovesForLayer_CPU with doGC == false
+# (FastGCStereo.h:22-72, 94-157).  Restated per proposal step so that it can be compared with the device path
+# (lexp_plan_pm_step) launch by launch; pinned against the compiled reference's own loop (oracle/_ref ref_pm_group).
+# ----------------------------------------------------------------------------
+def pm_rng_state(seed, cell_id):
+    """Start state of the cv::RNG stream of one (launch seed, cell): splitmix64 finaliser (= lexp::pm_rng_state)."""
+    M = 0xFFFFFFFFFFFFFFFF
+    z = (int(seed) + 0x9E3779B97F4A7C15 * ((int(cell_id) + 1) & 0xFFFFFFFF)) & M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    z = z ^ (z >> 31)
+    return z if z else 0xFFFFFFFF
+
+
+def pm_proposal(kind, m, state, cur_label, unit, min_disp, max_disp):
+    """kind 1: ExpansionProposer::getNextProposal (Proposer.h:69-75); kind 2: RandomProposer::getNextProposal (:120-148)."""
+    rng = CvRNG(state)
+    ux, uy, uw, uh = unit
+    n = rng.uniform_int(0, uw * uh)                 # selectRandomPixelInRect (:38-45)
+    sx, sy = ux + n % uw, uy + n // uw
+    label = np.array(cur_label[sy, sx], dtype=np.float32)
+    if kind == 1:
+        return label
+    return random_proposal(rng, label, sx, sy, m, min_disp, max_disp)
+
+
+def pm_step(energy, units, shareds, filts, kind, m, seed, cell_ids, cur_cost, cur_label, planes=None, mode=0, init=False):
+    """One proposal step for the (disjoint) cells of a group: proposal, ComputeUnaryPotential, `mask = cur > prop`, copy, setTo
+    (FastGCStereo.h:47-59).  init: unconditional write (initCurrentFast, :107-111).  Returns the planes that were evaluated."""
+    used = np.zeros((len(units), 4), np.float32)
+    for i, (u, t, f) in enumerate(zip(units, shareds, filts)):
+        if kind == 0:
+            pl = np.asarray(planes[i], dtype=np.float32)
+        else:
+            pl = pm_proposal(kind, m, pm_rng_state(seed, cell_ids[i]), cur_label, u, energy.MIN, energy.MAX)
+        used[i] = pl
+        q = energy.compute_unary_potential(f, t, pl, mode)
+        sl = (slice(t[1], t[1] + t[3]), slice(t[0], t[0] + t[2]))
+        mask = np.ones(q.shape, bool) if init else (cur_cost[sl] > q)
+        cur_cost[sl][mask] = q[mask]
+        cur_label[sl][mask] = pl
+    return used

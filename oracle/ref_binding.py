@@ -46,6 +46,10 @@ def lib():
         L.ref_layer_rects.argtypes = [vp, ip, ip, ip]
         L.ref_layer_group.argtypes = [vp, C.c_int, ip]
         L.ref_layer_group.restype = C.c_int
+        u64p = C.POINTER(C.c_uint64)
+        L.ref_pm_group.argtypes = [vp, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip, ip, C.c_int, C.c_float, C.c_float, fp, C.c_int, u64p, C.c_int,
+                                   fp, fp, fp, ip, C.c_int]
+        L.ref_pm_init.argtypes = [vp, C.c_int, C.c_int, ip, fp, C.c_int, fp, fp, C.c_int]
         _lib = L
     return _lib
 
@@ -77,6 +81,7 @@ class RefEnergy:
             vl, vr = _p(self.volL, C.c_float), _p(self.volR, C.c_float)
         else:
             self.D, vl, vr = 0, None, None
+        self.max_disp, self.min_disp = float(max_disp), float(min_disp)
         self.h = L.ref_create(kind, self.H, self.W, self.D, _p(self.imL, C.c_ubyte), _p(self.imR, C.c_ubyte), vl, vr, int(windR),
                               float(eps), float(th_col), float(th_grad), float(alpha), float(max_disp), float(min_disp))
         if not self.h:
@@ -131,6 +136,40 @@ class RefEnergy:
         if lib().ref_valid_mask(self.h, _p(pl, C.c_float), _p(r, C.c_int), _p(out, C.c_ubyte)):
             raise RuntimeError(lib().ref_last_error().decode())
         return out
+
+    def pm_group(self, units, shareds, filts, proposers, outer_iter, states, cur_cost, cur_label, list_planes=None, mode=0, nthreads=0):
+        """FastGCStereo.h:30-61 with doGC == false for the cells of one disjoint group, with the reference's own proposers.
+        proposers: [(kind, K)] with kind 0 = replayed plane list, 1 = ExpansionProposer, 2 = RandomProposer; states: uint64 [n][max_steps]
+        cv::RNG states set before each proposal; cur_cost [H][W] / cur_label [H][W][4] float32, updated in place.
+        Returns (planes [n][max_steps][4], steps [n])."""
+        n = len(units)
+        u, sh, fl = _i4(units), _i4(shareds), _i4(filts)
+        kinds = np.ascontiguousarray([k for k, _ in proposers], dtype=np.int32)
+        Ks = np.ascontiguousarray([K for _, K in proposers], dtype=np.int32)
+        st = np.ascontiguousarray(states, dtype=np.uint64)
+        assert st.ndim == 2 and st.shape[0] == n
+        max_steps = st.shape[1]
+        list_steps = int(sum(K for k, K in proposers if k == 0))
+        lp = _f(list_planes if list_planes is not None else np.zeros((n, max(list_steps, 1), 4), np.float32))
+        assert list_steps == 0 or lp.shape == (n, list_steps, 4)
+        assert cur_cost.dtype == np.float32 and cur_cost.flags.c_contiguous and cur_label.dtype == np.float32 and cur_label.flags.c_contiguous
+        out = np.zeros((n, max_steps, 4), np.float32)
+        steps = np.zeros(n, np.int32)
+        rc = lib().ref_pm_group(self.h, mode, n, _p(u, C.c_int), _p(sh, C.c_int), _p(fl, C.c_int), len(proposers), _p(kinds, C.c_int),
+                                _p(Ks, C.c_int), int(outer_iter), float(self.max_disp), float(self.min_disp), _p(lp, C.c_float), list_steps,
+                                _p(st, C.c_uint64), max_steps, _p(cur_cost, C.c_float), _p(cur_label, C.c_float), _p(out, C.c_float),
+                                _p(steps, C.c_int), nthreads)
+        if rc:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out, steps
+
+    def pm_init(self, units, labels, windR, cur_cost, cur_label, mode=0, nthreads=0):
+        """initCurrentFast (FastGCStereo.h:101-113) with the given label per unit region."""
+        u, lb = _i4(units), _f(labels)
+        rc = lib().ref_pm_init(self.h, mode, len(units), _p(u, C.c_int), _p(lb, C.c_float), int(windR), _p(cur_cost, C.c_float),
+                               _p(cur_label, C.c_float), nthreads)
+        if rc:
+            raise RuntimeError(lib().ref_last_error().decode())
 
     def create_random_label(self, x, y):
         out = np.empty(4, np.float32)

@@ -12,6 +12,7 @@
 #include "StereoEnergy.h"
 #include "CostVolumeEnergy.h"
 #include "LayerManager.h"
+#include "Proposer.h"
 #include <omp.h>
 #include <malloc.h>
 
@@ -177,6 +178,100 @@ int ref_random_proposals(float* labeling, int H, int W, const int unit[4], int o
     delete prop;
     return n;
 }
+// ---- the PatchMatch phase of one disjoint group: the body of FastGCStereo::localExpansionMovesForLayer_CPU with
+// doGC == false (FastGCStereo.h:30-61), re-typed here because FastGCStereo.h needs the un-vendored maxflow sources.  The
+// proposers are the reference's own ExpansionProposer / RandomProposer instances, created and driven exactly as at :41-46
+// (createInstance, startIterations, isContinued, getNextProposal); the energy is the reference's.  Two harness additions:
+// (1) cv::theRNG().state is set to states[n][k] right before proposal k of cell n is drawn (the reference leaves the
+// assignment of random streams to cells to the OpenMP runtime); (2) a replay proposer for the slots whose planes the
+// caller supplies (kind 0: fixed plane lists, the RansacProposer slot).
+namespace {
+class ListProposer : public IProposer {
+    const float* planes_;   // [K][4] of the current cell
+public:
+    ListProposer(int K, const float* planes) : IProposer(K), planes_(planes) {}
+    IProposer* createInstance() override { return new ListProposer(K, planes_); }
+    void startIterations(cv::Mat, cv::Rect, int) override { iter = 0; }
+    Plane getNextProposal() override { const float* p = planes_ + 4 * iter++; return Plane(p[0], p[1], p[2], p[3]); }
+    bool isContinued() override { return iter < K; }
+};
+}  // namespace
+// cells: n; rects as int[4] each; prop_kind[j] / prop_K[j]: the layer's proposer list (0 list, 1 ExpansionProposer, 2 RandomProposer);
+// list_planes: [n][total list steps][4]; states: [n][max_steps] cv::RNG states; cur_cost [H][W], cur_label [H][W][4] updated in
+// place; planes_out [n][max_steps][4] receives every proposal; steps_out[n] their count.  Returns < 0 on error.
+int ref_pm_group(void* h, int mode, int n, const int* units, const int* shareds, const int* filts, int nprop, const int* prop_kind,
+                 const int* prop_K, int outer_iter, float max_disp, float min_disp, const float* list_planes, int list_steps,
+                 const uint64_t* states, int max_steps, float* cur_cost, float* cur_label, float* planes_out, int* steps_out, int nthreads) {
+    ref_ctx* c = (ref_ctx*)h;
+    cv::Mat currentCost(c->H, c->W, CV_32F, cur_cost), currentLabeling(c->H, c->W, CV_32FC4, cur_label);
+    cv::Mat proposalCost = cv::Mat(c->H, c->W, CV_32F);                                                  // :25
+    int failed = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        try {
+            cv::Rect unitRegion(units[4 * i], units[4 * i + 1], units[4 * i + 2], units[4 * i + 3]);
+            cv::Rect sharedRegion(shareds[4 * i], shareds[4 * i + 1], shareds[4 * i + 2], shareds[4 * i + 3]);
+            cv::Rect filterRegion(filts[4 * i], filts[4 * i + 1], filts[4 * i + 2], filts[4 * i + 3]);
+            cv::Mat subCurrentCost = currentCost(sharedRegion);                                           // :36-38
+            cv::Mat subProposalCost = proposalCost(sharedRegion);
+            cv::Mat subCurrentLabeling = currentLabeling(sharedRegion);
+            StereoEnergy::Reusable reusable;
+            int step = 0, list_at = 0;
+            for (int j = 0; j < nprop; j++) {                                                             // :41
+                IProposer* prop;
+                if (prop_kind[j] == 1) { ExpansionProposer proto(prop_K[j]); prop = proto.createInstance(); }
+                else if (prop_kind[j] == 2) { RandomProposer proto(prop_K[j], max_disp, min_disp); prop = proto.createInstance(); }
+                else { ListProposer proto(prop_K[j], list_planes + ((size_t)i * list_steps + list_at) * 4); prop = proto.createInstance(); list_at += prop_K[j]; }
+                prop->startIterations(currentLabeling, unitRegion, outer_iter);                           // :44
+                while (prop->isContinued()) {                                                             // :45
+                    if (step >= max_steps) throw std::runtime_error("more proposals than max_steps");
+                    cv::theRNG().state = states[(size_t)i * max_steps + step];
+                    Plane label = prop->getNextProposal();                                                // :47
+                    float* po = planes_out + ((size_t)i * max_steps + step) * 4;
+                    po[0] = label.a; po[1] = label.b; po[2] = label.c; po[3] = label.v;
+                    c->energy->ComputeUnaryPotential(filterRegion, sharedRegion, proposalCost(filterRegion), label, reusable, mode);   // :49
+                    cv::Mat updateMask = subCurrentCost > subProposalCost;                                // :56
+                    subProposalCost.copyTo(subCurrentCost, updateMask);                                   // :58
+                    subCurrentLabeling.setTo(label.toScalar(), updateMask);                               // :59
+                    step++;
+                }
+                delete prop;
+            }
+            steps_out[i] = step;
+        } catch (const std::exception& e) {
+#pragma omp critical
+            { g_err = e.what(); failed++; }
+        }
+    }
+    return failed ? -failed : 0;
+}
+// initCurrentFast with a given label per unit region (FastGCStereo.h:101-113; the random draw of :105-106 is the caller's):
+// currentLabeling(unit) = label; ComputeUnaryPotential(unit +- windR, unit, currentCost(filterRegion), label)
+int ref_pm_init(void* h, int mode, int n, const int* units, const float* labels, int windR, float* cur_cost, float* cur_label, int nthreads) {
+    ref_ctx* c = (ref_ctx*)h;
+    cv::Mat currentCost(c->H, c->W, CV_32F, cur_cost), currentLabeling(c->H, c->W, CV_32FC4, cur_label);
+    const cv::Rect imageDomain(0, 0, c->W, c->H);
+    int failed = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for
+    for (int j = 0; j < n; j++) {
+        try {
+            cv::Rect unit(units[4 * j], units[4 * j + 1], units[4 * j + 2], units[4 * j + 3]);
+            Plane label(labels[4 * j], labels[4 * j + 1], labels[4 * j + 2], labels[4 * j + 3]);
+            currentLabeling(unit) = label.toScalar();                                                     // :107
+            const int R = windR;
+            cv::Rect filterRegion = cv::Rect(unit.x - R, unit.y - R, unit.width + R * 2, unit.height + R * 2) & imageDomain;   // :110
+            StereoEnergy::Reusable reusable;
+            c->energy->ComputeUnaryPotential(filterRegion, unit, currentCost(filterRegion), label, reusable, mode);            // :111
+        } catch (const std::exception& e) {
+#pragma omp critical
+            { g_err = e.what(); failed++; }
+        }
+    }
+    return failed ? -failed : 0;
+}
+
 void ref_plane_normal(const float plane[4], float out[3]) {
     cv::Vec<float, 3> n = Plane(plane[0], plane[1], plane[2], plane[3]).GetNormal();
     out[0] = n[0]; out[1] = n[1]; out[2] = n[2];

@@ -222,6 +222,12 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     return r;
 }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}   /* fibers of a block switch only at barriers */
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 static inline long long clock64() { return (long long)__builtin_ia32_rdtsc(); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

@@ -320,3 +320,52 @@ def test_adapter_compiles_against_the_reference_headers_and_harness_self_check()
         res = subprocess.run([build_ref.DROPIN, "--cpu-self-check", "--W", "96", "--H", "80"] + extra, capture_output=True, text=True, timeout=600)
         d = json.loads(res.stdout.strip().splitlines()[-1])
         assert res.returncode == 0 and d["ok"] is True and d["out_of_tolerance"] == 0 and d["move_calls"] > 1000, d
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# PatchMatch phase: the oracle's step-wise restatement against the reference's own loop, proposers and energy
+# ------------------------------------------------------------------------------------------------------------------
+def test_pm_phase_oracle_equals_the_reference_loop():
+    """oracle.pm_step / pm_proposal (what the device path is compared with) vs oracle/_ref's ref_pm_group: the body of
+    FastGCStereo::localExpansionMovesForLayer_CPU with doGC == false (FastGCStereo.h:30-61) driving the reference's own
+    ExpansionProposer / RandomProposer / CostVolumeEnergy, with cv::theRNG() started from the same per-(cell, step) states.
+    Same proposals bit for bit, same currentLabeling_ and the same currentCost_ (to 1 float ulp) after two groups of two layers."""
+    H, W, D, windR = 72, 96, 12, 12
+    imL, imR, volL, volR = make_scene(H, W, D)
+    ref = R.RefEnergy(imL, imR, volL, volR, windR=windR, eps=1e-4, th_col=0.5, max_disp=D - 1, min_disp=0.0, kind=0)
+    ora = O.CostVolumeEnergyOracle(imL, imR, volL, volR, windR, 1e-4, 0.5, D - 1)
+    try:
+        rng = O.CvRNG(21)
+        lay0 = O.make_layer(W, H, windR, 8)
+        units0 = lay0["unit"]
+        labels = np.stack([O.create_random_label(rng, u[0] + rng.uniform_int(0, u[2]), u[1] + rng.uniform_int(0, u[3]), 0.0, D - 1.0) for u in units0])
+        state = {}
+        for who in ("ref", "ora"):
+            state[who] = (np.full((H, W), np.inf, np.float32), np.zeros((H, W, 4), np.float32))
+        ref.pm_init(units0, labels, windR, *state["ref"])
+        fr0 = [(max(x - windR, 0), max(y - windR, 0), min(x + w + windR, W) - max(x - windR, 0), min(y + h + windR, H) - max(y - windR, 0)) for (x, y, w, h) in units0]
+        O.pm_step(ora, units0, units0, fr0, 0, 0, 0, None, *state["ora"], planes=labels, init=True)
+        assert np.array_equal(state["ref"][0], state["ora"][0]) and np.array_equal(state["ref"][1], state["ora"][1])
+        list_rng = O.CvRNG(77)
+        for li, (u, proposers) in enumerate([(8, [(1, 1), (0, 1), (2, 3)]), (22, [(1, 2), (0, 1)])]):   # Expansion, replayed list (Ransac slot), Random
+            lay = O.make_layer(W, H, windR, u)
+            for gi in (0, 5):
+                cells = lay["groups"][gi]
+                us = [lay["unit"][r] for r in cells]; ts = [lay["shared"][r] for r in cells]; fs = [lay["filter"][r] for r in cells]
+                steps = [(k, m) for k, K in proposers for m in range(K)]       # outer_iter = 1 below: Random m = 1 + iter
+                seeds = [1000 * li + 10 * gi + s for s in range(len(steps))]
+                states = np.array([[O.pm_rng_state(seeds[s], 100 * li + r) for s in range(len(steps))] for r in cells], dtype=np.uint64)
+                lists = np.stack([[O.create_random_label(list_rng, u_[0], u_[1], 0.0, D - 1.0)] for u_ in us])   # [n][1][4]
+                planes_ref, nsteps = ref.pm_group(us, ts, fs, proposers, 1, states, *state["ref"], list_planes=lists)
+                assert (nsteps == len(steps)).all()
+                for s, (kind, it) in enumerate(steps):
+                    used = O.pm_step(ora, us, ts, fs, kind, 1 + it, seeds[s], [100 * li + r for r in cells], *state["ora"],
+                                     planes=lists[:, 0] if kind == 0 else None)
+                    assert np.array_equal(used, planes_ref[:, s]), f"layer {li} group {gi} step {s}: proposals differ"
+                # the oracle's double guided filter equals the reference's up to 1 float ulp of the stored cost (summation order
+                # of the box filter); the labels -- the decisions `cur > prop` -- must be identical
+                assert np.allclose(state["ref"][0], state["ora"][0], rtol=2.5e-7, atol=0), f"layer {li} group {gi}: currentCost differs"
+                assert np.array_equal(state["ref"][1], state["ora"][1]), f"layer {li} group {gi}: currentLabeling differs"
+        assert np.isfinite(state["ora"][0]).all()
+    finally:
+        ref.close()
