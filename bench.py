@@ -465,6 +465,48 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
         L.host_unregister(ph)
     h2d = sum(g.plan.num_calls * 16 * g.n_steps for g in sweep.groups)
     d2h = sweep.local_target_px * 4
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "path": "unary maps: the 240 batched evaluations one by one through lexp_plan_eval_host, plane hypotheses H2D, every unary map "
+                   "D2H into the host cost image (what the graph-cut iterations need on the host, FastGCStereo.h:49-53)"}
+
+    # ---- end to end, PatchMatch phase (FastGCStereo.h:143-157, doGC == false): the SAME sweep -- every cell of every group visited
+    # with K = 9/3/3 proposals -- through lexp_pm_begin / lexp_plan_pm_step / lexp_pm_get: currentCost_ + currentLabeling_ go H2D
+    # from page-locked host memory, proposals + unary costs + the `cur > prop` update stay on the device, the state comes back D2H.
+    if not naive and world == 1:
+        from localexpstereo_b200 import synth
+        from localexpstereo_b200.sweep import PMSweep
+        pms = PMSweep(E)
+        st_cost = np.zeros((H, W), np.float32)
+        st_lab = np.zeros((H, W, 4), np.float32)
+        L.host_register(st_cost); L.host_register(st_lab)
+        pms.begin()
+        pms.init(synth.synthetic_planes(pms.init_units, 1, D, 99)[0])          # initCurrentFast with random labels
+        pms.get(out_cost=st_cost, out_labeling=st_lab)
+        pm_launches = 0
+
+        def pm_iteration(it):
+            pms.begin(st_cost, st_lab)                                             # H2D: 20 B per pixel
+            n = pms.iteration(it, 4321)                                            # 240 launches, device-resident
+            pms.get(out_cost=st_cost, out_labeling=st_lab)                         # D2H: 20 B per pixel (blocking)
+            return n
+
+        pm_launches = pm_iteration(0)  # warm-up
+        before = float(st_cost.mean())
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            pm_iteration(1 + i)
+        dt_pm = (time.perf_counter() - t0) / n_e2e
+        assert float(st_cost.mean()) < before and np.isfinite(st_cost).all()     # the sweep really lowered the energy
+        L.host_unregister(st_cost); L.host_unregister(st_lab)
+        pms.close()
+        e2e_unary = e2e
+        e2e = {"value": evals_per_step / dt_pm, "unit": UNIT, "h2d_bytes_per_step": H * W * 20, "d2h_bytes_per_step": H * W * 20,
+               "ms_per_step": dt_pm * 1e3, "launches_per_step": pm_launches,
+               "path": "PatchMatch-phase iteration (FastGCStereo.h:143-157, doGC == false) through lexp_pm_begin / lexp_plan_pm_step / "
+                       "lexp_pm_get: currentCost_ + currentLabeling_ H2D from page-locked host memory, the same 240 batched evaluations with "
+                       "device-side proposals and the fused cur > prop update, state D2H",
+               "unary_maps": e2e_unary}
 
     # ---- CPU baseline beside it (rank 0, N = 1): the reference's CPU implementation on a bounded sample
     cpu = None
@@ -485,7 +527,7 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
                        "cuda_graph": graph is not None,
                        "l2": "inputs larger than L2 (cost volume %.2f GB, random planes)" % (vol_h.nbytes / 1e9)},
             "clocks": clk,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # DRAM read+write of ONE layer-0 launch (500 cells, algorithmic 2.34e8 B) from the ncu --set full capture

@@ -63,7 +63,7 @@ struct lexp_plan {
     float* h_compact = nullptr;   // pinned
     // PatchMatch phase (lexp_plan_set_units / lexp_plan_pm_step)
     CallInfo* d_calls = nullptr;  // [ncalls] unitRegion, signals per step, cell id
-    int* d_cell_done = nullptr;   // [ncalls] completion counters of the group
+    CellSync* d_cell_sync = nullptr;   // [ncalls] completion counters / proposal hand-over of the group
     std::vector<int> items_per_call;
 };
 
@@ -229,7 +229,7 @@ void release_plan_memory(lexp_plan* pl) {
     cudaFree(pl->d_compact); pl->d_compact = nullptr;
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
     cudaFree(pl->d_calls); pl->d_calls = nullptr;
-    cudaFree(pl->d_cell_done); pl->d_cell_done = nullptr;
+    cudaFree(pl->d_cell_sync); pl->d_cell_sync = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -309,7 +309,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
         kp.pm_mode = pm->pm_mode; kp.prop_kind = pm->prop_kind; kp.prop_m = pm->prop_m; kp.step_index = pm->step_index;
         kp.seed = pm->seed; kp.planes_out = pm->planes_out;
         kp.cur_cost = c->d_cur_cost[mode]; kp.cur_label = c->d_cur_label[mode];
-        kp.calls = pl->d_calls; kp.cell_done = pl->d_cell_done;
+        kp.calls = pl->d_calls; kp.cell_sync = pl->d_cell_sync;
     }
     // the first step of a group is ordered after everything before it (its cells overlap the previous group's); the later
     // steps of the group may start early (programmatic dependent launch): per-cell counters order them
@@ -320,7 +320,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
 int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
     const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4;
     const int Hb = (H + 3) / 4;
-    const size_t nblk = (size_t)Hb * Wb * D * 16;
+    const size_t nblk = (size_t)Hb * Wb * D * 16 * (LEXP_VOL_PAIRS ? 2 : 1);   // LEXP_VOL_PAIRS: float2 per pixel and disparity
     if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], nblk * sizeof(float)));
     int* d_flag = nullptr;
     LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));
@@ -955,15 +955,15 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
         const lexp_rect& u = units[i];
         if (u.width <= 0 || u.height <= 0 || u.x < 0 || u.y < 0 || u.x + u.width > W || u.y + u.height > H)
             return fail(LEXP_ERR_INVALID, "unitRegion outside the image");
-        h[i] = CallInfo{u.x, u.y, u.width, u.height, pl->items_per_call[i] * kWarpsE, cell_ids ? cell_ids[i] : i, {0, 0}};
+        h[i] = CallInfo{u.x, u.y, u.width, u.height, pl->items_per_call[i] * kWarpsE, cell_ids ? cell_ids[i] : i, pl->items_per_call[i], 0};
     }
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
-    if (!pl->d_cell_done) LEXP_CUDA(cudaMalloc(&pl->d_cell_done, (size_t)pl->ncalls * sizeof(int)));
+    if (!pl->d_cell_sync) LEXP_CUDA(cudaMalloc(&pl->d_cell_sync, (size_t)pl->ncalls * sizeof(CellSync)));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     LEXP_CUDA(cudaMemcpy(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice));
-    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_done, 0, (size_t)pl->ncalls * sizeof(int), c->stream));
+    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, (size_t)pl->ncalls * sizeof(CellSync), c->stream));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     return LEXP_OK;
 }
@@ -986,7 +986,7 @@ int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int 
             dp = pl->d_planes;
         }
     }
-    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_done, 0, (size_t)pl->ncalls * sizeof(int), c->stream));
+    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, (size_t)pl->ncalls * sizeof(CellSync), c->stream));
     PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out)};
     return run_plan(c, pl, mode, dp, nullptr, 0, 0, 1, &pm);
 }

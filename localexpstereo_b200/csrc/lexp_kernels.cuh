@@ -76,6 +76,18 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_TRACE
 #define LEXP_TRACE 0
 #endif
+// LEXP_VOL_PAIRS: the blocked cost volume stores, for every disparity d, the PAIR (V[d], V[d+1]) of each pixel:
+//   float2[Hb][Wb][D][4 rows][4 px] (128 B per disparity of a 4x4 pixel block, pair D-1 = (V[D-1], V[D-1])).  The two samples of the
+//   linear interpolation (CostVolumeEnergy.h:83-92) are then ONE 8-byte load, and the 4 pixels of a block row fill exactly one
+//   32-byte sector: 8 instead of 16 sector requests and L1 wavefronts per 32 gathered pixels, no reliance on L1 to keep the other
+//   half of a sector for the next row.  Costs 2x the volume footprint in HBM (6.4 GB at 2048x1536x256; 2 x 34 GB at 4K).
+#ifndef LEXP_VOL_PAIRS
+#define LEXP_VOL_PAIRS 0
+#endif
+// LEXP_GATHER_NOALLOC: volume gathers bypass L1 allocation (only sensible with LEXP_VOL_PAIRS, where no sector is touched twice)
+#ifndef LEXP_GATHER_NOALLOC
+#define LEXP_GATHER_NOALLOC 0
+#endif
 #ifndef LEXP_MIN_CTAS
 #define LEXP_MIN_CTAS 2
 #endif
@@ -109,7 +121,16 @@ struct __align__(16) CallInfo {
     int ux, uy, uw, uh;      // unitRegion of the cell: where the proposers draw their source pixel (Proposer.h:38-45,69-75)
     int n_done_per_step;     // completion signals one proposal step of this cell produces (its work items x kWarpsE)
     int cell_id;             // global id of the cell (seeds its random stream; independent of how cells are sharded over GPUs)
-    int pad[2];
+    int n_items;             // work items (tiles) of the cell = tickets drawn per proposal step
+    int pad;
+};
+// per-call synchronisation record of a group (zeroed before the group's first step)
+struct __align__(16) CellSync {
+    int done;                // completion signals so far (all steps)
+    int ticket;              // work items that have started so far (all steps): the first one of a step draws the proposal
+    int ready;               // = step + 1 once `plane` holds the proposal of that step
+    int pad;
+    Plane4 plane;            // the proposal of the current step, shared by all work items of the cell
 };
 
 struct KParams {
@@ -144,7 +165,7 @@ struct KParams {
     float* __restrict__ cur_cost;       // float [H][W]   currentCost_[mode]
     float4* __restrict__ cur_label;     // float4[H][W]   currentLabeling_[mode] (Plane = 4 floats, Plane.h:4-8)
     const CallInfo* __restrict__ calls; // [ncalls]
-    int* cell_done;                     // [ncalls] completion counters of the group (zeroed before its first step)
+    CellSync* cell_sync;                // [ncalls] completion counters / proposal hand-over of the group (zeroed before its first step)
     Plane4* planes_out;                 // [ncalls] the plane each call evaluated in this step (optional: replay / logging)
 #if LEXP_TRACE
     long long* trace;                   // [items][kThreads / 32][4]
@@ -236,7 +257,7 @@ constexpr int kLinkAH = 32 * (4 + 1), kLinkHC = 32 * (1 + 3), kLinkCH = 32 * (3 
 // cv::getAffineTransform (6x6 system, Gaussian elimination with partial pivoting in double) and the inversion at the top of
 // cv::warpAffine -- same operations in the same order as oracle/_ref, every product and sum rounded separately (no FMA
 // contraction), so the 10-bit fixed-point source coordinates are bit-identical to the reference's.  One thread per CTA.
-__device__ inline void naive_inverse_affine(const Item& it, const Plane4& pl, int mode, double* iM) {
+__device__ LEXP_NOINLINE void naive_inverse_affine(const Item it, const Plane4 pl, int mode, double* iM) {
     const float sign = mode ? -1.0f : 1.0f;
     const float x00 = (float)it.fx, y00 = (float)it.fy;
     const float x11 = __fadd_rn(x00, (float)it.fw), y11 = __fadd_rn(y00, (float)it.fh);
@@ -367,6 +388,16 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 // Cost-volume samples: plain read-only loads.  Measured on B200 (profiles/r1_experiments.md): letting them allocate in
 // L1 (the d0 / d0+1 samples of a 4-pixel block share 128-byte lines) beats L1::no_allocate + L2 evict-first by 8 %.
 __device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ldg_pair(const float2* p) {
+#if LEXP_GATHER_NOALLOC && !defined(LEXP_EMU)
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+constexpr int kVolUnit = LEXP_VOL_PAIRS ? 8 : 4;   // bytes per pixel and disparity in the blocked volume
 
 template <int R_T, bool NAIVE>
 __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KParams P) {
@@ -376,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     F4* smem = reinterpret_cast<F4*>(smem_raw);
 
 #if LEXP_PDL && !defined(LEXP_EMU)
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (!P.pm_mode) asm volatile("griddepcontrol.launch_dependents;");
 #endif
 #if LEXP_TRACE
     unsigned tr_wait_in = 0, tr_wait_out = 0, tr_wait_ld = 0;  // 32-bit cycle counts: a work item runs for ~1e5 cycles
@@ -387,29 +418,52 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     Plane4 pl;
     if (!P.pm_mode) pl = P.planes[it.call];
     else {
-        // PatchMatch phase: this cell's previous proposal steps (all their work items) must have updated cur_cost / cur_label
-        // before the proposer reads a label and before this step's own update (FastGCStereo.h:41-60 is sequential per cell).
-        // The counters are written by CTAs of earlier launches of the stream, which may still be running (PDL): poll.
+        // PatchMatch phase.  (1) This cell's previous proposal steps (all their work items) must have updated cur_cost / cur_label
+        // before the proposer reads a label and before this step's own update (FastGCStereo.h:41-60 is sequential per cell); the
+        // counters are written by CTAs of earlier launches of the stream, which may still be running (PDL): poll.  (2) The proposal
+        // is drawn ONCE per (cell, step), by the first of the cell's work items to arrive (ticket), and handed to the others through
+        // global memory: no work item of the step can write a label before the proposer has read its source label.
         __shared__ Plane4 s_pl;
         if (tid == 0) {
             const CallInfo ci = P.calls[it.call];
+            CellSync* cs = P.cell_sync + it.call;
             const int need = P.step_index * ci.n_done_per_step;
-            while (ld_acquire(P.cell_done + it.call) < need) {
+            while (ld_acquire(&cs->done) < need) {
 #ifndef LEXP_EMU
                 __nanosleep(100);
 #endif
             }
+            const int ticket = atomicAdd(&cs->ticket, 1);
             Plane4 q;
-            if (P.prop_kind) {
-                const float4 g = pm_propose(ProposeArgs{P.seed, P.cur_label, P.W, P.prop_kind, P.prop_m, P.min_disp, P.max_disp},
-                                            ci.ux, ci.uy, ci.uw, ci.uh, ci.cell_id);
+            if (ticket == P.step_index * ci.n_items) {
+                if (P.prop_kind) {
+                    const float4 g = pm_propose(ProposeArgs{P.seed, P.cur_label, P.W, P.prop_kind, P.prop_m, P.min_disp, P.max_disp},
+                                                ci.ux, ci.uy, ci.uw, ci.uh, ci.cell_id);
+                    q = Plane4{g.x, g.y, g.z, g.w};
+                } else q = P.planes[it.call];
+                if (P.planes_out) P.planes_out[it.call] = q;
+                if (ci.n_items > 1) {
+                    __stcg(reinterpret_cast<float4*>(&cs->plane), make_float4(q.a, q.b, q.c, q.v));
+                    __threadfence();
+                    atomicExch(&cs->ready, P.step_index + 1);
+                }
+            } else {
+                while (ld_acquire(&cs->ready) < P.step_index + 1) {
+#ifndef LEXP_EMU
+                    __nanosleep(100);
+#endif
+                }
+                const float4 g = __ldcg(reinterpret_cast<const float4*>(&cs->plane));
                 q = Plane4{g.x, g.y, g.z, g.w};
-            } else q = P.planes[it.call];
+            }
             s_pl = q;
-            if (P.planes_out) P.planes_out[it.call] = q;   // every work item of the call writes the same value
         }
         __syncthreads();
         pl = s_pl;
+#if LEXP_PDL && !defined(LEXP_EMU)
+        // after the ticket: work items of the next step (next launch) must not overtake this step's in the ticket order
+        asm volatile("griddepcontrol.launch_dependents;");
+#endif
     }
     const int VW = it.ow + 4 * R;
     const int X0 = it.ox0 - 2 * R;
@@ -455,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             if (!NAIVE) {
                 s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);               // CostVolumeEnergy.h:73
 #if LEXP_A_ROWTAB
-                // row offset in the blocked volume, in 16-byte units (the s_Y0 slot is unused by the cost-volume energy)
+                // row offset in the blocked volume, in units of one 4-pixel block row (16 B; 32 B with LEXP_VOL_PAIRS); the s_Y0
+                // slot is unused by the cost-volume energy
                 reinterpret_cast<unsigned*>(s_Y0)[v] = (unsigned)(y >> 2) * ((unsigned)P.Wb * (unsigned)P.D * 4u) + (unsigned)(y & 3);
 #endif
             } else {
@@ -557,9 +612,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         // blocked volume: element (d, y, x) lives at ((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4:
         // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
 #if !LEXP_A_ROWTAB
-        const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
+        const size_t vblk = (size_t)P.Wb * P.D * 16 * kVolUnit;       // bytes per block row (4 image rows)
 #endif
-        const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
+        const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * kVolUnit;
 #if LEXP_A_ROWTAB && LEXP_MIN_CTAS <= 2 && !defined(LEXP_EMU)
         // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row); not with the 56-register
         // diet, where the extra live register pair spills
@@ -605,7 +660,19 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u; lf1[j] = fast ? 0.f : -1.f;  // outside filterRect: zero
                 if (colA && vi < vReal) {
                     int d0, d1;
+#if LEXP_VOL_PAIRS
+                    // one 8-byte load fetches (V[d0], V[d0 + 1]); pair D-1 holds V[D-1] twice, so the clamped cases read it too
+                    lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
 #if LEXP_A_ROWTAB
+                    const char* vrow = vcol + (size_t)reinterpret_cast<const unsigned*>(s_Y0)[vi] * 32;
+#else
+                    const int y = ys + vi;
+                    const char* vrow = vcol + (size_t)(y >> 2) * vblk + (y & 3) * 32;
+#endif
+                    const float2 v2 = ldg_pair(reinterpret_cast<const float2*>(vrow + (size_t)(unsigned)d0 * 128));
+                    lv0[j] = v2.x;
+                    lv1[j] = v2.y;
+#elif LEXP_A_ROWTAB
                     const char* vrow = vcol + (size_t)reinterpret_cast<const unsigned*>(s_Y0)[vi] * 16;
                     if (fast) {  // the second sample is always the next disparity: 64 bytes further in the blocked layout
                         lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
@@ -1030,7 +1097,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         if (P.pm_mode) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicAdd(P.cell_done + it.call, 1);
+            if (lane == 0) atomicAdd(&P.cell_sync[it.call].done, 1);
         }
     }
 #if LEXP_TRACE
@@ -1094,6 +1161,24 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict
 // rows of the streaming gather share 128-byte lines / DRAM pages instead of being scattered over ndisp slices
 // H*W*4 bytes apart.   grid = (ceil(W/32), ceil(H/4), ceil(D/8)), block = 256
 __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb) {
+#if LEXP_VOL_PAIRS
+    // LEXP_VOL_PAIRS: dst is float2[Hb][Wb][D][4 rows][4 px] = (V[d], V[min(d + 1, D - 1)]); the tile holds one more disparity
+    __shared__ float tile[9][4][33];  // [d][row][x]
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
+    for (int i = threadIdx.x; i < 9 * 4 * 32; i += 256) {
+        const int xx = i & 31, rr = (i >> 5) & 3, dd = i >> 7;
+        const int x = x0 + xx, y = y0 + rr, d = min(d0 + dd, D - 1);
+        tile[dd][rr][xx] = (y < H && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
+    }
+    __syncthreads();
+    float2* dst2 = reinterpret_cast<float2*>(dst);
+    for (int i = threadIdx.x; i < 8 * 8 * 16; i += 256) {
+        const int q = i & 3, rr = (i >> 2) & 3, dd = (i >> 4) & 7, xb = i >> 7;
+        const int d = d0 + dd;
+        if (d < D && (x0 >> 2) + xb < Wb)
+            dst2[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = make_float2(tile[dd][rr][xb * 4 + q], tile[dd + 1][rr][xb * 4 + q]);
+    }
+#else
     __shared__ float tile[8][4][33];  // [d][row][x]
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
     for (int i = threadIdx.x; i < 8 * 4 * 32; i += 256) {
@@ -1109,6 +1194,7 @@ __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __res
         if (d < D && (x0 >> 2) + xb < Wb)
             dst[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = tile[dd][rr][xb * 4 + q];
     }
+#endif
 }
 
 // NaiveStereoEnergy constructor (StereoEnergy.h:647-662): ExI = merge(I * (1 - alpha), alpha * Sobel_x(gray)), with

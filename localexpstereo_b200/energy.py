@@ -315,9 +315,12 @@ class CostVolumeEnergy:
         assert l is None or l.shape == (self.height, self.width, 4)
         check(lib().lexp_pm_begin(self._h, mode, None if c is None else c.ctypes.data, None if l is None else l.ctypes.data))
 
-    def pm_get(self, mode=0, want_cost=True, want_labeling=True):
-        cost = np.empty((self.height, self.width), np.float32) if want_cost else None
-        lab = np.empty((self.height, self.width, 4), np.float32) if want_labeling else None
+    def pm_get(self, mode=0, want_cost=True, want_labeling=True, out_cost=None, out_labeling=None):
+        """Copies the state back; `out_cost` / `out_labeling`: caller's (e.g. page-locked) arrays to fill instead of new ones."""
+        cost = out_cost if out_cost is not None else (np.empty((self.height, self.width), np.float32) if want_cost else None)
+        lab = out_labeling if out_labeling is not None else (np.empty((self.height, self.width, 4), np.float32) if want_labeling else None)
+        assert cost is None or (cost.dtype == np.float32 and cost.shape == (self.height, self.width) and cost.flags.c_contiguous)
+        assert lab is None or (lab.dtype == np.float32 and lab.shape == (self.height, self.width, 4) and lab.flags.c_contiguous)
         check(lib().lexp_pm_get(self._h, mode, None if cost is None else cost.ctypes.data, None if lab is None else lab.ctypes.data))
         return cost, lab
 

@@ -173,8 +173,8 @@ class PMSweep:
                 n_launch += 1
         return n_launch
 
-    def get(self):
-        return self.energy.pm_get(self.mode)
+    def get(self, out_cost=None, out_labeling=None):
+        return self.energy.pm_get(self.mode, out_cost=out_cost, out_labeling=out_labeling)
 
     def close(self):
         for g in self.groups:

@@ -15,6 +15,8 @@ VARIANTS = {
     "nopdl": ["-DLEXP_PDL=0"],                      # the round-2 defaults switched off one at a time (PDL and ROWTAB are on by default)
     "norowtab": ["-DLEXP_A_ROWTAB=0"],
     "r1": ["-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"],    # the round-1 kernel
+    "pairs": ["-DLEXP_VOL_PAIRS=1"],               # (V[d], V[d+1]) pairs in the blocked volume: one 8-byte gather per pixel
+    "pairsna": ["-DLEXP_VOL_PAIRS=1", "-DLEXP_GATHER_NOALLOC=1"],
     "occ3": ["-DLEXP_OCC3"],                        # 3 CTAs / SM: 56 registers, 75 KB shared-memory cap
     "pdl": ["-DLEXP_PDL=1"],                        # programmatic dependent launch between batched evaluations
     "occ3pdl": ["-DLEXP_OCC3", "-DLEXP_PDL=1"],

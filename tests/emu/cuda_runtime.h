@@ -54,6 +54,7 @@ struct dim3 {
 };
 static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{x, y, z, w}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 // ---- the fiber scheduler ------------------------------------------------------------------------------------------------
@@ -223,9 +224,11 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
 }
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}   /* fibers of a block switch only at barriers */
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
 static inline long long clock64() { return (long long)__builtin_ia32_rdtsc(); }

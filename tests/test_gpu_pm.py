@@ -23,10 +23,10 @@ def devmem():
     return _TorchDeviceMemory()
 
 
-def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1234):
+def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1234, scene=None):
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import PMSweep, expand_proposers, pm_seed
-    imL, imR, volL, volR = make_scene(H, W, D)
+    imL, imR, volL, volR = scene if scene is not None else make_scene(H, W, D)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
     E = L.CostVolumeEnergy(imL, None, volL, None, prm, D - 1)
     Or = O.CostVolumeEnergyOracle(imL, None, volL, None, windR, 1e-4, 0.5, D - 1)
@@ -106,3 +106,16 @@ def test_pm_phase_replay_r10(devmem):
     import localexpstereo_b200 as L
     props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 4)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]
     check_pm_result(run_pm_replay(devmem, 150, 210, 24, 20, [10, 31, 70], props, iterations=1, seed=9))
+
+
+def test_pm_phase_full_sweep_on_the_cones_crop(devmem):
+    """A full pm iteration (three layers, the reference's K = 9 / 3 / 3 evaluations per cell visit with the device schedule of
+    sweep.V3_PROPOSERS_DEVICE) on the natural-image crop of data/MiddV2/cones that the golden vectors use."""
+    import lexp_golden
+    from localexpstereo_b200.sweep import V3_PROPOSERS_DEVICE
+    G = lexp_golden.load()
+    H, W = G["imL"].shape[:2]
+    r = run_pm_replay(devmem, H, W, G["D"], G["windR"], [6, 18, 40], V3_PROPOSERS_DEVICE, iterations=1, seed=77,
+                      scene=(G["imL"], G["imR"], G["volL"], G["volR"]))
+    check_pm_result(r)
+    assert r["n_prop"] > 4000
