@@ -273,9 +273,15 @@ def run_reference(args, W, H, D, windR, rank, world):
 
 # ---------------------------------------------------------------------------------------------
 def run_ours(args, W, H, D, windR, rank, world, local_rank):
+    """Our arm.  `value`: the sweep (3 layers x 16 groups x K = 9/3/3 batched evaluations = 240 launches of lexp_fused_kernel) as the
+    device-resident PatchMatch phase -- proposals drawn on the device, unary costs, fused `cur > prop` update of currentCost_ /
+    currentLabeling_ in HBM; at N > 1 the cells of every group are sharded over the ranks and every accepted update is stored by
+    the kernel into all ranks' copies of the state over NVLink (no collective on the data path; NCCL only broadcasts the inputs once).
+    The image-based NaiveStereoEnergy workload (configs[0]) times the plain unary sweep instead (no device PatchMatch phase for it)."""
     import torch
     import localexpstereo_b200 as L
-    from localexpstereo_b200.sweep import UnarySweep
+    from localexpstereo_b200 import synth
+    from localexpstereo_b200.sweep import PMSweep, UnarySweep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -285,273 +291,283 @@ def run_ours(args, W, H, D, windR, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-
-    imL, vol_h = make_inputs(W, H, D)
-    vol_d = torch.from_numpy(vol_h).to(dev)
     naive = args.workload.endswith("_naive")
+    shard = world > 1 and not args.replicas
+    shard_rank, shard_world = (rank, world) if shard else (0, 1)
+
+    # ---- inputs: generated once (rank 0) and broadcast over NCCL to the ranks of a cell shard; one image pair per rank for --replicas
+    if shard:
+        img_t = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        vol_d = torch.empty((D, H, W), dtype=torch.float32, device=dev)
+        if rank == 0:
+            imL, vol_h = make_inputs(W, H, D)
+            img_t.copy_(torch.from_numpy(imL)); vol_d.copy_(torch.from_numpy(vol_h))
+        dist.broadcast(img_t, 0)
+        dist.broadcast(vol_d, 0)
+        imL = img_t.cpu().numpy()
+        vol_h = None if rank else vol_h
+        del img_t
+    else:
+        imL, vol_h = make_inputs(W, H, D)
+        vol_d = torch.from_numpy(vol_h).to(dev)
     if naive:  # -mode MiddV2: image-based energy, th_col 10 / th_grad 2 / alpha 0.9 (StereoEnergy.h:26-37), layers 5/15/25
-        from localexpstereo_b200 import synth
         prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS)
         imR_h = synth.synthetic_image(H, W, 43)
         E = L.NaiveStereoEnergy(imL, imR_h, prm, D - 1, device=local_rank)
     else:
         prm = L.Parameters(windR=windR, filterName="GF", filter_param1=EPS, th_col=TH_COL)
         E = L.CostVolumeEnergy(imL, None, vol_d, None, prm, D - 1, device=local_rank)
+    del vol_d  # the context keeps its own blocked copy
+    torch.cuda.empty_cache()
     stream = torch.cuda.current_stream(dev)
     E.set_stream(stream.cuda_stream)
-    shard_rank, shard_world = (0, 1) if args.replicas else (rank, world)
-    sweep = UnarySweep(E, unit_sizes=[5, 15, 25] if naive else None, rank=shard_rank, world=shard_world)
-    planes_h = all_planes(sweep, D)
-    planes_d = [torch.from_numpy(p).to(dev) for p in planes_h]
-    cost_d = torch.zeros((H, W), dtype=torch.float32, device=dev)
-    pitch = W * 4
-
-    # cell-shard exchange buffers: per group, every rank contributes its per-cell unary tiles (padded to the max)
-    gather = None
-    if world > 1 and not args.replicas:
-        sizes = torch.tensor([g.plan.target_px for g in sweep.groups], device=dev)
-        # groups are identical in count on all ranks only if every group has >= world cells; align by (layer, group) key
-        keys = [(g.layer, g.group) for g in sweep.groups]
-        all_keys = [None] * world
-        dist.all_gather_object(all_keys, keys)
-        common = [k for k in all_keys[0] if all(k in ak for ak in all_keys)]
-        mx = torch.zeros(len(common), dtype=torch.int64, device=dev)
-        mine = {k: g.plan.target_px for k, g in zip(keys, sweep.groups)}
-        loc = torch.tensor([mine[k] for k in common], dtype=torch.int64, device=dev)
-        dist.all_reduce(loc, op=dist.ReduceOp.MAX)
-        gather = {k: (torch.zeros(int(n), device=dev), torch.zeros(int(n) * world, device=dev)) for k, n in zip(common, loc.tolist())}
-
-    def sweep_device():
-        """One step of the bench: all batched evaluations of a sweep, outputs resident in HBM."""
-        for gi, g in enumerate(sweep.groups):
-            base = planes_d[gi].data_ptr()
-            n = g.plan.num_calls
-            key = (g.layer, g.group)
-            for k in range(g.n_steps):
-                last = (k == g.n_steps - 1)
-                if gather is not None and last and key in gather:
-                    g.plan.eval_device_tiles(base + k * n * 16, gather[key][0].data_ptr(), True, 0, planes_on_device=True)
-                else:
-                    g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), pitch, True, 0, planes_on_device=True)
-            if gather is not None and key in gather:
-                dist.all_gather_into_tensor(gather[key][1], gather[key][0])
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        sweep_device()
-    barrier()
-    # The 240 dependent launches (+ the per-group all-gathers) of a sweep are captured once into a CUDA graph and
-    # replayed: no per-launch CPU work inside the timed region.  Falls back to eager launches if capture fails.
-    graph = None
-    if not args.no_graph:
+    def timed(fn, n):
+        """n calls of fn on the current stream between two events, bracketed by barriers; ms per call, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def capture(fn):
+        """fn's launches as one CUDA graph (no per-launch CPU work in the timed region); eager launches if capture fails."""
+        if args.no_graph:
+            return fn, False
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 E.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-                sweep_device()
-            graph = g
+                fn()
+            E.set_stream(stream.cuda_stream)
+            torch.cuda.synchronize(dev)
+            return g.replay, True
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); using eager launches\n")
-            graph = None
-        E.set_stream(stream.cuda_stream)
-        torch.cuda.synchronize(dev)
-    run_step = (graph.replay if graph is not None else sweep_device)
-    for _ in range(2):
-        run_step()
-    barrier()
+            E.set_stream(stream.cuda_stream)
+            return fn, False
+
+    # ---- the unary-only sweep (round 1's `value`; still the headline for the NaiveStereoEnergy workload)
+    unary = UnarySweep(E, unit_sizes=[5, 15, 25] if naive else None, rank=shard_rank, world=shard_world)
+    planes_h = all_planes(unary, D)
+    evals_per_step = unary.total_filter_px * (world if args.replicas else 1)  # whole job, all ranks
+    unary_info = None
+    cost_d = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    if naive or world == 1:
+        planes_d = [torch.from_numpy(p).to(dev) for p in planes_h]
+
+        def sweep_unary():
+            for gi, g in enumerate(unary.groups):
+                base, n = planes_d[gi].data_ptr(), g.plan.num_calls
+                for k in range(g.n_steps):
+                    g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), W * 4, True, 0, planes_on_device=True)
+
+        for _ in range(args.warmup):
+            sweep_unary()
+        run_u, graph_u = capture(sweep_unary)
+        run_u(); run_u()
+        ms_u = timed(run_u, args.steps if naive else max(3, min(args.steps, 5)))
+        unary_info = {"ms_per_step": ms_u, "value": evals_per_step / (ms_u * 1e-3), "unit": UNIT, "cuda_graph": graph_u,
+                      "note": "the same 240 batched evaluations with host-supplied planes, unary maps written to an H x W image in HBM (no proposals, no update)"}
+
+    # ---- the PatchMatch-phase sweep: `value`
+    pms = None
     clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    l0 = E.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        run_step()
-    ev1.record(stream)
-    barrier()
-    launches = (E.launch_count - l0) if graph is None else sweep.launches_per_sweep * args.steps  # replayed kernel nodes
-    clk = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
-    evals_per_step = sweep.total_filter_px * (world if args.replicas else 1)  # whole job, all ranks
+    if not naive:
+        pms = PMSweep(E, rank=shard_rank, world=shard_world)
+        pms.begin()
+        if shard:
+            handles = [None] * world
+            dist.all_gather_object(handles, pms.energy.pm_ipc_export(0))
+            pms.connect(handles)
+            barrier()
+        init_labels = synth.synthetic_planes([pms.lm.layers[0].unitRegions[i] for i in range(len(pms.lm.layers[0].unitRegions))], 1, D, 99)[0]
+        pms.init(init_labels[pms.init_index])
+        launches_per_step = 0
+        for it in range(args.warmup):
+            launches_per_step = pms.iteration(it, 4321)
+        barrier()
+        IT = args.warmup  # the replayed iteration: fixed index (same proposal distribution every step; the state keeps evolving)
+        run_pm, graph_pm = capture(lambda: pms.iteration(IT, 4321))
+        run_pm(); run_pm()
+        if rank == 0:
+            clocks.start()
+        ms_per_step = timed(run_pm, args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        launches = launches_per_step * args.steps
+        graph_used = graph_pm
+        local_alg = unary.local_alg_bytes   # same cells, same K = 9/3/3 evaluations per cell visit as the unary sweep
+    else:
+        if rank == 0:
+            clocks.start()
+        ms_per_step = timed(run_u, args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        launches = unary.launches_per_sweep * args.steps
+        graph_used = graph_u
+        local_alg = unary.local_alg_bytes
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (lexp_fused_kernel).  It is the ONLY kernel of the timed region at N = 1, and with
-    # programmatic dependent launch consecutive launches overlap (the next one fills the last, partly empty wave), so a
-    # per-launch duration is not defined: achieved = algorithmic bytes of the sweep / the timed region's own duration
-    # (kernel_ms_per_step == ms_per_step; VERDICT r1 weak #2: the sum of eager per-launch events exceeded the replayed step).
-    # At N > 1 the step also holds the exchange: the kernel-only time is measured by a second graph without it (below).
+    # ---- roofline of the dominant kernel (lexp_fused_kernel).  It is the ONLY kernel of the timed region, and with programmatic
+    # dependent launch consecutive launches overlap (the next one fills the last, partly empty wave), so a per-launch duration is
+    # not defined: achieved = algorithmic bytes this rank's launches of a sweep move / the timed region's own duration
+    # (kernel_ms_per_step == ms_per_step; at N > 1 the stores into the peers' copies are part of the kernel).
     # `ms_by_layer`: one eager sweep bracketed per layer (3 event pairs; includes that layer's launch gaps).
     peak, peak_src = measured_peak_gbs()
-    lay_ev = []
-    cur = None
-    for gi, g in enumerate(sweep.groups):  # eager, layer by layer
-        if g.layer != cur:
-            if lay_ev:
-                e = torch.cuda.Event(enable_timing=True); e.record(stream); lay_ev[-1].append(e)
-            e = torch.cuda.Event(enable_timing=True); e.record(stream); lay_ev.append([g.layer, e]); cur = g.layer
-        base = planes_d[gi].data_ptr(); n = g.plan.num_calls
-        for k in range(g.n_steps):
-            g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), pitch, True, 0, planes_on_device=True)
-    e = torch.cuda.Event(enable_timing=True); e.record(stream); lay_ev[-1].append(e)
-    torch.cuda.synchronize(dev)
-    by_layer = {li: [e0.elapsed_time(e1), 0] for li, e0, e1 in lay_ev}
-    kern_ms = ms_per_step
-    if world > 1 and not args.replicas:  # kernel-only step on this rank (no exchange), max over ranks
-        kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kev0.record(stream)
-        for gi, g in enumerate(sweep.groups):
-            base = planes_d[gi].data_ptr(); n = g.plan.num_calls
-            for k in range(g.n_steps):
-                g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), pitch, True, 0, planes_on_device=True)
-        kev1.record(stream)
-        torch.cuda.synchronize(dev)
-        km = torch.tensor([kev0.elapsed_time(kev1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(km, op=dist.ReduceOp.MAX)
-        kern_ms = float(km.item())
-    achieved = sweep.local_alg_bytes / (kern_ms * 1e-3) / 1e9
-
-    # ---- end to end through the host-buffer API: planes H2D + unary tiles D2H every evaluation
-    cost_h = np.zeros((H, W), np.float32)
-    L.host_register(cost_h)  # page-locked + mapped: unary tiles land in the host image without a bounce buffer
-    for ph in planes_h:
-        L.host_register(ph)  # the per-step inputs (plane hypotheses) are copied H2D from pinned memory
-
-    def sweep_host():
-        for gi, g in enumerate(sweep.groups):
-            for k in range(g.n_steps):
-                g.plan.eval_host(planes_h[gi][k], cost_h, True, 0)
-
-    sweep_host()  # warm-up (allocates the pinned staging buffers)
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
-    for _ in range(n_e2e):
-        sweep_host()
-    torch.cuda.synchronize(dev)
-    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = evals_per_step / float(dt.item())
-    e2e_tiles = None
-    if args.e2e_tiles:  # optional: the same end-to-end sweep with per-cell contiguous tiles as the host output (lexp_plan_eval_host_tiles)
-        tiles_h = np.zeros(max(g.plan.target_px for g in sweep.groups), np.float32)
-        L.host_register(tiles_h)
-
-        def sweep_host_tiles():
-            for gi, g in enumerate(sweep.groups):
+    achieved = local_alg / (ms_per_step * 1e-3) / 1e9
+    by_layer = {}
+    if world == 1:
+        evs = []
+        if pms is not None:
+            gen, cur = pms.iteration_by_group(IT, 4321), None
+            for (li, gi, g, owners) in list(pms.schedule):
+                if li != cur:
+                    e = torch.cuda.Event(enable_timing=True); e.record(stream); evs.append((li, e)); cur = li
+                next(gen)
+            for _ in gen:
+                pass
+        else:
+            cur = None
+            for gi, g in enumerate(unary.groups):
+                if g.layer != cur:
+                    e = torch.cuda.Event(enable_timing=True); e.record(stream); evs.append((g.layer, e)); cur = g.layer
+                base, n = planes_d[gi].data_ptr(), g.plan.num_calls
                 for k in range(g.n_steps):
-                    g.plan.eval_host_tiles(planes_h[gi][k], tiles_h, True, 0)
+                    g.plan.eval_device(base + k * n * 16, cost_d.data_ptr(), W * 4, True, 0, planes_on_device=True)
+        e = torch.cuda.Event(enable_timing=True); e.record(stream); evs.append((None, e))
+        torch.cuda.synchronize(dev)
+        by_layer = {str(evs[i][0]): round(evs[i][1].elapsed_time(evs[i + 1][1]), 4) for i in range(len(evs) - 1)}
 
-        sweep_host_tiles()
+    # ---- end to end: the same sweep through the C-ABI with HOST buffers, copies inside the timed region
+    n_e2e = max(1, min(args.steps, 3))
+    e2e_unary = None
+    if naive or world == 1:
+        cost_h = np.zeros((H, W), np.float32)
+        L.host_register(cost_h)  # page-locked + mapped: unary tiles land in the host image without a bounce buffer
+        for ph in planes_h:
+            L.host_register(ph)  # the per-step inputs (plane hypotheses) are copied H2D from pinned memory
+
+        def sweep_host():
+            for gi, g in enumerate(unary.groups):
+                for k in range(g.n_steps):
+                    g.plan.eval_host(planes_h[gi][k], cost_h, True, 0)
+
+        sweep_host()  # warm-up (allocates the pinned staging buffers)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            sweep_host_tiles()
+        for _ in range(1 if not naive else n_e2e):
+            sweep_host()
         torch.cuda.synchronize(dev)
-        dtt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
-        e2e_tiles = evals_per_step / float(dtt.item())
-        L.host_unregister(tiles_h)
-    L.host_unregister(cost_h)
-    for ph in planes_h:
-        L.host_unregister(ph)
-    h2d = sum(g.plan.num_calls * 16 * g.n_steps for g in sweep.groups)
-    d2h = sweep.local_target_px * 4
-    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "path": "unary maps: the 240 batched evaluations one by one through lexp_plan_eval_host, plane hypotheses H2D, every unary map "
-                   "D2H into the host cost image (what the graph-cut iterations need on the host, FastGCStereo.h:49-53)"}
-
-    # ---- end to end, PatchMatch phase (FastGCStereo.h:143-157, doGC == false): the SAME sweep -- every cell of every group visited
-    # with K = 9/3/3 proposals -- through lexp_pm_begin / lexp_plan_pm_step / lexp_pm_get: currentCost_ + currentLabeling_ go H2D
-    # from page-locked host memory, proposals + unary costs + the `cur > prop` update stay on the device, the state comes back D2H.
-    if not naive and world == 1:
-        from localexpstereo_b200 import synth
-        from localexpstereo_b200.sweep import PMSweep
-        pms = PMSweep(E)
+        dt = (time.perf_counter() - t0) / (1 if not naive else n_e2e)
+        L.host_unregister(cost_h)
+        for ph in planes_h:
+            L.host_unregister(ph)
+        e2e_unary = {"value": evals_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": sum(g.plan.num_calls * 16 * g.n_steps for g in unary.groups),
+                     "d2h_bytes_per_step": unary.local_target_px * 4,
+                     "path": "unary maps: the 240 batched evaluations one by one through lexp_plan_eval_host, plane hypotheses H2D, every unary "
+                             "map D2H into the host cost image (what the graph-cut iterations need on the host, FastGCStereo.h:49-53)"}
+    if pms is not None:
+        # PatchMatch-phase iteration (FastGCStereo.h:143-157, doGC == false) through lexp_pm_begin / lexp_plan_pm_step / lexp_pm_get:
+        # currentCost_ + currentLabeling_ go H2D from page-locked host memory on every rank, the sweep runs on the device(s), and
+        # rank 0 -- whose copy of the state every rank's kernels have written -- brings the state back D2H.
         st_cost = np.zeros((H, W), np.float32)
         st_lab = np.zeros((H, W, 4), np.float32)
         L.host_register(st_cost); L.host_register(st_lab)
-        pms.begin()
-        pms.init(synth.synthetic_planes(pms.init_units, 1, D, 99)[0])          # initCurrentFast with random labels
         pms.get(out_cost=st_cost, out_labeling=st_lab)
-        pm_launches = 0
+        before = float(st_cost.mean())
 
         def pm_iteration(it):
             pms.begin(st_cost, st_lab)                                             # H2D: 20 B per pixel
-            n = pms.iteration(it, 4321)                                            # 240 launches, device-resident
-            pms.get(out_cost=st_cost, out_labeling=st_lab)                         # D2H: 20 B per pixel (blocking)
-            return n
+            if dist is not None:
+                dist.barrier()                                                     # no peer may write into a copy that is still being uploaded
+            pms.iteration(it, 4321)                                                # 240 launches, device-resident
+            if rank == 0 or not shard:
+                pms.get(out_cost=st_cost, out_labeling=st_lab)                     # D2H: 20 B per pixel (blocking)
+            else:
+                E.sync()
+            if dist is not None:
+                dist.barrier()
 
-        pm_launches = pm_iteration(0)  # warm-up
-        before = float(st_cost.mean())
+        pm_iteration(IT + 1)  # warm-up
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            pm_iteration(1 + i)
-        dt_pm = (time.perf_counter() - t0) / n_e2e
-        assert float(st_cost.mean()) < before and np.isfinite(st_cost).all()     # the sweep really lowered the energy
+            pm_iteration(IT + 2 + i)
+        dtp = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        dt_pm = float(dtp.item())
+        if rank == 0:
+            assert np.isfinite(st_cost).all() and float(st_cost.mean()) <= before   # the sweeps really lowered the energy
         L.host_unregister(st_cost); L.host_unregister(st_lab)
-        pms.close()
-        e2e_unary = e2e
-        e2e = {"value": evals_per_step / dt_pm, "unit": UNIT, "h2d_bytes_per_step": H * W * 20, "d2h_bytes_per_step": H * W * 20,
-               "ms_per_step": dt_pm * 1e3, "launches_per_step": pm_launches,
+        e2e = {"value": evals_per_step / dt_pm, "unit": UNIT, "h2d_bytes_per_step": H * W * 20 * world,
+               "d2h_bytes_per_step": H * W * 20 * (world if args.replicas else 1), "ms_per_step": dt_pm * 1e3,
                "path": "PatchMatch-phase iteration (FastGCStereo.h:143-157, doGC == false) through lexp_pm_begin / lexp_plan_pm_step / "
-                       "lexp_pm_get: currentCost_ + currentLabeling_ H2D from page-locked host memory, the same 240 batched evaluations with "
-                       "device-side proposals and the fused cur > prop update, state D2H",
-               "unary_maps": e2e_unary}
+                       "lexp_pm_get: currentCost_ + currentLabeling_ H2D from page-locked host memory (every rank), the 240 batched "
+                       "evaluations with device-side proposals and the fused cur > prop update, state D2H (rank 0's copy holds everything)"}
+        if e2e_unary is not None:
+            e2e["unary_maps"] = e2e_unary
+    else:
+        e2e = e2e_unary
 
     # ---- CPU baseline beside it (rank 0, N = 1): the reference's CPU implementation on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_beside(W, H, D, windR, imL, None if naive else vol_h, naive, imR_h if naive else None, sweep.groups, sweep.layer, planes_h)
+        cpu = cpu_baseline_beside(W, H, D, windR, imL, None if naive else vol_h, naive, imR_h if naive else None, unary.groups, unary.layer, planes_h)
 
     if rank == 0:
+        if naive:
+            par = "unary sweep"
+        elif args.replicas:
+            par = f"replicas x{world} (one image pair per GPU), PatchMatch-phase sweep"
+        else:
+            par = f"cell-shard x{world}, PatchMatch-phase sweep" + (": accepted updates stored into all ranks' copies of the state by the kernel "
+                                                                   "(peer memory over NVLink), epoch flags at group boundaries; inputs broadcast once over NCCL" if world > 1 else "")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.replicas else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "W": W, "H": H, "ndisp": D, "windR": windR, "th_col": TH_COL, "eps": EPS,
-                       "layers_unit": sweep.unit_sizes, "steps_per_layer": sweep.steps,
-                       "evals_per_step": evals_per_step, "target_px_per_step": sweep.total_target_px,
-                       "batched_evaluations_per_step": sweep.launches_per_sweep,
-                       "parallelism": (f"replicas x{world} (one image pair per GPU)" if args.replicas else
-                                       f"cell-shard x{world}" + (", all-gather of per-cell unary tiles per group" if world > 1 else "")),
-                       "cuda_graph": graph is not None,
-                       "l2": "inputs larger than L2 (cost volume %.2f GB, random planes)" % (vol_h.nbytes / 1e9)},
+                       "layers_unit": unary.unit_sizes, "steps_per_layer": unary.steps,
+                       "evals_per_step": evals_per_step, "target_px_per_step": unary.total_target_px,
+                       "batched_evaluations_per_step": launches // max(args.steps, 1),
+                       "parallelism": par, "cuda_graph": graph_used,
+                       "l2": "inputs larger than L2 (cost volume %.2f GB; proposals follow the evolving state)" % (4.0 * D * H * W / 1e9)},
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # DRAM read+write of ONE layer-0 launch (500 cells, algorithmic 2.34e8 B) from the ncu --set full capture
-                         # summarised in profiles/r1_final_fused_ncu_L0.md; only known for the default workload at N = 1
-                         "traffic": (230713088 + 9571072) if (args.workload == "synthetic_2048x1536x256_r20" and world == 1) else None,
-                         "traffic_note": "per layer-0 launch of 500 cells (algorithmic 2.34e8 B); profiles/r1_final_fused_ncu_L0.md",
+                         # summarised in profiles/r2_fused_ncu_L0.md; only known for the default workload at N = 1
+                         "traffic": (229575680 + 9689856) if (args.workload == "synthetic_2048x1536x256_r20" and world == 1) else None,
+                         "traffic_note": "per layer-0 launch of 500 cells (algorithmic 2.34e8 B); profiles/r2_fused_ncu_L0.md",
                          "kernel": "lexp_fused_kernel", "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": sweep.local_alg_bytes, "kernel_ms_per_step": kern_ms,
-                         "ms_by_layer": {str(k): round(v[0], 4) for k, v in by_layer.items()}},
+                         "algorithmic_bytes_per_step": local_alg, "kernel_ms_per_step": ms_per_step, "ms_by_layer": by_layer},
         }
+        if unary_info is not None and not naive:
+            out["unary_sweep"] = unary_info
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        if e2e_tiles is not None:
-            out["e2e_tiles"] = {"value": e2e_tiles, "unit": UNIT, "note": "host output as per-cell contiguous tiles (lexp_plan_eval_host_tiles), zero-copy"}
         print(json.dumps(out), flush=True)
     if dist is not None:
-        # A captured graph holds NCCL work: tearing the process group down underneath it can hang.  All results are
-        # printed; synchronise, then leave without running destructors.
+        # captured graphs and peer mappings: synchronise, then leave without running destructors
         barrier()
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
-    graph = None
-    sweep.close()
+    if pms is not None:
+        pms.close()
+    unary.close()
     E.close()
 
 
@@ -564,7 +580,6 @@ def main():
     ap.add_argument("--workload", default="synthetic_2048x1536x256_r20", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the sweep eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--e2e-tiles", action="store_true", help="also time the end-to-end sweep with per-cell tile output (adds `e2e_tiles`)")
     ap.add_argument("--replicas", action="store_true",
                     help="BASELINE.json configs[3] style: every rank sweeps its OWN image pair (weak scaling, no data-path collective) "
                          "instead of sharding the cells of one pair (default, strong scaling)")

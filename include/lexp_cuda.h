@@ -180,6 +180,32 @@ LEXP_API int lexp_plan_set_units(lexp_plan* plan, const lexp_rect* unit_rects, c
 LEXP_API int lexp_plan_pm_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int step_index, int kind, int m, uint64_t seed,
                                const lexp_plane* planes, int planes_on_device, lexp_plane* d_planes_out, int flags);
 
+/* ---- multi-GPU cell shard of the PatchMatch phase: one context (process) per GPU, every rank holds the
+ * read-only inputs and a full copy of currentCost_ / currentLabeling_, and evaluates its share of the cells of every group.  The
+ * exchange is fused into the kernel: the epilogue stores every accepted update into ALL copies (peer memory over NVLink /
+ * NVSwitch), and ranks meet at group boundaries through epoch flags written into peer memory by the last work item of a group's
+ * last step and polled by the first step of the next group.  No host round trip and no library collective on the data path
+ * (NCCL is only used by the caller to broadcast the inputs once).
+ * lexp_pm_ipc_export: after lexp_pm_begin; writes LEXP_PM_IPC_BYTES bytes (CUDA IPC handles of cost, labeling, flags) that the caller
+ * all-gathers; lexp_pm_ipc_connect: maps the peers' state (handles = world x LEXP_PM_IPC_BYTES, rank order).  lexp_pm_connect_local:
+ * the same for contexts living in one process (tests; also multi-device single-process callers). */
+#define LEXP_PM_IPC_BYTES 192
+#define LEXP_PM_MAX_PEERS 8
+LEXP_API int lexp_pm_ipc_export(lexp_ctx* ctx, int mode, void* handles_out);
+LEXP_API int lexp_pm_ipc_connect(lexp_ctx* ctx, int mode, int rank, int world, const void* all_handles);
+LEXP_API int lexp_pm_connect_local(lexp_ctx* ctx, int mode, int rank, int world, lexp_ctx* const* peer_contexts);
+/* lexp_plan_pm_step with the group-boundary protocol of the cell shard.  Groups are numbered by epochs that only grow; the
+ * epochs passed here are RELATIVE to a per-context device counter (the epoch base) that lexp_pm_advance_epoch advances in stream
+ * order -- so the launches of one iteration can be captured into a CUDA graph and replayed.  publish_epoch != 0 (last step of
+ * a group): when the launch completes, flags[rank] = base + publish_epoch is stored on every copy.  wait_mask / wait_epochs
+ * (int[LEXP_PM_MAX_PEERS]; first step of a group): every work item first waits until flags[r] >= base + wait_epochs[r] for every
+ * rank r in wait_mask -- the last earlier group each rank owned cells of (<= 0 for groups of the previous iteration). */
+LEXP_API int lexp_plan_pm_step_ex(lexp_ctx* ctx, lexp_plan* plan, int mode, int step_index, int kind, int m, uint64_t seed,
+                                  const lexp_plane* planes, int planes_on_device, lexp_plane* d_planes_out, int flags,
+                                  int publish_epoch, const int* wait_epochs, unsigned wait_mask);
+/* epoch base += delta (= the number of groups issued since the last call), asynchronous on the context stream. */
+LEXP_API int lexp_pm_advance_epoch(lexp_ctx* ctx, int mode, int delta);
+
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
 LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,

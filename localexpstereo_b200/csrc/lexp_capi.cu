@@ -64,6 +64,8 @@ struct lexp_plan {
     // PatchMatch phase (lexp_plan_set_units / lexp_plan_pm_step)
     CallInfo* d_calls = nullptr;  // [ncalls] unitRegion, signals per step, cell id
     CellSync* d_cell_sync = nullptr;   // [ncalls] completion counters / proposal hand-over of the group
+    int* d_launch_done = nullptr;      // completion counter of the group's last launch (multi-GPU: who publishes the epoch flag);
+                                       // lives behind the CellSync records and is zeroed with them
     std::vector<int> items_per_call;
 };
 
@@ -83,6 +85,16 @@ struct lexp_ctx {
     float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[Hb][Wb][D][4][4] (owned)
     float* d_cur_cost[2] = {nullptr, nullptr};     // PatchMatch phase: currentCost_[mode]   float [H][W]
     float4* d_cur_label[2] = {nullptr, nullptr};   //                   currentLabeling_[mode] Plane[H][W]
+    int* d_flags[2] = {nullptr, nullptr};          // epoch flags int[kMaxPeers] of the multi-GPU cell shard (peers store into them);
+                                                   // d_flags[m][kMaxPeers] is this rank's epoch base (lexp_pm_advance_epoch)
+    struct Peers {                                 // copies of the state the epilogue writes: entry 0 = this context's own
+        int world = 1, rank = 0;
+        float* cost[kMaxPeers] = {};
+        float4* label[kMaxPeers] = {};
+        int* flags[kMaxPeers] = {};
+        void* ipc_opened[3 * kMaxPeers] = {};      // cudaIpcOpenMemHandle mappings to close
+        int n_opened = 0;
+    } peers[2];
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
@@ -229,7 +241,7 @@ void release_plan_memory(lexp_plan* pl) {
     cudaFree(pl->d_compact); pl->d_compact = nullptr;
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
     cudaFree(pl->d_calls); pl->d_calls = nullptr;
-    cudaFree(pl->d_cell_sync); pl->d_cell_sync = nullptr;
+    cudaFree(pl->d_cell_sync); pl->d_cell_sync = nullptr; pl->d_launch_done = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -260,6 +272,9 @@ struct PmArgs {   // PatchMatch phase (lexp_plan_pm_step); nullptr = plain unary
     int pm_mode, prop_kind, prop_m, step_index;
     unsigned long long seed;
     Plane4* planes_out;
+    int publish_epoch;
+    int wait_epochs[kMaxPeers];
+    unsigned wait_mask;
 };
 
 int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float* d_out, long long pitch, int compact,
@@ -305,11 +320,21 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     kp.thresh_gradient = c->p.th_grad * c->p.alpha;          // StereoEnergy.h:664
     kp.mode = mode;
     kp.fast_ok = (c->vol_finite[mode] && c->p.min_disp == 0.0f && c->p.max_disp == (float)(c->p.ndisp - 1) && c->p.th_col >= 0.0f) ? 1 : 0;
+    kp.smem_plane_off = (int)pl->smem - 16;
     if (pm) {
         kp.pm_mode = pm->pm_mode; kp.prop_kind = pm->prop_kind; kp.prop_m = pm->prop_m; kp.step_index = pm->step_index;
         kp.seed = pm->seed; kp.planes_out = pm->planes_out;
         kp.cur_cost = c->d_cur_cost[mode]; kp.cur_label = c->d_cur_label[mode];
         kp.calls = pl->d_calls; kp.cell_sync = pl->d_cell_sync;
+        const lexp_ctx::Peers& pr = c->peers[mode];
+        kp.n_copies = pr.world; kp.my_rank = pr.rank;
+        kp.copy_cost[0] = c->d_cur_cost[mode]; kp.copy_label[0] = c->d_cur_label[mode]; kp.copy_flags[0] = c->d_flags[mode];
+        for (int i = 1; i < pr.world; i++) { kp.copy_cost[i] = pr.cost[i]; kp.copy_label[i] = pr.label[i]; kp.copy_flags[i] = pr.flags[i]; }
+        kp.publish_epoch = pm->publish_epoch; kp.wait_mask = pm->wait_mask;
+        for (int i = 0; i < kMaxPeers; i++) kp.wait_epochs[i] = pm->wait_epochs[i];
+        kp.epoch_base = c->d_flags[mode] + kMaxPeers;
+        kp.err_flag = c->d_flags[mode] + kMaxPeers + 1;
+        kp.launch_done = pl->d_launch_done;
     }
     // the first step of a group is ordered after everything before it (its cells overlap the previous group's); the later
     // steps of the group may start early (programmatic dependent launch): per-cell counters order them
@@ -405,8 +430,12 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_gs[m]);
         cudaFree(c->d_exi[m]);
         cudaFree(c->d_vol[m]);
+#ifndef LEXP_EMU
+        for (int i = 0; i < c->peers[m].n_opened; i++) cudaIpcCloseMemHandle(c->peers[m].ipc_opened[i]);
+#endif
         cudaFree(c->d_cur_cost[m]);
         cudaFree(c->d_cur_label[m]);
+        cudaFree(c->d_flags[m]);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -913,6 +942,10 @@ int lexp_pm_begin(lexp_ctx* c, int mode, const float* cost, const lexp_plane* la
     const size_t HW = (size_t)c->p.height * c->p.width;
     if (!c->d_cur_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_cur_cost[mode], HW * sizeof(float)));
     if (!c->d_cur_label[mode]) LEXP_CUDA(cudaMalloc(&c->d_cur_label[mode], HW * sizeof(float4)));
+    if (!c->d_flags[mode]) {
+        LEXP_CUDA(cudaMalloc(&c->d_flags[mode], (kMaxPeers + 2) * sizeof(int)));   // + epoch base + error flag
+        LEXP_CUDA(cudaMemsetAsync(c->d_flags[mode], 0, (kMaxPeers + 2) * sizeof(int), c->stream));   // epochs only grow: never reset while peers run
+    }
     if (cost) LEXP_CUDA(cudaMemcpyAsync(c->d_cur_cost[mode], cost, HW * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     else {
         LEXP_LAUNCH(lexp_fill_f32, 148 * 4, 256, 0, c->stream, c->d_cur_cost[mode], HW, __builtin_inff());   // currentCost_ = INFINITY (:137)
@@ -933,7 +966,10 @@ int lexp_pm_get(lexp_ctx* c, int mode, float* cost, lexp_plane* labeling) {
     const size_t HW = (size_t)c->p.height * c->p.width;
     if (cost) LEXP_CUDA(cudaMemcpyAsync(cost, c->d_cur_cost[mode], HW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (labeling) LEXP_CUDA(cudaMemcpyAsync(labeling, c->d_cur_label[mode], HW * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    int err = 0;
+    LEXP_CUDA(cudaMemcpyAsync(&err, c->d_flags[mode] + kMaxPeers + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    if (err) return fail(LEXP_ERR_STATE, "a wait for a peer rank's group epoch timed out (multi-GPU cell shard): the state is incomplete");
     return LEXP_OK;
 }
 
@@ -960,22 +996,26 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
-    if (!pl->d_cell_sync) LEXP_CUDA(cudaMalloc(&pl->d_cell_sync, (size_t)pl->ncalls * sizeof(CellSync)));
+    if (!pl->d_cell_sync) {
+        LEXP_CUDA(cudaMalloc(&pl->d_cell_sync, ((size_t)pl->ncalls + 1) * sizeof(CellSync)));
+        pl->d_launch_done = reinterpret_cast<int*>(pl->d_cell_sync + pl->ncalls);
+    }
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     LEXP_CUDA(cudaMemcpy(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice));
-    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, (size_t)pl->ncalls * sizeof(CellSync), c->stream));
+    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, ((size_t)pl->ncalls + 1) * sizeof(CellSync), c->stream));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     return LEXP_OK;
 }
 
-int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes,
-                      int planes_on_device, lexp_plane* d_planes_out, int flags) {
+int lexp_plan_pm_step_ex(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes,
+                         int planes_on_device, lexp_plane* d_planes_out, int flags, int publish_epoch, const int* wait_epochs, unsigned wait_mask) {
     if (!c || !pl || pl->ctx != c || mode < 0 || mode > 1 || step_index < 0) return fail(LEXP_ERR_INVALID, "bad argument");
     if (kind < LEXP_PROP_LIST || kind > LEXP_PROP_RANDOM || m < 0 || m > 120) return fail(LEXP_ERR_INVALID, "bad proposer kind / m");
     if (kind == LEXP_PROP_LIST && !planes) return fail(LEXP_ERR_INVALID, "LEXP_PROP_LIST needs planes");
     if (!pl->d_calls) return fail(LEXP_ERR_STATE, "lexp_plan_set_units has not been called for this plan");
     if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
     if (c->p.energy_kind != 0) return fail(LEXP_ERR_INVALID, "the device PatchMatch phase is implemented for the cost-volume energy");
+    if (publish_epoch < 0 || (wait_mask >> kMaxPeers) || (wait_mask && !wait_epochs)) return fail(LEXP_ERR_INVALID, "bad epoch / mask");
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const Plane4* dp = nullptr;
@@ -986,9 +1026,100 @@ int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int 
             dp = pl->d_planes;
         }
     }
-    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, (size_t)pl->ncalls * sizeof(CellSync), c->stream));
-    PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out)};
+    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, ((size_t)pl->ncalls + 1) * sizeof(CellSync), c->stream));
+    PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out),
+              publish_epoch, {0, 0, 0, 0, 0, 0, 0, 0}, wait_mask};
+    if (wait_epochs)
+        for (int i = 0; i < kMaxPeers; i++) pm.wait_epochs[i] = wait_epochs[i];
     return run_plan(c, pl, mode, dp, nullptr, 0, 0, 1, &pm);
+}
+
+int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes,
+                      int planes_on_device, lexp_plane* d_planes_out, int flags) {
+    return lexp_plan_pm_step_ex(c, pl, mode, step_index, kind, m, seed, planes, planes_on_device, d_planes_out, flags, 0, nullptr, 0u);
+}
+
+int lexp_pm_advance_epoch(lexp_ctx* c, int mode, int delta) {
+    if (!c || mode < 0 || mode > 1 || delta < 0) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_flags[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    LEXP_LAUNCH(lexp_add_i32, 1, 1, 0, c->stream, c->d_flags[mode] + kMaxPeers, delta);
+    LEXP_CUDA(cudaGetLastError());
+    c->launches++;
+    return LEXP_OK;
+}
+
+int lexp_pm_ipc_export(lexp_ctx* c, int mode, void* out) {
+    if (!c || !out || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+#ifdef LEXP_EMU
+    return fail(LEXP_ERR_INVALID, "no inter-process memory on the emulator");
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && LEXP_PM_IPC_BYTES == 3 * 64, "handle layout");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(out);
+    LEXP_CUDA(cudaIpcGetMemHandle(&h[0], c->d_cur_cost[mode]));
+    LEXP_CUDA(cudaIpcGetMemHandle(&h[1], c->d_cur_label[mode]));
+    LEXP_CUDA(cudaIpcGetMemHandle(&h[2], c->d_flags[mode]));
+    return LEXP_OK;
+#endif
+}
+
+int lexp_pm_ipc_connect(lexp_ctx* c, int mode, int rank, int world, const void* all) {
+    if (!c || !all || mode < 0 || mode > 1 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+#ifdef LEXP_EMU
+    return fail(LEXP_ERR_INVALID, "no inter-process memory on the emulator");
+#else
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    lexp_ctx::Peers& pr = c->peers[mode];
+    for (int i = 0; i < pr.n_opened; i++) cudaIpcCloseMemHandle(pr.ipc_opened[i]);
+    pr = lexp_ctx::Peers();
+    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(all);
+    int slot = 1;   // entry 0 is this rank's own copy
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        void* p[3];
+        for (int k = 0; k < 3; k++) {
+            LEXP_CUDA(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+            pr.ipc_opened[pr.n_opened++] = p[k];
+        }
+        pr.cost[slot] = (float*)p[0]; pr.label[slot] = (float4*)p[1]; pr.flags[slot] = (int*)p[2];
+        slot++;
+    }
+    pr.world = world; pr.rank = rank;
+    return LEXP_OK;
+#endif
+}
+
+int lexp_pm_connect_local(lexp_ctx* c, int mode, int rank, int world, lexp_ctx* const* peer_ctx) {
+    if (!c || !peer_ctx || mode < 0 || mode > 1 || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (peer_ctx[rank] != c) return fail(LEXP_ERR_INVALID, "peer_contexts[rank] must be this context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    lexp_ctx::Peers pr;
+    int slot = 1;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        lexp_ctx* o = peer_ctx[r];
+        if (!o || !o->d_cur_cost[mode] || o->p.height != c->p.height || o->p.width != c->p.width)
+            return fail(LEXP_ERR_STATE, "peer context without a PatchMatch-phase state of the same size");
+#ifndef LEXP_EMU
+        if (o->p.device != c->p.device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->p.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(LEXP_ERR_CUDA, std::string("peer access: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+#endif
+        pr.cost[slot] = o->d_cur_cost[mode]; pr.label[slot] = o->d_cur_label[mode]; pr.flags[slot] = o->d_flags[mode];
+        slot++;
+    }
+    pr.world = world; pr.rank = rank;
+    c->peers[mode] = pr;
+    return LEXP_OK;
 }
 
 // LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).

@@ -103,6 +103,7 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 constexpr int kMinCtas = LEXP_MIN_CTAS;  // resident CTAs per SM the kernel is compiled for (register cap 65536 / (kMinCtas * 352))
 constexpr int kG = LEXP_KG;            // rows per gather batch of team A (one batch of loads in flight)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
+constexpr int kMaxPeers = 8;                // GPUs of one NVSwitch domain that share a PatchMatch-phase state
 
 struct __align__(16) Item {  // one CTA work item (64 B)
     int fx, fy, fw, fh;      // filterRect of the call
@@ -157,6 +158,7 @@ struct KParams {
     int fast_ok;                        // MIN == 0, MAX == D-1, th_col >= 0 and the volume holds no NaN/Inf
     // ---- device-side PatchMatch phase (pm_mode != 0): proposal -> unary cost -> `mask = cur > prop; copy; setTo`
     // (FastGCStereo.h:34-60 with doGC == false) without leaving the device
+    int smem_plane_off;                 // byte offset of a 16-byte slot at the end of the launch's dynamic shared memory
     int pm_mode;                        // 0: unary costs only (out); 1: fused update of cur_cost / cur_label; 2: initialisation (unconditional write, :105-113)
     int prop_kind;                      // 0: planes[call] (host list / RANSAC slot), 1: ExpansionProposer, 2: RandomProposer
     int prop_m;                         // RandomProposer: m = outerIter + iter (Proposer.h:124)
@@ -167,6 +169,21 @@ struct KParams {
     const CallInfo* __restrict__ calls; // [ncalls]
     CellSync* cell_sync;                // [ncalls] completion counters / proposal hand-over of the group (zeroed before its first step)
     Plane4* planes_out;                 // [ncalls] the plane each call evaluated in this step (optional: replay / logging)
+    // ---- multi-GPU cell shard of the PatchMatch phase: every rank holds a full copy of the state; an accepted update
+    // is stored into ALL copies by the kernel itself (peer memory over NVLink), ranks meet at group boundaries through epoch flags
+    int n_copies;                       // copies of the state the epilogue writes (1: only this device's)
+    float* copy_cost[kMaxPeers];        // [n_copies] currentCost_ of this rank (entry 0) and of its peers (P2P-mapped)
+    float4* copy_label[kMaxPeers];      // [n_copies]
+    int* copy_flags[kMaxPeers];         // [n_copies] epoch flags int[kMaxPeers] of every copy: flags[r] = last group rank r completed
+    int my_rank;
+    // epochs are relative to *epoch_base (a device counter the host advances once per iteration): the launches of an iteration
+    // can then be replayed as a CUDA graph while the epochs keep growing
+    const int* epoch_base;
+    int* err_flag;                      // set to 1 if a wait for a peer gave up (the host then reports an error instead of hanging)
+    int publish_epoch;                  // != 0: the last work item of this launch stores flags[my_rank] = base + publish_epoch on every copy
+    int wait_epochs[kMaxPeers];         // every work item first waits until flags[r] >= base + wait_epochs[r] for all ranks r in wait_mask
+    unsigned wait_mask;
+    int* launch_done;                   // completion counter of this launch (zeroed with the group's CellSync records)
 #if LEXP_TRACE
     long long* trace;                   // [items][kThreads / 32][4]
 #endif
@@ -191,7 +208,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
 #else
     const int rows = 8 * kCH * srow_stride(vw);
 #endif
-    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 3) * 16;  // + 6 doubles (NAIVE: inverse affine map)
+    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 4) * 16;  // + 6 doubles (NAIVE: inverse affine map) + the plane of the call (PatchMatch phase)
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -375,6 +392,22 @@ __device__ LEXP_NOINLINE float4 pm_propose(const ProposeArgs P, const int ux, co
     return out;
 }
 // acquire load / polling of a completion counter written by CTAs of earlier launches that may still be running (PDL)
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {   // a flag written by another GPU
+#ifndef LEXP_EMU
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *reinterpret_cast<const volatile int*>(p);
+#endif
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+#ifndef LEXP_EMU
+    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#else
+    *reinterpret_cast<volatile int*>(p) = v;
+#endif
+}
 __device__ __forceinline__ int ld_acquire(const int* p) {
 #ifndef LEXP_EMU
     int v;
@@ -423,8 +456,21 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         // counters are written by CTAs of earlier launches of the stream, which may still be running (PDL): poll.  (2) The proposal
         // is drawn ONCE per (cell, step), by the first of the cell's work items to arrive (ticket), and handed to the others through
         // global memory: no work item of the step can write a label before the proposer has read its source label.
-        __shared__ Plane4 s_pl;
+        Plane4& s_pl = *reinterpret_cast<Plane4*>(smem_raw + P.smem_plane_off);   // last 16 bytes of the work item's dynamic shared memory
         if (tid == 0) {
+            if (P.wait_mask) {   // group boundary of the multi-GPU cell shard: the peers' updates of the earlier groups must have landed
+                const int base = *P.epoch_base;
+                for (int r = 0; r < kMaxPeers; r++)
+                    if ((P.wait_mask >> r) & 1u) {
+                        unsigned polls = 0;   // a peer that never arrives (a crashed rank) must not hang this GPU: give up after seconds
+                        while (ld_acquire_sys(P.copy_flags[0] + r) < base + P.wait_epochs[r]) {
+#ifndef LEXP_EMU
+                            __nanosleep(200);
+#endif
+                            if (++polls > (1u << 24)) { atomicExch(P.err_flag, 1); break; }
+                        }
+                    }
+            }
             const CallInfo ci = P.calls[it.call];
             CellSync* cs = P.cell_sync + it.call;
             const int need = P.step_index * ci.n_done_per_step;
@@ -1074,6 +1120,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                                 if (P.pm_mode == 2 || cc[r] > q) {
                                     P.cur_cost[cpix] = q;
                                     P.cur_label[cpix] = make_float4(pl.a, pl.b, pl.c, pl.v);
+                                    for (int p = 1; p < P.n_copies; p++) {   // the peers' copies: plain stores over NVLink
+                                        P.copy_cost[p][cpix] = q;
+                                        P.copy_label[p][cpix] = make_float4(pl.a, pl.b, pl.c, pl.v);
+                                    }
                                 }
                                 cpix += (size_t)P.W;
                             } else {
@@ -1095,9 +1145,21 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             }
         }
         if (P.pm_mode) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
-            __threadfence();
+            if (P.n_copies > 1) __threadfence_system(); else __threadfence();
             __syncwarp();
-            if (lane == 0) atomicAdd(&P.cell_sync[it.call].done, 1);
+            if (lane == 0) {
+                atomicAdd(&P.cell_sync[it.call].done, 1);
+                if (P.publish_epoch) {
+                    // last step of a group on the multi-GPU cell shard: the warp that completes the launch tells every peer that this
+                    // rank's updates of the group are in place (all stores above were fenced system-wide before their increments)
+                    const int fin = atomicAdd(P.launch_done, 1) + 1;
+                    if (fin == (int)gridDim.x * kWarpsE) {
+                        __threadfence_system();
+                        const int e = *P.epoch_base + P.publish_epoch;
+                        for (int p = 0; p < P.n_copies; p++) st_release_sys(P.copy_flags[p] + P.my_rank, e);
+                    }
+                }
+            }
         }
     }
 #if LEXP_TRACE
@@ -1224,6 +1286,8 @@ __global__ void lexp_scan_nonfinite(const float* __restrict__ vol, size_t n, int
     if (bad) atomicOr(flag, 1);  // emulated threads do not run in warp lock-step
 #endif
 }
+
+__global__ void lexp_add_i32(int* p, int delta) { *p += delta; }
 
 __global__ void lexp_fill_f32(float* __restrict__ dst, size_t n, float v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -199,7 +199,8 @@ class Plan:
         ids = None if cell_ids is None else np.ascontiguousarray(cell_ids, dtype=np.int32)
         check(lib().lexp_plan_set_units(self._h, u.ctypes.data, None if ids is None else ids.ctypes.data))
 
-    def pm_step(self, step_index, kind, m=0, seed=0, planes=None, planes_on_device=False, d_planes_out=0, init=False, mode=0):
+    def pm_step(self, step_index, kind, m=0, seed=0, planes=None, planes_on_device=False, d_planes_out=0, init=False, mode=0,
+                publish_epoch=0, wait_epochs=None, wait_mask=0):
         """One proposal step of FastGCStereo.h:41-60 (doGC == false) for all cells of the plan, asynchronous:
         kind = PROP_LIST (planes: numpy [n][4] or a device pointer) | PROP_EXPANSION | PROP_RANDOM (m = outerIter + iter)."""
         ptr = None
@@ -210,8 +211,13 @@ class Plan:
                 self._pl_keep = _plane_array(planes)
                 assert len(self._pl_keep) == self.num_calls
                 ptr = self._pl_keep.ctypes.data
-        check(lib().lexp_plan_pm_step(self.energy._h, self._h, mode, int(step_index), int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                      ptr, int(planes_on_device), int(d_planes_out) or None, 1 if init else 0))
+        we = None
+        if wait_mask:
+            self._we_keep = np.zeros(8, np.int32)
+            self._we_keep[:len(wait_epochs)] = wait_epochs
+            we = self._we_keep.ctypes.data
+        check(lib().lexp_plan_pm_step_ex(self.energy._h, self._h, mode, int(step_index), int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                         ptr, int(planes_on_device), int(d_planes_out) or None, 1 if init else 0, int(publish_epoch), we, int(wait_mask)))
 
     def close(self):
         if self._h:
@@ -323,6 +329,26 @@ class CostVolumeEnergy:
         assert lab is None or (lab.dtype == np.float32 and lab.shape == (self.height, self.width, 4) and lab.flags.c_contiguous)
         check(lib().lexp_pm_get(self._h, mode, None if cost is None else cost.ctypes.data, None if lab is None else lab.ctypes.data))
         return cost, lab
+
+    # multi-GPU cell shard: every rank's copy of the state is written by all ranks' kernels (peer memory over NVLink)
+    def pm_ipc_export(self, mode=0) -> bytes:
+        buf = C.create_string_buffer(192)
+        check(lib().lexp_pm_ipc_export(self._h, mode, buf))
+        return buf.raw
+
+    def pm_ipc_connect(self, rank, world, all_handles, mode=0):
+        """all_handles: the `world` exports in rank order (e.g. from torch.distributed.all_gather_object)."""
+        blob = b"".join(all_handles)
+        assert len(blob) == 192 * world
+        check(lib().lexp_pm_ipc_connect(self._h, mode, rank, world, blob))
+
+    def pm_connect_local(self, rank, peers, mode=0):
+        """peers: the contexts of all ranks living in this process (tests, single-process multi-device callers)."""
+        arr = (C.c_void_p * len(peers))(*[p._h for p in peers])
+        check(lib().lexp_pm_connect_local(self._h, mode, rank, len(peers), arr))
+
+    def pm_advance_epoch(self, delta, mode=0):
+        check(lib().lexp_pm_advance_epoch(self._h, mode, int(delta)))
 
     def pm_device_state(self, mode=0):
         """(device pointer of currentCost float[H][W], device pointer of currentLabeling Plane[H][W])."""

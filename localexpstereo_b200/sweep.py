@@ -118,60 +118,117 @@ def expand_proposers(proposers, outer_iter, max_disp, min_disp=0.0):
 
 class PMSweep:
     """Device-resident PatchMatch phase of one view: state (currentCost_, currentLabeling_) in HBM, one plan per (layer, group),
-    one launch per proposal step; nothing crosses PCIe between `begin` / `init` and `get`."""
+    one launch per proposal step; nothing crosses PCIe between `begin` / `init` and `get`.
+
+    Multi-GPU cell shard (rank / world): the cells of every group are dealt round-robin to ranks; every rank holds a full copy of
+    the state and, after `connect` / `connect_local`, its kernels store accepted updates into all copies.  Groups are numbered
+    by epochs (the same on every rank, whether it owns cells of a group or not): the last step of a group publishes the epoch,
+    the first step of the next group a rank takes part in waits for the latest epoch of every rank that has published one."""
 
     def __init__(self, energy: CostVolumeEnergy, unit_sizes=None, proposers=None, rank=0, world=1, mode=0):
-        self.energy, self.mode = energy, mode
+        self.energy, self.mode, self.rank, self.world = energy, mode, rank, world
         self.unit_sizes = unit_sizes or v3_layer_units(energy.width)
         self.proposers = proposers or V3_PROPOSERS_DEVICE
         self.lm = LayerManager(energy.width, energy.height, energy.params.windR)
-        self.groups: List[GroupPlan] = []
-        self.evals_per_iteration = None
+        self.groups: List[GroupPlan] = []          # this rank's plans
+        self.schedule = []                         # every (layer, group) in order: (GroupPlan or None, [ranks that own cells])
         cell_base = 0
         for li, u in enumerate(self.unit_sizes):
             lay = self.lm.addLayer(u)
             for gi, cells in enumerate(lay.disjointRegionSets):
+                owners = [r for r in range(world) if len(shard_cells(cells, r, world))]
                 mine = shard_cells(cells, rank, world)
-                if len(mine) == 0:
-                    continue
-                plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])
-                plan.set_units([lay.unitRegions[r] for r in mine], cell_base + mine)
-                self.groups.append(GroupPlan(li, gi, mine, plan, 0))
+                gp = None
+                if len(mine):
+                    plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])
+                    plan.set_units([lay.unitRegions[r] for r in mine], cell_base + mine)
+                    gp = GroupPlan(li, gi, mine, plan, 0)
+                    self.groups.append(gp)
+                self.schedule.append((li, gi, gp, owners))
             cell_base += len(lay.unitRegions)
         # initCurrentFast (FastGCStereo.h:101-113): every unit region of layer 0 with filterRegion = unit +- windR
         lay0 = self.lm.layers[0]
         R, W, H = energy.params.windR, energy.width, energy.height
-        self.init_units = [lay0.unitRegions[r] for r in range(len(lay0.unitRegions))][rank::world]
+        n0 = len(lay0.unitRegions)
+        self.init_owners = [r for r in range(world) if len(range(r, n0, world))]
+        self.init_units = [lay0.unitRegions[r] for r in range(n0)][rank::world]
+        self.init_index = np.arange(n0)[rank::world]          # which of the layer-0 units this rank initialises
         fr = []
         for (x, y, w, h) in self.init_units:
             x0, y0, x1, y1 = max(x - R, 0), max(y - R, 0), min(x + w + R, W), min(y + h + R, H)
             fr.append((x0, y0, x1 - x0, y1 - y0))
-        self.init_plan = energy.make_plan(fr, self.init_units)
-        self.init_plan.set_units(self.init_units, np.arange(len(lay0.unitRegions))[rank::world])
+        self.init_plan = energy.make_plan(fr, self.init_units) if len(fr) else None
+        if self.init_plan is not None:
+            self.init_plan.set_units(self.init_units, self.init_index)
+        # epochs relative to the device-side epoch base (advanced once per init / iteration, lexp_pm_advance_epoch)
+        self.rel = 0                        # groups issued since the base was last advanced
+        self.last_rel = [None] * 8          # last epoch every rank has published, relative to the base (None: never)
+
+    # ---- multi-GPU wiring (after begin(): the state must exist) ------------------------------------------------------------
+    def connect(self, all_handles):
+        self.energy.pm_ipc_connect(self.rank, self.world, all_handles, self.mode)
+
+    def connect_local(self, peer_energies):
+        self.energy.pm_connect_local(self.rank, peer_energies, self.mode)
+
+    def _sync_args(self, first, last):
+        """publish_epoch / wait_epochs / wait_mask of one step of the group that is being issued (relative epoch self.rel + 1)."""
+        if self.world == 1:
+            return {}
+        a = {"publish_epoch": self.rel + 1 if last else 0}
+        if first:
+            a["wait_epochs"] = [0 if e is None else e for e in self.last_rel]
+            a["wait_mask"] = sum(1 << r for r, e in enumerate(self.last_rel) if e is not None and r != self.rank)
+        return a
+
+    def _group_done(self, owners):
+        self.rel += 1
+        for r in owners:
+            self.last_rel[r] = self.rel
+
+    def _advance(self):
+        """All groups of an init / iteration have been issued: move the device epoch base past them."""
+        if self.world > 1:
+            self.energy.pm_advance_epoch(self.rel, self.mode)
+        self.last_rel = [None if e is None else e - self.rel for e in self.last_rel]
+        self.rel = 0
 
     def begin(self, cost=None, labeling=None):
         self.energy.pm_begin(self.mode, cost, labeling)
 
     def init(self, labels):
-        """labels [n units of layer 0][4]: `currentLabeling(unit) = label; ComputeUnaryPotential(unit +- R, unit, ...)` (:107-111)."""
-        self.init_plan.pm_step(0, PROP_LIST, planes=labels, init=True, mode=self.mode)
+        """labels [this rank's units of layer 0][4] (all units at world == 1): `currentLabeling(unit) = label;
+        ComputeUnaryPotential(unit +- R, unit, ...)` (:107-111)."""
+        if self.init_plan is not None:
+            self.init_plan.pm_step(0, PROP_LIST, planes=labels, init=True, mode=self.mode, **self._sync_args(True, True))
+        self._group_done(self.init_owners)
+        self._advance()
 
     def iteration(self, iteration, seed, list_planes=None, planes_out=None):
         """One pm iteration over all layers (FastGCStereo.h:153-157).  list_planes: {(layer, group): [list steps][n][4]} for PROP_LIST
         slots; planes_out: optional {(layer, group): device pointer of [steps][n] planes}.  Returns the number of launches."""
-        n_launch = 0
+        return sum(self.iteration_by_group(iteration, seed, list_planes, planes_out))
+
+    def iteration_by_group(self, iteration, seed, list_planes=None, planes_out=None):
+        """Generator form of `iteration`: issues one (layer, group) per step and yields its number of launches (lets a
+        single-process test interleave several ranks)."""
         E = self.energy
-        for g in self.groups:
-            steps = expand_proposers(self.proposers[g.layer], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY)
-            li_at = 0
-            for k, (kind, m) in enumerate(steps):
-                pl = None
-                if kind == PROP_LIST:
-                    pl = list_planes[(g.layer, g.group)][li_at]; li_at += 1
-                out = 0 if planes_out is None else planes_out[(g.layer, g.group)] + k * g.plan.num_calls * 16
-                g.plan.pm_step(k, kind, m, pm_seed(seed, self.mode, iteration, g.layer, g.group, k), planes=pl, d_planes_out=out, mode=self.mode)
-                n_launch += 1
-        return n_launch
+        for (li, gi, g, owners) in self.schedule:
+            n_launch = 0
+            if g is not None:
+                steps = expand_proposers(self.proposers[li], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY)
+                li_at = 0
+                for k, (kind, m) in enumerate(steps):
+                    pl = None
+                    if kind == PROP_LIST:
+                        pl = list_planes[(li, gi)][li_at]; li_at += 1
+                    out = 0 if planes_out is None else planes_out[(li, gi)] + k * g.plan.num_calls * 16
+                    g.plan.pm_step(k, kind, m, pm_seed(seed, self.mode, iteration, li, gi, k), planes=pl, d_planes_out=out, mode=self.mode,
+                                   **self._sync_args(k == 0, k == len(steps) - 1))
+                    n_launch += 1
+            self._group_done(owners)
+            yield n_launch
+        self._advance()
 
     def get(self, out_cost=None, out_labeling=None):
         return self.energy.pm_get(self.mode, out_cost=out_cost, out_labeling=out_labeling)
@@ -179,5 +236,6 @@ class PMSweep:
     def close(self):
         for g in self.groups:
             g.plan.close()
-        self.init_plan.close()
+        if self.init_plan is not None:
+            self.init_plan.close()
         self.groups = []

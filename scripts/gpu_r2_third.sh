@@ -1,11 +1,12 @@
-# round 2, third GPU call: device-side PatchMatch phase (tests + e2e in the bench), pair-layout gather variants
+# round 2, third GPU call: device-side PatchMatch phase (tests + the bench built around it), pair-layout gather variants
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_pm.py tests/test_gpu_parity.py -x -q -m gpu -s 2>&1 | tail -12 > gpurun_out/r2c_tests.log; cat gpurun_out/r2c_tests.log
+timeout 900 python -m pytest tests/test_gpu_pm.py tests/test_gpu_parity.py -x -q -m gpu -s 2>&1 | tail -14 > gpurun_out/r2c_tests.log; cat gpurun_out/r2c_tests.log
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r2c_bench.json 2> gpurun_out/r2c_bench.err; tail -3 gpurun_out/r2c_bench.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r2c_bench.json'))
-print('value %.3e ms %.2f frac %.3f | e2e(pm) %.3e (%.2f ms) | e2e unary maps %.3e' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e'].get('ms_per_step', 0), d['e2e'].get('unary_maps', {}).get('value', 0)))
+print('value %.3e ms %.2f frac %.3f | unary sweep %.2f ms | e2e(pm) %.3e (%.2f ms) | e2e unary maps %.3e' % (d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('unary_sweep',{}).get('ms_per_step',0), d['e2e']['value'], d['e2e'].get('ms_per_step', 0), d['e2e'].get('unary_maps', {}).get('value', 0)))
+print(d['roofline']['ms_by_layer'], d['clocks'])
 PY
 bash scripts/gpu_variants.sh pairs pairsna > gpurun_out/r2c_variants.log 2>&1; cat gpurun_out/variants.txt

@@ -225,6 +225,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
 static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_ACQ_REL); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}   /* fibers of a block switch only at barriers */
 template <class T> static inline T __ldcg(const T* p) { return *p; }

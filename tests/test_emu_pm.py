@@ -25,3 +25,7 @@ def test_emu_pm_phase_replay_small(devmem):
 
 def test_emu_pm_phase_replay_r10(devmem):
     _pm.test_pm_phase_replay_r10(devmem)
+
+
+def test_emu_pm_phase_cell_shard_two_ranks_in_one_process():
+    _pm.test_pm_phase_cell_shard_two_ranks_in_one_process()

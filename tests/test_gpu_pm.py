@@ -119,3 +119,53 @@ def test_pm_phase_full_sweep_on_the_cones_crop(devmem):
                       scene=(G["imL"], G["imR"], G["volL"], G["volR"]))
     check_pm_result(r)
     assert r["n_prop"] > 4000
+
+
+def test_pm_phase_cell_shard_two_ranks_in_one_process():
+    """The multi-GPU cell shard of the PatchMatch phase with both "ranks" in this process (two contexts, lexp_pm_connect_local):
+    every rank evaluates its share of the cells of every group and its kernels store accepted updates into BOTH copies of the
+    state; epoch flags order the groups.  Both copies must end up bit-identical to the single-rank sweep (same cells, same random
+    streams, same planes -- the shard only changes who computes what).  Ranks are issued group by group and synchronised in
+    between, since two contexts on ONE device could otherwise starve each other while polling."""
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import PMSweep
+    from localexpstereo_b200 import synth
+    H, W, D, windR = 96, 128, 12, 12
+    imL, imR, volL, volR = make_scene(H, W, D)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 3)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1)]]
+    units = [8, 20, 44]   # the last layer has groups with a single cell: one rank sits those groups out
+    Es = [L.CostVolumeEnergy(imL, None, volL, None, prm, D - 1) for _ in range(3)]
+    try:
+        single = PMSweep(Es[2], unit_sizes=units, proposers=props)
+        labels = synth.synthetic_planes(single.init_units, 1, D, 5)[0]
+        single.begin(); single.init(labels)
+        for it in range(2):
+            single.iteration(it, 31)
+        ref_cost, ref_lab = single.get()
+        ranks = [PMSweep(Es[r], unit_sizes=units, proposers=props, rank=r, world=2) for r in range(2)]
+        for S in ranks:
+            S.begin()
+        for S in ranks:
+            S.connect_local(Es[:2])
+        for r, S in enumerate(ranks):
+            S.init(labels[r::2])
+        for E in Es[:2]:
+            E.sync()
+        for it in range(2):
+            gens = [S.iteration_by_group(it, 31) for S in ranks]
+            for _ in ranks[0].schedule:
+                for g in gens:
+                    next(g)
+                for E in Es[:2]:
+                    E.sync()
+        assert any(len(o) == 1 for (_, _, _, o) in ranks[0].schedule), "the test should contain a group owned by one rank only"
+        for r, S in enumerate(ranks):
+            c, l = S.get()
+            assert np.array_equal(c, ref_cost), f"rank {r}: currentCost differs from the single-rank sweep"
+            assert np.array_equal(l, ref_lab), f"rank {r}: currentLabeling differs from the single-rank sweep"
+        for S in ranks + [single]:
+            S.close()
+    finally:
+        for E in Es:
+            E.close()
