@@ -173,8 +173,12 @@ LEXP_API int lexp_pm_device_state(lexp_ctx* ctx, int mode, float** d_cost, lexp_
 /* unitRegion of every call of the plan (where its proposers draw, LayerManager.h:117-121) and a global id per cell (seeds
  * the cell's random streams; NULL: 0..n-1).  Required before lexp_plan_pm_step. */
 LEXP_API int lexp_plan_set_units(lexp_plan* plan, const lexp_rect* unit_rects, const int* cell_ids);
+/* Zero the per-cell completion counters of all plans of the context (asynchronous).  Call once before the steps of an
+ * initialisation or of an iteration are issued (never between its groups: all launches of an iteration are chained by
+ * programmatic dependent launch and may overlap). */
+LEXP_API int lexp_pm_reset_sync(lexp_ctx* ctx);
 /* One proposal step for all cells of the plan (asynchronous, on the context stream).  step_index = 0, 1, ... within the
- * group (0 resets the group's completion counters; the steps of a group must be issued in order).  kind / m: LEXP_PROP_*;
+ * group visit (the steps of a group must be issued in order; lexp_pm_reset_sync between two visits of the same group).  kind / m: LEXP_PROP_*;
  * seed: random stream of this (view, iteration, layer, group, step).  planes: LEXP_PROP_LIST only.  d_planes_out: optional
  * device array [ncalls] receiving the plane every call evaluated.  Always with the validity check (ComputeUnaryPotential). */
 LEXP_API int lexp_plan_pm_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int step_index, int kind, int m, uint64_t seed,
@@ -194,7 +198,9 @@ LEXP_API int lexp_plan_pm_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int ste
 LEXP_API int lexp_pm_ipc_export(lexp_ctx* ctx, int mode, void* handles_out);
 LEXP_API int lexp_pm_ipc_connect(lexp_ctx* ctx, int mode, int rank, int world, const void* all_handles);
 LEXP_API int lexp_pm_connect_local(lexp_ctx* ctx, int mode, int rank, int world, lexp_ctx* const* peer_contexts);
-/* lexp_plan_pm_step with the group-boundary protocol of the cell shard.  Groups are numbered by epochs that only grow; the
+/* lexp_plan_pm_step with the group-boundary protocol.  Consecutive groups overlap spatially, so the first step of a group must
+ * not start before the previous group has finished -- on this device and, on the multi-GPU cell shard, on the peers.  Since the
+ * launches of an iteration may overlap on the device, this is done with flags too.  Groups are numbered by epochs that only grow; the
  * epochs passed here are RELATIVE to a per-context device counter (the epoch base) that lexp_pm_advance_epoch advances in stream
  * order -- so the launches of one iteration can be captured into a CUDA graph and replayed.  publish_epoch != 0 (last step of
  * a group): when the launch completes, flags[rank] = base + publish_epoch is stored on every copy.  wait_mask / wait_epochs

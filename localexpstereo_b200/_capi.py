@@ -64,6 +64,7 @@ SYMBOLS = {
     "lexp_plan_set_units": (C.c_int, [_P, _P, _P]),
     "lexp_plan_pm_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, C.c_int]),
     "lexp_plan_pm_step_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_uint]),
+    "lexp_pm_reset_sync": (C.c_int, [_P]),
     "lexp_pm_advance_epoch": (C.c_int, [_P, C.c_int, C.c_int]),
     "lexp_pm_ipc_export": (C.c_int, [_P, C.c_int, _P]),
     "lexp_pm_ipc_connect": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),

@@ -63,9 +63,8 @@ struct lexp_plan {
     float* h_compact = nullptr;   // pinned
     // PatchMatch phase (lexp_plan_set_units / lexp_plan_pm_step)
     CallInfo* d_calls = nullptr;  // [ncalls] unitRegion, signals per step, cell id
-    CellSync* d_cell_sync = nullptr;   // [ncalls] completion counters / proposal hand-over of the group
-    int* d_launch_done = nullptr;      // completion counter of the group's last launch (multi-GPU: who publishes the epoch flag);
-                                       // lives behind the CellSync records and is zeroed with them
+    long long sync_off = -1;           // byte offset in the context's synchronisation arena of CellSync[ncalls + 1]: per-call completion
+                                       // counters / proposal hand-over, then the completion counter of the group's last launch
     std::vector<int> items_per_call;
 };
 
@@ -85,6 +84,8 @@ struct lexp_ctx {
     float* d_vol[2] = {nullptr, nullptr};   // blocked copy float[Hb][Wb][D][4][4] (owned)
     float* d_cur_cost[2] = {nullptr, nullptr};     // PatchMatch phase: currentCost_[mode]   float [H][W]
     float4* d_cur_label[2] = {nullptr, nullptr};   //                   currentLabeling_[mode] Plane[H][W]
+    char* d_sync_arena = nullptr;                  // CellSync records of all plans (zeroed by lexp_pm_reset_sync once per iteration)
+    size_t sync_cap = 0, sync_used = 0;
     int* d_flags[2] = {nullptr, nullptr};          // epoch flags int[kMaxPeers] of the multi-GPU cell shard (peers store into them);
                                                    // d_flags[m][kMaxPeers] is this rank's epoch base (lexp_pm_advance_epoch)
     struct Peers {                                 // copies of the state the epilogue writes: entry 0 = this context's own
@@ -105,7 +106,7 @@ struct lexp_ctx {
     size_t smem_cap = 0;         // upper bound on a work item's dynamic shared memory, 0: none (LEXP_SMEM_CAP)
     size_t smem_limit = 0;
     size_t window_max = 0;
-    bool smem_configured = false;
+    bool smem_configured[2] = {false, false};
     bool own_stream = true;
     bool vol_finite[2] = {false, false};
     // single-cell plans of lexp_eval_cell, keyed by (filterRect, targetRect): the unchanged reference loop calls the
@@ -180,7 +181,7 @@ void report_trace(lexp_ctx* c, int nitems) {
 }
 #endif
 
-template <int R_T, bool NAIVE>
+template <int R_T, bool NAIVE, bool PM>
 int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem, bool allow_pdl) {
     KParams kp = kp_in;
 #if LEXP_TRACE
@@ -195,10 +196,10 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem, b
         kp.trace = c->d_trace;
     }
 #endif
-    auto kern = lexp_fused_kernel<R_T, NAIVE>;
-    if (!c->smem_configured) {  // one R instantiation per context
+    auto kern = lexp_fused_kernel<R_T, NAIVE, PM>;
+    if (!c->smem_configured[PM]) {  // one R instantiation per context (and one more for the PatchMatch phase)
         LEXP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
-        c->smem_configured = true;
+        c->smem_configured[PM] = true;
     }
 #if LEXP_PDL && !defined(LEXP_EMU)
     if (c->pdl && allow_pdl) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
@@ -224,14 +225,21 @@ int launch_fused(lexp_ctx* c, const KParams& kp, int nitems, size_t smem, bool a
     if (smem > c->smem_limit) return fail(LEXP_ERR_INVALID, "tile needs more shared memory than the device offers");
     if (c->p.energy_kind == 1) {
         switch (c->R) {
-            case 10: return launch_fused_t<10, true>(c, kp, nitems, smem, allow_pdl);
-            default: return launch_fused_t<0, true>(c, kp, nitems, smem, allow_pdl);
+            case 10: return launch_fused_t<10, true, false>(c, kp, nitems, smem, allow_pdl);
+            default: return launch_fused_t<0, true, false>(c, kp, nitems, smem, allow_pdl);
+        }
+    }
+    if (kp.pm_mode) {   // PatchMatch phase: proposal prologue + fused update epilogue compiled in
+        switch (c->R) {
+            case 10: return launch_fused_t<10, false, true>(c, kp, nitems, smem, allow_pdl);
+            case 16: return launch_fused_t<16, false, true>(c, kp, nitems, smem, allow_pdl);
+            default: return launch_fused_t<0, false, true>(c, kp, nitems, smem, allow_pdl);
         }
     }
     switch (c->R) {
-        case 10: return launch_fused_t<10, false>(c, kp, nitems, smem, allow_pdl);
-        case 16: return launch_fused_t<16, false>(c, kp, nitems, smem, allow_pdl);
-        default: return launch_fused_t<0, false>(c, kp, nitems, smem, allow_pdl);
+        case 10: return launch_fused_t<10, false, false>(c, kp, nitems, smem, allow_pdl);
+        case 16: return launch_fused_t<16, false, false>(c, kp, nitems, smem, allow_pdl);
+        default: return launch_fused_t<0, false, false>(c, kp, nitems, smem, allow_pdl);
     }
 }
 
@@ -241,7 +249,6 @@ void release_plan_memory(lexp_plan* pl) {
     cudaFree(pl->d_compact); pl->d_compact = nullptr;
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
     cudaFree(pl->d_calls); pl->d_calls = nullptr;
-    cudaFree(pl->d_cell_sync); pl->d_cell_sync = nullptr; pl->d_launch_done = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -325,7 +332,8 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
         kp.pm_mode = pm->pm_mode; kp.prop_kind = pm->prop_kind; kp.prop_m = pm->prop_m; kp.step_index = pm->step_index;
         kp.seed = pm->seed; kp.planes_out = pm->planes_out;
         kp.cur_cost = c->d_cur_cost[mode]; kp.cur_label = c->d_cur_label[mode];
-        kp.calls = pl->d_calls; kp.cell_sync = pl->d_cell_sync;
+        kp.calls = pl->d_calls;
+        kp.cell_sync = reinterpret_cast<CellSync*>(c->d_sync_arena + pl->sync_off);
         const lexp_ctx::Peers& pr = c->peers[mode];
         kp.n_copies = pr.world; kp.my_rank = pr.rank;
         kp.copy_cost[0] = c->d_cur_cost[mode]; kp.copy_label[0] = c->d_cur_label[mode]; kp.copy_flags[0] = c->d_flags[mode];
@@ -334,11 +342,11 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
         for (int i = 0; i < kMaxPeers; i++) kp.wait_epochs[i] = pm->wait_epochs[i];
         kp.epoch_base = c->d_flags[mode] + kMaxPeers;
         kp.err_flag = c->d_flags[mode] + kMaxPeers + 1;
-        kp.launch_done = pl->d_launch_done;
+        kp.launch_done = reinterpret_cast<int*>(kp.cell_sync + pl->ncalls);
     }
-    // the first step of a group is ordered after everything before it (its cells overlap the previous group's); the later
-    // steps of the group may start early (programmatic dependent launch): per-cell counters order them
-    return launch_fused(c, kp, pl->nitems, pl->smem, !(pm && pm->step_index == 0));
+    // PatchMatch phase: every launch may start early (programmatic dependent launch); the steps of a cell are ordered by its
+    // counters, the groups by epoch flags (lexp_plan_pm_step_ex)
+    return launch_fused(c, kp, pl->nitems, pl->smem, true);
 }
 
 // scan the caller's volume for NaN/Inf and re-lay it out into the context's blocked copy
@@ -437,6 +445,7 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_cur_label[m]);
         cudaFree(c->d_flags[m]);
     }
+    cudaFree(c->d_sync_arena);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return LEXP_OK;
@@ -996,14 +1005,32 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
-    if (!pl->d_cell_sync) {
-        LEXP_CUDA(cudaMalloc(&pl->d_cell_sync, ((size_t)pl->ncalls + 1) * sizeof(CellSync)));
-        pl->d_launch_done = reinterpret_cast<int*>(pl->d_cell_sync + pl->ncalls);
-    }
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
     LEXP_CUDA(cudaMemcpy(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice));
-    LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, ((size_t)pl->ncalls + 1) * sizeof(CellSync), c->stream));
-    LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    if (pl->sync_off < 0) {   // a slice of the context's synchronisation arena (offsets survive a re-allocation of the arena)
+        const size_t need = ((size_t)pl->ncalls + 1) * sizeof(CellSync);
+        if (c->sync_used + need > c->sync_cap) {
+            const size_t cap = std::max<size_t>(2 * c->sync_cap, std::max<size_t>(1 << 20, c->sync_used + need));
+            char* na = nullptr;
+            LEXP_CUDA(cudaMalloc(&na, cap));
+            LEXP_CUDA(cudaMemsetAsync(na, 0, cap, c->stream));
+            LEXP_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_sync_arena);   // the stream is idle (synchronised above); the records are zeroed before every iteration anyway
+            c->d_sync_arena = na; c->sync_cap = cap;
+        }
+        pl->sync_off = (long long)c->sync_used;
+        c->sync_used += need;
+    }
+    return LEXP_OK;
+}
+
+// Zero the completion counters of ALL plans of the context (asynchronous): once before the steps of an initialisation / iteration
+// are issued -- not between groups, so that all launches of an iteration form one programmatic-dependent-launch chain.
+int lexp_pm_reset_sync(lexp_ctx* c) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    if (c->sync_used) LEXP_CUDA(cudaMemsetAsync(c->d_sync_arena, 0, c->sync_used, c->stream));
     return LEXP_OK;
 }
 
@@ -1012,7 +1039,7 @@ int lexp_plan_pm_step_ex(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, i
     if (!c || !pl || pl->ctx != c || mode < 0 || mode > 1 || step_index < 0) return fail(LEXP_ERR_INVALID, "bad argument");
     if (kind < LEXP_PROP_LIST || kind > LEXP_PROP_RANDOM || m < 0 || m > 120) return fail(LEXP_ERR_INVALID, "bad proposer kind / m");
     if (kind == LEXP_PROP_LIST && !planes) return fail(LEXP_ERR_INVALID, "LEXP_PROP_LIST needs planes");
-    if (!pl->d_calls) return fail(LEXP_ERR_STATE, "lexp_plan_set_units has not been called for this plan");
+    if (!pl->d_calls || pl->sync_off < 0) return fail(LEXP_ERR_STATE, "lexp_plan_set_units has not been called for this plan");
     if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
     if (c->p.energy_kind != 0) return fail(LEXP_ERR_INVALID, "the device PatchMatch phase is implemented for the cost-volume energy");
     if (publish_epoch < 0 || (wait_mask >> kMaxPeers) || (wait_mask && !wait_epochs)) return fail(LEXP_ERR_INVALID, "bad epoch / mask");
@@ -1026,7 +1053,6 @@ int lexp_plan_pm_step_ex(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, i
             dp = pl->d_planes;
         }
     }
-    if (step_index == 0) LEXP_CUDA(cudaMemsetAsync(pl->d_cell_sync, 0, ((size_t)pl->ncalls + 1) * sizeof(CellSync), c->stream));
     PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out),
               publish_epoch, {0, 0, 0, 0, 0, 0, 0, 0}, wait_mask};
     if (wait_epochs)

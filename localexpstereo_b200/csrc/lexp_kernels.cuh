@@ -432,7 +432,7 @@ __device__ __forceinline__ float2 ldg_pair(const float2* p) {
 }
 constexpr int kVolUnit = LEXP_VOL_PAIRS ? 8 : 4;   // bytes per pixel and disparity in the blocked volume
 
-template <int R_T, bool NAIVE>
+template <int R_T, bool NAIVE, bool PM>
 __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KParams P) {
     const int R = R_T > 0 ? R_T : P.R;
     const int K = 2 * R + 1;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     F4* smem = reinterpret_cast<F4*>(smem_raw);
 
 #if LEXP_PDL && !defined(LEXP_EMU)
-    if (!P.pm_mode) asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.launch_dependents;");
 #endif
 #if LEXP_TRACE
     unsigned tr_wait_in = 0, tr_wait_out = 0, tr_wait_ld = 0;  // 32-bit cycle counts: a work item runs for ~1e5 cycles
@@ -449,16 +449,50 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     const Item it = P.items[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     Plane4 pl;
-    if (!P.pm_mode) pl = P.planes[it.call];
-    else {
-        // PatchMatch phase.  (1) This cell's previous proposal steps (all their work items) must have updated cur_cost / cur_label
-        // before the proposer reads a label and before this step's own update (FastGCStereo.h:41-60 is sequential per cell); the
-        // counters are written by CTAs of earlier launches of the stream, which may still be running (PDL): poll.  (2) The proposal
-        // is drawn ONCE per (cell, step), by the first of the cell's work items to arrive (ticket), and handed to the others through
-        // global memory: no work item of the step can write a label before the proposer has read its source label.
-        Plane4& s_pl = *reinterpret_cast<Plane4*>(smem_raw + P.smem_plane_off);   // last 16 bytes of the work item's dynamic shared memory
+    if (!PM) pl = P.planes[it.call];
+    const int VW = it.ow + 4 * R;
+    const int X0 = it.ox0 - 2 * R;
+    const int W2 = VW - 2 * R;
+    const int SW = srow_stride(VW);   // row stride of hb1 (stage-1 column sums, VW columns)
+#if LEXP_LINK_STRIDES
+    const int SW2 = srow_stride(W2), SW3 = srow_stride(it.ow);  // ho1 / hb2 hold W2 columns, ho2 the ow output columns
+#else
+    const int SW2 = SW, SW3 = SW;
+#endif
+    const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
+    // streamed rows y = ys + v, v in [0, VHs): the dependency cone of the tile, minus leading rows above
+    // the filterRect (they are zero padding).  Rows >= fy1 are zero rows that flush the running sums.
+    const int ys = max(it.oy0 - 2 * R, it.fy);
+    const int VHs = it.oy0 + it.oh + 2 * R - ys;
+    const int vReal = min(VHs, fy1 - ys);                    // rows [0, vReal) lie inside the filterRect
+    const int vC0 = max(it.oy0 - R, it.fy) + R - ys;         // first v whose stage-1 centre row (y - R) is needed
+    const int vC1 = min(VHs, fy1 + R - ys);                  // centre rows >= fy1 are zero rows
+    const int vE0 = it.oy0 + 2 * R - ys;                     // first v whose stage-2 centre row (y - 2R) is an output row
+
+    uint2* ring1 = reinterpret_cast<uint2*>(smem);   // [K][VW] {p, packed guide}: the products are recomputed when a row leaves the window
+    F4* ring2 = smem + (K * VW + 1) / 2;              // [K][W2]
+    F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
+    F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW2] stage-1 box sums     (index: column - X0 - R)
+    F4* hb2 = ho1 + 2 * kCH * SW2;         // [2][CH][SW2] stage-2 column sums  (index: column - X0 - R)
+    F4* ho2 = hb2 + 2 * kCH * SW2;         // [2][CH][SW3] stage-2 box sums     (index: column - X0 - 2R)
+    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW3);  // [VHs] 1 / (#rows of the window inside filterRect)
+    float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
+    int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
+    double* s_iM = reinterpret_cast<double*>(s_Y0 + 4 * ((it.oh + 4 * R + 3) / 4));  // [6] NAIVE: inverse affine map of the call
+
+    if (PM) {
+        // PatchMatch phase.  (0) Group boundary: the previous group (this rank's and, on the multi-GPU cell shard, the peers') must
+        // have finished -- its last launch stored an epoch flag when its last work item completed; all launches of an iteration are
+        // chained by programmatic dependent launch, so this launch may have started long before.  (1) This cell's previous proposal
+        // steps (all their work items) must have updated cur_cost / cur_label before the proposer reads a label and before this
+        // step's own update (FastGCStereo.h:41-60 is sequential per cell): per-cell counters, written by CTAs of earlier launches
+        // that may still be running.  (2) The proposal is drawn ONCE per (cell, step), by the first of the cell's work items to
+        // arrive (ticket; tickets of the next step can only be taken after all of this step's, because of (1)), and handed to the
+        // others through global memory: no work item of the step can write a label before the proposer has read its source label.
+        // Warp 0 does this while the other warps zero the shared-memory rings.
+        Plane4& s_pl = *reinterpret_cast<Plane4*>(smem_raw + P.smem_plane_off);   // last 16 bytes of the launch's dynamic shared memory
         if (tid == 0) {
-            if (P.wait_mask) {   // group boundary of the multi-GPU cell shard: the peers' updates of the earlier groups must have landed
+            if (P.wait_mask) {
                 const int base = *P.epoch_base;
                 for (int r = 0; r < kMaxPeers; r++)
                     if ((P.wait_mask >> r) & 1u) {
@@ -504,43 +538,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             }
             s_pl = q;
         }
+        {   // zero-fill (the box filter is zero padded, GuidedFilter.h:43 BORDER_CONSTANT) by warps 1.. meanwhile
+            const int total = (K * VW + 1) / 2 + K * W2 + 2 * kCH * (SW + 2 * SW2 + SW3);
+            if (tid >= 32) for (int i = tid - 32; i < total; i += kThreads - 32) smem[i] = f4zero();
+        }
         __syncthreads();
         pl = s_pl;
-#if LEXP_PDL && !defined(LEXP_EMU)
-        // after the ticket: work items of the next step (next launch) must not overtake this step's in the ticket order
-        asm volatile("griddepcontrol.launch_dependents;");
-#endif
     }
-    const int VW = it.ow + 4 * R;
-    const int X0 = it.ox0 - 2 * R;
-    const int W2 = VW - 2 * R;
-    const int SW = srow_stride(VW);   // row stride of hb1 (stage-1 column sums, VW columns)
-#if LEXP_LINK_STRIDES
-    const int SW2 = srow_stride(W2), SW3 = srow_stride(it.ow);  // ho1 / hb2 hold W2 columns, ho2 the ow output columns
-#else
-    const int SW2 = SW, SW3 = SW;
-#endif
-    const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
-    // streamed rows y = ys + v, v in [0, VHs): the dependency cone of the tile, minus leading rows above
-    // the filterRect (they are zero padding).  Rows >= fy1 are zero rows that flush the running sums.
-    const int ys = max(it.oy0 - 2 * R, it.fy);
-    const int VHs = it.oy0 + it.oh + 2 * R - ys;
-    const int vReal = min(VHs, fy1 - ys);                    // rows [0, vReal) lie inside the filterRect
-    const int vC0 = max(it.oy0 - R, it.fy) + R - ys;         // first v whose stage-1 centre row (y - R) is needed
-    const int vC1 = min(VHs, fy1 + R - ys);                  // centre rows >= fy1 are zero rows
-    const int vE0 = it.oy0 + 2 * R - ys;                     // first v whose stage-2 centre row (y - 2R) is an output row
-
-    uint2* ring1 = reinterpret_cast<uint2*>(smem);   // [K][VW] {p, packed guide}: the products are recomputed when a row leaves the window
-    F4* ring2 = smem + (K * VW + 1) / 2;              // [K][W2]
-    F4* hb1 = ring2 + K * W2;              // [2][CH][SW] stage-1 column sums   (index: column - X0)
-    F4* ho1 = hb1 + 2 * kCH * SW;          // [2][CH][SW2] stage-1 box sums     (index: column - X0 - R)
-    F4* hb2 = ho1 + 2 * kCH * SW2;         // [2][CH][SW2] stage-2 column sums  (index: column - X0 - R)
-    F4* ho2 = hb2 + 2 * kCH * SW2;         // [2][CH][SW3] stage-2 box sums     (index: column - X0 - 2R)
-    float* s_invny = reinterpret_cast<float*>(ho2 + 2 * kCH * SW3);  // [VHs] 1 / (#rows of the window inside filterRect)
-    float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
-    int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
-    double* s_iM = reinterpret_cast<double*>(s_Y0 + 4 * ((it.oh + 4 * R + 3) / 4));  // [6] NAIVE: inverse affine map of the call
-
     if (NAIVE) {
         if (tid == 0) naive_inverse_affine(it, pl, P.mode, s_iM);
         __syncthreads();
@@ -548,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 
     {   // zero-fill: the box filter is zero padded (GuidedFilter.h:43 BORDER_CONSTANT)
         const int total = (K * VW + 1) / 2 + K * W2 + 2 * kCH * (SW + 2 * SW2 + SW3);
-        for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
+        if (!PM) for (int i = tid; i < total; i += kThreads) smem[i] = f4zero();
         for (int v = tid; v < VHs; v += kThreads) {
             const int y = ys + v;
             s_invny[v] = 1.0f / (float)(min(y + R, fy1 - 1) - max(y - R, it.fy) + 1);  // GuidedFilter.h:324
@@ -1046,7 +1050,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         }
         uint32_t gq[kCH];
         float cq[kCH];   // PatchMatch phase: the pixel's current cost, prefetched with the guide (L2 only: other SMs wrote it)
-        const bool pm_update = P.pm_mode == 1;
+        const bool pm_update = PM && P.pm_mode == 1;
         int vi = 0;
         const unsigned int* pg = reinterpret_cast<const unsigned int*>(P.guide) + (size_t)(ys - 2 * R) * P.W + (colE ? XE : it.ox0);
         auto issue = [&]() {
@@ -1113,7 +1117,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                                                 dmp >= lo && dmp <= hi && dmm >= lo && dmm <= hi;
                                 if (!ok) q = kCostInvalid;  // CostVolumeEnergy.h:180-182
                             }
-                            if (P.pm_mode) {
+                            if (PM) {
                                 // `updateMask = subCurrentCost > subProposalCost; copyTo; setTo` (FastGCStereo.h:56-60); NaN never
                                 // updates.  Initialisation (pm_mode 2, :105-113) writes unconditionally.  Ordering against the cell's
                                 // previous steps is by its completion counter (prologue), not by griddepcontrol.wait.
@@ -1144,7 +1148,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 consume_end(3, c, nChunks, kLinkHE);
             }
         }
-        if (P.pm_mode) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
+        if (PM) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
             if (P.n_copies > 1) __threadfence_system(); else __threadfence();
             __syncwarp();
             if (lane == 0) {

@@ -347,6 +347,9 @@ class CostVolumeEnergy:
         arr = (C.c_void_p * len(peers))(*[p._h for p in peers])
         check(lib().lexp_pm_connect_local(self._h, mode, rank, len(peers), arr))
 
+    def pm_reset_sync(self):
+        check(lib().lexp_pm_reset_sync(self._h))
+
     def pm_advance_epoch(self, delta, mode=0):
         check(lib().lexp_pm_advance_epoch(self._h, mode, int(delta)))
 

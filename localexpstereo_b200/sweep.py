@@ -116,6 +116,50 @@ def expand_proposers(proposers, outer_iter, max_disp, min_disp=0.0):
     return steps
 
 
+def pm_schedule(lm: LayerManager, unit_sizes, world):
+    """The (layer, group) sequence of one pm iteration on a `world`-rank cell shard, identical on every rank:
+    [(layer, group, cells_by_rank, owners)] with cells_by_rank[r] = the cells rank r evaluates (round-robin deal of the group's
+    cells) and owners = the ranks that own at least one cell.  Adds the layers to `lm`."""
+    out = []
+    for li, u in enumerate(unit_sizes):
+        lay = lm.addLayer(u)
+        for gi, cells in enumerate(lay.disjointRegionSets):
+            by_rank = [shard_cells(cells, r, world) for r in range(world)]
+            out.append((li, gi, by_rank, [r for r in range(world) if len(by_rank[r])]))
+    return out
+
+
+class EpochClock:
+    """Host-side bookkeeping of the group epochs of the multi-GPU cell shard (lexp_plan_pm_step_ex).  Groups are numbered
+    1, 2, ... identically on every rank; `rel` counts the groups issued since the device-side epoch base was last advanced
+    (once per init / iteration, so that an iteration's launches carry the same relative numbers every time and can be replayed
+    as a CUDA graph); last_rel[r] is the last epoch rank r published, relative to the current base (None: never)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world, self.rel, self.last_rel, self.base = rank, world, 0, [None] * 8, 0
+
+    def sync_args(self, first, last):
+        """publish_epoch / wait_epochs / wait_mask of one step of the group being issued (relative epoch rel + 1)."""
+        a = {"publish_epoch": self.rel + 1 if last else 0}
+        if first:   # including this rank's own previous groups: the launches of an iteration overlap on the device
+            a["wait_epochs"] = [0 if e is None else e for e in self.last_rel]
+            a["wait_mask"] = sum(1 << r for r, e in enumerate(self.last_rel) if e is not None)
+        return a
+
+    def group_done(self, owners):
+        self.rel += 1
+        for r in owners:
+            self.last_rel[r] = self.rel
+
+    def advance(self):
+        """All groups of an init / iteration have been issued: returns the delta for lexp_pm_advance_epoch."""
+        delta = self.rel
+        self.last_rel = [None if e is None else e - delta for e in self.last_rel]
+        self.base += delta
+        self.rel = 0
+        return delta
+
+
 class PMSweep:
     """Device-resident PatchMatch phase of one view: state (currentCost_, currentLabeling_) in HBM, one plan per (layer, group),
     one launch per proposal step; nothing crosses PCIe between `begin` / `init` and `get`.
@@ -132,20 +176,16 @@ class PMSweep:
         self.lm = LayerManager(energy.width, energy.height, energy.params.windR)
         self.groups: List[GroupPlan] = []          # this rank's plans
         self.schedule = []                         # every (layer, group) in order: (GroupPlan or None, [ranks that own cells])
-        cell_base = 0
-        for li, u in enumerate(self.unit_sizes):
-            lay = self.lm.addLayer(u)
-            for gi, cells in enumerate(lay.disjointRegionSets):
-                owners = [r for r in range(world) if len(shard_cells(cells, r, world))]
-                mine = shard_cells(cells, rank, world)
-                gp = None
-                if len(mine):
-                    plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])
-                    plan.set_units([lay.unitRegions[r] for r in mine], cell_base + mine)
-                    gp = GroupPlan(li, gi, mine, plan, 0)
-                    self.groups.append(gp)
-                self.schedule.append((li, gi, gp, owners))
-            cell_base += len(lay.unitRegions)
+        sched = pm_schedule(self.lm, self.unit_sizes, world)
+        cell_base = np.cumsum([0] + [len(l.unitRegions) for l in self.lm.layers])   # global cell ids: layer after layer
+        for (li, gi, by_rank, owners) in sched:
+            lay, mine, gp = self.lm.layers[li], by_rank[rank], None
+            if len(mine):
+                plan = energy.make_plan([lay.filterRegions[r] for r in mine], [lay.sharedRegions[r] for r in mine])
+                plan.set_units([lay.unitRegions[r] for r in mine], cell_base[li] + mine)
+                gp = GroupPlan(li, gi, mine, plan, 0)
+                self.groups.append(gp)
+            self.schedule.append((li, gi, gp, owners))
         # initCurrentFast (FastGCStereo.h:101-113): every unit region of layer 0 with filterRegion = unit +- windR
         lay0 = self.lm.layers[0]
         R, W, H = energy.params.windR, energy.width, energy.height
@@ -160,9 +200,7 @@ class PMSweep:
         self.init_plan = energy.make_plan(fr, self.init_units) if len(fr) else None
         if self.init_plan is not None:
             self.init_plan.set_units(self.init_units, self.init_index)
-        # epochs relative to the device-side epoch base (advanced once per init / iteration, lexp_pm_advance_epoch)
-        self.rel = 0                        # groups issued since the base was last advanced
-        self.last_rel = [None] * 8          # last epoch every rank has published, relative to the base (None: never)
+        self.clock = EpochClock(rank, world)
 
     # ---- multi-GPU wiring (after begin(): the state must exist) ------------------------------------------------------------
     def connect(self, all_handles):
@@ -171,27 +209,9 @@ class PMSweep:
     def connect_local(self, peer_energies):
         self.energy.pm_connect_local(self.rank, peer_energies, self.mode)
 
-    def _sync_args(self, first, last):
-        """publish_epoch / wait_epochs / wait_mask of one step of the group that is being issued (relative epoch self.rel + 1)."""
-        if self.world == 1:
-            return {}
-        a = {"publish_epoch": self.rel + 1 if last else 0}
-        if first:
-            a["wait_epochs"] = [0 if e is None else e for e in self.last_rel]
-            a["wait_mask"] = sum(1 << r for r, e in enumerate(self.last_rel) if e is not None and r != self.rank)
-        return a
-
-    def _group_done(self, owners):
-        self.rel += 1
-        for r in owners:
-            self.last_rel[r] = self.rel
-
     def _advance(self):
         """All groups of an init / iteration have been issued: move the device epoch base past them."""
-        if self.world > 1:
-            self.energy.pm_advance_epoch(self.rel, self.mode)
-        self.last_rel = [None if e is None else e - self.rel for e in self.last_rel]
-        self.rel = 0
+        self.energy.pm_advance_epoch(self.clock.advance(), self.mode)
 
     def begin(self, cost=None, labeling=None):
         self.energy.pm_begin(self.mode, cost, labeling)
@@ -199,9 +219,10 @@ class PMSweep:
     def init(self, labels):
         """labels [this rank's units of layer 0][4] (all units at world == 1): `currentLabeling(unit) = label;
         ComputeUnaryPotential(unit +- R, unit, ...)` (:107-111)."""
+        self.energy.pm_reset_sync()
         if self.init_plan is not None:
-            self.init_plan.pm_step(0, PROP_LIST, planes=labels, init=True, mode=self.mode, **self._sync_args(True, True))
-        self._group_done(self.init_owners)
+            self.init_plan.pm_step(0, PROP_LIST, planes=labels, init=True, mode=self.mode, **self.clock.sync_args(True, True))
+        self.clock.group_done(self.init_owners)
         self._advance()
 
     def iteration(self, iteration, seed, list_planes=None, planes_out=None):
@@ -213,6 +234,7 @@ class PMSweep:
         """Generator form of `iteration`: issues one (layer, group) per step and yields its number of launches (lets a
         single-process test interleave several ranks)."""
         E = self.energy
+        E.pm_reset_sync()
         for (li, gi, g, owners) in self.schedule:
             n_launch = 0
             if g is not None:
@@ -224,9 +246,9 @@ class PMSweep:
                         pl = list_planes[(li, gi)][li_at]; li_at += 1
                     out = 0 if planes_out is None else planes_out[(li, gi)] + k * g.plan.num_calls * 16
                     g.plan.pm_step(k, kind, m, pm_seed(seed, self.mode, iteration, li, gi, k), planes=pl, d_planes_out=out, mode=self.mode,
-                                   **self._sync_args(k == 0, k == len(steps) - 1))
+                                   **self.clock.sync_args(k == 0, k == len(steps) - 1))
                     n_launch += 1
-            self._group_done(owners)
+            self.clock.group_done(owners)
             yield n_launch
         self._advance()
 

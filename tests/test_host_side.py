@@ -126,6 +126,70 @@ def test_cell_shard_all_gather_world2_gloo():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _pm_shard_worker(rank, world, port, q):
+    """Host-side logic of the multi-GPU PatchMatch-phase cell shard across real processes: every rank derives the same
+    (layer, group) schedule and cell ownership, and the epoch every rank waits for is exactly the one its peer publishes."""
+    import torch.distributed as dist
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import EpochClock, pm_schedule
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lm = L.LayerManager(210, 150, 20)
+    sched = pm_schedule(lm, [10, 31, 70], world)
+    ok = True
+    for (li, gi, by_rank, owners) in sched:   # a partition of every group's cells
+        cells = sorted(int(c) for r in range(world) for c in by_rank[r])
+        ok &= cells == sorted(lm.layers[li].disjointRegionSets[gi]) and owners == [r for r in range(world) if len(by_rank[r])]
+    clock = EpochClock(rank, world)
+    published, waited = [], []   # absolute epochs
+    n0 = len(lm.layers[0].unitRegions)
+    rounds = [[(None, None, None, [r for r in range(world) if len(range(r, n0, world))])]] + [sched, sched]   # init, two iterations
+    for groups in rounds:
+        for (_, _, by_rank, owners) in groups:
+            mine = by_rank is None or len(by_rank[rank]) > 0
+            if mine and rank in owners:
+                a = clock.sync_args(True, True)
+                published.append(clock.base + a["publish_epoch"])
+                waited.append({r: clock.base + a["wait_epochs"][r] for r in range(world) if (a["wait_mask"] >> r) & 1 and r != rank})
+            clock.group_done(owners)
+        clock.advance()
+    allp, allw = [None] * world, [None] * world
+    dist.all_gather_object(allp, published)
+    dist.all_gather_object(allw, waited)
+    for a in range(world):            # every awaited epoch is one the peer really publishes, and it is published earlier
+        for j, w in enumerate(allw[a]):
+            for r, e in w.items():
+                ok &= e in allp[r] and e < allp[a][j]
+    ok &= all(p == sorted(set(p)) for p in allp) and len(allw[rank]) > 40
+    # graph replay: from the second iteration on the relative numbers repeat exactly
+    c2 = EpochClock(rank, world)
+    seqs = []
+    for groups in rounds + [sched]:
+        seq = []
+        for (_, _, by_rank, owners) in groups:
+            seq.append(c2.sync_args(True, True))
+            c2.group_done(owners)
+        c2.advance()
+        seqs.append(seq)
+    ok &= seqs[2] == seqs[3]
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_pm_cell_shard_schedule_and_epochs_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pm_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_synthetic_planes_distribution():
     from localexpstereo_b200 import synth
     import localexpstereo_b200 as L
