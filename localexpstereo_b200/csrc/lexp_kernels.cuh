@@ -88,6 +88,17 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_GATHER_NOALLOC
 #define LEXP_GATHER_NOALLOC 0
 #endif
+// LEXP_STATS_TMA: team C's guided-filter statistics (36 of the 47 algorithmic bytes per eval: dense rectangular rows) are staged
+//   into a shared-memory ring by the TMA unit -- cp.async.bulk global -> shared, completion on an mbarrier -- LEXP_STATS_STAGES
+//   chunks ahead instead of being loaded into registers one chunk ahead.  ncu (profiles/r2_fused_ncu_L0.md): team C is the team
+//   the pipeline waits for and 29 % of its stall samples are long_scoreboard on exactly these loads; one chunk of lead (~1700
+//   cycles) does not cover a loaded DRAM round trip, a second register set spills (80-register cap), the ring costs no registers.
+#ifndef LEXP_STATS_TMA
+#define LEXP_STATS_TMA 0
+#endif
+#ifndef LEXP_STATS_STAGES
+#define LEXP_STATS_STAGES 4
+#endif
 #ifndef LEXP_MIN_CTAS
 #define LEXP_MIN_CTAS 2
 #endif
@@ -200,6 +211,17 @@ __host__ __device__ inline int srow_stride(int vw) {
     int s = sidx(vw + kRun + 7) + 1;
     return s + ((12 - (s & 7)) & 7);  // == 4 (mod 8) float4 units: the 2 rows x 4 runs of a quarter-warp hit 8 bank groups
 }
+// LEXP_STATS_TMA: one ring stage = one chunk of team C's statistics: statA / statB rows [kCH][w2] float4, statC rows [kCH][w2c] float
+// (w2c: room for the 16-byte alignment shift of a row start); then one mbarrier per stage
+__host__ __device__ inline int stats_w2c(int w2) { return (w2 + 7 + 3) & ~3; }
+__host__ __device__ inline int stats_stage_bytes(int w2) { return kCH * (2 * w2 * 16 + stats_w2c(w2) * 4); }
+__host__ __device__ inline size_t stats_ring_bytes(int w2) {
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+    return (size_t)LEXP_STATS_STAGES * stats_stage_bytes(w2) + 16 * ((LEXP_STATS_STAGES + 1) / 2);
+#else
+    return 0;
+#endif
+}
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
@@ -208,7 +230,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
 #else
     const int rows = 8 * kCH * srow_stride(vw);
 #endif
-    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 4) * 16;  // + 6 doubles (NAIVE: inverse affine map) + the plane of the call (PatchMatch phase)
+    return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 3) * 16 + stats_ring_bytes(vw - 2 * R) + 16;  // + 6 doubles (NAIVE: inverse affine map) + statistics ring + the plane slot (PatchMatch phase) at the very end
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FFMA2) --------------------------------------------
@@ -238,6 +260,27 @@ inline u64 sub2(u64 a, u64 b) { float a0, a1, b0, b1; up2(a, a0, a1); up2(b, b0,
 __device__ __forceinline__ F4 f4add(F4 a, F4 b) { return F4{add2(a.lo, b.lo), add2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), sub2(a.hi, b.hi)}; }
 __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
+
+// ---- mbarrier + bulk asynchronous copy (TMA unit, non-tensor form: contiguous bytes global -> shared) ---------------------
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#endif
 
 // ---- named barriers: pairwise producer/consumer hand-off between warp teams ------------------------
 // link L (0: A->H1 via hb1, 1: H1->C via ho1, 2: C->H2 via hb2, 3: H2->E via ho2), buffer parity b:
@@ -479,6 +522,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
     int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
     double* s_iM = reinterpret_cast<double*>(s_Y0 + 4 * ((it.oh + 4 * R + 3) / 4));  // [6] NAIVE: inverse affine map of the call
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+    // statistics ring of team C (TMA unit): LEXP_STATS_STAGES stages, then their mbarriers; behind s_iM (6 doubles)
+    unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_iM) + 48;
+    const int stageB = stats_stage_bytes(W2);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + LEXP_STATS_STAGES * stageB);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < LEXP_STATS_STAGES; i++) mbar_init(s_full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
 
     if (PM) {
         // PatchMatch phase.  (0) Group boundary: the previous group (this rank's and, on the multi-GPU cell shard, the peers') must
@@ -893,7 +947,62 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const float4* pa = P.statA + pix0;
         const float4* pb = P.statB + pix0;
         const float* pc = P.statC + pix0;
-#if !LEXP_C_ROLLING
+#if !LEXP_C_ROLLING || (LEXP_STATS_TMA && !defined(LEXP_EMU))
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+        // ---- statistics through the TMA unit: chunk c lives in ring stage c % NS; after the bar.sync of consume_begin(1, c) every
+        // thread of the team has read chunk c, so thread 0 refills that stage with chunk c + NS right there (NS - 1 chunks of lead)
+        constexpr int NS = LEXP_STATS_STAGES;
+        const int W2c = stats_w2c(W2);
+        const int XC0 = X0 + R;
+        const int xa = max(XC0, it.fx), xb = min(XC0 + W2, fx1);       // columns of the tile's (a, b) strip inside the filterRect
+        auto tma_issue = [&](int chunk) {
+            unsigned char* stg = s_ring + (chunk % NS) * stageB;
+            uint64_t* bar = s_full + (chunk % NS);
+            unsigned bytes = 0;
+            int nrow = 0;
+#pragma unroll
+            for (int r = 0; r < kCH; r++) {
+                const int v = chunk * kCH + r;
+                if (v >= vC0 && v < vC1 && xb > xa) { bytes += 2u * (unsigned)(xb - xa) * 16u + (unsigned)(((((ys + v - R) * P.W + xa) & 3) + (xb - xa) + 3) & ~3) * 4u; nrow++; }
+            }
+            if (!nrow) { mbar_arrive(bar); return; }
+            mbar_expect_tx(bar, bytes);
+#pragma unroll
+            for (int r = 0; r < kCH; r++) {
+                const int v = chunk * kCH + r;
+                if (v >= vC0 && v < vC1 && xb > xa) {
+                    const size_t g0 = (size_t)(ys + v - R) * P.W + xa;
+                    bulk_g2s(stg + (size_t)(r * W2 + (xa - XC0)) * 16, P.statA + g0, (unsigned)(xb - xa) * 16u, bar);
+                    bulk_g2s(stg + (size_t)kCH * W2 * 16 + (size_t)(r * W2 + (xa - XC0)) * 16, P.statB + g0, (unsigned)(xb - xa) * 16u, bar);
+                    const size_t g0a = g0 & ~(size_t)3;   // statC rows start at any float: copy from the 16-byte boundary below
+                    bulk_g2s(stg + (size_t)2 * kCH * W2 * 16 + (size_t)r * W2c * 4, P.statC + g0a, (unsigned)(((int)(g0 - g0a) + (xb - xa) + 3) & ~3) * 4u, bar);
+                }
+            }
+        };
+        if (t == 0)
+            for (int ch = 0; ch < NS && ch < nChunks; ch++) tma_issue(ch);
+        for (int c = 0; c < nChunks; c++) {
+            {
+                float4 ca[kCH], cb[kCH];
+                float cc[kCH];
+                mbar_wait(s_full + (c % NS), (unsigned)((c / NS) & 1));
+                const unsigned char* stg = s_ring + (c % NS) * stageB;
+#pragma unroll
+                for (int r = 0; r < kCH; r++) {
+                    const int v = c * kCH + r;
+                    ca[r] = make_float4(0.f, 0.f, 0.f, 0.f); cb[r] = ca[r]; cc[r] = 0.f;
+                    if (colC && v >= vC0 && v < vC1) {
+                        ca[r] = reinterpret_cast<const float4*>(stg)[r * W2 + t];
+                        cb[r] = reinterpret_cast<const float4*>(stg + (size_t)kCH * W2 * 16)[r * W2 + t];
+                        cc[r] = reinterpret_cast<const float*>(stg + (size_t)2 * kCH * W2 * 16)[r * W2c + (((ys + v - R) * P.W + xa) & 3) + (XC - xa)];
+                    }
+                }
+                consume_begin(1, c, kLinkHC);
+                if (t == 0 && c + NS < nChunks) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the team's generic-proxy reads of this stage, then the async-proxy refill
+                    tma_issue(c + NS);
+                }
+#else
         auto issue = [&]() {
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
@@ -926,6 +1035,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 }
                 issue();
                 consume_begin(1, c, kLinkHC);
+#endif
                 produce_begin(2, c, kLinkCH);
                 if (t < W2) {
                     const F4* ho = ho1 + (c & 1) * kCH * SW2 + sidx(t);

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+bash scripts/gpu_variants.sh tma4 tma3 tma6 > gpurun_out/r2e_variants.log 2>&1; cat gpurun_out/variants.txt; tail -5 gpurun_out/r2e_variants.log
