@@ -353,7 +353,7 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
 int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
     const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4;
     const int Hb = (H + 3) / 4;
-    const size_t nblk = (size_t)Hb * Wb * D * 16 * (LEXP_VOL_PAIRS ? 2 : 1);   // LEXP_VOL_PAIRS: float2 per pixel and disparity
+    const size_t nblk = (size_t)Hb * Wb * D * 16;
     if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], nblk * sizeof(float)));
     int* d_flag = nullptr;
     LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));

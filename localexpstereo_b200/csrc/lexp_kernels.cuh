@@ -76,18 +76,6 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_TRACE
 #define LEXP_TRACE 0
 #endif
-// LEXP_VOL_PAIRS: the blocked cost volume stores, for every disparity d, the PAIR (V[d], V[d+1]) of each pixel:
-//   float2[Hb][Wb][D][4 rows][4 px] (128 B per disparity of a 4x4 pixel block, pair D-1 = (V[D-1], V[D-1])).  The two samples of the
-//   linear interpolation (CostVolumeEnergy.h:83-92) are then ONE 8-byte load, and the 4 pixels of a block row fill exactly one
-//   32-byte sector: 8 instead of 16 sector requests and L1 wavefronts per 32 gathered pixels, no reliance on L1 to keep the other
-//   half of a sector for the next row.  Costs 2x the volume footprint in HBM (6.4 GB at 2048x1536x256; 2 x 34 GB at 4K).
-#ifndef LEXP_VOL_PAIRS
-#define LEXP_VOL_PAIRS 0
-#endif
-// LEXP_GATHER_NOALLOC: volume gathers bypass L1 allocation (only sensible with LEXP_VOL_PAIRS, where no sector is touched twice)
-#ifndef LEXP_GATHER_NOALLOC
-#define LEXP_GATHER_NOALLOC 0
-#endif
 // LEXP_STATS_TMA: team C's guided-filter statistics (36 of the 47 algorithmic bytes per eval: dense rectangular rows) are staged
 //   into a shared-memory ring by the TMA unit -- cp.async.bulk global -> shared, completion on an mbarrier -- LEXP_STATS_STAGES
 //   chunks ahead instead of being loaded into registers one chunk ahead.  ncu (profiles/r2_fused_ncu_L0.md): team C is the team
@@ -464,16 +452,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 // Cost-volume samples: plain read-only loads.  Measured on B200 (profiles/r1_experiments.md): letting them allocate in
 // L1 (the d0 / d0+1 samples of a 4-pixel block share 128-byte lines) beats L1::no_allocate + L2 evict-first by 8 %.
 __device__ __forceinline__ float ldg_stream(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float2 ldg_pair(const float2* p) {
-#if LEXP_GATHER_NOALLOC && !defined(LEXP_EMU)
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-constexpr int kVolUnit = LEXP_VOL_PAIRS ? 8 : 4;   // bytes per pixel and disparity in the blocked volume
 
 template <int R_T, bool NAIVE, bool PM>
 __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KParams P) {
@@ -613,8 +591,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             if (!NAIVE) {
                 s_dbase[v] = __fadd_rn(__fmul_rn(pl.b, (float)y), pl.c);               // CostVolumeEnergy.h:73
 #if LEXP_A_ROWTAB
-                // row offset in the blocked volume, in units of one 4-pixel block row (16 B; 32 B with LEXP_VOL_PAIRS); the s_Y0
-                // slot is unused by the cost-volume energy
+                // row offset in the blocked volume, in 16-byte units (the s_Y0 slot is unused by the cost-volume energy)
                 reinterpret_cast<unsigned*>(s_Y0)[v] = (unsigned)(y >> 2) * ((unsigned)P.Wb * (unsigned)P.D * 4u) + (unsigned)(y & 3);
 #endif
             } else {
@@ -716,9 +693,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         // blocked volume: element (d, y, x) lives at ((((y/4) * Wb + x/4) * D + d) * 4 + y%4) * 4 + x%4:
         // a 128-byte line holds 2 disparities of a 4x4 pixel block, so the rows of a gather batch share lines
 #if !LEXP_A_ROWTAB
-        const size_t vblk = (size_t)P.Wb * P.D * 16 * kVolUnit;       // bytes per block row (4 image rows)
+        const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
 #endif
-        const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * kVolUnit;
+        const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
 #if LEXP_A_ROWTAB && LEXP_MIN_CTAS <= 2 && !defined(LEXP_EMU)
         // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row); not with the 56-register
         // diet, where the extra live register pair spills
@@ -764,19 +741,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 lv0[j] = 0.f; lv1[j] = 0.f; lg[j] = 0u; lf1[j] = fast ? 0.f : -1.f;  // outside filterRect: zero
                 if (colA && vi < vReal) {
                     int d0, d1;
-#if LEXP_VOL_PAIRS
-                    // one 8-byte load fetches (V[d0], V[d0 + 1]); pair D-1 holds V[D-1] twice, so the clamped cases read it too
-                    lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
 #if LEXP_A_ROWTAB
-                    const char* vrow = vcol + (size_t)reinterpret_cast<const unsigned*>(s_Y0)[vi] * 32;
-#else
-                    const int y = ys + vi;
-                    const char* vrow = vcol + (size_t)(y >> 2) * vblk + (y & 3) * 32;
-#endif
-                    const float2 v2 = ldg_pair(reinterpret_cast<const float2*>(vrow + (size_t)(unsigned)d0 * 128));
-                    lv0[j] = v2.x;
-                    lv1[j] = v2.y;
-#elif LEXP_A_ROWTAB
                     const char* vrow = vcol + (size_t)reinterpret_cast<const unsigned*>(s_Y0)[vi] * 16;
                     if (fast) {  // the second sample is always the next disparity: 64 bytes further in the blocked layout
                         lf1[j] = weights(__fadd_rn(ax, s_dbase[vi]), d0, d1);  // :76
@@ -1337,24 +1302,6 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict
 // rows of the streaming gather share 128-byte lines / DRAM pages instead of being scattered over ndisp slices
 // H*W*4 bytes apart.   grid = (ceil(W/32), ceil(H/4), ceil(D/8)), block = 256
 __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb) {
-#if LEXP_VOL_PAIRS
-    // LEXP_VOL_PAIRS: dst is float2[Hb][Wb][D][4 rows][4 px] = (V[d], V[min(d + 1, D - 1)]); the tile holds one more disparity
-    __shared__ float tile[9][4][33];  // [d][row][x]
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
-    for (int i = threadIdx.x; i < 9 * 4 * 32; i += 256) {
-        const int xx = i & 31, rr = (i >> 5) & 3, dd = i >> 7;
-        const int x = x0 + xx, y = y0 + rr, d = min(d0 + dd, D - 1);
-        tile[dd][rr][xx] = (y < H && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
-    }
-    __syncthreads();
-    float2* dst2 = reinterpret_cast<float2*>(dst);
-    for (int i = threadIdx.x; i < 8 * 8 * 16; i += 256) {
-        const int q = i & 3, rr = (i >> 2) & 3, dd = (i >> 4) & 7, xb = i >> 7;
-        const int d = d0 + dd;
-        if (d < D && (x0 >> 2) + xb < Wb)
-            dst2[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = make_float2(tile[dd][rr][xb * 4 + q], tile[dd + 1][rr][xb * 4 + q]);
-    }
-#else
     __shared__ float tile[8][4][33];  // [d][row][x]
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
     for (int i = threadIdx.x; i < 8 * 4 * 32; i += 256) {
@@ -1370,7 +1317,6 @@ __global__ void lexp_relayout_volume(const float* __restrict__ src, float* __res
         if (d < D && (x0 >> 2) + xb < Wb)
             dst[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = tile[dd][rr][xb * 4 + q];
     }
-#endif
 }
 
 // NaiveStereoEnergy constructor (StereoEnergy.h:647-662): ExI = merge(I * (1 - alpha), alpha * Sobel_x(gray)), with

@@ -15,8 +15,6 @@ VARIANTS = {
     "nopdl": ["-DLEXP_PDL=0"],                      # the round-2 defaults switched off one at a time (PDL and ROWTAB are on by default)
     "norowtab": ["-DLEXP_A_ROWTAB=0"],
     "r1": ["-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"],    # the round-1 kernel
-    "pairs": ["-DLEXP_VOL_PAIRS=1"],               # (V[d], V[d+1]) pairs in the blocked volume: one 8-byte gather per pixel
-    "pairsna": ["-DLEXP_VOL_PAIRS=1", "-DLEXP_GATHER_NOALLOC=1"],
     "tma3": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=3"],   # team C's statistics staged by the TMA unit (cp.async.bulk + mbarrier ring)
     "tma4": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=4"],
     "tma6": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=6"],

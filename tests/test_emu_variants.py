@@ -8,7 +8,7 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["r1", "trace", "occ3rowtab", "pairs"])  # r1 = PDL and ROWTAB (round-2 defaults) off; occ3 (incl. link strides): tests/test_emu_occ3.py
+@pytest.mark.parametrize("variant", ["r1", "trace", "occ3rowtab"])  # r1 = PDL and ROWTAB (round-2 defaults) off; occ3 (incl. link strides): tests/test_emu_occ3.py
 def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
     monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it
@@ -38,14 +38,6 @@ def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monke
     if variant == "trace":
         lines = open(tmp_path / "trace.txt").read().strip().splitlines()
         assert len(lines) >= 3 and all(" | A total " in l and " | E total " in l for l in lines)
-
-
-@pytest.mark.parametrize("seed", [6])
-def test_pairs_variant_fuzz(seed):
-    """LEXP_VOL_PAIRS: (V[d], V[d+1]) pairs in the blocked volume, one 8-byte gather per pixel, all sampler branches."""
-    import test_emu_fuzz as _f
-    with emu_lib.emulated(variant="pairs"):
-        _f.test_random_rects_and_planes_match_the_oracle(seed)
 
 
 @pytest.mark.parametrize("seed", [5, 17])
