@@ -81,6 +81,19 @@ LEXP_API int lexp_set_image(lexp_ctx* ctx, int mode, const uint8_t* bgr_host, pt
 LEXP_API int lexp_set_volume_host(lexp_ctx* ctx, int mode, const float* vol_host);
 LEXP_API int lexp_set_volume_device(lexp_ctx* ctx, int mode, const float* vol_device);
 
+/* The same with the reference's volume preparation (main.cpp:146-199, 353-370) fused into the one re-layout pass:
+ *   LEXP_VOL_FILL             fillOutOfView(vol, mode, 0) (main.cpp:146-176): columns that look outside the other view repeat the
+ *                             first valid one (view 0: x < d takes x = d; view 1: x > W-1-d takes x = W-1-d);
+ *   LEXP_VOL_RIGHT_FROM_LEFT  (mode must be 1) `vol` is the LEFT volume as loaded (im0.acrt, not yet filled); the context's view-1
+ *                             volume becomes fillOutOfView(convertVolumeL2R(fillOutOfView(vol, 0)), 1) (main.cpp:356-365), i.e.
+ *                             volR[d][y][x] = volL[d][y][min(x + d, W-1)] -- no second volume on the host, no im1.acrt.
+ * The host variant uploads in slabs of disparities (LEXP_UPLOAD_SLAB_MB, default 512): no second full-size device copy. */
+#define LEXP_VOL_PLAIN 0
+#define LEXP_VOL_FILL 1
+#define LEXP_VOL_RIGHT_FROM_LEFT 2
+LEXP_API int lexp_set_volume_host_ex(lexp_ctx* ctx, int mode, const float* vol_host, int transform);
+LEXP_API int lexp_set_volume_device_ex(lexp_ctx* ctx, int mode, const float* vol_device, int transform);
+
 /* Debug / parity: copy the 9 statistics planes [mean_r,g,b, inv_rr,rg,rb,gg,gb,bb] (float[9][H][W]) to the host. */
 LEXP_API int lexp_get_stats(lexp_ctx* ctx, int mode, float* out9_host);
 

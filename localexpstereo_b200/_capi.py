@@ -39,6 +39,8 @@ SYMBOLS = {
     "lexp_set_image": (C.c_int, [_P, C.c_int, _P, C.c_ssize_t]),
     "lexp_set_volume_host": (C.c_int, [_P, C.c_int, _P]),
     "lexp_set_volume_device": (C.c_int, [_P, C.c_int, _P]),
+    "lexp_set_volume_host_ex": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "lexp_set_volume_device_ex": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "lexp_get_stats": (C.c_int, [_P, C.c_int, _P]),
     "lexp_eval_cell": (C.c_int, [_P, C.c_int, C.POINTER(Rect), C.POINTER(Rect), C.POINTER(PlaneC), _P, C.c_ssize_t, C.c_int]),
     "lexp_eval_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_ssize_t, C.c_int]),

@@ -349,22 +349,39 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
     return launch_fused(c, kp, pl->nitems, pl->smem, true);
 }
 
-// scan the caller's volume for NaN/Inf and re-lay it out into the context's blocked copy
-int ingest_volume(lexp_ctx* c, int mode, const float* d_src) {
-    const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4;
-    const int Hb = (H + 3) / 4;
-    const size_t nblk = (size_t)Hb * Wb * D * 16;
-    if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], nblk * sizeof(float)));
-    int* d_flag = nullptr;
-    LEXP_CUDA(cudaMalloc(&d_flag, sizeof(int)));
-    cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream);
-    LEXP_LAUNCH(lexp_scan_nonfinite, 148 * 8, 256, 0, c->stream, d_src, (size_t)D * H * W, d_flag);
-    dim3 grd((W + 31) / 32, Hb, (D + 7) / 8);
-    LEXP_LAUNCH(lexp_relayout_volume, grd, 256, 0, c->stream, d_src, c->d_vol[mode], D, H, W, Wb);
+// Scan a slab (disparities [d_lo, d_lo + nd) of the caller's volume, on the device) for NaN/Inf and re-lay it out into the context's
+// blocked copy, applying the volume-preparation transform of lexp_relayout_volume on the way.  Asynchronous; d_flag accumulates.
+int ingest_slab(lexp_ctx* c, int mode, const float* d_src, int d_lo, int nd, int transform, int* d_flag) {
+    const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4, Hb = (H + 3) / 4;
+    LEXP_LAUNCH(lexp_scan_nonfinite, 148 * 8, 256, 0, c->stream, d_src, (size_t)nd * H * W, d_flag);
+    dim3 grd((W + 31) / 32, Hb, (nd + 7) / 8);
+    LEXP_LAUNCH(lexp_relayout_volume, grd, 256, 0, c->stream, d_src, c->d_vol[mode], D, H, W, Wb, d_lo, nd, transform);
     c->launches += 2;
+    LEXP_CUDA(cudaGetLastError());
+    return LEXP_OK;
+}
+
+int check_transform(int mode, int transform) {
+    if (transform < LEXP_VOL_PLAIN || transform > LEXP_VOL_RIGHT_FROM_LEFT) return fail(LEXP_ERR_INVALID, "bad volume transform");
+    if (transform == LEXP_VOL_RIGHT_FROM_LEFT && mode != 1) return fail(LEXP_ERR_INVALID, "LEXP_VOL_RIGHT_FROM_LEFT prepares view 1");
+    return LEXP_OK;
+}
+// relayout selector: fillOutOfView depends on the view (main.cpp:153-175)
+int kernel_transform(int mode, int transform) {
+    return transform == LEXP_VOL_PLAIN ? 0 : transform == LEXP_VOL_RIGHT_FROM_LEFT ? 3 : (mode == 0 ? 1 : 2);
+}
+
+int alloc_volume(lexp_ctx* c, int mode, int** d_flag) {
+    const int D = c->p.ndisp, H = c->p.height, W = c->p.width, Wb = (W + 3) / 4, Hb = (H + 3) / 4;
+    if (!c->d_vol[mode]) LEXP_CUDA(cudaMalloc(&c->d_vol[mode], (size_t)Hb * Wb * D * 16 * sizeof(float)));
+    LEXP_CUDA(cudaMalloc(d_flag, sizeof(int)));
+    LEXP_CUDA(cudaMemsetAsync(*d_flag, 0, sizeof(int), c->stream));
+    return LEXP_OK;
+}
+
+int finish_volume(lexp_ctx* c, int mode, int* d_flag) {
     int h = 1;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_flag);
     if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("volume ingest: ") + cudaGetErrorString(e));
@@ -493,31 +510,60 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     return LEXP_OK;
 }
 
-int lexp_set_volume_host(lexp_ctx* c, int mode, const float* vol) {
+// Host volume float[D][H][W]: uploaded in slabs of disparities through two device staging buffers (the re-layout of one slab
+// overlaps the upload of the next), never as a second full-size device copy (17 GB per view at 4K).
+int lexp_set_volume_host_ex(lexp_ctx* c, int mode, const float* vol, int transform) {
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    { int rc = check_transform(mode, transform); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
-    const size_t n = (size_t)c->p.ndisp * c->p.height * c->p.width;
-    float* tmp = nullptr;
-    LEXP_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
-    cudaError_t e = cudaMemcpy(tmp, vol, n * sizeof(float), cudaMemcpyHostToDevice);
+    const int D = c->p.ndisp, H = c->p.height, W = c->p.width;
+    const size_t plane = (size_t)H * W;
+    int slab = (int)std::max<size_t>(8, std::min<size_t>((size_t)D, ((size_t)env_int("LEXP_UPLOAD_SLAB_MB", 512) << 20) / (plane * sizeof(float))));
+    slab = std::min(D, (slab + 7) / 8 * 8);
+    int* d_flag = nullptr;
+    { int rc = alloc_volume(c, mode, &d_flag); if (rc) return rc; }
+    float* stage[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2] = {nullptr, nullptr};
     int rc = LEXP_OK;
-    if (e != cudaSuccess) rc = fail(LEXP_ERR_CUDA, std::string("volume upload: ") + cudaGetErrorString(e));
-    else rc = ingest_volume(c, mode, tmp);
-    cudaFree(tmp);
-    return rc;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&stage[i], (size_t)slab * plane * sizeof(float));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming);
+    }
+    const int tk = kernel_transform(mode, transform);
+    for (int d_lo = 0, i = 0; d_lo < D && e == cudaSuccess && rc == LEXP_OK; d_lo += slab, i ^= 1) {
+        const int nd = std::min(slab, D - d_lo);
+        e = cudaEventSynchronize(freed[i]);   // the re-layout that last read this staging buffer has finished (no-op the first time)
+        if (e == cudaSuccess) e = cudaMemcpy(stage[i], vol + (size_t)d_lo * plane, (size_t)nd * plane * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        rc = ingest_slab(c, mode, stage[i], d_lo, nd, tk, d_flag);
+        if (rc == LEXP_OK) e = cudaEventRecord(freed[i], c->stream);
+    }
+    if (e != cudaSuccess && rc == LEXP_OK) rc = fail(LEXP_ERR_CUDA, std::string("volume upload: ") + cudaGetErrorString(e));
+    const int rc2 = finish_volume(c, mode, d_flag);   // synchronises the stream
+    for (int i = 0; i < 2; i++) { cudaFree(stage[i]); if (freed[i]) cudaEventDestroy(freed[i]); }
+    return rc ? rc : rc2;
 }
 
-int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) {
+int lexp_set_volume_device_ex(lexp_ctx* c, int mode, const float* vol, int transform) {
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    { int rc = check_transform(mode, transform); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(c->mu);
     cudaPointerAttributes at;
     LEXP_CUDA(cudaPointerGetAttributes(&at, vol));
     if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
         return fail(LEXP_ERR_INVALID, "lexp_set_volume_device needs a device pointer");
     LEXP_CUDA(cudaSetDevice(c->p.device));
-    return ingest_volume(c, mode, vol);
+    int* d_flag = nullptr;
+    { int rc = alloc_volume(c, mode, &d_flag); if (rc) return rc; }
+    const int rc = ingest_slab(c, mode, vol, 0, c->p.ndisp, kernel_transform(mode, transform), d_flag);
+    const int rc2 = finish_volume(c, mode, d_flag);
+    return rc ? rc : rc2;
 }
+
+int lexp_set_volume_host(lexp_ctx* c, int mode, const float* vol) { return lexp_set_volume_host_ex(c, mode, vol, LEXP_VOL_PLAIN); }
+int lexp_set_volume_device(lexp_ctx* c, int mode, const float* vol) { return lexp_set_volume_device_ex(c, mode, vol, LEXP_VOL_PLAIN); }
 
 int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {
     if (!c || !out9 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");

@@ -1301,20 +1301,35 @@ __global__ void lexp_stats_finish(const int* __restrict__ rs, float4* __restrict
 // contiguous (64 B per disparity), so the two samples (d0, d0+1) of a pixel, of its neighbours in x AND of the next
 // rows of the streaming gather share 128-byte lines / DRAM pages instead of being scattered over ndisp slices
 // H*W*4 bytes apart.   grid = (ceil(W/32), ceil(H/4), ceil(D/8)), block = 256
-__global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb) {
+// Volume preparation fused into the same pass (main.cpp:146-199, 353-370): `transform` selects which source column the element
+// (d, y, x) is read from --
+//   0 plain; 1 fillOutOfView(vol, 0): x' = max(x, d); 2 fillOutOfView(vol, 1): x' = min(x, W - 1 - d);
+//   3 the RIGHT view derived from the (unfilled) LEFT volume: fillOutOfView(convertVolumeL2R(fillOutOfView(volL, 0)), 1), i.e.
+//     volR[d][y][x] = volL[d][y][min(x + d, W - 1)]  (margin = 0, main.cpp:363).
+// `src` holds the disparities [d_lo, d_lo + nd) of the caller's volume (a slab of the host upload, or the whole volume).
+__global__ void lexp_relayout_volume(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int Wb, int d_lo, int nd,
+                                     int transform) {
     __shared__ float tile[8][4][33];  // [d][row][x]
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 4, d0 = blockIdx.z * 8;   // d0: relative to the slab
     for (int i = threadIdx.x; i < 8 * 4 * 32; i += 256) {
         const int xx = i & 31, rr = (i >> 5) & 3, dd = i >> 7;
-        const int x = x0 + xx, y = y0 + rr, d = d0 + dd;
-        tile[dd][rr][xx] = (d < D && y < H && x < W) ? src[((size_t)d * H + y) * W + x] : 0.0f;
+        const int x = x0 + xx, y = y0 + rr, ds = d0 + dd, d = d_lo + ds;
+        float v = 0.0f;
+        if (ds < nd && y < H && x < W) {
+            int xs = x;
+            if (transform == 1) xs = max(x, min(d, W - 1));
+            else if (transform == 2) xs = min(x, max(W - 1 - d, 0));
+            else if (transform == 3) xs = min(x + d, W - 1);
+            v = src[((size_t)ds * H + y) * W + xs];
+        }
+        tile[dd][rr][xx] = v;
     }
     __syncthreads();
     // consecutive threads write consecutive floats of the destination: [xb 8][d 8][row 4][px 4]
     for (int i = threadIdx.x; i < 8 * 8 * 16; i += 256) {
         const int q = i & 3, rr = (i >> 2) & 3, dd = (i >> 4) & 7, xb = i >> 7;
-        const int d = d0 + dd;
-        if (d < D && (x0 >> 2) + xb < Wb)
+        const int d = d_lo + d0 + dd;
+        if (d0 + dd < nd && (x0 >> 2) + xb < Wb)
             dst[((((size_t)blockIdx.y * Wb + (x0 >> 2) + xb) * D + d) * 4 + rr) * 4 + q] = tile[dd][rr][xb * 4 + q];
     }
 }

@@ -135,6 +135,7 @@ def host_unregister(array: np.ndarray):
 
 
 PROP_LIST, PROP_EXPANSION, PROP_RANDOM = 0, 1, 2   # LEXP_PROP_* of include/lexp_cuda.h
+VOL_PLAIN, VOL_FILL, VOL_RIGHT_FROM_LEFT = 0, 1, 2   # LEXP_VOL_*
 
 
 class Plan:
@@ -271,15 +272,20 @@ class CostVolumeEnergy:
     def _ndisp(vol):
         return int(vol.shape[0])
 
-    def _set_volume(self, mode, vol):
+    def _set_volume(self, mode, vol, transform=VOL_PLAIN):
         if isinstance(vol, np.ndarray):
             v = np.ascontiguousarray(vol, dtype=np.float32)
             assert v.shape == (self.ndisp, self.height, self.width)
-            check(lib().lexp_set_volume_host(self._h, mode, v.ctypes.data))
-        else:  # torch CUDA tensor (duck-typed): borrowed, kept alive here
+            check(lib().lexp_set_volume_host_ex(self._h, mode, v.ctypes.data, int(transform)))
+        else:  # torch CUDA tensor (duck-typed): only read during the call
             assert tuple(vol.shape) == (self.ndisp, self.height, self.width) and vol.is_contiguous() and vol.is_cuda
-            self._keep.append(vol)
-            check(lib().lexp_set_volume_device(self._h, mode, vol.data_ptr()))
+            check(lib().lexp_set_volume_device_ex(self._h, mode, vol.data_ptr(), int(transform)))
+
+    def set_volume(self, mode, vol, transform=VOL_PLAIN):
+        """(Re)load the cost volume of a view with the reference's volume preparation fused into the upload (main.cpp:146-199):
+        VOL_FILL = fillOutOfView(vol, mode); VOL_RIGHT_FROM_LEFT (mode 1) = the right volume derived from the LEFT one,
+        fillOutOfView(convertVolumeL2R(fillOutOfView(volL, 0)), 1)."""
+        self._set_volume(mode, vol, transform)
 
     # --- the two virtuals of StereoEnergy (StereoEnergy.h:625-626) -------------------------------
     def ComputeUnaryPotentialWithoutCheck(self, filterRect, targetRect, costs: np.ndarray, plane, reusable=None, mode=0):

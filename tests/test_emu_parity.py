@@ -65,6 +65,7 @@ test_emu_nonzero_min_disparity_and_odd_max = _p.test_nonzero_min_disparity_and_o
 test_emu_golden_vectors_through_the_c_abi = _g.test_golden_vectors_through_the_c_abi
 test_emu_textureless_guides = _p.test_textureless_guides
 test_emu_plan_outlives_its_energy = _p.test_plan_outlives_its_energy
+test_emu_volume_preparation_on_the_device = _p.test_volume_preparation_on_the_device
 
 
 def test_emu_result_does_not_depend_on_the_thread_schedule(scene):

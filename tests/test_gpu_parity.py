@@ -343,3 +343,52 @@ def test_plan_outlives_its_energy():
     with pytest.raises(L.LexpError):
         plan.eval_host(np.array([[0, 0, 3.0, 0]], np.float32), img, True, 0)   # the context is gone: an error, not a crash
     plan.close()
+
+
+def test_volume_preparation_on_the_device(devmem):
+    """fillOutOfView / convertVolumeL2R (main.cpp:146-199) fused into the upload's re-layout pass.  The energy
+    built from the raw left volume with LEXP_VOL_FILL (view 0) and LEXP_VOL_RIGHT_FROM_LEFT (view 1) must produce exactly the costs
+    of an energy that was given the volumes prepared on the host by the oracle's restatement of the two functions; host upload in
+    several slabs (LEXP_UPLOAD_SLAB_MB) and the device-pointer path."""
+    import os
+    import localexpstereo_b200 as L
+    H, W, D, windR = 70, 95, 21, 12     # W not a multiple of 4, D not a multiple of 8: ragged blocks and slabs
+    imL, imR, volL, _ = make_scene(H, W, D)
+    prepL = O.fill_out_of_view(volL.copy(), 0)
+    prepR = O.fill_out_of_view(O.convert_volume_l2r(prepL), 1)
+    assert np.array_equal(prepR, np.stack([volL[d][:, np.minimum(np.arange(W) + d, W - 1)] for d in range(D)]))   # the closed form the kernel uses
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    ref = L.CostVolumeEnergy(imL, imR, prepL, prepR, prm, D - 1)
+    old = os.environ.get("LEXP_UPLOAD_SLAB_MB")
+    os.environ["LEXP_UPLOAD_SLAB_MB"] = "0"     # smallest slab (8 disparities): 3 slabs, the last one ragged
+    try:
+        got = L.CostVolumeEnergy(imL, imR, None, None, prm, D - 1)
+        got.set_volume(0, volL, L.VOL_FILL)
+        got.set_volume(1, volL, L.VOL_RIGHT_FROM_LEFT)
+        dev = L.CostVolumeEnergy(imL, imR, None, None, prm, D - 1)
+        d_vol = devmem.upload(volL)
+        dev.set_volume(0, d_vol if hasattr(d_vol, "is_cuda") else volL, L.VOL_FILL)
+        dev.set_volume(1, d_vol if hasattr(d_vol, "is_cuda") else volL, L.VOL_RIGHT_FROM_LEFT)
+    finally:
+        if old is None:
+            os.environ.pop("LEXP_UPLOAD_SLAB_MB")
+        else:
+            os.environ["LEXP_UPLOAD_SLAB_MB"] = old
+    try:
+        lay = L.LayerManager(W, H, windR).addLayer(9)
+        rng = O.CvRNG(4)
+        for mode in (0, 1):
+            g = lay.disjointRegionSets[3 + mode]
+            planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+            fr, tr = [lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g]
+            imgs = []
+            for E in (ref, got, dev):
+                img = np.full((H, W), -7.0, np.float32)
+                E.ComputeUnaryPotentialBatch(fr, tr, img, planes, mode=mode)
+                imgs.append(img)
+            assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2]) and (imgs[0] != -7.0).any()
+        with pytest.raises(L.LexpError):
+            got.set_volume(0, volL, L.VOL_RIGHT_FROM_LEFT)   # the derived volume is view 1's
+    finally:
+        for E in (ref, got, dev):
+            E.close()
