@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <array>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <condition_variable>
 #include <map>
 #include <set>
@@ -118,9 +121,12 @@ struct lexp_ctx {
     std::mutex plans_mu;
     std::set<lexp_plan*> live_plans;
     // Combining of CONCURRENT lexp_eval_cell calls.  The unchanged reference loop issues one blocking call per cell from an OpenMP
-    // `parallel for` over the cells of a disjoint group (FastGCStereo.h:30-49): while one call owns the device, the calls of the
-    // other threads queue up here and are then evaluated together as ONE batched launch (same work items, same results).
-    // A call that finds the device idle and the queue empty takes the plain single-cell path.
+    // `parallel for` over the cells of a disjoint group (FastGCStereo.h:30-49).  Every call queues a request; the first thread to find
+    // no leader becomes one: it gives the other threads of the group a few microseconds to arrive (they all return from the previous
+    // proposal at about the same time), then evaluates the whole queue with ONE batched launch (the cached work items of the cells
+    // concatenated -- same items, bit-identical results) whose compact tiles land in a mapped pinned buffer; every caller then copies
+    // its own tile into its cost image, in parallel.  Waiting threads poll their own request (no condition variable: with 128 OpenMP
+    // threads one notify_all per batch cost more than the kernel); leadership is handed to a queued request when a batch is done.
     struct CellReq {
         int mode, with_check;
         lexp_plan* pl;
@@ -129,18 +135,23 @@ struct lexp_ctx {
         ptrdiff_t step_bytes;
         int status = LEXP_OK;
         std::string err;
-        bool done = false;
+        const float* tile = nullptr;           // where the leader's batch put this call's compact tile (pinned host memory)
+        std::atomic<int>* copies_left = nullptr;   // the batch's count of tiles not yet copied out: the buffer is reused after it hits 0
+        std::atomic<int> state{0};             // 0 queued, 1 done (tile ready / error), 2 lead the next batch
     };
     std::mutex comb_mu;
-    std::condition_variable comb_cv;
     std::vector<CellReq*> comb_q;
-    bool comb_busy = false;
+    bool comb_leader = false;      // a leader is collecting / running a batch
     bool combine = true;           // LEXP_COMBINE=0: every call on its own (the round-1 behaviour)
-    Item* cb_items = nullptr;      // reusable buffers of the combined launches
-    Plane4* cb_planes = nullptr;
-    float* cb_dout = nullptr;
-    float* cb_hout = nullptr;      // pinned
-    size_t cb_items_cap = 0, cb_planes_cap = 0, cb_out_cap = 0;
+    int comb_window_us = 30;       // LEXP_COMBINE_WINDOW_US: how long a leader waits for the queue to stop growing
+    std::atomic<size_t> comb_seen{1};   // largest batch so far: a leader stops collecting as soon as that many calls are queued
+    struct CombBuf {               // staging of one batch: pinned (mapped) host memory, plus device copies of items / planes
+        Item* h_items = nullptr; Plane4* h_planes = nullptr; float* h_out = nullptr;
+        Item* d_items = nullptr; Plane4* d_planes = nullptr; float* d_out = nullptr;   // d_out: device address of h_out (zero-copy)
+        size_t items_cap = 0, planes_cap = 0, out_cap = 0;
+        std::atomic<int> copies_left{0};
+    } cb[2];
+    int cb_next = 0;
     int64_t combined_batches = 0, combined_calls = 0;
 #if LEXP_TRACE
     long long* d_trace = nullptr;
@@ -421,6 +432,7 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->ctas_per_sm = env_int("LEXP_CTAS_PER_SM", kMinCtas);
     c->pdl = LEXP_PDL && !env_int("LEXP_PDL_OFF", 0);
     c->combine = env_int("LEXP_COMBINE", 1) != 0;
+    c->comb_window_us = std::max(0, env_int("LEXP_COMBINE_WINDOW_US", 30));
     c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", kMinCtas > 2 ? (int)(233472 / kMinCtas - 1024) : 0);
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
@@ -449,8 +461,12 @@ int lexp_destroy(lexp_ctx* c) {
         pl->ctx = nullptr;
     }
     c->live_plans.clear();
-    cudaFree(c->cb_items); cudaFree(c->cb_planes); cudaFree(c->cb_dout);
-    if (c->cb_hout) cudaFreeHost(c->cb_hout);
+    for (auto& b : c->cb) {
+        cudaFree(b.d_items); cudaFree(b.d_planes);
+        if (b.h_items) cudaFreeHost(b.h_items);
+        if (b.h_planes) cudaFreeHost(b.h_planes);
+        if (b.h_out) cudaFreeHost(b.h_out);
+    }
     for (int m = 0; m < 2; m++) {
         cudaFree(c->d_gs[m]);
         cudaFree(c->d_exi[m]);
@@ -803,75 +819,82 @@ int lexp_eval_batch(lexp_ctx* c, int mode, int n, const lexp_rect* filt, const l
 
 namespace {
 
-// One batched launch for the queued single-cell requests of one (mode, with_check): the work items of the cached per-cell
-// plans are concatenated (call index = position in the batch, compact outputs back to back), evaluated like the staged path
-// of lexp_plan_eval_host, and every tile is copied into its caller's image.
+// One batched launch for the queued single-cell requests of one (mode, with_check): the work items of the cached per-cell plans are
+// concatenated in pinned staging memory (call index = position in the batch, compact outputs back to back), the kernel writes the
+// compact tiles straight into mapped pinned host memory, and every request learns where its tile is (the callers copy them out).
 int run_combined(lexp_ctx* c, const std::vector<lexp_ctx::CellReq*>& reqs) {
-    std::vector<Item> items;
-    std::vector<Plane4> planes(reqs.size());
-    std::vector<size_t> off(reqs.size());
-    size_t nout = 0, smem = 0;
-    for (size_t i = 0; i < reqs.size(); i++) {
-        const lexp_plan* pl = reqs[i]->pl;
-        off[i] = nout;
-        for (Item it : pl->h_items) {
-            it.call = (int)i;
-            it.compact_off += (int)nout;  // the plan's own call starts at offset 0
-            items.push_back(it);
-        }
-        nout += (size_t)pl->sum_s;
-        smem = std::max(smem, pl->smem);
-        const lexp_plane& p = reqs[i]->plane;
-        planes[i] = Plane4{p.a, p.b, p.c, p.v};
-    }
+    size_t nitems = 0, nout = 0, smem = 0;
+    for (auto* r : reqs) { nitems += r->pl->h_items.size(); nout += (size_t)r->pl->sum_s; smem = std::max(smem, r->pl->smem); }
     if (nout > 0x7fffffffULL) return fail(LEXP_ERR_INVALID, "combined output too large");
     std::lock_guard<std::mutex> lk(c->mu);
     LEXP_CUDA(cudaSetDevice(c->p.device));
-    if (items.size() > c->cb_items_cap || planes.size() > c->cb_planes_cap || nout > c->cb_out_cap) {
+    lexp_ctx::CombBuf& b = c->cb[c->cb_next];
+    c->cb_next ^= 1;
+    // the callers of the batch that used this buffer two batches ago must have copied their tiles out
+    for (int spin = 0; b.copies_left.load(std::memory_order_acquire) > 0; spin++)
+        if (spin > 64) std::this_thread::yield();
+    if (nitems > b.items_cap || reqs.size() > b.planes_cap || nout > b.out_cap) {
         LEXP_CUDA(cudaStreamSynchronize(c->stream));
-        if (items.size() > c->cb_items_cap) {
-            cudaFree(c->cb_items); c->cb_items = nullptr; c->cb_items_cap = 0;
-            LEXP_CUDA(cudaMalloc(&c->cb_items, 2 * items.size() * sizeof(Item)));
-            c->cb_items_cap = 2 * items.size();
+        if (nitems > b.items_cap) {
+            cudaFree(b.d_items); b.d_items = nullptr; if (b.h_items) cudaFreeHost(b.h_items); b.h_items = nullptr; b.items_cap = 0;
+            LEXP_CUDA(cudaMalloc(&b.d_items, 2 * nitems * sizeof(Item)));
+            LEXP_CUDA(cudaHostAlloc(&b.h_items, 2 * nitems * sizeof(Item), cudaHostAllocDefault));
+            b.items_cap = 2 * nitems;
         }
-        if (planes.size() > c->cb_planes_cap) {
-            cudaFree(c->cb_planes); c->cb_planes = nullptr; c->cb_planes_cap = 0;
-            LEXP_CUDA(cudaMalloc(&c->cb_planes, 2 * planes.size() * sizeof(Plane4)));
-            c->cb_planes_cap = 2 * planes.size();
+        if (reqs.size() > b.planes_cap) {
+            cudaFree(b.d_planes); b.d_planes = nullptr; if (b.h_planes) cudaFreeHost(b.h_planes); b.h_planes = nullptr; b.planes_cap = 0;
+            LEXP_CUDA(cudaMalloc(&b.d_planes, 2 * reqs.size() * sizeof(Plane4)));
+            LEXP_CUDA(cudaHostAlloc(&b.h_planes, 2 * reqs.size() * sizeof(Plane4), cudaHostAllocDefault));
+            b.planes_cap = 2 * reqs.size();
         }
-        if (nout > c->cb_out_cap) {
-            cudaFree(c->cb_dout); c->cb_dout = nullptr;
-            if (c->cb_hout) { cudaFreeHost(c->cb_hout); c->cb_hout = nullptr; }
-            c->cb_out_cap = 0;
-            LEXP_CUDA(cudaMalloc(&c->cb_dout, 2 * nout * sizeof(float)));
-            LEXP_CUDA(cudaHostAlloc(&c->cb_hout, 2 * nout * sizeof(float), cudaHostAllocDefault));
-            c->cb_out_cap = 2 * nout;
+        if (nout > b.out_cap) {
+            if (b.h_out) cudaFreeHost(b.h_out);
+            b.h_out = nullptr; b.d_out = nullptr; b.out_cap = 0;
+            LEXP_CUDA(cudaHostAlloc(&b.h_out, 2 * nout * sizeof(float), cudaHostAllocMapped));
+            LEXP_CUDA(cudaHostGetDevicePointer(&b.d_out, b.h_out, 0));
+            b.out_cap = 2 * nout;
         }
     }
-    LEXP_CUDA(cudaMemcpyAsync(c->cb_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, c->stream));
-    LEXP_CUDA(cudaMemcpyAsync(c->cb_planes, planes.data(), planes.size() * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+    size_t at = 0, off = 0;
+    for (size_t i = 0; i < reqs.size(); i++) {
+        const lexp_plan* pl = reqs[i]->pl;
+        for (Item it : pl->h_items) {
+            it.call = (int)i;
+            it.compact_off += (int)off;  // the plan's own call starts at offset 0
+            b.h_items[at++] = it;
+        }
+        reqs[i]->tile = b.h_out + off;
+        reqs[i]->copies_left = &b.copies_left;
+        off += (size_t)pl->sum_s;
+        const lexp_plane& p = reqs[i]->plane;
+        b.h_planes[i] = Plane4{p.a, p.b, p.c, p.v};
+    }
+    LEXP_CUDA(cudaMemcpyAsync(b.d_items, b.h_items, nitems * sizeof(Item), cudaMemcpyHostToDevice, c->stream));
+    LEXP_CUDA(cudaMemcpyAsync(b.d_planes, b.h_planes, reqs.size() * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
     lexp_plan batch;  // a view: nothing in it is owned
     batch.ctx = c;
     batch.ncalls = (int)reqs.size();
-    batch.nitems = (int)items.size();
+    batch.nitems = (int)nitems;
     batch.smem = smem;
-    batch.d_items = c->cb_items;
-    int rc = run_plan(c, &batch, reqs[0]->mode, c->cb_planes, c->cb_dout, 0, 1, reqs[0]->with_check);
+    batch.d_items = b.d_items;
+    int rc = run_plan(c, &batch, reqs[0]->mode, b.d_planes, b.d_out, 0, 1, reqs[0]->with_check);
     batch.d_items = nullptr;
     if (rc) return rc;
-    LEXP_CUDA(cudaMemcpyAsync(c->cb_hout, c->cb_dout, nout * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < reqs.size(); i++) {  // costs(targetRect) only (CostVolumeEnergy.h:169-171)
-        const lexp_rect& t = reqs[i]->pl->targ[0];
-        const float* src = c->cb_hout + off[i];
-        for (int y = 0; y < t.height; y++) {
-            float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(reqs[i]->base) + (ptrdiff_t)(t.y + y) * reqs[i]->step_bytes) + t.x;
-            memcpy(dst, src + (size_t)y * t.width, (size_t)t.width * sizeof(float));
-        }
-    }
+    b.copies_left.store((int)reqs.size(), std::memory_order_release);
     c->combined_batches++;
     c->combined_calls += (int64_t)reqs.size();
     return LEXP_OK;
+}
+
+// a caller's own part of a combined batch: costs(targetRect) only (CostVolumeEnergy.h:169-171)
+void copy_out_tile(lexp_ctx::CellReq& r) {
+    const lexp_rect& t = r.pl->targ[0];
+    for (int y = 0; y < t.height; y++) {
+        float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(r.base) + (ptrdiff_t)(t.y + y) * r.step_bytes) + t.x;
+        memcpy(dst, r.tile + (size_t)y * t.width, (size_t)t.width * sizeof(float));
+    }
+    r.copies_left->fetch_sub(1, std::memory_order_acq_rel);
 }
 
 }  // namespace
@@ -907,45 +930,61 @@ int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect
     }
     if (!c->combine || mode < 0 || mode > 1) return lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
 
-    std::unique_lock<std::mutex> lk(c->comb_mu);
-    if (!c->comb_busy && c->comb_q.empty()) {  // nobody else is calling: the plain single-cell path
-        c->comb_busy = true;
-        lk.unlock();
-        const int rc = lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check);
-        lk.lock();
-        c->comb_busy = false;
-        if (!c->comb_q.empty()) c->comb_cv.notify_all();  // calls that arrived meanwhile: one of them becomes the leader
-        return rc;
-    }
     lexp_ctx::CellReq req;
     req.mode = mode; req.with_check = with_check; req.pl = pl; req.plane = *plane; req.base = base; req.step_bytes = step_bytes;
-    c->comb_q.push_back(&req);
+    bool lead = false;
+    {
+        std::lock_guard<std::mutex> lk(c->comb_mu);
+        c->comb_q.push_back(&req);
+        if (!c->comb_leader) { c->comb_leader = true; lead = true; }
+    }
     for (;;) {
-        c->comb_cv.wait(lk, [&] { return req.done || !c->comb_busy; });
-        if (req.done) break;
-        // the device is free and this request is still queued: lead one batch
-        c->comb_busy = true;
+        if (!lead) {   // poll the own request: done, or asked to lead the next batch
+            int st, spins = 0;
+            while ((st = req.state.load(std::memory_order_acquire)) == 0)
+                if (++spins > 256) std::this_thread::yield();
+            if (st == 1) break;
+            req.state.store(0, std::memory_order_relaxed);   // st == 2: lead
+        }
+        // ---- leader: give the group's other threads a moment to arrive, then serve everything that is queued
+        using clk = std::chrono::steady_clock;
+        const auto t0 = clk::now();
+        size_t seen = 0;
+        auto last_growth = t0;
+        for (;;) {
+            size_t n;
+            { std::lock_guard<std::mutex> lk(c->comb_mu); n = c->comb_q.size(); }
+            const auto now = clk::now();
+            if (n != seen) { seen = n; last_growth = now; }
+            if (n >= c->comb_seen.load(std::memory_order_relaxed) || now - t0 > std::chrono::microseconds(c->comb_window_us) ||
+                now - last_growth > std::chrono::microseconds(c->comb_window_us / 4 + 1)) break;
+        }
         std::vector<lexp_ctx::CellReq*> all;
-        all.swap(c->comb_q);
-        lk.unlock();
+        { std::lock_guard<std::mutex> lk(c->comb_mu); all.swap(c->comb_q); if (all.size() > c->comb_seen.load()) c->comb_seen.store(all.size()); }
         // one launch per (mode, with_check) present in the queue (the reference's loop uses a single combination at a time)
         while (!all.empty()) {
             std::vector<lexp_ctx::CellReq*> grp, rest;
             for (auto* r : all) (r->mode == all[0]->mode && r->with_check == all[0]->with_check ? grp : rest).push_back(r);
-            const int rc = run_combined(c, grp);
-            for (auto* r : grp) { r->status = rc; if (rc) r->err = g_err; }
+            const int rc = grp.size() == 1 && grp[0] == &req && rest.empty()
+                               ? lexp_plan_eval_host(c, pl, mode, plane, base, step_bytes, with_check)   // alone: the plain single-cell path
+                               : run_combined(c, grp);
+            for (auto* r : grp) {
+                r->status = rc;
+                if (rc) { r->err = g_err; r->tile = nullptr; }
+                if (r != &req) r->state.store(1, std::memory_order_release);
+            }
             all.swap(rest);
-            lk.lock();
-            for (auto* r : grp) r->done = true;
-            lk.unlock();
         }
-        lk.lock();
-        c->comb_busy = false;
-        c->comb_cv.notify_all();
-        if (req.done) break;
+        {   // hand the leadership to a request that arrived meanwhile, or retire
+            std::lock_guard<std::mutex> lk(c->comb_mu);
+            if (c->comb_q.empty()) c->comb_leader = false;
+            else c->comb_q.front()->state.store(2, std::memory_order_release);
+        }
+        break;   // the leader's own request was part of its batch
     }
-    if (req.status) g_err = req.err;
-    return req.status;
+    if (req.status) { g_err = req.err; return req.status; }
+    if (req.tile) copy_out_tile(req);
+    return LEXP_OK;
 }
 
 int lexp_combine_stats(const lexp_ctx* c, int64_t* batches, int64_t* calls) {

@@ -510,6 +510,35 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         for (int i = 0; i < LEXP_STATS_STAGES; i++) mbar_init(s_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const int st_xa = max(X0 + R, it.fx), st_xb = min(X0 + R + W2, fx1);   // columns of the tile's (a, b) strip inside the filterRect
+    // one chunk of statistics rows -> ring stage chunk % NS: up to 3 bulk copies per row (statA, statB: float4 rows; statC: a float row
+    // that starts at any float, copied from the 16-byte boundary below it), completion counted in bytes on the stage's mbarrier
+    auto tma_issue = [&](int chunk) {
+        unsigned char* stg = s_ring + (chunk % LEXP_STATS_STAGES) * stageB;
+        uint64_t* bar = s_full + (chunk % LEXP_STATS_STAGES);
+        const int W2c = stats_w2c(W2);
+        unsigned bytes = 0;
+#pragma unroll
+        for (int r = 0; r < kCH; r++) {
+            const int v = chunk * kCH + r;
+            if (v >= vC0 && v < vC1 && st_xb > st_xa)
+                bytes += 2u * (unsigned)(st_xb - st_xa) * 16u + (unsigned)(((((ys + v - R) * P.W + st_xa) & 3) + (st_xb - st_xa) + 3) & ~3) * 4u;
+        }
+        if (!bytes) { mbar_arrive(bar); return; }
+        mbar_expect_tx(bar, bytes);
+#pragma unroll
+        for (int r = 0; r < kCH; r++) {
+            const int v = chunk * kCH + r;
+            if (v >= vC0 && v < vC1 && st_xb > st_xa) {
+                const size_t g0 = (size_t)(ys + v - R) * P.W + st_xa;
+                const size_t so = (size_t)(r * W2 + (st_xa - (X0 + R))) * 16;
+                bulk_g2s(stg + so, P.statA + g0, (unsigned)(st_xb - st_xa) * 16u, bar);
+                bulk_g2s(stg + (size_t)kCH * W2 * 16 + so, P.statB + g0, (unsigned)(st_xb - st_xa) * 16u, bar);
+                const size_t g0a = g0 & ~(size_t)3;
+                bulk_g2s(stg + (size_t)2 * kCH * W2 * 16 + (size_t)r * W2c * 4, P.statC + g0a, (unsigned)(((int)(g0 - g0a) + (st_xb - st_xa) + 3) & ~3) * 4u, bar);
+            }
+        }
+    };
 #endif
 
     if (PM) {
@@ -839,9 +868,23 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const int vmin = st2 ? vE0 : vC0, vmax = st2 ? VHs : vC1;
         const F4* inb = st2 ? hb2 : hb1;
         F4* outb = st2 ? ho2 : ho1;
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+        // team H2's lane 0 feeds team C's statistics ring.  When H2 has passed consume_begin(2, c), team C has finished iteration c,
+        // in which it read chunk c + 1 out of the ring: the stages of all chunks <= c + 1 are free and are refilled with the chunks
+        // up to c + 1 + NS.  (H2 is the team with the most slack: profiles/r2_fused_ncu_L0.md.)
+        int st_next = 0;
+        if (st2 && lane == 0)
+            for (; st_next < LEXP_STATS_STAGES && st_next < nChunks; st_next++) tma_issue(st_next);
+#endif
         for (int c = 0; c < nChunks; c++) {
             const int v = c * kCH + r;
             consume_begin(lin, c, nin);
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+            if (st2 && lane == 0 && st_next < nChunks && st_next <= c + 1 + LEXP_STATS_STAGES) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // team C's generic-proxy reads of the stage, then the async-proxy refill
+                for (; st_next < nChunks && st_next <= c + 1 + LEXP_STATS_STAGES; st_next++) tma_issue(st_next);
+            }
+#endif
             produce_begin(lout, c, nout);
             if (k < nruns && v >= vmin && v < vmax) {
                 const F4* in = inb + ((c & 1) * kCH + r) * (st2 ? SW2 : SW) + 9 * k;
@@ -912,63 +955,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const float4* pa = P.statA + pix0;
         const float4* pb = P.statB + pix0;
         const float* pc = P.statC + pix0;
-#if !LEXP_C_ROLLING || (LEXP_STATS_TMA && !defined(LEXP_EMU))
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
-        // ---- statistics through the TMA unit: chunk c lives in ring stage c % NS; after the bar.sync of consume_begin(1, c) every
-        // thread of the team has read chunk c, so thread 0 refills that stage with chunk c + NS right there (NS - 1 chunks of lead)
-        constexpr int NS = LEXP_STATS_STAGES;
-        const int W2c = stats_w2c(W2);
-        const int XC0 = X0 + R;
-        const int xa = max(XC0, it.fx), xb = min(XC0 + W2, fx1);       // columns of the tile's (a, b) strip inside the filterRect
-        auto tma_issue = [&](int chunk) {
-            unsigned char* stg = s_ring + (chunk % NS) * stageB;
-            uint64_t* bar = s_full + (chunk % NS);
-            unsigned bytes = 0;
-            int nrow = 0;
-#pragma unroll
-            for (int r = 0; r < kCH; r++) {
-                const int v = chunk * kCH + r;
-                if (v >= vC0 && v < vC1 && xb > xa) { bytes += 2u * (unsigned)(xb - xa) * 16u + (unsigned)(((((ys + v - R) * P.W + xa) & 3) + (xb - xa) + 3) & ~3) * 4u; nrow++; }
-            }
-            if (!nrow) { mbar_arrive(bar); return; }
-            mbar_expect_tx(bar, bytes);
-#pragma unroll
-            for (int r = 0; r < kCH; r++) {
-                const int v = chunk * kCH + r;
-                if (v >= vC0 && v < vC1 && xb > xa) {
-                    const size_t g0 = (size_t)(ys + v - R) * P.W + xa;
-                    bulk_g2s(stg + (size_t)(r * W2 + (xa - XC0)) * 16, P.statA + g0, (unsigned)(xb - xa) * 16u, bar);
-                    bulk_g2s(stg + (size_t)kCH * W2 * 16 + (size_t)(r * W2 + (xa - XC0)) * 16, P.statB + g0, (unsigned)(xb - xa) * 16u, bar);
-                    const size_t g0a = g0 & ~(size_t)3;   // statC rows start at any float: copy from the 16-byte boundary below
-                    bulk_g2s(stg + (size_t)2 * kCH * W2 * 16 + (size_t)r * W2c * 4, P.statC + g0a, (unsigned)(((int)(g0 - g0a) + (xb - xa) + 3) & ~3) * 4u, bar);
-                }
-            }
-        };
-        if (t == 0)
-            for (int ch = 0; ch < NS && ch < nChunks; ch++) tma_issue(ch);
-        for (int c = 0; c < nChunks; c++) {
-            {
-                float4 ca[kCH], cb[kCH];
-                float cc[kCH];
-                mbar_wait(s_full + (c % NS), (unsigned)((c / NS) & 1));
-                const unsigned char* stg = s_ring + (c % NS) * stageB;
-#pragma unroll
-                for (int r = 0; r < kCH; r++) {
-                    const int v = c * kCH + r;
-                    ca[r] = make_float4(0.f, 0.f, 0.f, 0.f); cb[r] = ca[r]; cc[r] = 0.f;
-                    if (colC && v >= vC0 && v < vC1) {
-                        ca[r] = reinterpret_cast<const float4*>(stg)[r * W2 + t];
-                        cb[r] = reinterpret_cast<const float4*>(stg + (size_t)kCH * W2 * 16)[r * W2 + t];
-                        cc[r] = reinterpret_cast<const float*>(stg + (size_t)2 * kCH * W2 * 16)[r * W2c + (((ys + v - R) * P.W + xa) & 3) + (XC - xa)];
-                    }
-                }
-                consume_begin(1, c, kLinkHC);
-                if (t == 0 && c + NS < nChunks) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the team's generic-proxy reads of this stage, then the async-proxy refill
-                    tma_issue(c + NS);
-                }
-#else
+#if !LEXP_C_ROLLING
         auto issue = [&]() {
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+            if (vi < nChunks * kCH) mbar_wait(s_full + ((vi / kCH) % LEXP_STATS_STAGES), (unsigned)(((vi / kCH) / LEXP_STATS_STAGES) & 1));
+#endif
 #pragma unroll
             for (int r = 0; r < kCH; r++) {
                 sa[r] = make_float4(0.f, 0.f, 0.f, 0.f); sb[r] = sa[r]; sc[r] = 0.f;
@@ -978,9 +969,18 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #else
                 if (colC && vi >= vC0 && vi < vC1) {
 #endif
+#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+                    // the row was staged by the TMA unit (team H2 issues the copies LEXP_STATS_STAGES chunks ahead): shared-memory reads,
+                    // one chunk ahead of their use like the global loads they replace
+                    const unsigned char* stg = s_ring + ((vi / kCH) % LEXP_STATS_STAGES) * stageB;
+                    sa[r] = reinterpret_cast<const float4*>(stg)[r * W2 + t];
+                    sb[r] = reinterpret_cast<const float4*>(stg + (size_t)kCH * W2 * 16)[r * W2 + t];
+                    sc[r] = reinterpret_cast<const float*>(stg + (size_t)2 * kCH * W2 * 16)[r * stats_w2c(W2) + (((ys + vi - R) * P.W + st_xa) & 3) + (XC - st_xa)];
+#else
                     sa[r] = __ldg(pa);
                     sb[r] = __ldg(pb);
                     sc[r] = __ldg(pc);
+#endif
                 }
                 vi++;
                 pa += P.W; pb += P.W; pc += P.W;
@@ -1000,7 +1000,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 }
                 issue();
                 consume_begin(1, c, kLinkHC);
-#endif
                 produce_begin(2, c, kLinkCH);
                 if (t < W2) {
                     const F4* ho = ho1 + (c & 1) * kCH * SW2 + sidx(t);

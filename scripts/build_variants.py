@@ -17,7 +17,7 @@ VARIANTS = {
     "r1": ["-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"],    # the round-1 kernel
     "tma3": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=3"],   # team C's statistics staged by the TMA unit (cp.async.bulk + mbarrier ring)
     "tma4": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=4"],
-    "tma6": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=6"],
+    "tma5": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=5"],
     "occ3": ["-DLEXP_OCC3"],                        # 3 CTAs / SM: 56 registers, 75 KB shared-memory cap
     "pdl": ["-DLEXP_PDL=1"],                        # programmatic dependent launch between batched evaluations
     "occ3pdl": ["-DLEXP_OCC3", "-DLEXP_PDL=1"],

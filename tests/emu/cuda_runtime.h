@@ -248,7 +248,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2
 typedef struct emu_stream* cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaStreamNonBlocking = 1 };
-enum { cudaHostAllocDefault = 0, cudaHostRegisterPortable = 1, cudaHostRegisterMapped = 2 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostRegisterPortable = 1, cudaHostRegisterMapped = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaLimit { cudaLimitPersistingL2CacheSize = 6 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
@@ -305,8 +305,7 @@ template <class T> static inline cudaError_t cudaMalloc(T** p, size_t bytes) {
     return cudaSuccess;
 }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
@@ -327,6 +326,13 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
 }
 static inline cudaError_t cudaHostRegister(void* p, size_t n, unsigned) { std::lock_guard<std::mutex> g(emu::reg_mu()); emu::registered()[p] = n; return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void* p) { std::lock_guard<std::mutex> g(emu::reg_mu()); return emu::registered().erase(p) ? cudaSuccess : cudaErrorInvalidValue; }
+// pinned allocations: mapped ones are registered so that cudaHostGetDevicePointer finds them
+template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned flags) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess && (flags & cudaHostAllocMapped)) { std::lock_guard<std::mutex> g(emu::reg_mu()); emu::registered()[(void*)*p] = bytes; }
+    return e;
+}
+static inline cudaError_t cudaFreeHost(void* p) { { std::lock_guard<std::mutex> g(emu::reg_mu()); emu::registered().erase(p); } free(p); return cudaSuccess; }
 // zero-copy is available only inside registered ranges (as with cudaHostRegisterMapped)
 template <class T> static inline cudaError_t cudaHostGetDevicePointer(T** dev, void* host, unsigned) {
     std::lock_guard<std::mutex> g(emu::reg_mu());
