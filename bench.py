@@ -233,21 +233,27 @@ def run_reference(args, W, H, D, windR, rank, world):
     """CPU arm with all host threads, on a bounded sample of the sweep (group 0 of every layer, all proposal steps)."""
     if rank != 0:
         return
-    import localexpstereo_b200 as L
-    from localexpstereo_b200.sweep import V3_STEPS, v3_layer_units
-    from localexpstereo_b200 import synth
+    # nothing of the product is loaded in this process (VERDICT r1 weak #7): the cell rectangles come from the reference's own
+    # LayerManager (oracle/_ref) or, without it, from the oracle's restatement; inputs from the package's pure-numpy generators
+    from localexpstereo_b200 import synth   # numpy only; importing the package does not load liblexp_cuda.so
+    from oracle import lexp_oracle as O
     naive = args.workload.endswith("_naive")
     imL, vol = make_inputs(W, H, D)
     imR = synth.synthetic_image(H, W, 43) if naive else None
     arm = CpuArm(W, H, D, windR, imL, None if naive else vol, naive=naive, imR=imR)
-    lm = L.LayerManager(W, H, windR)
-    units = [5, 15, 25] if naive else v3_layer_units(W)
+    try:
+        from oracle import ref_binding
+        make_layer = ref_binding.layer if (ref_binding.available() or ref_binding.build_ref.reference_present()) else O.make_layer
+    except Exception:
+        make_layer = O.make_layer
+    units = [5, 15, 25] if naive else [int(W * 0.01), int(W * 0.03), int(W * 0.09)]   # main.cpp:304-306 / 395-397
+    steps = [9, 3, 3]                                                                     # Exp(1)+Ransac(1)+Random(7) | Exp(2)+Ransac(1) x 2
     sample = []  # (filter rects, target rects, planes [K][n][4]) of group 0 of every layer: 15 of the 240 batched evaluations
     for li, u in enumerate(units):
-        lay = lm.addLayer(u)
-        cells = lay.disjointRegionSets[0]
-        pls = np.ascontiguousarray(synth.synthetic_planes(lay.unitRegions, V3_STEPS[li], D, 7 + li)[:, cells, :])
-        sample.append(([lay.filterRegions[r] for r in cells], [lay.sharedRegions[r] for r in cells], pls))
+        lay = make_layer(W, H, windR, u)
+        cells = lay["groups"][0]
+        pls = np.ascontiguousarray(synth.synthetic_planes(lay["unit"], steps[li], D, 7 + li)[:, cells, :])
+        sample.append(([lay["filter"][r] for r in cells], [lay["shared"][r] for r in cells], pls))
     kind, nthr = arm.calibrate(*sample[0])
     for _ in range(args.warmup):
         arm.time_sample(sample)
