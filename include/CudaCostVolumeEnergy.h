@@ -16,6 +16,8 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 class CudaCostVolumeEnergy : public StereoEnergy {
 protected:
@@ -158,6 +160,57 @@ public:
         // cv::Mat header over cell i's tile: what the fusion step reads as `subProposalCost` (FastGCStereo.h:37,52-58)
         cv::Mat tile(float* tiles, size_t i) const { return cv::Mat(targets_[i].height, targets_[i].width, CV_32F, tiles + offsets_[i]); }
 #endif
+    };
+
+    // The PatchMatch phase of FastGCStereo::run on the device: `for (iteration < pmInit) for (layers) localExpansionMovesForLayer_CPU(...,
+    // doGC = false)` (FastGCStereo.h:143-157) and initCurrentFast (:94-131), with currentCost_ / currentLabeling_ resident in HBM, the
+    // proposals of ExpansionProposer / RandomProposer drawn on the device and the `cur > prop` update fused into the unary-cost kernel.
+    // A maintainer replaces the pm loop of run() by:
+    //     CudaCostVolumeEnergy::PatchMatchPhase pm(energy, mode, {5, 15, 25}, {{{LEXP_PROP_EXPANSION, 1}, {LEXP_PROP_RANDOM, 8}}, ...});
+    //     pm.begin(); pm.init(labels); for (it < pmInit) pm.iteration(it, seed); pm.get(currentCost_[mode], currentLabeling_[mode]);
+    class PatchMatchPhase {
+        lexp_ctx* ctx_;
+        lexp_pm_sweep* sweep_ = nullptr;
+        int mode_;
+
+    public:
+        typedef std::vector<std::pair<int, int>> ProposerList;   // (LEXP_PROP_EXPANSION | LEXP_PROP_RANDOM, K) in the order of layer.proposers
+        PatchMatchPhase(const CudaCostVolumeEnergy& e, int mode, const std::vector<int>& unitSizes, const std::vector<ProposerList>& proposers,
+                        int rank = 0, int world = 1)
+            : ctx_(e.context()), mode_(mode) {
+            if (unitSizes.size() != proposers.size()) throw std::invalid_argument("PatchMatchPhase: one proposer list per layer");
+            std::vector<int> np, kind, K;
+            for (const ProposerList& pl : proposers) {
+                np.push_back((int)pl.size());
+                for (const auto& p : pl) { kind.push_back(p.first); K.push_back(p.second); }
+            }
+            check(lexp_pm_sweep_create(ctx_, mode, (int)unitSizes.size(), unitSizes.data(), np.data(), kind.data(), K.data(), rank, world, &sweep_));
+        }
+        ~PatchMatchPhase() { lexp_pm_sweep_destroy(sweep_); }
+        PatchMatchPhase(const PatchMatchPhase&) = delete;
+        PatchMatchPhase& operator=(const PatchMatchPhase&) = delete;
+
+        // currentCost_[mode] = INFINITY, currentLabeling_[mode] = 0 (FastGCStereo.h:137), or the caller's H x W mats (CV_32F / CV_32FC4, continuous)
+        void begin() { check(lexp_pm_begin(ctx_, mode_, nullptr, nullptr)); }
+        void begin(const cv::Mat& currentCost, const cv::Mat& currentLabeling) {
+            static_assert(sizeof(Plane) == sizeof(lexp_plane), "Plane must stay {a,b,c,v} floats (Plane.h:4-8)");
+            check(lexp_pm_begin(ctx_, mode_, reinterpret_cast<const float*>(currentCost.data), reinterpret_cast<const lexp_plane*>(currentLabeling.data)));
+        }
+        int numInitLabels() const { return lexp_pm_sweep_num_init_labels(sweep_); }
+        // initCurrentFast (:101-113): labels[j] = createRandomLabel(random pixel of unitRegions[j]) of layer 0, drawn by the caller
+        void init(const std::vector<Plane>& labels) {
+            if ((int)labels.size() != numInitLabels()) throw std::invalid_argument("PatchMatchPhase: one label per unit region of layer 0");
+            check(lexp_pm_sweep_init(sweep_, reinterpret_cast<const lexp_plane*>(labels.data())));
+        }
+        int iteration(int iteration, uint64_t seed) {
+            int n = 0;
+            check(lexp_pm_sweep_iteration(sweep_, iteration, seed, &n));
+            return n;
+        }
+        // blocking: the state back into the caller's continuous H x W mats
+        void get(cv::Mat& currentCost, cv::Mat& currentLabeling) const {
+            check(lexp_pm_get(ctx_, mode_, reinterpret_cast<float*>(currentCost.data), reinterpret_cast<lexp_plane*>(currentLabeling.data)));
+        }
     };
 
 private:

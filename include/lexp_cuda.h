@@ -225,6 +225,25 @@ LEXP_API int lexp_plan_pm_step_ex(lexp_ctx* ctx, lexp_plan* plan, int mode, int 
 /* epoch base += delta (= the number of groups issued since the last call), asynchronous on the context stream. */
 LEXP_API int lexp_pm_advance_epoch(lexp_ctx* ctx, int mode, int delta);
 
+/* ---- The whole PatchMatch phase as one object: what a maintainer calls instead of the pmInit loop of FastGCStereo::run
+ * (FastGCStereo.h:143-157).  It owns one plan per (layer, group) of LayerManager::addLayer(unit_sizes[l]) (LayerManager.h:88-185),
+ * the proposer list of every layer as (kind, K) pairs in the order of main.cpp:391-397 (LEXP_PROP_EXPANSION / LEXP_PROP_RANDOM; a
+ * LEXP_PROP_LIST slot is not allowed here -- use lexp_plan_pm_step for replays), and the epoch bookkeeping of the group boundaries.
+ * rank / world: the multi-GPU cell shard (0 / 1 on a single GPU); connect the contexts first (lexp_pm_ipc_connect). */
+typedef struct lexp_pm_sweep lexp_pm_sweep;
+LEXP_API int lexp_pm_sweep_create(lexp_ctx* ctx, int mode, int n_layers, const int* unit_sizes, const int* n_proposers,
+                                  const int* proposer_kind, const int* proposer_K, int rank, int world, lexp_pm_sweep** out);
+LEXP_API int lexp_pm_sweep_destroy(lexp_pm_sweep* sweep);
+/* number of unit regions of layer 0 (= labels lexp_pm_sweep_init expects) */
+LEXP_API int lexp_pm_sweep_num_init_labels(const lexp_pm_sweep* sweep);
+/* initCurrentFast (FastGCStereo.h:101-113) with one label per unit region of layer 0 (all of them, in LayerManager order; a rank of
+ * a cell shard evaluates its share).  lexp_pm_begin first.  Asynchronous. */
+LEXP_API int lexp_pm_sweep_init(lexp_pm_sweep* sweep, const lexp_plane* labels_host);
+/* One pm iteration over all layers (FastGCStereo.h:147-157, doGC == false): every cell of every group visited with its layer's
+ * proposers, RandomProposer with m = iteration + iter and its early stop (Proposer.h:149-152).  Asynchronous; returns the number
+ * of kernel launches issued through *n_launches (may be NULL). */
+LEXP_API int lexp_pm_sweep_iteration(lexp_pm_sweep* sweep, int iteration, uint64_t seed, int* n_launches);
+
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
 LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,

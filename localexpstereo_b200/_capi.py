@@ -71,6 +71,11 @@ SYMBOLS = {
     "lexp_pm_ipc_export": (C.c_int, [_P, C.c_int, _P]),
     "lexp_pm_ipc_connect": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "lexp_pm_connect_local": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "lexp_pm_sweep_create": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "lexp_pm_sweep_destroy": (C.c_int, [_P]),
+    "lexp_pm_sweep_num_init_labels": (C.c_int, [_P]),
+    "lexp_pm_sweep_init": (C.c_int, [_P, _P]),
+    "lexp_pm_sweep_iteration": (C.c_int, [_P, C.c_int, C.c_uint64, C.POINTER(C.c_int)]),
     "lexp_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, _P, _P]),
 }
 

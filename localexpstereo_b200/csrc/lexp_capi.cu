@@ -12,8 +12,13 @@
 #include <atomic>
 #include <chrono>
 #include <thread>
+#include <climits>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <set>
 #include <mutex>
 #include <string>
@@ -44,6 +49,16 @@ int fail(int code, const std::string& msg) {
         if (e__ != cudaSuccess)                                                                          \
             return fail(LEXP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));            \
     } while (0)
+
+// futex on a 32-bit word: block while *addr == expected / wake every waiter (the combiner's followers sleep in the kernel instead of
+// spinning: with 128 OpenMP threads on 128 hardware threads, polling starves the one thread that stages and launches the batch)
+void futex_wait(std::atomic<int>* addr, int expected) { syscall(SYS_futex, reinterpret_cast<int*>(addr), FUTEX_WAIT_PRIVATE, expected, nullptr, nullptr, 0); }
+void futex_wake_all(std::atomic<int>* addr) { syscall(SYS_futex, reinterpret_cast<int*>(addr), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0); }
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
 
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -141,6 +156,8 @@ struct lexp_ctx {
     };
     std::mutex comb_mu;
     std::vector<CellReq*> comb_q;
+    std::atomic<int> comb_n{0};    // = comb_q.size(), readable without the mutex (the leader's collection window polls it)
+    std::atomic<int> comb_gen{0};  // bumped (and futex-woken) whenever requests change state: what waiting callers sleep on
     bool comb_leader = false;      // a leader is collecting / running a batch
     bool combine = true;           // LEXP_COMBINE=0: every call on its own (the round-1 behaviour)
     int comb_window_us = 30;       // LEXP_COMBINE_WINDOW_US: how long a leader waits for the queue to stop growing
@@ -831,8 +848,9 @@ int run_combined(lexp_ctx* c, const std::vector<lexp_ctx::CellReq*>& reqs) {
     lexp_ctx::CombBuf& b = c->cb[c->cb_next];
     c->cb_next ^= 1;
     // the callers of the batch that used this buffer two batches ago must have copied their tiles out
-    for (int spin = 0; b.copies_left.load(std::memory_order_acquire) > 0; spin++)
-        if (spin > 64) std::this_thread::yield();
+    for (int spin = 0; b.copies_left.load(std::memory_order_acquire) > 0; spin++) {
+        if (spin > 2000) std::this_thread::sleep_for(std::chrono::microseconds(5)); else cpu_relax();
+    }
     if (nitems > b.items_cap || reqs.size() > b.planes_cap || nout > b.out_cap) {
         LEXP_CUDA(cudaStreamSynchronize(c->stream));
         if (nitems > b.items_cap) {
@@ -936,31 +954,40 @@ int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect
     {
         std::lock_guard<std::mutex> lk(c->comb_mu);
         c->comb_q.push_back(&req);
+        c->comb_n.store((int)c->comb_q.size(), std::memory_order_release);
         if (!c->comb_leader) { c->comb_leader = true; lead = true; }
     }
     for (;;) {
-        if (!lead) {   // poll the own request: done, or asked to lead the next batch
-            int st, spins = 0;
-            while ((st = req.state.load(std::memory_order_acquire)) == 0)
-                if (++spins > 256) std::this_thread::yield();
+        if (!lead) {   // sleep until the own request is done, or is asked to lead the next batch
+            int st;
+            for (int spin = 0;; spin++) {
+                const int g = c->comb_gen.load(std::memory_order_acquire);
+                if ((st = req.state.load(std::memory_order_acquire)) != 0) break;
+                if (spin < 200) cpu_relax(); else futex_wait(&c->comb_gen, g);
+            }
             if (st == 1) break;
             req.state.store(0, std::memory_order_relaxed);   // st == 2: lead
         }
         // ---- leader: give the group's other threads a moment to arrive, then serve everything that is queued
         using clk = std::chrono::steady_clock;
         const auto t0 = clk::now();
-        size_t seen = 0;
+        int seen = 0;
         auto last_growth = t0;
         for (;;) {
-            size_t n;
-            { std::lock_guard<std::mutex> lk(c->comb_mu); n = c->comb_q.size(); }
+            const int n = c->comb_n.load(std::memory_order_acquire);
             const auto now = clk::now();
             if (n != seen) { seen = n; last_growth = now; }
-            if (n >= c->comb_seen.load(std::memory_order_relaxed) || now - t0 > std::chrono::microseconds(c->comb_window_us) ||
+            if ((size_t)n >= c->comb_seen.load(std::memory_order_relaxed) || now - t0 > std::chrono::microseconds(c->comb_window_us) ||
                 now - last_growth > std::chrono::microseconds(c->comb_window_us / 4 + 1)) break;
+            for (int i = 0; i < 64; i++) cpu_relax();
         }
         std::vector<lexp_ctx::CellReq*> all;
-        { std::lock_guard<std::mutex> lk(c->comb_mu); all.swap(c->comb_q); if (all.size() > c->comb_seen.load()) c->comb_seen.store(all.size()); }
+        {
+            std::lock_guard<std::mutex> lk(c->comb_mu);
+            all.swap(c->comb_q);
+            c->comb_n.store(0, std::memory_order_release);
+        }
+        if (all.size() > c->comb_seen.load()) c->comb_seen.store(all.size());
         // one launch per (mode, with_check) present in the queue (the reference's loop uses a single combination at a time)
         while (!all.empty()) {
             std::vector<lexp_ctx::CellReq*> grp, rest;
@@ -980,6 +1007,8 @@ int lexp_eval_cell(lexp_ctx* c, int mode, const lexp_rect* filt, const lexp_rect
             if (c->comb_q.empty()) c->comb_leader = false;
             else c->comb_q.front()->state.store(2, std::memory_order_release);
         }
+        c->comb_gen.fetch_add(1, std::memory_order_acq_rel);   // one wake-up for everybody whose state changed
+        futex_wake_all(&c->comb_gen);
         break;   // the leader's own request was part of its batch
     }
     if (req.status) { g_err = req.err; return req.status; }
@@ -1231,6 +1260,160 @@ int lexp_pm_connect_local(lexp_ctx* c, int mode, int rank, int world, lexp_ctx* 
     pr.world = world; pr.rank = rank;
     c->peers[mode] = pr;
     return LEXP_OK;
+}
+
+// ---- the PatchMatch phase as one object (host-side schedule of FastGCStereo.h:143-157 around lexp_plan_pm_step_ex) -----------
+struct lexp_pm_sweep {
+    lexp_ctx* ctx = nullptr;
+    int mode = 0, rank = 0, world = 1;
+    struct Group { lexp_plan* plan; int layer, group; std::vector<int> owners; };
+    std::vector<Group> sched;                                  // every (layer, group) in order, the same on all ranks
+    std::vector<std::vector<std::pair<int, int>>> proposers;   // per layer: (kind, K)
+    lexp_plan* init_plan = nullptr;
+    std::vector<int> init_owners, init_index;                  // ranks that initialise units; this rank's units of layer 0
+    int n_init = 0;
+    int rel = 0;                                               // groups issued since the epoch base was last advanced
+    int last_rel[kMaxPeers];
+    bool has[kMaxPeers];
+};
+
+namespace {
+// random stream of one launch (= localexpstereo_b200.sweep.pm_seed)
+uint64_t pm_launch_seed(uint64_t base, int mode, int iteration, int layer, int group, int step) {
+    uint64_t z = base * 0x9E3779B97F4A7C15ull + (uint64_t)(mode + 1) * 0xD1B54A32D192ED03ull + (uint64_t)(iteration + 1) * 0x8CB92BA72F3D8DD7ull +
+                 (uint64_t)(layer + 1) * 0xABC98388FB8FAC03ull + (uint64_t)(group + 1) * 0x2545F4914F6CDD1Dull + (uint64_t)(step + 1) * 0xDA942042E4DD58B5ull;
+    z = (z ^ (z >> 33)) * 0xFF51AFD7ED558CCDull;
+    return z ^ (z >> 29);
+}
+int sweep_step(lexp_pm_sweep* s, lexp_plan* plan, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes, int flags, bool first, bool last) {
+    int we[kMaxPeers];
+    unsigned mask = 0;
+    for (int r = 0; r < kMaxPeers; r++) { we[r] = s->has[r] ? s->last_rel[r] : 0; if (first && s->has[r]) mask |= 1u << r; }
+    return lexp_plan_pm_step_ex(s->ctx, plan, s->mode, step_index, kind, m, seed, planes, 0, nullptr, flags, last ? s->rel + 1 : 0, we, mask);
+}
+void sweep_group_done(lexp_pm_sweep* s, const std::vector<int>& owners) {
+    s->rel++;
+    for (int r : owners) { s->last_rel[r] = s->rel; s->has[r] = true; }
+}
+int sweep_advance(lexp_pm_sweep* s) {
+    const int delta = s->rel;
+    for (int r = 0; r < kMaxPeers; r++) s->last_rel[r] -= delta;
+    s->rel = 0;
+    return lexp_pm_advance_epoch(s->ctx, s->mode, delta);
+}
+}  // namespace
+
+int lexp_pm_sweep_create(lexp_ctx* c, int mode, int n_layers, const int* unit_sizes, const int* n_prop, const int* prop_kind, const int* prop_K,
+                         int rank, int world, lexp_pm_sweep** out) {
+    if (!c || !unit_sizes || !n_prop || !prop_kind || !prop_K || !out || n_layers < 1 || mode < 0 || mode > 1 || world < 1 || world > kMaxPeers ||
+        rank < 0 || rank >= world)
+        return fail(LEXP_ERR_INVALID, "bad argument");
+    auto s = std::unique_ptr<lexp_pm_sweep>(new lexp_pm_sweep());
+    s->ctx = c; s->mode = mode; s->rank = rank; s->world = world;
+    for (int r = 0; r < kMaxPeers; r++) { s->last_rel[r] = 0; s->has[r] = false; }
+    const int W = c->p.width, H = c->p.height, windR = c->p.windR;
+    int cell_base = 0, pk = 0;
+    auto cleanup = [&]() { for (auto& g : s->sched) lexp_plan_destroy(g.plan); lexp_plan_destroy(s->init_plan); };
+    for (int li = 0; li < n_layers; li++) {
+        s->proposers.emplace_back();
+        for (int j = 0; j < n_prop[li]; j++, pk++) {
+            if ((prop_kind[pk] != LEXP_PROP_EXPANSION && prop_kind[pk] != LEXP_PROP_RANDOM) || prop_K[pk] < 0) { cleanup(); return fail(LEXP_ERR_INVALID, "proposer kinds: LEXP_PROP_EXPANSION / LEXP_PROP_RANDOM"); }
+            s->proposers.back().push_back({prop_kind[pk], prop_K[pk]});
+        }
+        int hb = 0, wb = 0;
+        int rc = lexp_layer_geometry(W, H, windR, unit_sizes[li], &hb, &wb, nullptr, nullptr, nullptr, nullptr);
+        if (rc) { cleanup(); return rc; }
+        const int n = hb * wb;
+        std::vector<lexp_rect> unit(n), shared(n), filt(n);
+        std::vector<int> group_of(n);
+        rc = lexp_layer_geometry(W, H, windR, unit_sizes[li], &hb, &wb, unit.data(), shared.data(), filt.data(), group_of.data());
+        if (rc) { cleanup(); return rc; }
+        for (int g = 0; g < 16; g++) {   // disjointRegionSets in group order, empty ones erased (LayerManager.h:168-182)
+            std::vector<int> cells;
+            for (int r = 0; r < n; r++) if (group_of[r] == g) cells.push_back(r);
+            if (cells.empty()) continue;
+            lexp_pm_sweep::Group G{nullptr, li, (int)std::count_if(s->sched.begin(), s->sched.end(), [li](const lexp_pm_sweep::Group& x) { return x.layer == li; }), {}};
+            for (int r = 0; r < world; r++) if ((int)cells.size() > r) G.owners.push_back(r);   // round-robin deal: rank r owns cells[r::world]
+            std::vector<lexp_rect> f, t, u;
+            std::vector<int> ids;
+            for (size_t k = (size_t)rank; k < cells.size(); k += (size_t)world) { f.push_back(filt[cells[k]]); t.push_back(shared[cells[k]]); u.push_back(unit[cells[k]]); ids.push_back(cell_base + cells[k]); }
+            if (!f.empty()) {
+                rc = lexp_plan_create(c, (int)f.size(), f.data(), t.data(), &G.plan);
+                if (!rc) rc = lexp_plan_set_units(G.plan, u.data(), ids.data());
+                if (rc) { lexp_plan_destroy(G.plan); cleanup(); return rc; }
+            }
+            s->sched.push_back(G);
+        }
+        if (li == 0) {   // initCurrentFast: filterRegion = unit +- windR (FastGCStereo.h:109-110)
+            s->n_init = n;
+            std::vector<lexp_rect> f, u;
+            for (int r = rank; r < n; r += world) {
+                const lexp_rect& q = unit[r];
+                const int x0 = std::max(q.x - windR, 0), y0 = std::max(q.y - windR, 0), x1 = std::min(q.x + q.width + windR, W), y1 = std::min(q.y + q.height + windR, H);
+                f.push_back(lexp_rect{x0, y0, x1 - x0, y1 - y0}); u.push_back(q); s->init_index.push_back(r);
+            }
+            for (int r = 0; r < world; r++) if (n > r) s->init_owners.push_back(r);
+            if (!f.empty()) {
+                rc = lexp_plan_create(c, (int)f.size(), f.data(), u.data(), &s->init_plan);
+                if (!rc) rc = lexp_plan_set_units(s->init_plan, u.data(), s->init_index.data());
+                if (rc) { cleanup(); return rc; }
+            }
+        }
+        cell_base += n;
+    }
+    *out = s.release();
+    return LEXP_OK;
+}
+
+int lexp_pm_sweep_destroy(lexp_pm_sweep* s) {
+    if (!s) return LEXP_OK;
+    for (auto& g : s->sched) lexp_plan_destroy(g.plan);
+    lexp_plan_destroy(s->init_plan);
+    delete s;
+    return LEXP_OK;
+}
+
+int lexp_pm_sweep_num_init_labels(const lexp_pm_sweep* s) { return s ? s->n_init : 0; }
+
+int lexp_pm_sweep_init(lexp_pm_sweep* s, const lexp_plane* labels) {
+    if (!s || !labels) return fail(LEXP_ERR_INVALID, "bad argument");
+    int rc = lexp_pm_reset_sync(s->ctx);
+    if (rc) return rc;
+    if (s->init_plan) {
+        std::vector<lexp_plane> mine;
+        for (int r : s->init_index) mine.push_back(labels[r]);
+        rc = sweep_step(s, s->init_plan, 0, LEXP_PROP_LIST, 0, 0, mine.data(), LEXP_PM_INIT, true, true);
+        if (rc) return rc;
+    }
+    sweep_group_done(s, s->init_owners);
+    return sweep_advance(s);
+}
+
+int lexp_pm_sweep_iteration(lexp_pm_sweep* s, int iteration, uint64_t seed, int* n_launches) {
+    if (!s || iteration < 0) return fail(LEXP_ERR_INVALID, "bad argument");
+    int rc = lexp_pm_reset_sync(s->ctx);
+    if (rc) return rc;
+    const float range = s->ctx->p.max_disp - s->ctx->p.min_disp;
+    int launches = 0;
+    for (auto& g : s->sched) {
+        if (g.plan) {
+            std::vector<std::pair<int, int>> steps;   // (kind, m) as the `while (prop->isContinued())` loops produce them (FastGCStereo.h:41-46)
+            for (auto& pr : s->proposers[g.layer])
+                for (int it = 0; it < pr.second; it++) {
+                    if (pr.first == LEXP_PROP_RANDOM && (double)(range * exp2f(-(float)(iteration + it + 1))) < 0.1) break;   // Proposer.h:149-152
+                    steps.push_back({pr.first, pr.first == LEXP_PROP_RANDOM ? iteration + it : 0});
+                }
+            for (size_t k = 0; k < steps.size(); k++) {
+                rc = sweep_step(s, g.plan, (int)k, steps[k].first, steps[k].second, pm_launch_seed(seed, s->mode, iteration, g.layer, g.group, (int)k), nullptr, 0,
+                                k == 0, k + 1 == steps.size());
+                if (rc) return rc;
+                launches++;
+            }
+        }
+        sweep_group_done(s, g.owners);
+    }
+    if (n_launches) *n_launches = launches;
+    return sweep_advance(s);
 }
 
 // LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).

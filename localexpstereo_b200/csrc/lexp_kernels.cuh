@@ -28,8 +28,14 @@
 
 namespace lexp {
 
+#if defined(LEXP_STATS_TMA) && LEXP_STATS_TMA && !defined(LEXP_EMU)
+#define LEXP_TMA_ON 1
+#else
+#define LEXP_TMA_ON 0
+#endif
 constexpr int kWarpsA = 4, kWarpsH = 2, kWarpsC = 3, kWarpsE = 2;
-constexpr int kThreads = 32 * (kWarpsA + kWarpsH + kWarpsC + kWarpsE);  // 352
+constexpr int kWarpsT = LEXP_TMA_ON;   // LEXP_STATS_TMA: a 12th warp whose lane 0 feeds team C's statistics ring through the TMA unit
+constexpr int kThreads = 32 * (kWarpsA + kWarpsH + kWarpsC + kWarpsE + kWarpsT);  // 352 (384)
 constexpr int kMaxVW = 32 * kWarpsA;   // virtual tile width  ow + 4R
 constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
 constexpr int kMaxOW = 32 * kWarpsE;   // output columns
@@ -204,8 +210,8 @@ __host__ __device__ inline int srow_stride(int vw) {
 __host__ __device__ inline int stats_w2c(int w2) { return (w2 + 7 + 3) & ~3; }
 __host__ __device__ inline int stats_stage_bytes(int w2) { return kCH * (2 * w2 * 16 + stats_w2c(w2) * 4); }
 __host__ __device__ inline size_t stats_ring_bytes(int w2) {
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
-    return (size_t)LEXP_STATS_STAGES * stats_stage_bytes(w2) + 16 * ((LEXP_STATS_STAGES + 1) / 2);
+#if LEXP_TMA_ON
+    return (size_t)LEXP_STATS_STAGES * stats_stage_bytes(w2) + 16 * LEXP_STATS_STAGES;   // stages, then a full and an empty mbarrier each
 #else
     return 0;
 #endif
@@ -250,7 +256,7 @@ __device__ __forceinline__ F4 f4sub(F4 a, F4 b) { return F4{sub2(a.lo, b.lo), su
 __device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
 
 // ---- mbarrier + bulk asynchronous copy (TMA unit, non-tensor form: contiguous bytes global -> shared) ---------------------
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+#if LEXP_TMA_ON
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
@@ -500,14 +506,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     float* s_dbase = s_invny + 4 * ((it.oh + 4 * R + 3) / 4);        // [VHs] b*y + c of the plane  (NAIVE: int X0 of the warp)
     int* s_Y0 = reinterpret_cast<int*>(s_dbase + 4 * ((it.oh + 4 * R + 3) / 4));  // [VHs] NAIVE: fixed-point source row
     double* s_iM = reinterpret_cast<double*>(s_Y0 + 4 * ((it.oh + 4 * R + 3) / 4));  // [6] NAIVE: inverse affine map of the call
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+#if LEXP_TMA_ON
     // statistics ring of team C (TMA unit): LEXP_STATS_STAGES stages, then their mbarriers; behind s_iM (6 doubles)
     unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_iM) + 48;
     const int stageB = stats_stage_bytes(W2);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + LEXP_STATS_STAGES * stageB);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + LEXP_STATS_STAGES * stageB);   // [NS] completed by the copies' bytes
+    uint64_t* s_empty = s_full + LEXP_STATS_STAGES;                                          // [NS] completed by team C's 96 threads
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < LEXP_STATS_STAGES; i++) mbar_init(s_full + i, 1);
+        for (int i = 0; i < LEXP_STATS_STAGES; i++) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 32 * kWarpsC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int st_xa = max(X0 + R, it.fx), st_xb = min(X0 + R + W2, fx1);   // columns of the tile's (a, b) strip inside the filterRect
@@ -557,12 +564,12 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 const int base = *P.epoch_base;
                 for (int r = 0; r < kMaxPeers; r++)
                     if ((P.wait_mask >> r) & 1u) {
-                        unsigned polls = 0;   // a peer that never arrives (a crashed rank) must not hang this GPU: give up after seconds
-                        while (ld_acquire_sys(P.copy_flags[0] + r) < base + P.wait_epochs[r]) {
+                        unsigned polls = 0;   // a peer that never arrives (a crashed rank) must not hang this GPU: give up after ~10 s,
+                        while (ld_acquire_sys(P.copy_flags[0] + r) < base + P.wait_epochs[r]) {   // and at once when somebody already has
 #ifndef LEXP_EMU
                             __nanosleep(200);
 #endif
-                            if (++polls > (1u << 24)) { atomicExch(P.err_flag, 1); break; }
+                            if (++polls > (1u << 25) || ((polls & 1023u) == 0 && ld_acquire(P.err_flag))) { atomicExch(P.err_flag, 1); break; }
                         }
                     }
             }
@@ -868,23 +875,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const int vmin = st2 ? vE0 : vC0, vmax = st2 ? VHs : vC1;
         const F4* inb = st2 ? hb2 : hb1;
         F4* outb = st2 ? ho2 : ho1;
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
-        // team H2's lane 0 feeds team C's statistics ring.  When H2 has passed consume_begin(2, c), team C has finished iteration c,
-        // in which it read chunk c + 1 out of the ring: the stages of all chunks <= c + 1 are free and are refilled with the chunks
-        // up to c + 1 + NS.  (H2 is the team with the most slack: profiles/r2_fused_ncu_L0.md.)
-        int st_next = 0;
-        if (st2 && lane == 0)
-            for (; st_next < LEXP_STATS_STAGES && st_next < nChunks; st_next++) tma_issue(st_next);
-#endif
         for (int c = 0; c < nChunks; c++) {
             const int v = c * kCH + r;
             consume_begin(lin, c, nin);
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
-            if (st2 && lane == 0 && st_next < nChunks && st_next <= c + 1 + LEXP_STATS_STAGES) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // team C's generic-proxy reads of the stage, then the async-proxy refill
-                for (; st_next < nChunks && st_next <= c + 1 + LEXP_STATS_STAGES; st_next++) tma_issue(st_next);
-            }
-#endif
             produce_begin(lout, c, nout);
             if (k < nruns && v >= vmin && v < vmax) {
                 const F4* in = inb + ((c & 1) * kCH + r) * (st2 ? SW2 : SW) + 9 * k;
@@ -957,7 +950,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const float* pc = P.statC + pix0;
 #if !LEXP_C_ROLLING
         auto issue = [&]() {
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+#if LEXP_TMA_ON
             if (vi < nChunks * kCH) mbar_wait(s_full + ((vi / kCH) % LEXP_STATS_STAGES), (unsigned)(((vi / kCH) / LEXP_STATS_STAGES) & 1));
 #endif
 #pragma unroll
@@ -969,7 +962,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
 #else
                 if (colC && vi >= vC0 && vi < vC1) {
 #endif
-#if LEXP_STATS_TMA && !defined(LEXP_EMU)
+#if LEXP_TMA_ON
                     // the row was staged by the TMA unit (team H2 issues the copies LEXP_STATS_STAGES chunks ahead): shared-memory reads,
                     // one chunk ahead of their use like the global loads they replace
                     const unsigned char* stg = s_ring + ((vi / kCH) % LEXP_STATS_STAGES) * stageB;
@@ -985,6 +978,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 vi++;
                 pa += P.W; pb += P.W; pc += P.W;
             }
+#if LEXP_TMA_ON
+            if (vi <= nChunks * kCH) mbar_arrive(s_empty + ((vi / kCH - 1) % LEXP_STATS_STAGES));   // this thread has read the stage
+#endif
         };
         issue();
         for (int c = 0; c < nChunks; c++) {
@@ -1099,7 +1095,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             produce_end(2, c, kLinkCH);
         }
 #endif
-    } else {
+    } else if (warp < kWarpsA + kWarpsH + kWarpsC + kWarpsE) {
         // =========================================================================== team E
         const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);
         const int XE = it.ox0 + t;
@@ -1240,6 +1236,20 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             }
         }
     }
+#if LEXP_TMA_ON
+    else {
+        // =========================================================================== team T (one lane): the statistics ring's producer
+        // chunk k goes to stage k % NS once team C's 96 threads have read chunk k - NS out of it (empty barrier); NS chunks of lead
+        if (lane == 0)
+            for (int k = 0; k < nChunks; k++) {
+                if (k >= LEXP_STATS_STAGES) {
+                    mbar_wait(s_empty + (k % LEXP_STATS_STAGES), (unsigned)(((k / LEXP_STATS_STAGES) - 1) & 1));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // team C's generic-proxy reads, then the async-proxy refill
+                }
+                tma_issue(k);
+            }
+    }
+#endif
 #if LEXP_TRACE
     if (lane == 0 && P.trace) {
         long long* o = P.trace + ((size_t)blockIdx.x * (kThreads / 32) + warp) * 4;

@@ -261,3 +261,48 @@ class PMSweep:
         if self.init_plan is not None:
             self.init_plan.close()
         self.groups = []
+
+
+class NativePMSweep:
+    """The same PatchMatch phase driven by the library's own schedule object (lexp_pm_sweep_*: what the C++ adapter
+    CudaCostVolumeEnergy::PatchMatchPhase calls): one C call per initialisation / iteration instead of one per proposal step."""
+
+    def __init__(self, energy: CostVolumeEnergy, unit_sizes=None, proposers=None, rank=0, world=1, mode=0):
+        import ctypes as C
+        from ._capi import check, lib
+        self.energy, self.mode = energy, mode
+        units = np.ascontiguousarray(unit_sizes or v3_layer_units(energy.width), dtype=np.int32)
+        props = proposers or V3_PROPOSERS_DEVICE
+        n_prop = np.ascontiguousarray([len(p) for p in props], dtype=np.int32)
+        kinds = np.ascontiguousarray([k for p in props for k, _ in p], dtype=np.int32)
+        Ks = np.ascontiguousarray([K for p in props for _, K in p], dtype=np.int32)
+        h = C.c_void_p()
+        check(lib().lexp_pm_sweep_create(energy._h, mode, len(units), units.ctypes.data, n_prop.ctypes.data, kinds.ctypes.data, Ks.ctypes.data,
+                                         rank, world, C.byref(h)))
+        self._h = h
+        self.num_init_labels = lib().lexp_pm_sweep_num_init_labels(self._h)
+
+    def begin(self, cost=None, labeling=None):
+        self.energy.pm_begin(self.mode, cost, labeling)
+
+    def init(self, labels):
+        from ._capi import check, lib
+        lb = np.ascontiguousarray(labels, dtype=np.float32)
+        assert lb.shape == (self.num_init_labels, 4)
+        check(lib().lexp_pm_sweep_init(self._h, lb.ctypes.data))
+
+    def iteration(self, iteration, seed):
+        import ctypes as C
+        from ._capi import check, lib
+        n = C.c_int(0)
+        check(lib().lexp_pm_sweep_iteration(self._h, int(iteration), int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(n)))
+        return n.value
+
+    def get(self, out_cost=None, out_labeling=None):
+        return self.energy.pm_get(self.mode, out_cost=out_cost, out_labeling=out_labeling)
+
+    def close(self):
+        from ._capi import lib
+        if self._h:
+            lib().lexp_pm_sweep_destroy(self._h)
+            self._h = None

@@ -18,6 +18,9 @@ int main(int argc, char**) {
         gp.evaluate(ps, im, 0, true);
         gp.evaluateTiles(ps, nullptr, 1, false);
         (void)gp.cells(); (void)gp.tileFloats();
+        CudaCostVolumeEnergy::PatchMatchPhase pm(e, 0, {5, 15}, {{{LEXP_PROP_EXPANSION, 1}, {LEXP_PROP_RANDOM, 8}}, {{LEXP_PROP_EXPANSION, 3}}});
+        pm.begin(); pm.begin(im, im); pm.init(ps); (void)pm.iteration(0, 1234u); pm.get(im, im);
+        if (e.failed()) e.throwIfFailed();
         CudaNaiveStereoEnergy n(im, im, Parameters(), 63.f);
         n.ComputeUnaryPotential(r, r, im, Plane{0, 0, 0, 0}, ru, 1);
     }

@@ -29,3 +29,7 @@ def test_emu_pm_phase_replay_r10(devmem):
 
 def test_emu_pm_phase_cell_shard_two_ranks_in_one_process():
     _pm.test_pm_phase_cell_shard_two_ranks_in_one_process()
+
+
+def test_emu_native_sweep_object_equals_the_python_schedule():
+    _pm.test_native_sweep_object_equals_the_python_schedule()

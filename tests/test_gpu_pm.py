@@ -169,3 +169,33 @@ def test_pm_phase_cell_shard_two_ranks_in_one_process():
     finally:
         for E in Es:
             E.close()
+
+
+def test_native_sweep_object_equals_the_python_schedule():
+    """lexp_pm_sweep_* (the schedule object of the library, used by the C++ adapter) against sweep.PMSweep (one C call per proposal
+    step): same launches, same seeds, same epochs -> bit-identical state, over an initialisation and two iterations including a
+    RandomProposer that stops early in the second one."""
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import PMSweep, NativePMSweep
+    from localexpstereo_b200 import synth
+    H, W, D, windR = 96, 128, 12, 12
+    imL, imR, volL, volR = make_scene(H, W, D)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 7)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]   # 11 * 0.5^(it + i + 1) < 0.1 stops Random early
+    outs = []
+    launches = []
+    for cls in (PMSweep, NativePMSweep):
+        E = L.CostVolumeEnergy(imL, None, volL, None, prm, D - 1)
+        S = cls(E, unit_sizes=[8, 22], proposers=props)
+        try:
+            n0 = len(S.init_units) if cls is PMSweep else S.num_init_labels
+            lm = L.LayerManager(W, H, windR).addLayer(8)
+            labels = synth.synthetic_planes(lm.unitRegions, 1, D, 5)[0]
+            assert len(labels) == n0
+            S.begin(); S.init(labels)
+            launches.append([S.iteration(it, 77) for it in (0, 3)])
+            outs.append(S.get())
+        finally:
+            S.close(); E.close()
+    assert launches[0] == launches[1] and launches[0][1] < launches[0][0]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
