@@ -1219,7 +1219,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             }
         }
         if (PM) {   // this work item's part of the proposal step is done: publish (release) to the cell's counter
-            if (P.n_copies > 1) __threadfence_system(); else __threadfence();
+            // the peers' copies only have to be complete when the group's epoch is published (last step of the group): the steps of a
+            // cell in between run on this GPU and read its own copy, so a device-scope fence orders them (a system-scope fence waits for
+            // the NVLink round trip of every remote store -- microseconds on the per-step critical path)
+            if (P.n_copies > 1 && P.publish_epoch) __threadfence_system(); else __threadfence();
             __syncwarp();
             if (lane == 0) {
                 atomicAdd(&P.cell_sync[it.call].done, 1);
