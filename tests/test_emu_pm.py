@@ -33,3 +33,7 @@ def test_emu_pm_phase_cell_shard_two_ranks_in_one_process():
 
 def test_emu_native_sweep_object_equals_the_python_schedule():
     _pm.test_native_sweep_object_equals_the_python_schedule()
+
+
+def test_emu_pm_phase_replay_right_view(devmem):
+    _pm.test_pm_phase_replay_right_view(devmem)

@@ -23,14 +23,14 @@ def devmem():
     return _TorchDeviceMemory()
 
 
-def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1234, scene=None):
+def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1234, scene=None, mode=0):
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import PMSweep, expand_proposers, pm_seed
     imL, imR, volL, volR = scene if scene is not None else make_scene(H, W, D)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
-    E = L.CostVolumeEnergy(imL, None, volL, None, prm, D - 1)
-    Or = O.CostVolumeEnergyOracle(imL, None, volL, None, windR, 1e-4, 0.5, D - 1)
-    S = PMSweep(E, unit_sizes=units, proposers=proposers)
+    E = L.CostVolumeEnergy(imL, imR if mode else None, volL, volR if mode else None, prm, D - 1)
+    Or = O.CostVolumeEnergyOracle(imL, imR if mode else None, volL, volR if mode else None, windR, 1e-4, 0.5, D - 1)
+    S = PMSweep(E, unit_sizes=units, proposers=proposers, mode=mode)
     try:
         # ---- device: begin (cost = +inf), initCurrentFast with seeded random labels, `iterations` pm iterations
         rng = O.CvRNG(seed)
@@ -54,7 +54,7 @@ def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1
         lay0 = S.lm.layers[0]
         R = windR
         fr0 = [(max(x - R, 0), max(y - R, 0), min(x + w + R, W) - max(x - R, 0), min(y + h + R, H) - max(y - R, 0)) for (x, y, w, h) in S.init_units]
-        O.pm_step(Or, S.init_units, S.init_units, fr0, 0, 0, 0, None, cost_o, lab_o, planes=init_labels, init=True)
+        O.pm_step(Or, S.init_units, S.init_units, fr0, 0, 0, 0, None, cost_o, lab_o, planes=init_labels, init=True, mode=mode)
         n_prop = n_same = n_close = 0
         cell_base = np.cumsum([0] + [len(l.unitRegions) for l in S.lm.layers])
         for it in range(iterations):
@@ -64,13 +64,13 @@ def run_pm_replay(devmem, H, W, D, windR, units, proposers, iterations=1, seed=1
                 ids = cell_base[g.layer] + g.cells
                 for k, (kind, m) in enumerate(expand_proposers(proposers[g.layer], it, D - 1.0)):
                     dev_planes = rec_host[(it, g.layer, g.group)][k]
-                    sd = pm_seed(seed, 0, it, g.layer, g.group, k)
+                    sd = pm_seed(seed, mode, it, g.layer, g.group, k)
                     for i, u in enumerate(us):   # (1) the oracle's proposer on the oracle's state
                         mine = O.pm_proposal(kind, m, O.pm_rng_state(sd, ids[i]), lab_o, u, 0.0, D - 1.0)
                         n_prop += 1
                         n_same += int(np.array_equal(mine, dev_planes[i]))
                         n_close += int(np.allclose(mine, dev_planes[i], rtol=2e-6, atol=1e-6))
-                    O.pm_step(Or, us, ts, fs, 0, 0, 0, None, cost_o, lab_o, planes=dev_planes)
+                    O.pm_step(Or, us, ts, fs, 0, 0, 0, None, cost_o, lab_o, planes=dev_planes, mode=mode)
         return dict(cost_d=cost_d, lab_d=lab_d, cost_o=cost_o, lab_o=lab_o, n_prop=n_prop, n_same=n_same, n_close=n_close)
     finally:
         S.close()
@@ -99,6 +99,13 @@ def test_pm_phase_replay_small(devmem):
     import localexpstereo_b200 as L
     props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 3)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]
     check_pm_result(run_pm_replay(devmem, 72, 96, 12, 12, [8, 22], props, iterations=2, seed=5))
+
+
+def test_pm_phase_replay_right_view(devmem):
+    """mode = 1 (the right view of doDual runs, FastGCStereo.h:145-157): its own volume, guide and state."""
+    import localexpstereo_b200 as L
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 2)], [(L.PROP_EXPANSION, 1)]]
+    check_pm_result(run_pm_replay(devmem, 60, 80, 10, 12, [8, 22], props, iterations=1, seed=11, mode=1))
 
 
 def test_pm_phase_replay_r10(devmem):
