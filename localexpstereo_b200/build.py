@@ -24,7 +24,7 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    # LEXP_NVCC_DEFS: extra -D flags for build-time kernel variants (experiments only, e.g. "-DLEXP_OCC3"); a variant build is
+    # LEXP_NVCC_DEFS: extra -D flags for build-time kernel variants (experiments only, e.g. "-DLEXP_STATS_TMA=1"); a variant build is
     # always forced and the next plain build() restores the default kernel because the .so is older than this marker
     extra = os.environ.get("LEXP_NVCC_DEFS", "").split()
     marker = SO + ".variant"

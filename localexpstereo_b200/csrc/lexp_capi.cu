@@ -450,7 +450,7 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->pdl = LEXP_PDL && !env_int("LEXP_PDL_OFF", 0);
     c->combine = env_int("LEXP_COMBINE", 1) != 0;
     c->comb_window_us = std::max(0, env_int("LEXP_COMBINE_WINDOW_US", 30));
-    c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", kMinCtas > 2 ? (int)(233472 / kMinCtas - 1024) : 0);
+    c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", 0);
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {

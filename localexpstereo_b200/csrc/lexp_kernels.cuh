@@ -41,24 +41,9 @@ constexpr int kMaxW2 = 32 * kWarpsC;   // (a,b) columns       ow + 2R
 constexpr int kMaxOW = 32 * kWarpsE;   // output columns
 constexpr int kRun = 8;                // columns per H task
 constexpr int kCH = 2;                 // rows per pipeline chunk
-// ---- build-time variants (default: the round-1 kernel; nothing below changes its code) --------------------------------
-// LEXP_OCC3: the "three CTAs per SM" register diet measured only at compile time so far (ptxas: 56 registers, no spills):
-//   gather batches of 4 rows instead of 6, team C re-loads each statistics row as soon as it has been consumed (one
-//   register set instead of two), team H re-reads the elements that leave the window from shared memory instead of
-//   holding them in 28 registers; the planner then caps a work item's shared memory at 75 KB (lexp_capi.cu).
-#ifdef LEXP_OCC3
-#define LEXP_MIN_CTAS 3
-#define LEXP_KG 4
-#define LEXP_C_ROLLING 1
-#define LEXP_H_REREAD 1
-#define LEXP_LINK_STRIDES 1
-#endif
-// LEXP_LINK_STRIDES: the row buffers of the four links get the stride their own width needs (hb1: VW columns, ho1 / hb2:
-//   VW - 2R, ho2: VW - 4R) instead of all using the widest: 5.5 KB less shared memory for a 60-column tile (76.8 -> 71.3 KB at
-//   R = 10), which is what lets three CTAs of the typical layer-0 tile share an SM.
-#ifndef LEXP_LINK_STRIDES
-#define LEXP_LINK_STRIDES 0
-#endif
+// ---- build-time switches -------------------------------------------------------------------------------------------------
+// (round 2 measured and removed the three-CTAs-per-SM register diet and its ingredients -- rolling statistics prefetch, H re-reads,
+//  per-link buffer strides, 4-row gather batches: profiles/r2_variants.md)
 // LEXP_A_ROWTAB: the byte offset of a volume row inside the blocked layout, (y / 4) * block-row pitch + (y % 4) * 16, is looked up
 //   in a per-tile shared-memory table (16-byte units, filled in the prologue next to the plane's b*y + c) instead of being
 //   recomputed with 64-bit multiplies for every row of every column: ~19 -> ~5 address instructions per gathered row in team A.
@@ -93,20 +78,8 @@ constexpr int kCH = 2;                 // rows per pipeline chunk
 #ifndef LEXP_STATS_STAGES
 #define LEXP_STATS_STAGES 4
 #endif
-#ifndef LEXP_MIN_CTAS
-#define LEXP_MIN_CTAS 2
-#endif
-#ifndef LEXP_KG
-#define LEXP_KG 6
-#endif
-#ifndef LEXP_C_ROLLING
-#define LEXP_C_ROLLING 0
-#endif
-#ifndef LEXP_H_REREAD
-#define LEXP_H_REREAD 0
-#endif
-constexpr int kMinCtas = LEXP_MIN_CTAS;  // resident CTAs per SM the kernel is compiled for (register cap 65536 / (kMinCtas * 352))
-constexpr int kG = LEXP_KG;            // rows per gather batch of team A (one batch of loads in flight)
+constexpr int kMinCtas = 2;           // resident CTAs per SM the kernel is compiled for (register cap 65536 / (kMinCtas * kThreads))
+constexpr int kG = 6;                 // rows per gather batch of team A (one batch of loads in flight)
 constexpr float kCostInvalid = 1000000.0f;  // StereoEnergy.h:45
 constexpr int kMaxPeers = 8;                // GPUs of one NVSwitch domain that share a PatchMatch-phase state
 
@@ -219,11 +192,7 @@ __host__ __device__ inline size_t stats_ring_bytes(int w2) {
 __host__ __device__ inline size_t fused_smem_bytes(int vw, int oh, int R) {
     const int K = 2 * R + 1;
     const int vh = oh + 4 * R;
-#if LEXP_LINK_STRIDES
-    const int rows = 2 * kCH * (srow_stride(vw) + 2 * srow_stride(vw - 2 * R) + srow_stride(vw - 4 * R));
-#else
     const int rows = 8 * kCH * srow_stride(vw);
-#endif
     return (size_t)((K * vw + 1) / 2 + K * (vw - 2 * R) + rows + 3 * ((vh + 3) / 4) + 3) * 16 + stats_ring_bytes(vw - 2 * R) + 16;  // + 6 doubles (NAIVE: inverse affine map) + statistics ring + the plane slot (PatchMatch phase) at the very end
 }
 
@@ -481,11 +450,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
     const int X0 = it.ox0 - 2 * R;
     const int W2 = VW - 2 * R;
     const int SW = srow_stride(VW);   // row stride of hb1 (stage-1 column sums, VW columns)
-#if LEXP_LINK_STRIDES
-    const int SW2 = srow_stride(W2), SW3 = srow_stride(it.ow);  // ho1 / hb2 hold W2 columns, ho2 the ow output columns
-#else
     const int SW2 = SW, SW3 = SW;
-#endif
     const int fx1 = it.fx + it.fw, fy1 = it.fy + it.fh;
     // streamed rows y = ys + v, v in [0, VHs): the dependency cone of the tile, minus leading rows above
     // the filterRect (they are zero padding).  Rows >= fy1 are zero rows that flush the running sums.
@@ -732,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const size_t vblk = (size_t)P.Wb * P.D * 64;       // bytes per block row (4 image rows)
 #endif
         const char* vcol = reinterpret_cast<const char*>(P.vol) + ((size_t)(XAc >> 2) * P.D * 16 + (XAc & 3)) * 4;
-#if LEXP_A_ROWTAB && LEXP_MIN_CTAS <= 2 && !defined(LEXP_EMU)
+#if LEXP_A_ROWTAB && !defined(LEXP_EMU)
         // keep the column base as ONE 64-bit pointer (otherwise: offset + uniform base, re-added per row); not with the 56-register
         // diet, where the extra live register pair spills
         asm volatile("" : "+l"(vcol));
@@ -883,7 +848,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 const F4* in = inb + ((c & 1) * kCH + r) * (st2 ? SW2 : SW) + 9 * k;
                 F4* out = outb + ((c & 1) * kCH + r) * (st2 ? SW3 : SW2) + 9 * k;
                 if (R_T > 0) {
-#if !LEXP_H_REREAD
                     F4 w[kRun - 1];
                     F4 s = in[0], s2 = in[1];  // two partial sums: halves the dependent FADD2 chain
                     w[0] = s; w[1] = s2;
@@ -901,22 +865,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                         s = f4add(s, f4sub(in[jn + (jn >> 3)], w[j - 1]));
                         out[j] = s;
                     }
-#else   // same sums in the same order; the 7 elements that leave the window are read again instead of kept in registers
-                    F4 s = in[0], s2 = in[1];
-#pragma unroll
-                    for (int j = 2; j < 2 * R_T + 1; j++) {
-                        const F4 x = in[j + (j >> 3)];
-                        if (j & 1) s2 = f4add(s2, x); else s = f4add(s, x);
-                    }
-                    s = f4add(s, s2);
-                    out[0] = s;
-#pragma unroll
-                    for (int j = 1; j < kRun; j++) {
-                        const int jn = 2 * R_T + j;
-                        s = f4add(s, f4sub(in[jn + (jn >> 3)], in[j - 1]));
-                        out[j] = s;
-                    }
-#endif
                 } else {
                     F4 s = in[0];
                     for (int j = 1; j < K; j++) s = f4add(s, in[sidx(j)]);
@@ -948,7 +896,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
         const float4* pa = P.statA + pix0;
         const float4* pb = P.statB + pix0;
         const float* pc = P.statC + pix0;
-#if !LEXP_C_ROLLING
         auto issue = [&]() {
 #if LEXP_TMA_ON
             if (vi < nChunks * kCH) mbar_wait(s_full + ((vi / kCH) % LEXP_STATS_STAGES), (unsigned)(((vi / kCH) / LEXP_STATS_STAGES) & 1));
@@ -1035,66 +982,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                 produce_end(2, c, kLinkCH);
             }
         }
-#else
-        // LEXP_C_ROLLING: each statistics row is re-loaded (for the next chunk) right after it has been copied out, so only one
-        // register set + one row is live instead of two sets; the loads of chunk c + 1 are issued while chunk c is processed
-        unsigned pix = (unsigned)pix0;  // one 32-bit pixel index instead of three 64-bit row pointers (H * W < 2^32)
-        auto issue_row = [&](int r) {
-            sa[r] = make_float4(0.f, 0.f, 0.f, 0.f); sb[r] = sa[r]; sc[r] = 0.f;
-            if (colC && vi >= vC0 && vi < vC1) {
-                sa[r] = __ldg(P.statA + pix);
-                sb[r] = __ldg(P.statB + pix);
-                sc[r] = __ldg(P.statC + pix);
-            }
-            vi++;
-            pix += (unsigned)P.W;
-        };
-#pragma unroll
-        for (int r = 0; r < kCH; r++) issue_row(r);
-        for (int c = 0; c < nChunks; c++) {
-            consume_begin(1, c, kLinkHC);
-            produce_begin(2, c, kLinkCH);
-            const F4* ho = ho1 + (c & 1) * kCH * SW2 + sidx(t < W2 ? t : 0);
-            F4* hb = hb2 + (c & 1) * kCH * SW2 + sidx(t < W2 ? t : 0);
-#pragma unroll
-            for (int r = 0; r < kCH; r++) {
-                LEXP_LOADS_LANDED("+f"(sa[r].x), "+f"(sa[r].y), "+f"(sa[r].z), "+f"(sa[r].w), "+f"(sb[r].x), "+f"(sb[r].y),
-                                  "+f"(sb[r].z), "+f"(sb[r].w), "+f"(sc[r]));
-                const float4 ca = sa[r], cb = sb[r];
-                const float cc = sc[r];
-                issue_row(r);
-                const int v = c * kCH + r;
-                if (t < W2 && v >= vC0 && v < VHs) {
-                    F4 ab = f4zero();
-                    if (colC && v < vC1) {
-                        const float invN = inv_nx * s_invny[v - R];
-                        const F4 B = ho[r * SW2];
-                        float Bp, B0, B1, B2;
-                        up2(B.lo, Bp, B0); up2(B.hi, B1, B2);
-                        const float m0 = ca.x, m1 = ca.y, m2 = ca.z, i00 = ca.w;
-                        const float i01 = cb.x, i02 = cb.y, i11 = cb.z, i12 = cb.w, i22 = cc;
-                        const float mp = Bp * invN;                      // GuidedFilter.h:206
-                        const float c0 = fmaf(B0, invN, -m0 * mp);       // :212-214
-                        const float c1 = fmaf(B1, invN, -m1 * mp);
-                        const float c2 = fmaf(B2, invN, -m2 * mp);
-                        const float a0 = i00 * c0 + i01 * c1 + i02 * c2;  // :216-218
-                        const float a1 = i01 * c0 + i11 * c1 + i12 * c2;
-                        const float a2 = i02 * c0 + i12 * c1 + i22 * c2;
-                        const float bb = mp - a0 * m0 - a1 * m1 - a2 * m2;  // :220
-                        ab = F4{pk2(a0, a1), pk2(a2, bb)};
-                    }
-                    F4* sl = ring2 + slot * W2 + t;
-                    const F4 old = *sl;
-                    *sl = ab;
-                    acc = f4add(acc, f4sub(ab, old));
-                    hb[r * SW2] = acc;  // column sum centred on row y - 2R
-                    slot = (slot + 1 == K) ? 0 : slot + 1;
-                }
-            }
-            consume_end(1, c, nChunks, kLinkHC);
-            produce_end(2, c, kLinkCH);
-        }
-#endif
     } else if (warp < kWarpsA + kWarpsH + kWarpsC + kWarpsE) {
         // =========================================================================== team E
         const int t = tid - 32 * (kWarpsA + kWarpsH + kWarpsC);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Builds the prepared build-time kernel variants of lexp_kernels.cuh next to the product library, as
 variants/liblexp_cuda_<name>.so (git-ignored, but shipped to the GPU box), and prints the ptxas resource lines.
-Run here (nvcc cross-compiles), then `gpurun -- bash scripts/gpu_variants.sh occ3 pdl occ3pdl`."""
+Run here (nvcc cross-compiles), then `gpurun -- bash scripts/gpu_variants.sh tma4 r1`."""
 import os
 import re
 import subprocess
@@ -18,17 +18,7 @@ VARIANTS = {
     "tma3": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=3"],   # team C's statistics staged by the TMA unit (cp.async.bulk + mbarrier ring)
     "tma4": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=4"],
     "tma5": ["-DLEXP_STATS_TMA=1", "-DLEXP_STATS_STAGES=5"],
-    "occ3": ["-DLEXP_OCC3"],                        # 3 CTAs / SM: 56 registers, 75 KB shared-memory cap
-    "pdl": ["-DLEXP_PDL=1"],                        # programmatic dependent launch between batched evaluations
-    "occ3pdl": ["-DLEXP_OCC3", "-DLEXP_PDL=1"],
-    "kg4": ["-DLEXP_KG=4"],                         # single knobs of occ3 at 2 CTAs / SM (register relief only)
-    "crolling": ["-DLEXP_C_ROLLING=1"],
-    "hreread": ["-DLEXP_H_REREAD=1"],
-    "linkstr": ["-DLEXP_LINK_STRIDES=1"],           # per-link row-buffer strides at 2 CTAs / SM: 5.5 KB less shared memory, more L1
-    "rowtab": ["-DLEXP_A_ROWTAB=1"],                # team A: row-offset table instead of 64-bit address arithmetic per gathered row
-    "occ3rowtab": ["-DLEXP_OCC3", "-DLEXP_A_ROWTAB=1"],
     "trace": ["-DLEXP_TRACE=1"],                    # diagnosis: per-team wait / busy cycles of every launch (scripts/gpu_trace.sh)
-    "occ3trace": ["-DLEXP_OCC3", "-DLEXP_TRACE=1"],
 }
 
 

@@ -1,5 +1,5 @@
 # On the GPU box: per-team wait/busy breakdown of the fused kernel (diagnosis build -DLEXP_TRACE=1 from scripts/build_variants.py).
-#   gpurun --timeout 900 -- bash scripts/gpu_trace.sh [trace|occ3trace]
+#   gpurun --timeout 900 -- bash scripts/gpu_trace.sh [trace]
 cd $GRAFT_REPO_ROOT
 V=${1:-trace}
 mkdir -p gpurun_out

@@ -1,4 +1,4 @@
-# On the GPU box (gpurun -- bash scripts/gpu_variants.sh occ3 pdl occ3pdl): A/B the prepared kernel variants built by
+# On the GPU box (gpurun -- bash scripts/gpu_variants.sh tma4 r1): A/B the prepared kernel variants built by
 # scripts/build_variants.py.  For each: swap the library in, run the fast GPU parity tests, then a short bench; results go to
 # gpurun_out/variants.txt.  The shipped library is restored at the end.
 cd $GRAFT_REPO_ROOT

@@ -12,9 +12,7 @@ if HERE not in sys.path:
 
 _emu = {}
 
-VARIANTS = {"": (), "r1": ("-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"), "occ3": ("-DLEXP_OCC3",), "pdl": ("-DLEXP_PDL=1",), "occ3pdl": ("-DLEXP_OCC3", "-DLEXP_PDL=1"),
-            "trace": ("-DLEXP_TRACE=1",), "linkstr": ("-DLEXP_LINK_STRIDES=1",),
-            "rowtab": ("-DLEXP_A_ROWTAB=1",), "occ3rowtab": ("-DLEXP_OCC3", "-DLEXP_A_ROWTAB=1")}  # build-time kernel variants (lexp_kernels.cuh), "" = the shipped kernel
+VARIANTS = {"": (), "r1": ("-DLEXP_PDL=0", "-DLEXP_A_ROWTAB=0"), "trace": ("-DLEXP_TRACE=1",)}  # build-time kernel variants (lexp_kernels.cuh), "" = the shipped kernel
 
 
 def load(variant=""):

@@ -1,6 +1,6 @@
 """Other prepared build-time kernel variants (lexp_kernels.cuh) on the CPU emulator: they must stay correct whatever their
-speed turns out to be (scripts/gpu_variants.sh measures that on a B200).  `pdl` = programmatic dependent launch (the
-griddepcontrol instructions themselves are no-ops here: launches run one after the other), `occ3pdl` = both."""
+speed turns out to be (scripts/gpu_variants.sh measures that on a B200): the round-1 kernel (programmatic dependent launch and
+the row-offset table switched off) and the diagnosis build."""
 import numpy as np
 import pytest
 
@@ -8,7 +8,7 @@ from emu import emu_lib
 import test_gpu_golden as _g
 
 
-@pytest.mark.parametrize("variant", ["r1", "trace", "occ3rowtab"])  # r1 = PDL and ROWTAB (round-2 defaults) off; occ3 (incl. link strides): tests/test_emu_occ3.py
+@pytest.mark.parametrize("variant", ["r1", "trace"])  # r1 = PDL and ROWTAB (round-2 defaults) off
 def test_variant_reproduces_golden_vectors_and_the_shipped_kernel(variant, monkeypatch, tmp_path):
     import lexp_golden
     monkeypatch.setenv("LEXP_TRACE_FILE", str(tmp_path / "trace.txt"))  # only the `trace` (diagnosis) build writes it

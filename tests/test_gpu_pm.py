@@ -112,7 +112,7 @@ def test_pm_phase_replay_r10(devmem):
     """The R = 10 instantiation (windR 20, the BASELINE configuration), three layers with multi-tile cells in the last one."""
     import localexpstereo_b200 as L
     props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 4)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]
-    check_pm_result(run_pm_replay(devmem, 150, 210, 24, 20, [10, 31, 70], props, iterations=1, seed=9))
+    check_pm_result(run_pm_replay(devmem, 120, 170, 16, 20, [10, 31, 56], props, iterations=1, seed=9))
 
 
 def test_pm_phase_full_sweep_on_the_cones_crop(devmem):
@@ -137,11 +137,11 @@ def test_pm_phase_cell_shard_two_ranks_in_one_process():
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import PMSweep
     from localexpstereo_b200 import synth
-    H, W, D, windR = 96, 128, 12, 12
+    H, W, D, windR = 72, 100, 12, 12
     imL, imR, volL, volR = make_scene(H, W, D)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
-    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 3)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1)]]
-    units = [8, 20, 44]   # the last layer has groups with a single cell: one rank sits those groups out
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 2)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1)]]
+    units = [8, 20, 36]   # the last layer has groups with a single cell: one rank sits those groups out
     Es = [L.CostVolumeEnergy(imL, None, volL, None, prm, D - 1) for _ in range(3)]
     try:
         single = PMSweep(Es[2], unit_sizes=units, proposers=props)
@@ -185,10 +185,10 @@ def test_native_sweep_object_equals_the_python_schedule():
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import PMSweep, NativePMSweep
     from localexpstereo_b200 import synth
-    H, W, D, windR = 96, 128, 12, 12
+    H, W, D, windR = 64, 88, 12, 12
     imL, imR, volL, volR = make_scene(H, W, D)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
-    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 7)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]   # 11 * 0.5^(it + i + 1) < 0.1 stops Random early
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 7)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)]]   # 11 * 0.5^(it + i + 1) < 0.1 stops Random early
     outs = []
     launches = []
     for cls in (PMSweep, NativePMSweep):
