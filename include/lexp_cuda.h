@@ -156,6 +156,12 @@ LEXP_API void* lexp_stream(lexp_ctx* ctx);
 /* Run all subsequent work of this context on the caller's stream (e.g. torch's current stream, or a stream that is
  * being captured into a CUDA graph: lexp_plan_eval_device* issue only graph-capturable work).  Does not synchronise. */
 LEXP_API int lexp_set_stream(lexp_ctx* ctx, void* cuda_stream);
+/* Opt in to overlapping launches (programmatic dependent launch) for lexp_plan_eval_device[_tiles] with planes_on_device != 0: a launch
+ * may then start -- and read its plane array -- while the context's previous launches are still running (it fills their partly empty
+ * last wave; outputs stay ordered).  The caller guarantees that the plane arrays are complete before the PREVIOUS launch of the context was
+ * issued (e.g. all proposal steps generated up front).  Off by default; launches whose planes come from the host never overlap; the
+ * PatchMatch phase orders itself by flags and always overlaps. */
+LEXP_API int lexp_set_overlap(lexp_ctx* ctx, int on);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 LEXP_API int64_t lexp_launch_count(const lexp_ctx* ctx);
 /* Concurrent lexp_eval_cell calls (the OpenMP loop of FastGCStereo.h:30-49, one blocking call per cell and thread) are

@@ -58,6 +58,7 @@ SYMBOLS = {
     "lexp_sync": (C.c_int, [_P]),
     "lexp_stream": (_P, [_P]),
     "lexp_set_stream": (C.c_int, [_P, _P]),
+    "lexp_set_overlap": (C.c_int, [_P, C.c_int]),
     "lexp_launch_count": (C.c_int64, [_P]),
     "lexp_combine_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lexp_pm_begin": (C.c_int, [_P, C.c_int, _P, _P]),

@@ -121,6 +121,7 @@ struct lexp_ctx {
     int num_sms = 148;
     int ctas_per_sm = kMinCtas;  // CTA slots per SM the planner fills (LEXP_CTAS_PER_SM)
     bool pdl = false;            // launch with programmatic stream serialization (builds with -DLEXP_PDL=1; LEXP_PDL_OFF=1 disables)
+    bool overlap = false;        // lexp_set_overlap: launches with device-resident planes may overlap their predecessors
     size_t smem_cap = 0;         // upper bound on a work item's dynamic shared memory, 0: none (LEXP_SMEM_CAP)
     size_t smem_limit = 0;
     size_t window_max = 0;
@@ -312,8 +313,12 @@ struct PmArgs {   // PatchMatch phase (lexp_plan_pm_step); nullptr = plain unary
     unsigned wait_mask;
 };
 
+// overlap_ok: the launch may start while the previous launches of the stream are still running (programmatic dependent launch).
+// Only when nothing this launch reads at its start was produced by the work right before it in the stream: never after a
+// host-to-device copy of its planes (measured: such a launch can read the plane array before the copy has landed), and for
+// device-resident planes only if the caller opted in (lexp_set_overlap).
 int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float* d_out, long long pitch, int compact,
-             int with_check, const PmArgs* pm = nullptr) {
+             int with_check, const PmArgs* pm = nullptr, bool overlap_ok = false) {
     if (mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "mode must be 0 or 1");
     if (c->p.energy_kind == 1) {
         if (!c->d_exi[0] || !c->d_exi[1]) return fail(LEXP_ERR_STATE, "NaiveStereoEnergy needs the images of both views");
@@ -372,9 +377,9 @@ int run_plan(lexp_ctx* c, lexp_plan* pl, int mode, const Plane4* d_planes, float
         kp.err_flag = c->d_flags[mode] + kMaxPeers + 1;
         kp.launch_done = reinterpret_cast<int*>(kp.cell_sync + pl->ncalls);
     }
-    // PatchMatch phase: every launch may start early (programmatic dependent launch); the steps of a cell are ordered by its
-    // counters, the groups by epoch flags (lexp_plan_pm_step_ex)
-    return launch_fused(c, kp, pl->nitems, pl->smem, true);
+    // PatchMatch phase with device-side proposers: every launch may start early; the steps of a cell are ordered by its counters, the
+    // groups by epoch flags (lexp_plan_pm_step_ex)
+    return launch_fused(c, kp, pl->nitems, pl->smem, overlap_ok);
 }
 
 // Scan a slab (disparities [d_lo, d_lo + nd) of the caller's volume, on the device) for NaN/Inf and re-lay it out into the context's
@@ -744,7 +749,7 @@ int lexp_plan_eval_device(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane
         LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
         dp = pl->d_planes;
     }
-    return run_plan(c, pl, mode, dp, d_cost_image, step_bytes / 4, 0, with_check);
+    return run_plan(c, pl, mode, dp, d_cost_image, step_bytes / 4, 0, with_check, nullptr, planes_on_device && c->overlap);
 }
 
 int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, int planes_on_device,
@@ -757,7 +762,7 @@ int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp
         LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
         dp = pl->d_planes;
     }
-    return run_plan(c, pl, mode, dp, d_tiles, 0, 1, with_check);
+    return run_plan(c, pl, mode, dp, d_tiles, 0, 1, with_check, nullptr, planes_on_device && c->overlap);
 }
 
 // Host planes in, per-call contiguous tiles out into HOST memory; blocking.  For the step-wise restructured loop
@@ -1057,6 +1062,13 @@ int lexp_set_stream(lexp_ctx* c, void* s) {
 }
 int64_t lexp_launch_count(const lexp_ctx* c) { return c ? c->launches : 0; }
 
+int lexp_set_overlap(lexp_ctx* c, int on) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->overlap = on != 0;
+    return LEXP_OK;
+}
+
 // ---- PatchMatch phase on the device (FastGCStereo.h:94-157 with doGC == false) ---------------------------------------------
 int lexp_pm_begin(lexp_ctx* c, int mode, const float* cost, const lexp_plane* labeling) {
     if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
@@ -1171,7 +1183,7 @@ int lexp_plan_pm_step_ex(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, i
               publish_epoch, {0, 0, 0, 0, 0, 0, 0, 0}, wait_mask};
     if (wait_epochs)
         for (int i = 0; i < kMaxPeers; i++) pm.wait_epochs[i] = wait_epochs[i];
-    return run_plan(c, pl, mode, dp, nullptr, 0, 0, 1, &pm);
+    return run_plan(c, pl, mode, dp, nullptr, 0, 0, 1, &pm, kind != LEXP_PROP_LIST || (planes_on_device && c->overlap));
 }
 
 int lexp_plan_pm_step(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, int kind, int m, uint64_t seed, const lexp_plane* planes,

@@ -376,6 +376,10 @@ class CostVolumeEnergy:
         """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(lib().lexp_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
+    def set_overlap(self, on=True):
+        """Opt in to overlapping launches for eval_device(..., planes_on_device=True): see lexp_set_overlap."""
+        check(lib().lexp_set_overlap(self._h, int(bool(on))))
+
     @property
     def launch_count(self) -> int:
         return int(lib().lexp_launch_count(self._h))
