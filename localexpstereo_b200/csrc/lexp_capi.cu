@@ -1408,13 +1408,14 @@ int lexp_pm_sweep_iteration(lexp_pm_sweep* s, int iteration, uint64_t seed, int*
     const float range = s->ctx->p.max_disp - s->ctx->p.min_disp;
     int launches = 0;
     for (auto& g : s->sched) {
+        std::vector<std::pair<int, int>> steps;   // (kind, m) as the `while (prop->isContinued())` loops produce them (FastGCStereo.h:41-46)
+        for (auto& pr : s->proposers[g.layer])
+            for (int it = 0; it < pr.second; it++) {
+                if (pr.first == LEXP_PROP_RANDOM && (double)(range * exp2f(-(float)(iteration + it + 1))) < 0.1) break;   // Proposer.h:149-152
+                steps.push_back({pr.first, pr.first == LEXP_PROP_RANDOM ? iteration + it : 0});
+            }
+        if (steps.empty()) { sweep_group_done(s, {}); continue; }   // every proposer stopped early: no rank launches or publishes anything
         if (g.plan) {
-            std::vector<std::pair<int, int>> steps;   // (kind, m) as the `while (prop->isContinued())` loops produce them (FastGCStereo.h:41-46)
-            for (auto& pr : s->proposers[g.layer])
-                for (int it = 0; it < pr.second; it++) {
-                    if (pr.first == LEXP_PROP_RANDOM && (double)(range * exp2f(-(float)(iteration + it + 1))) < 0.1) break;   // Proposer.h:149-152
-                    steps.push_back({pr.first, pr.first == LEXP_PROP_RANDOM ? iteration + it : 0});
-                }
             for (size_t k = 0; k < steps.size(); k++) {
                 rc = sweep_step(s, g.plan, (int)k, steps[k].first, steps[k].second, pm_launch_seed(seed, s->mode, iteration, g.layer, g.group, (int)k), nullptr, 0,
                                 k == 0, k + 1 == steps.size());

@@ -248,6 +248,10 @@ class PMSweep:
                     g.plan.pm_step(k, kind, m, pm_seed(seed, self.mode, iteration, li, gi, k), planes=pl, d_planes_out=out, mode=self.mode,
                                    **self.clock.sync_args(k == 0, k == len(steps) - 1))
                     n_launch += 1
+                if not steps:        # every proposer stopped early: nothing is launched for this group on any rank, nothing is published
+                    owners = []
+            elif not expand_proposers(self.proposers[li], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY):
+                owners = []
             self.clock.group_done(owners)
             yield n_launch
         self._advance()
