@@ -122,6 +122,10 @@ struct lexp_ctx {
     int ctas_per_sm = kMinCtas;  // CTA slots per SM the planner fills (LEXP_CTAS_PER_SM)
     bool pdl = false;            // launch with programmatic stream serialization (builds with -DLEXP_PDL=1; LEXP_PDL_OFF=1 disables)
     bool overlap = false;        // lexp_set_overlap: launches with device-resident planes may overlap their predecessors
+    bool chain_ok = false;       // the last operation this context put on its stream was a launch of lexp_fused_kernel: only then may the
+                                 // next launch carry the programmatic-serialization attribute.  After a memcpy / memset (plane upload, counter
+                                 // reset, state upload) the next launch is an ordinary one: a kernel launched with the attribute right after a
+                                 // copy was observed reading the copy's destination before the copy had landed
     size_t smem_cap = 0;         // upper bound on a work item's dynamic shared memory, 0: none (LEXP_SMEM_CAP)
     size_t smem_limit = 0;
     size_t window_max = 0;
@@ -231,7 +235,7 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem, b
         c->smem_configured[PM] = true;
     }
 #if LEXP_PDL && !defined(LEXP_EMU)
-    if (c->pdl && allow_pdl) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
+    if (c->pdl && allow_pdl && c->chain_ok) {  // programmatic dependent launch: see LEXP_PDL in lexp_kernels.cuh
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)nitems); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
@@ -244,6 +248,7 @@ int launch_fused_t(lexp_ctx* c, const KParams& kp_in, int nitems, size_t smem, b
     LEXP_LAUNCH(kern, nitems, kThreads, smem, c->stream, kp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
+    c->chain_ok = true;
 #if LEXP_TRACE
     report_trace(c, nitems);
 #endif
@@ -509,6 +514,7 @@ int lexp_destroy(lexp_ctx* c) {
 int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     if (!c || !bgr || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int H = c->p.height, W = c->p.width;
     const size_t HW = (size_t)H * W;
@@ -554,6 +560,7 @@ int lexp_set_volume_host_ex(lexp_ctx* c, int mode, const float* vol, int transfo
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     { int rc = check_transform(mode, transform); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int D = c->p.ndisp, H = c->p.height, W = c->p.width;
     const size_t plane = (size_t)H * W;
@@ -588,6 +595,7 @@ int lexp_set_volume_device_ex(lexp_ctx* c, int mode, const float* vol, int trans
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     { int rc = check_transform(mode, transform); if (rc) return rc; }
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     cudaPointerAttributes at;
     LEXP_CUDA(cudaPointerGetAttributes(&at, vol));
     if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
@@ -607,6 +615,7 @@ int lexp_get_stats(lexp_ctx* c, int mode, float* out9) {
     if (!c || !out9 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     if (!c->d_statA[mode]) return fail(LEXP_ERR_STATE, "image not set");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const size_t HW = (size_t)c->p.height * c->p.width;
     float* d9 = nullptr;
@@ -748,6 +757,7 @@ int lexp_plan_eval_device(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane
     if (!planes_on_device) {
         LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
         dp = pl->d_planes;
+        c->chain_ok = false;
     }
     return run_plan(c, pl, mode, dp, d_cost_image, step_bytes / 4, 0, with_check, nullptr, planes_on_device && c->overlap);
 }
@@ -761,6 +771,7 @@ int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp
     if (!planes_on_device) {
         LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
         dp = pl->d_planes;
+        c->chain_ok = false;
     }
     return run_plan(c, pl, mode, dp, d_tiles, 0, 1, with_check, nullptr, planes_on_device && c->overlap);
 }
@@ -772,6 +783,7 @@ int lexp_plan_eval_device_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp
 int lexp_plan_eval_host_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, float* tiles, int with_check) {
     if (!c || !pl || !planes || !tiles || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
     void* dptr = nullptr;
@@ -795,6 +807,7 @@ int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
                         ptrdiff_t step_bytes, int with_check) {
     if (!c || !pl || !planes || !cost_image || pl->ctx != c) return fail(LEXP_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     {   // zero-copy path: the caller's image is page-locked + mapped (lexp_host_register)
         void* dptr = nullptr;
@@ -849,6 +862,7 @@ int run_combined(lexp_ctx* c, const std::vector<lexp_ctx::CellReq*>& reqs) {
     for (auto* r : reqs) { nitems += r->pl->h_items.size(); nout += (size_t)r->pl->sum_s; smem = std::max(smem, r->pl->smem); }
     if (nout > 0x7fffffffULL) return fail(LEXP_ERR_INVALID, "combined output too large");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     lexp_ctx::CombBuf& b = c->cb[c->cb_next];
     c->cb_next ^= 1;
@@ -1052,6 +1066,7 @@ void* lexp_stream(lexp_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int lexp_set_stream(lexp_ctx* c, void* s) {
     if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     // no synchronisation here (the call must be legal while the caller captures a CUDA graph): ordering between the
     // old and the new stream is the caller's business
@@ -1073,6 +1088,7 @@ int lexp_set_overlap(lexp_ctx* c, int on) {
 int lexp_pm_begin(lexp_ctx* c, int mode, const float* cost, const lexp_plane* labeling) {
     if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const size_t HW = (size_t)c->p.height * c->p.width;
     if (!c->d_cur_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_cur_cost[mode], HW * sizeof(float)));
@@ -1097,6 +1113,7 @@ int lexp_pm_get(lexp_ctx* c, int mode, float* cost, lexp_plane* labeling) {
     if (!c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const size_t HW = (size_t)c->p.height * c->p.width;
     if (cost) LEXP_CUDA(cudaMemcpyAsync(cost, c->d_cur_cost[mode], HW * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1129,6 +1146,7 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
         h[i] = CallInfo{u.x, u.y, u.width, u.height, pl->items_per_call[i] * kWarpsE, cell_ids ? cell_ids[i] : i, pl->items_per_call[i], 0};
     }
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
@@ -1155,6 +1173,7 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
 int lexp_pm_reset_sync(lexp_ctx* c) {
     if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (c->sync_used) LEXP_CUDA(cudaMemsetAsync(c->d_sync_arena, 0, c->sync_used, c->stream));
     return LEXP_OK;
@@ -1177,6 +1196,7 @@ int lexp_plan_pm_step_ex(lexp_ctx* c, lexp_plan* pl, int mode, int step_index, i
         if (!planes_on_device) {
             LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
             dp = pl->d_planes;
+            c->chain_ok = false;
         }
     }
     PmArgs pm{(flags & LEXP_PM_INIT) ? 2 : 1, kind, m, step_index, (unsigned long long)seed, reinterpret_cast<Plane4*>(d_planes_out),
@@ -1195,6 +1215,7 @@ int lexp_pm_advance_epoch(lexp_ctx* c, int mode, int delta) {
     if (!c || mode < 0 || mode > 1 || delta < 0) return fail(LEXP_ERR_INVALID, "bad argument");
     if (!c->d_flags[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     LEXP_LAUNCH(lexp_add_i32, 1, 1, 0, c->stream, c->d_flags[mode] + kMaxPeers, delta);
     LEXP_CUDA(cudaGetLastError());

@@ -541,10 +541,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
             const CallInfo ci = P.calls[it.call];
             CellSync* cs = P.cell_sync + it.call;
             const int need = P.step_index * ci.n_done_per_step;
-            while (ld_acquire(&cs->done) < need) {
-#ifndef LEXP_EMU
+            for (unsigned polls = 0; ld_acquire(&cs->done) < need;) {   // bounded like every wait in this kernel: an ordering bug or a lost
+#ifndef LEXP_EMU                                                        // peer must surface as an error (lexp_pm_get), never as a hung GPU
                 __nanosleep(100);
 #endif
+                if (++polls > (1u << 25) || ((polls & 1023u) == 0 && ld_acquire(P.err_flag))) { atomicExch(P.err_flag, 1); break; }
             }
             const int ticket = atomicAdd(&cs->ticket, 1);
             Plane4 q;
@@ -561,10 +562,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lexp_fused_kernel(const KP
                     atomicExch(&cs->ready, P.step_index + 1);
                 }
             } else {
-                while (ld_acquire(&cs->ready) < P.step_index + 1) {
+                for (unsigned polls = 0; ld_acquire(&cs->ready) < P.step_index + 1;) {
 #ifndef LEXP_EMU
                     __nanosleep(100);
 #endif
+                    if (++polls > (1u << 25) || ((polls & 1023u) == 0 && ld_acquire(P.err_flag))) { atomicExch(P.err_flag, 1); break; }
                 }
                 const float4 g = __ldcg(reinterpret_cast<const float4*>(&cs->plane));
                 q = Plane4{g.x, g.y, g.z, g.w};

@@ -20,6 +20,11 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a GPU test that hangs (a kernel polling a flag that never comes) must end the process, not the box: pytest-timeout's
+        # thread method exits the interpreter, which tears the CUDA context down (a signal cannot interrupt a blocked driver call)
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(420, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
