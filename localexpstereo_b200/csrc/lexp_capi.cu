@@ -554,8 +554,11 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     return LEXP_OK;
 }
 
-// Host volume float[D][H][W]: uploaded in slabs of disparities through two device staging buffers (the re-layout of one slab
-// overlaps the upload of the next), never as a second full-size device copy (17 GB per view at 4K).
+// Host volume float[D][H][W]: uploaded in slabs of disparities through one device staging buffer, never as a second full-size device
+// copy (17 GB per view at 4K).  Every copy is issued ON THE CONTEXT'S STREAM: the stream is non-blocking, so a plain cudaMemcpy (legacy
+// default stream) is not ordered against its kernels -- and a synchronous copy from pageable memory returns once the data is staged,
+// possibly before the DMA has landed: the re-layout kernel was observed reading a slab that had not arrived yet (flaky 1e-2 cost errors
+// on the GPU).  Stream order also protects the staging buffer: the copy of slab k+1 follows the re-layout of slab k.
 int lexp_set_volume_host_ex(lexp_ctx* c, int mode, const float* vol, int transform) {
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     { int rc = check_transform(mode, transform); if (rc) return rc; }
@@ -568,26 +571,19 @@ int lexp_set_volume_host_ex(lexp_ctx* c, int mode, const float* vol, int transfo
     slab = std::min(D, (slab + 7) / 8 * 8);
     int* d_flag = nullptr;
     { int rc = alloc_volume(c, mode, &d_flag); if (rc) return rc; }
-    float* stage[2] = {nullptr, nullptr};
-    cudaEvent_t freed[2] = {nullptr, nullptr};
+    float* stage = nullptr;
     int rc = LEXP_OK;
-    cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
-        e = cudaMalloc(&stage[i], (size_t)slab * plane * sizeof(float));
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming);
-    }
+    cudaError_t e = cudaMalloc(&stage, (size_t)slab * plane * sizeof(float));
     const int tk = kernel_transform(mode, transform);
-    for (int d_lo = 0, i = 0; d_lo < D && e == cudaSuccess && rc == LEXP_OK; d_lo += slab, i ^= 1) {
+    for (int d_lo = 0; d_lo < D && e == cudaSuccess && rc == LEXP_OK; d_lo += slab) {
         const int nd = std::min(slab, D - d_lo);
-        e = cudaEventSynchronize(freed[i]);   // the re-layout that last read this staging buffer has finished (no-op the first time)
-        if (e == cudaSuccess) e = cudaMemcpy(stage[i], vol + (size_t)d_lo * plane, (size_t)nd * plane * sizeof(float), cudaMemcpyHostToDevice);
+        e = cudaMemcpyAsync(stage, vol + (size_t)d_lo * plane, (size_t)nd * plane * sizeof(float), cudaMemcpyHostToDevice, c->stream);
         if (e != cudaSuccess) break;
-        rc = ingest_slab(c, mode, stage[i], d_lo, nd, tk, d_flag);
-        if (rc == LEXP_OK) e = cudaEventRecord(freed[i], c->stream);
+        rc = ingest_slab(c, mode, stage, d_lo, nd, tk, d_flag);
     }
     if (e != cudaSuccess && rc == LEXP_OK) rc = fail(LEXP_ERR_CUDA, std::string("volume upload: ") + cudaGetErrorString(e));
     const int rc2 = finish_volume(c, mode, d_flag);   // synchronises the stream
-    for (int i = 0; i < 2; i++) { cudaFree(stage[i]); if (freed[i]) cudaEventDestroy(freed[i]); }
+    cudaFree(stage);
     return rc ? rc : rc2;
 }
 
@@ -709,7 +705,9 @@ int lexp_plan_create(lexp_ctx* c, int n, const lexp_rect* filt, const lexp_rect*
     pl->h_items = items;
     cudaError_t e = cudaMalloc(&pl->d_items, items.size() * sizeof(Item));
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_planes, (size_t)n * sizeof(Plane4));
-    if (e == cudaSuccess) e = cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice);
+    // on the context's (non-blocking) stream, then synchronised: a legacy-stream cudaMemcpy is not ordered against the launches that read the items
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_items, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
         cudaFree(pl->d_items); cudaFree(pl->d_planes);
         delete pl;
@@ -1149,8 +1147,8 @@ int lexp_plan_set_units(lexp_plan* pl, const lexp_rect* units, const int* cell_i
     c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     if (!pl->d_calls) LEXP_CUDA(cudaMalloc(&pl->d_calls, (size_t)pl->ncalls * sizeof(CallInfo)));
+    LEXP_CUDA(cudaMemcpyAsync(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice, c->stream));   // stream-ordered (see lexp_plan_create)
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
-    LEXP_CUDA(cudaMemcpy(pl->d_calls, h.data(), h.size() * sizeof(CallInfo), cudaMemcpyHostToDevice));
     if (pl->sync_off < 0) {   // a slice of the context's synchronisation arena (offsets survive a re-allocation of the arena)
         const size_t need = ((size_t)pl->ncalls + 1) * sizeof(CellSync);
         if (c->sync_used + need > c->sync_cap) {
