@@ -250,6 +250,31 @@ LEXP_API int lexp_pm_sweep_init(lexp_pm_sweep* sweep, const lexp_plane* labels_h
  * of kernel launches issued through *n_launches (may be NULL). */
 LEXP_API int lexp_pm_sweep_iteration(lexp_pm_sweep* sweep, int iteration, uint64_t seed, int* n_launches);
 
+/* ---- Pairwise terms and the expansion move on the device: the graph-cut iterations of
+ * FastGCStereo::run (FastGCStereo.h:171-184, localExpansionMovesForLayer_CPU with doGC == true) on the same device-resident state as
+ * the PatchMatch phase (lexp_pm_begin / lexp_pm_get).
+ *
+ * lexp_set_smoothness: Parameters::lambda / omega / th_smooth / epsilon (StereoEnergy.h:14-39; defaults 1, 10, 1, 0.01 as
+ * main.cpp:73 paramsGF).  The coefficient maps smoothnessCoeff[mode][k] of StereoEnergy::initSmoothnessCoeff (StereoEnergy.h:131-163)
+ * are (re)built on the device when first needed after this call or after lexp_set_image.
+ * lexp_get_smooth_coeff: the eight maps without their margin, float[8][H][W] in the reference's neighbour order (StereoEnergy.h:47-56). */
+LEXP_API int lexp_set_smoothness(lexp_ctx* ctx, float lambda, float omega, float th_smooth, float epsilon);
+LEXP_API int lexp_get_smooth_coeff(lexp_ctx* ctx, int mode, float* out8_host);
+/* StereoEnergy::computeSmoothnessTermsExpansion(currentLabeling_m, label1, region, cost00, cost01, cost10, onlyForward = true, mode)
+ * (StereoEnergy.h:398-453) for n (region, proposal) pairs at once, on the current labeling of view `mode` (lexp_pm_begin).  out_host:
+ * per call, back to back, float[3][4][region.height][region.width] = cost00, cost01, cost10 for the forward neighbours NB_GE, NB_EG,
+ * NB_LG, NB_GG (the only ones the reference fills with onlyForward).  Blocking. */
+LEXP_API int lexp_pairwise_terms(lexp_ctx* ctx, int mode, int n, const lexp_rect* regions, const lexp_plane* planes, float* out_host);
+/* One proposal step of a group with the graph-cut move: for every call (cell) of the plan -- proposal (kind / m / seed / planes as
+ * lexp_plan_pm_step), ComputeUnaryPotential on the cell's filterRect, then FastGCStereo::expansionMoveBK on its targetRect
+ * (= sharedRegion): graph of FastGCStereo.h:424-549 from the unary costs, the pairwise terms and the boundary terms, its minimum cut,
+ * and `copyTo / setTo` of cost and label where the proposal wins (FastGCStereo.h:53-59).  The cells of the plan must be pairwise
+ * non-adjacent (a disjoint group of LayerManager, LayerManager.h:168-173).  lexp_plan_set_units first.  Asynchronous, stream ordered.
+ * d_planes_out: optional device array [ncalls] (the plane every call evaluated); d_flows_out: optional device array double[ncalls]
+ * (the value expansionMoveBK returns: the minimum-cut energy of the move). */
+LEXP_API int lexp_plan_gc_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int kind, int m, uint64_t seed, const lexp_plane* planes,
+                               int planes_on_device, lexp_plane* d_planes_out, double* d_flows_out);
+
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
 LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,

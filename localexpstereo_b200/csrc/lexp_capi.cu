@@ -3,6 +3,7 @@
 // launches the sm_100a kernels of lexp_kernels.cuh.  No CPU compute fallback exists here.
 #include "../../include/lexp_cuda.h"
 #include "lexp_kernels.cuh"
+#include "lexp_gc.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -84,6 +85,9 @@ struct lexp_plan {
     long long sync_off = -1;           // byte offset in the context's synchronisation arena of CellSync[ncalls + 1]: per-call completion
                                        // counters / proposal hand-over, then the completion counter of the group's last launch
     std::vector<int> items_per_call;
+    // graph-cut move (lexp_plan_gc_step): region + scratch offset of every call
+    GcCell* d_gc_cells = nullptr;
+    long long gc_nodes = 0;       // sum of the calls' targetRect areas
 };
 
 struct lexp_ctx {
@@ -114,6 +118,14 @@ struct lexp_ctx {
         void* ipc_opened[3 * kMaxPeers] = {};      // cudaIpcOpenMemHandle mappings to close
         int n_opened = 0;
     } peers[2];
+    // pairwise terms / graph-cut move (lexp_gc.cuh)
+    float sm_lambda = 1.0f, sm_omega = 10.0f, sm_th = 1.0f, sm_eps = 0.01f;   // Parameters of main.cpp:73 (paramsGF) / StereoEnergy.h:26-36
+    float4* d_coef[2] = {nullptr, nullptr};        // forward smoothness coefficients {GE, EG, LG, GG} per pixel (smoothnessCoeff[mode])
+    bool coef_valid[2] = {false, false};
+    float* d_prop_cost[2] = {nullptr, nullptr};    // proposalCost image of the graph-cut steps (FastGCStereo.h:25)
+    float* d_gc_scratch = nullptr;                 // kGcWords planes of gc_scratch_nodes words: the residual network of a group's moves
+    long long gc_scratch_nodes = 0;
+    int gc_threads = 1024, gc_relabel_every = 24, gc_max_rounds = 1 << 22;
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
@@ -283,6 +295,7 @@ void release_plan_memory(lexp_plan* pl) {
     cudaFree(pl->d_compact); pl->d_compact = nullptr;
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
     cudaFree(pl->d_calls); pl->d_calls = nullptr;
+    cudaFree(pl->d_gc_cells); pl->d_gc_cells = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -461,6 +474,8 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->combine = env_int("LEXP_COMBINE", 1) != 0;
     c->comb_window_us = std::max(0, env_int("LEXP_COMBINE_WINDOW_US", 30));
     c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", 0);
+    c->gc_threads = std::min(1024, std::max(32, env_int("LEXP_GC_THREADS", 1024) / 32 * 32));
+    c->gc_relabel_every = std::max(1, env_int("LEXP_GC_RELABEL_EVERY", 24));
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
@@ -504,7 +519,10 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_cur_cost[m]);
         cudaFree(c->d_cur_label[m]);
         cudaFree(c->d_flags[m]);
+        cudaFree(c->d_coef[m]);
+        cudaFree(c->d_prop_cost[m]);
     }
+    cudaFree(c->d_gc_scratch);
     cudaFree(c->d_sync_arena);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -518,6 +536,7 @@ int lexp_set_image(lexp_ctx* c, int mode, const uint8_t* bgr, ptrdiff_t step) {
     LEXP_CUDA(cudaSetDevice(c->p.device));
     const int H = c->p.height, W = c->p.width;
     const size_t HW = (size_t)H * W;
+    c->coef_valid[mode] = false;
     std::vector<uchar4> tmp(HW);
     for (int y = 0; y < H; y++) {
         const uint8_t* row = bgr + (ptrdiff_t)y * step;
@@ -1119,6 +1138,7 @@ int lexp_pm_get(lexp_ctx* c, int mode, float* cost, lexp_plane* labeling) {
     int err = 0;
     LEXP_CUDA(cudaMemcpyAsync(&err, c->d_flags[mode] + kMaxPeers + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LEXP_CUDA(cudaStreamSynchronize(c->stream));
+    if (err == 2) return fail(LEXP_ERR_STATE, "a graph-cut move stopped at its round limit: the state is not the result of minimum cuts");
     if (err) return fail(LEXP_ERR_STATE, "a wait for a peer rank's group epoch timed out (multi-GPU cell shard): the state is incomplete");
     return LEXP_OK;
 }
@@ -1216,6 +1236,150 @@ int lexp_pm_advance_epoch(lexp_ctx* c, int mode, int delta) {
     c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     LEXP_LAUNCH(lexp_add_i32, 1, 1, 0, c->stream, c->d_flags[mode] + kMaxPeers, delta);
+    LEXP_CUDA(cudaGetLastError());
+    c->launches++;
+    return LEXP_OK;
+}
+
+// ---- pairwise terms and the graph-cut move (lexp_gc.cuh) ------------------------------------------------------------------------------
+namespace {
+// smoothnessCoeff[mode] on the device (StereoEnergy.h:131-163), rebuilt after lexp_set_image / lexp_set_smoothness.  Caller holds c->mu.
+int ensure_coef(lexp_ctx* c, int mode) {
+    if (c->coef_valid[mode]) return LEXP_OK;
+    if (!c->d_guide[mode]) return fail(LEXP_ERR_STATE, "image of this view not set");
+    const int H = c->p.height, W = c->p.width;
+    if (!c->d_coef[mode]) LEXP_CUDA(cudaMalloc(&c->d_coef[mode], (size_t)H * W * sizeof(float4)));
+    dim3 blk(128), grd((W + 127) / 128, H);
+    LEXP_LAUNCH(lexp_smooth_coeff_kernel, grd, blk, 0, c->stream, c->d_guide[mode], c->d_coef[mode], H, W, c->sm_omega, c->sm_eps);
+    LEXP_CUDA(cudaGetLastError());
+    c->launches++;
+    c->coef_valid[mode] = true;
+    return LEXP_OK;
+}
+int upload_gc_cells(lexp_ctx* c, int n, const lexp_rect* regions, GcCell** d_cells, long long* nodes) {
+    std::vector<GcCell> h((size_t)n);
+    long long at = 0;
+    for (int i = 0; i < n; i++) {
+        h[i] = GcCell{regions[i].x, regions[i].y, regions[i].width, regions[i].height, at};
+        at += (long long)regions[i].width * regions[i].height;
+    }
+    LEXP_CUDA(cudaMalloc(d_cells, (size_t)n * sizeof(GcCell)));
+    LEXP_CUDA(cudaMemcpyAsync(*d_cells, h.data(), (size_t)n * sizeof(GcCell), cudaMemcpyHostToDevice, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));   // h is pageable and local
+    *nodes = at;
+    return LEXP_OK;
+}
+}  // namespace
+
+int lexp_set_smoothness(lexp_ctx* c, float lambda, float omega, float th_smooth, float epsilon) {
+    if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
+    if (!(omega > 0.0f) || !(lambda >= 0.0f) || !(th_smooth >= 0.0f) || !(epsilon >= 0.0f)) return fail(LEXP_ERR_INVALID, "bad smoothness parameters");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->sm_lambda = lambda; c->sm_omega = omega; c->sm_th = th_smooth; c->sm_eps = epsilon;
+    c->coef_valid[0] = c->coef_valid[1] = false;
+    return LEXP_OK;
+}
+
+int lexp_get_smooth_coeff(lexp_ctx* c, int mode, float* out8) {
+    if (!c || !out8 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    { int rc = ensure_coef(c, mode); if (rc) return rc; }
+    const int H = c->p.height, W = c->p.width;
+    const size_t HW = (size_t)H * W;
+    float* d8 = nullptr;
+    LEXP_CUDA(cudaMalloc(&d8, 8 * HW * sizeof(float)));
+    dim3 blk(128), grd((W + 127) / 128, H);
+    LEXP_LAUNCH(lexp_smooth_coeff_unpack, grd, blk, 0, c->stream, c->d_coef[mode], d8, H, W);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out8, d8, 8 * HW * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d8);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("get_smooth_coeff: ") + cudaGetErrorString(e));
+    return LEXP_OK;
+}
+
+int lexp_pairwise_terms(lexp_ctx* c, int mode, int n, const lexp_rect* regions, const lexp_plane* planes, float* out_host) {
+    if (!c || !regions || !planes || !out_host || n <= 0 || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_label[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    const int H = c->p.height, W = c->p.width;
+    for (int i = 0; i < n; i++)
+        if (regions[i].width <= 0 || regions[i].height <= 0 || regions[i].x < 0 || regions[i].y < 0 || regions[i].x + regions[i].width > W ||
+            regions[i].y + regions[i].height > H) return fail(LEXP_ERR_INVALID, "region outside the image");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    { int rc = ensure_coef(c, mode); if (rc) return rc; }
+    GcCell* d_cells = nullptr;
+    Plane4* d_planes = nullptr;
+    float* d_out = nullptr;
+    long long nodes = 0;
+    int rc = upload_gc_cells(c, n, regions, &d_cells, &nodes);
+    cudaError_t e = cudaSuccess;
+    if (rc == LEXP_OK) {
+        e = cudaMalloc(&d_planes, (size_t)n * sizeof(Plane4));
+        if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)nodes * 12 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes, planes, (size_t)n * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            LEXP_LAUNCH(lexp_pairwise_kernel, n, 256, 0, c->stream, d_cells, d_planes, c->d_cur_label[mode], c->d_coef[mode], d_out, H, W, c->sm_lambda, c->sm_th);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)nodes * 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(d_cells); cudaFree(d_planes); cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("pairwise_terms: ") + cudaGetErrorString(e));
+    return LEXP_OK;
+}
+
+int lexp_plan_gc_step(lexp_ctx* c, lexp_plan* pl, int mode, int kind, int m, uint64_t seed, const lexp_plane* planes, int planes_on_device,
+                      lexp_plane* d_planes_out, double* d_flows_out) {
+    if (!c || !pl || pl->ctx != c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (kind < LEXP_PROP_LIST || kind > LEXP_PROP_RANDOM || m < 0 || m > 120) return fail(LEXP_ERR_INVALID, "bad proposer kind / m");
+    if (kind == LEXP_PROP_LIST && !planes) return fail(LEXP_ERR_INVALID, "LEXP_PROP_LIST needs planes");
+    if (!pl->d_calls) return fail(LEXP_ERR_STATE, "lexp_plan_set_units has not been called for this plan");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    c->chain_ok = false;   // copies / other kernels around the fused launch: it is an ordinary one
+    { int rc = ensure_coef(c, mode); if (rc) return rc; }
+    const int H = c->p.height, W = c->p.width;
+    if (!c->d_prop_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_prop_cost[mode], (size_t)H * W * sizeof(float)));
+    if (!pl->d_gc_cells) { int rc = upload_gc_cells(c, pl->ncalls, pl->targ.data(), &pl->d_gc_cells, &pl->gc_nodes); if (rc) return rc; }
+    if (pl->gc_nodes > c->gc_scratch_nodes) {   // the residual network of the largest group so far
+        LEXP_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_gc_scratch); c->d_gc_scratch = nullptr; c->gc_scratch_nodes = 0;
+        LEXP_CUDA(cudaMalloc(&c->d_gc_scratch, (size_t)pl->gc_nodes * kGcWords * sizeof(float)));
+        c->gc_scratch_nodes = pl->gc_nodes;
+    }
+    // (1) the proposals (FastGCStereo.h:47): the PatchMatch phase's device proposers, or the caller's list
+    Plane4* dp = pl->d_planes;
+    if (kind == LEXP_PROP_LIST) {
+        if (planes_on_device) dp = const_cast<Plane4*>(reinterpret_cast<const Plane4*>(planes));
+        else LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (kind != LEXP_PROP_LIST || d_planes_out) {
+        LEXP_LAUNCH(lexp_gc_propose_kernel, (pl->ncalls + 127) / 128, 128, 0, c->stream, pl->d_calls, pl->ncalls, dp, reinterpret_cast<Plane4*>(d_planes_out),
+                    (unsigned long long)seed, c->d_cur_label[mode], W, kind, m, c->p.min_disp, c->p.max_disp);
+        LEXP_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    // (2) ComputeUnaryPotential(filterRegion, sharedRegion, proposalCost(filterRegion), label) (:49)
+    { int rc = run_plan(c, pl, mode, dp, c->d_prop_cost[mode], W, 0, 1); if (rc) return rc; }
+    c->chain_ok = false;
+    // (3) expansionMoveBK + copyTo / setTo (:53-59)
+    GcParams gp{};
+    gp.cells = pl->d_gc_cells; gp.planes = dp; gp.prop_cost = c->d_prop_cost[mode];
+    gp.cur_cost = c->d_cur_cost[mode]; gp.cur_label = c->d_cur_label[mode]; gp.coef = c->d_coef[mode];
+    gp.scratch = c->d_gc_scratch; gp.scratch_nodes = c->gc_scratch_nodes;
+    gp.flows_out = d_flows_out; gp.iters_out = nullptr; gp.err_flag = c->d_flags[mode] + kMaxPeers + 1;
+    gp.H = H; gp.W = W; gp.lambda = c->sm_lambda; gp.th_smooth = c->sm_th;
+    gp.relabel_every = c->gc_relabel_every; gp.max_rounds = c->gc_max_rounds;
+    LEXP_LAUNCH(lexp_gc_move_kernel, pl->ncalls, c->gc_threads, 0, c->stream, gp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
     return LEXP_OK;

@@ -220,6 +220,21 @@ class Plan:
         check(lib().lexp_plan_pm_step_ex(self.energy._h, self._h, mode, int(step_index), int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                          ptr, int(planes_on_device), int(d_planes_out) or None, 1 if init else 0, int(publish_epoch), we, int(wait_mask)))
 
+    def gc_step(self, kind, m=0, seed=0, planes=None, planes_on_device=False, d_planes_out=0, d_flows_out=0, mode=0):
+        """One proposal step of FastGCStereo.h:41-60 with doGC == true for all cells of the plan, asynchronous: proposal, unary cost,
+        FastGCStereo::expansionMoveBK (graph of :424-549 + its minimum cut) and the copyTo / setTo of the winners -- on the device.
+        d_flows_out: optional device pointer of double[n] receiving the minimum-cut energy of every move."""
+        ptr = None
+        if kind == PROP_LIST:
+            if planes_on_device:
+                ptr = int(planes)
+            else:
+                self._pl_keep = _plane_array(planes)
+                assert len(self._pl_keep) == self.num_calls
+                ptr = self._pl_keep.ctypes.data
+        check(lib().lexp_plan_gc_step(self.energy._h, self._h, mode, int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr,
+                                      int(planes_on_device), int(d_planes_out) or None, int(d_flows_out) or None))
+
     def close(self):
         if self._h:
             lib().lexp_plan_destroy(self._h)
@@ -317,6 +332,32 @@ class CostVolumeEnergy:
         out = np.empty((9, self.height, self.width), dtype=np.float32)
         check(lib().lexp_get_stats(self._h, mode, out.ctypes.data))
         return out
+
+    # --- pairwise terms (StereoEnergy.h:131-163, 398-453) -------------------------------------------------------------------------
+    def set_smoothness(self, lam=1.0, omega=10.0, th_smooth=1.0, epsilon=0.01):
+        """Parameters::lambda / omega / th_smooth / epsilon (StereoEnergy.h:26-36); the coefficient maps are rebuilt on the device."""
+        check(lib().lexp_set_smoothness(self._h, float(lam), float(omega), float(th_smooth), float(epsilon)))
+
+    def smooth_coeff(self, mode=0) -> np.ndarray:
+        """smoothnessCoeff[mode] without its margin: float32 [8][H][W], neighbours in the order of StereoEnergy::NB_*."""
+        out = np.empty((8, self.height, self.width), dtype=np.float32)
+        check(lib().lexp_get_smooth_coeff(self._h, mode, out.ctypes.data))
+        return out
+
+    def computeSmoothnessTermsExpansion(self, regions, planes, mode=0):
+        """StereoEnergy::computeSmoothnessTermsExpansion(.., onlyForward = true) for n (region, proposal) pairs on the device state of
+        view `mode` (pm_begin).  Returns a list of (cost00, cost01, cost10), each float32 [4][h][w] for NB_GE, NB_EG, NB_LG, NB_GG."""
+        rg, pl = _rect_array(regions), _plane_array(planes)
+        assert len(rg) == len(pl)
+        sizes = [int(r[2]) * int(r[3]) for r in rg.reshape(-1, 4)]
+        out = np.empty(12 * sum(sizes), np.float32)
+        check(lib().lexp_pairwise_terms(self._h, mode, len(pl), rg.ctypes.data, pl.ctypes.data, out.ctypes.data))
+        res, at = [], 0
+        for r, n in zip(rg.reshape(-1, 4), sizes):
+            blk = out[at:at + 12 * n].reshape(3, 4, int(r[3]), int(r[2]))
+            res.append((blk[0], blk[1], blk[2]))
+            at += 12 * n
+        return res
 
     # --- PatchMatch phase state: currentCost_[mode] / currentLabeling_[mode] resident on the device ------------------------
     def pm_begin(self, mode=0, cost=None, labeling=None):

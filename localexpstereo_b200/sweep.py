@@ -267,6 +267,35 @@ class PMSweep:
         self.groups = []
 
 
+class GCSweep(PMSweep):
+    """The graph-cut iterations of FastGCStereo::run (FastGCStereo.h:171-184: localExpansionMovesForLayer_CPU with doGC == true) on
+    the same device-resident state and the same (layer, group, proposal step) schedule as the PatchMatch phase: every step is
+    proposals -> ComputeUnaryPotential -> expansionMoveBK (pairwise terms, graph, minimum cut) -> copyTo / setTo, all on the device
+    (Plan.gc_step); the steps are ordered by the stream.  Single-GPU (the cell shard of the PatchMatch phase is not wired here).
+    `begin` / `init` / `iteration` (pm iterations) are inherited; `gc_iteration` is one iteration of the main loop."""
+
+    def __init__(self, energy: CostVolumeEnergy, unit_sizes=None, proposers=None, mode=0, lam=1.0, omega=10.0, th_smooth=1.0, epsilon=0.01):
+        super().__init__(energy, unit_sizes, proposers, 0, 1, mode)
+        energy.set_smoothness(lam, omega, th_smooth, epsilon)
+
+    def gc_iteration(self, iteration, seed, list_planes=None, planes_out=None, flows_out=None):
+        """list_planes / planes_out as PMSweep.iteration; flows_out: optional {(layer, group): device pointer of double [steps][n]}
+        receiving the minimum-cut energy of every move.  Returns the number of proposal steps issued."""
+        E, n = self.energy, 0
+        for (li, gi, g, _owners) in self.schedule:
+            steps = expand_proposers(self.proposers[li], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY)
+            li_at = 0
+            for k, (kind, m) in enumerate(steps):
+                pl = None
+                if kind == PROP_LIST:
+                    pl = list_planes[(li, gi)][li_at]; li_at += 1
+                out = 0 if planes_out is None else planes_out[(li, gi)] + k * g.plan.num_calls * 16
+                fl = 0 if flows_out is None else flows_out[(li, gi)] + k * g.plan.num_calls * 8
+                g.plan.gc_step(kind, m, pm_seed(seed, self.mode, iteration, li, gi, k), planes=pl, d_planes_out=out, d_flows_out=fl, mode=self.mode)
+                n += 1
+        return n
+
+
 class NativePMSweep:
     """The same PatchMatch phase driven by the library's own schedule object (lexp_pm_sweep_*: what the C++ adapter
     CudaCostVolumeEnergy::PatchMatchPhase calls): one C call per initialisation / iteration instead of one per proposal step."""

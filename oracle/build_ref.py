@@ -28,7 +28,7 @@ DROPIN = os.path.join(OUT_DIR, "dropin_check")  # the reference's loop + include
 DROPIN_EMU = os.path.join(OUT_DIR, "dropin_check_emu")  # same program linked to tests/emu/liblexp_emu.so (kernel source on CPU fibers)
 CXX = os.environ.get("LEXP_REF_CXX", "/usr/bin/g++")
 ROOT = os.path.dirname(HERE)
-SOURCES = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(HERE, "dropin_check.cpp"), os.path.join(HERE, "cvshim", "opencv2", "opencv.hpp"),
+SOURCES = [os.path.join(HERE, "ref_driver.cpp"), os.path.join(HERE, "maxflow", "graph.h"), os.path.join(HERE, "refstub", "Evaluator.h"), os.path.join(HERE, "dropin_check.cpp"), os.path.join(HERE, "cvshim", "opencv2", "opencv.hpp"),
            os.path.join(ROOT, "include", "CudaCostVolumeEnergy.h"), os.path.join(ROOT, "include", "lexp_cuda.h"), os.path.abspath(__file__)]
 
 
@@ -46,6 +46,15 @@ def _dialect_fixed_guided_filter(text):
             lines[i] = new
             n += 1
     return "\n".join(lines), n
+
+
+def _dialect_fixed_optimiser(text):
+    """MSVC-only constructs of PMStereoBase.h / FastGCStereo.h: default arguments that bind a temporary to a non-const reference
+    (`cv::Mat& x = cv::Mat()`, PMStereoBase.h:87, FastGCStereo.h:133) and the qualified spelling `NaiveStereoEnergy::Reusable()`
+    (FastGCStereo.h:111,128), both mapped to the shim's `lexp_msvc_default_arg` (a fresh default instance per use)."""
+    new = re.sub(r"(cv::Mat\s*&\s*\w+\s*=\s*)cv::Mat\(\)", r"\1lexp_msvc_default_arg()", text)
+    new = new.replace("NaiveStereoEnergy::Reusable()", "Reusable()")
+    return new, sum(1 for a, b in zip(text.split("\n"), new.split("\n")) if a != b)
 
 
 def available():
@@ -77,8 +86,15 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"dialect fix touched {n} lines of GuidedFilter.h, expected 17: the reference changed")
         with open(os.path.join(gen, "GuidedFilter.h"), "w", encoding="latin-1") as f:
             f.write(fixed)
+        for name, expect in (("PMStereoBase.h", 1), ("FastGCStereo.h", 3)):
+            with open(os.path.join(REF_DIR, name), "r", encoding="latin-1") as f:
+                fixed, n = _dialect_fixed_optimiser(f.read())
+            if n != expect:
+                raise RuntimeError(f"dialect fix touched {n} lines of {name}, expected {expect}: the reference changed")
+            with open(os.path.join(gen, name), "w", encoding="latin-1") as f:
+                f.write(fixed)
         cmd = [CXX, "-std=c++14", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-fpermissive", "-w",
-               "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", REF_DIR,
+               "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", os.path.join(HERE, "refstub"), "-I", REF_DIR,
                os.path.join(HERE, "ref_driver.cpp"), "-o", LIB + ".tmp"]
         if verbose:
             print(" ".join(cmd))
@@ -88,7 +104,7 @@ def build(force=False, verbose=False):
         os.replace(LIB + ".tmp", LIB)
         if have_cuda_lib:  # the drop-in harness needs the product library to link against (it is run on the GPU box only)
             cmd = [CXX, "-std=c++14", "-O2", "-fopenmp", "-ffp-contract=off", "-fpermissive", "-w",
-                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
+                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", os.path.join(HERE, "refstub"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
                    os.path.join(HERE, "dropin_check.cpp"), "-o", DROPIN + ".tmp", "-L", cuda_dir, "-llexp_cuda",
                    "-Wl,-rpath,$ORIGIN/../../localexpstereo_b200"]
             if verbose:
@@ -100,7 +116,7 @@ def build(force=False, verbose=False):
         emu_dir = os.path.join(ROOT, "tests", "emu")
         if os.path.exists(os.path.join(emu_dir, "liblexp_emu.so")):  # CPU twin: the adapter + the kernel source, no GPU
             cmd = [CXX, "-std=c++14", "-O2", "-fopenmp", "-ffp-contract=off", "-fpermissive", "-w",
-                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
+                   "-I", gen, "-I-", "-I", os.path.join(HERE, "cvshim"), "-I", os.path.join(HERE, "refstub"), "-I", REF_DIR, "-I", os.path.join(ROOT, "include"),
                    os.path.join(HERE, "dropin_check.cpp"), "-o", DROPIN_EMU + ".tmp", "-L", emu_dir, "-llexp_emu",
                    "-Wl,-rpath,$ORIGIN/../../tests/emu"]
             r = subprocess.run(cmd, capture_output=True, text=True)

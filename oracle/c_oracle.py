@@ -38,6 +38,7 @@ def lib():
         L.oracle_unary_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_grid_mincut.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -103,3 +104,17 @@ class COracle:
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def grid_mincut(tr, cap):
+    """Minimum cut of an expansion-move graph: tr float32 [h][w] net terminal capacities (source - sink), cap float32 [4][h][w]
+    forward arc capacities (GE, EG, LG, GG).  Returns (mask bool [h][w]: True = SOURCE segment = takes the proposal, max flow)."""
+    tr = np.ascontiguousarray(tr, dtype=np.float32)
+    cap = np.ascontiguousarray(cap, dtype=np.float32)
+    h, w = tr.shape
+    assert cap.shape == (4, h, w)
+    mask = np.empty((h, w), np.uint8)
+    f = C.c_double(0.0)
+    if lib().oracle_grid_mincut(w, h, tr.ctypes.data, cap.ctypes.data, mask.ctypes.data, C.byref(f)):
+        raise MemoryError("oracle_grid_mincut")
+    return mask.astype(bool), f.value

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdarg>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -113,6 +114,7 @@ template <class T> struct Rect_ {
     T x, y, width, height;
     Rect_() : x(0), y(0), width(0), height(0) {}
     Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
+    Rect_(const Point_<T>& p, const Size_<T>& s) : x(p.x), y(p.y), width(s.width), height(s.height) {}
     Point_<T> tl() const { return Point_<T>(x, y); }
     Point_<T> br() const { return Point_<T>(x + width, y + height); }
     Size_<T> size() const { return Size_<T>(width, height); }
@@ -533,6 +535,11 @@ template <class Cmp> inline Mat compare_(const Mat& a, double s, Cmp cmp) {
 }
 inline Mat operator>(const Mat& a, double s) { return compare_(a, s, [](double x, double y) { return x > y; }); }
 inline Mat operator<(const Mat& a, double s) { return compare_(a, s, [](double x, double y) { return x < y; }); }
+inline Mat operator==(const Mat& a, double s) { return compare_(a, s, [](double x, double y) { return x == y; }); }
+// only named by the reference's post-processing / debug output (PMStereoBase.h:165, FastGCStereo.h:165), which the oracle never runs
+inline void dilate(const Mat&, const OutputArray&, const Mat&) { shim_fail("dilate: not part of the hot path"); }
+inline bool imwrite(const std::string&, const Mat&) { return false; }
+inline std::string format(const char* fmt, ...) { char b[1024]; va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap); return b; }
 inline Mat operator>(const Mat& a, const Mat& b) {
     check_same(a, b);
     Mat r(a.rows, a.cols, CV_8UC1);

@@ -295,3 +295,94 @@ int oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Minimum cut of the expansion-move graph (FastGCStereo.h:424-557), for the graph-cut oracle (lexp_oracle.gc_step).
+ * The graph is the one expansionMoveBK hands to the (un-vendored) Boykov-Kolmogorov library: nodes = pixels of a w x h
+ * region; node s has the net terminal capacity tr[s] = (sum of its source weights) - (sum of its sink weights), i.e.
+ * tr > 0: an arc source -> s, tr < 0: an arc s -> sink; cap[d][s] is the capacity of the arc s -> s + n_d for the four
+ * forward neighbours d = 0 (+1,0), 1 (0,+1), 2 (-1,+1), 3 (+1,+1); the reverse arcs start at 0.
+ * Result: mask[s] = 1 <=> BK's what_segment(s) == SOURCE <=> the sink is NOT reachable from s in the residual graph
+ * of a maximum flow (oracle/maxflow/graph.h explains why that is BK's answer); *maxflow = value of the flow.
+ * Algorithm: Dinic on the grid (BFS levels, iterative DFS), residuals in float as BK keeps them for
+ * Graph<float, float, double>.
+ * ------------------------------------------------------------------------------------------------------------------ */
+static const int GDX[8] = {1, 0, -1, 1, -1, 0, 1, -1}, GDY[8] = {0, 1, 1, 1, 0, -1, -1, -1};   /* opposite of d: d ^ 4 */
+
+int oracle_grid_mincut(int w, int h, const float* tr_in, const float* cap, unsigned char* mask, double* maxflow) {
+    const int n = w * h;
+    float* tr = (float*)malloc((size_t)n * sizeof(float));
+    float* res = (float*)calloc((size_t)n * 8, sizeof(float));
+    int* level = (int*)malloc((size_t)n * sizeof(int));
+    int* it = (int*)malloc((size_t)n * sizeof(int));
+    int* queue = (int*)malloc((size_t)n * sizeof(int));
+    int* path = (int*)malloc((size_t)(n + 1) * sizeof(int));   /* direction taken at every node of the DFS path */
+    int* pnode = (int*)malloc((size_t)(n + 1) * sizeof(int));
+    if (!tr || !res || !level || !it || !queue || !path || !pnode) return -1;
+    memcpy(tr, tr_in, (size_t)n * sizeof(float));
+    for (int d = 0; d < 4; d++)
+        for (int s = 0; s < n; s++) {
+            const int x = s % w + GDX[d], y = s / w + GDY[d];
+            if (x >= 0 && x < w && y >= 0 && y < h) res[(size_t)d * n + s] = cap[(size_t)d * n + s];
+        }
+    double flow = 0.0;
+    for (;;) {
+        int qh = 0, qt = 0, sink_seen = 0;
+        for (int s = 0; s < n; s++) { level[s] = 0; if (tr[s] > 0) { level[s] = 1; queue[qt++] = s; } }
+        while (qh < qt) {
+            const int v = queue[qh++];
+            if (tr[v] < 0) sink_seen = 1;
+            for (int d = 0; d < 8; d++) {
+                const int x = v % w + GDX[d], y = v / w + GDY[d];
+                if (x < 0 || x >= w || y < 0 || y >= h) continue;
+                const int u = y * w + x;
+                if (res[(size_t)d * n + v] > 0 && !level[u]) { level[u] = level[v] + 1; queue[qt++] = u; }
+            }
+        }
+        if (!sink_seen) break;
+        for (int s = 0; s < n; s++) it[s] = 0;
+        for (int s = 0; s < n; s++) {
+            while (tr[s] > 0 && level[s] == 1) {
+                int len = 0, v = s, found = 0;
+                pnode[0] = s;
+                for (;;) {
+                    if (tr[v] < 0) { found = 1; break; }
+                    int advanced = 0;
+                    for (; it[v] < 8; it[v]++) {
+                        const int d = it[v];
+                        const int x = v % w + GDX[d], y = v / w + GDY[d];
+                        if (x < 0 || x >= w || y < 0 || y >= h) continue;
+                        const int u = y * w + x;
+                        if (res[(size_t)d * n + v] > 0 && level[u] == level[v] + 1) { path[len++] = d; v = u; pnode[len] = v; advanced = 1; break; }
+                    }
+                    if (advanced) continue;
+                    level[v] = -1;
+                    if (len == 0) break;
+                    len--; v = pnode[len];
+                }
+                if (!found) break;
+                float f = tr[s];
+                if (-tr[v] < f) f = -tr[v];
+                for (int k = 0; k < len; k++) { const float r = res[(size_t)path[k] * n + pnode[k]]; if (r < f) f = r; }
+                for (int k = 0; k < len; k++) { res[(size_t)path[k] * n + pnode[k]] -= f; res[(size_t)(path[k] ^ 4) * n + pnode[k + 1]] += f; }
+                tr[s] -= f; tr[v] += f;
+                flow += (double)f;
+            }
+        }
+    }
+    /* sink side: backward BFS from the nodes with sink capacity through arcs u -> v with residual capacity */
+    int qh = 0, qt = 0;
+    for (int s = 0; s < n; s++) { mask[s] = 1; if (tr[s] < 0) { mask[s] = 0; queue[qt++] = s; } }
+    while (qh < qt) {
+        const int v = queue[qh++];
+        for (int d = 0; d < 8; d++) {   /* u = v + n_d reaches v through its arc of direction d ^ 4 */
+            const int x = v % w + GDX[d], y = v / w + GDY[d];
+            if (x < 0 || x >= w || y < 0 || y >= h) continue;
+            const int u = y * w + x;
+            if (mask[u] && res[(size_t)(d ^ 4) * n + u] > 0) { mask[u] = 0; queue[qt++] = u; }
+        }
+    }
+    if (maxflow) *maxflow = flow;
+    free(tr); free(res); free(level); free(it); free(queue); free(path); free(pnode);
+    return 0;
+}

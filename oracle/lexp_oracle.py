@@ -687,3 +687,187 @@ def pm_step(energy, units, shareds, filts, kind, m, seed, cell_ids, cur_cost, cu
         cur_cost[sl][mask] = q[mask]
         cur_label[sl][mask] = pl
     return used
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pairwise terms and the expansion move
+# ---------------------------------------------------------------------------------------------------------------------
+NEIGHBORS = [(-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, -1), (-1, 1), (1, 1)]   # StereoEnergy.h:100-110 (NB_LE .. NB_GG)
+FORWARD = [1, 3, 6, 7]   # NB_GE, NB_EG, NB_LG, NB_GG: the neighbours with n.y * width + n.x > 0 (StereoEnergy.h:421)
+
+
+def _shifted(a, dx, dy, fill=0):
+    """b[y, x] = a[y + dy, x + dx], `fill` where that lies outside (a view of a zero-margined copy, StereoEnergy.h:136-143)."""
+    H, W = a.shape[:2]
+    m = np.full((H + 2, W + 2) + a.shape[2:], fill, a.dtype)
+    m[1:-1, 1:-1] = a
+    return m[1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+
+
+def smoothness_coeff(im8, omega=10.0, epsilon=0.01):
+    """StereoEnergy::initSmoothnessCoeff (StereoEnergy.h:131-163) without the margin: float32 [8][H][W].
+    coeff_k = max(epsilon, exp(-channelSum(|I(p + n_k) - I(p)|) / omega)), zero where p + n_k is outside the image."""
+    I = np.asarray(im8).astype(np.float32)
+    H, W = I.shape[:2]
+    out = np.zeros((8, H, W), np.float32)
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    for k, (dx, dy) in enumerate(NEIGHBORS):
+        d = np.abs(_shifted(I, dx, dy) - I)                               # absdiff (:144)
+        s = (d[..., 0] + d[..., 1]) + d[..., 2]                           # channelSum (Utilities.hpp:224-229)
+        c = np.exp((s * np.float32(-1.0)).astype(np.float64) * (1.0 / float(omega))).astype(np.float32)   # -m / omega as MatExpr: scale in double (:145)
+        c = np.maximum(np.float32(epsilon), c)                            # :146
+        inside = (xs + dx >= 0) & (xs + dx < W) & (ys + dy >= 0) & (ys + dy < H)
+        out[k] = np.where(inside, c, np.float32(0))                       # :148-156
+    return out
+
+
+def _disp(lab, X, Y):
+    """cvutils::channelDot(label, coord) with coord = (x, y, 1, 0): the 4-term row sum in float (Utilities.hpp:215-222)."""
+    a, b, c, v = (lab[..., i].astype(np.float32) for i in range(4))
+    X, Y = np.float32(X) if np.isscalar(X) else X.astype(np.float32), np.float32(Y) if np.isscalar(Y) else Y.astype(np.float32)
+    return ((a * X + b * Y) + c) + v * np.float32(0)
+
+
+def smoothness_terms_expansion(labeling, plane, region, coeff, lam=1.0, th_smooth=1.0):
+    """StereoEnergy::computeSmoothnessTermsExpansion(labeling0_m, label1, region, .., onlyForward = true) (StereoEnergy.h:398-453).
+    labeling float32 [H][W][4] (its margin is zero, PMStereoBase.h:44), coeff = smoothness_coeff(..)[8][H][W].
+    Returns cost00, cost01, cost10: float32 [8][h][w], filled for the forward neighbours only."""
+    lab = np.asarray(labeling, np.float32)
+    H, W = lab.shape[:2]
+    x0, y0, w, h = (int(v) for v in region)
+    l1 = np.asarray(plane, np.float32).reshape(1, 1, 4)
+    lam, th = np.float32(lam), np.float32(th_smooth)
+    xs, ys = np.meshgrid(np.arange(x0, x0 + w), np.arange(y0, y0 + h))
+    sl = (slice(y0, y0 + h), slice(x0, x0 + w))
+    L_ee = lab[sl]
+    d0_ee_ee = _disp(L_ee, xs, ys)                                        # :405
+    d1_ee = _disp(l1, xs, ys)                                             # :406
+    c00, c01, c10 = (np.zeros((8, h, w), np.float32) for _ in range(3))
+    for k in FORWARD:
+        dx, dy = NEIGHBORS[k]
+        inside = (xs + dx >= 0) & (xs + dx < W) & (ys + dy >= 0) & (ys + dy < H)
+        L_le = _shifted(lab, dx, dy)[sl]                                  # zero label in the margin
+        qx, qy = np.where(inside, xs + dx, 0), np.where(inside, ys + dy, 0)
+        one = inside.astype(np.float32)                                   # coordinates_m is (x, y, 1, 0) inside, zero in the margin
+
+        def disp_at_le(L):
+            a, b, c, v = (L[..., i].astype(np.float32) for i in range(4))
+            return ((a * qx.astype(np.float32) + b * qy.astype(np.float32)) + c * one) + v * np.float32(0)
+        d0_le_ee = _disp(L_le, xs, ys)                                    # :426
+        d0_ee_le = disp_at_le(L_ee)                                       # :427
+        d0_le_le = disp_at_le(L_le)                                       # :428
+        d1_le = disp_at_le(np.broadcast_to(l1, L_ee.shape))               # :429
+        co = coeff[k][sl]
+
+        def term(a0, a1, b0, b1):
+            c = np.abs(a0 - a1) + np.abs(b0 - b1)
+            c = np.where(c > th, th, c)                                   # THRESH_TRUNC
+            return (lam * c) * co                                         # Mat::mul(coeff, lambda)
+        c00[k] = term(d0_ee_ee, d0_le_ee, d0_ee_le, d0_le_le)             # :441-443
+        c01[k] = term(d0_ee_ee, d1_ee, d0_ee_le, d1_le)                   # :445-447
+        c10[k] = term(d1_ee, d0_le_ee, d1_le, d0_le_le)                   # :449-451
+    return c00, c01, c10
+
+
+def _get_z(lab, X, Y):
+    """Plane::GetZ(cv::Point) = a x + b y + c (Plane.h:55-58)."""
+    a, b, c = (lab[..., i].astype(np.float32) for i in range(3))
+    return (a * np.float32(X) + b * np.float32(Y)) + c
+
+
+def smoothness_term(ls, lt, ps, k, coeff, lam, th_smooth):
+    """StereoEnergy::computeSmoothnessTerm(ls, lt, ps, neighborId, mode) (StereoEnergy.h:234-239)."""
+    pt = (ps[0] + NEIGHBORS[k][0], ps[1] + NEIGHBORS[k][1])
+    ls, lt = np.asarray(ls, np.float32), np.asarray(lt, np.float32)
+    s = np.abs(_get_z(ls, *ps) - _get_z(lt, *ps)) + np.abs(_get_z(ls, *pt) - _get_z(lt, *pt))
+    return (np.float32(coeff[k][ps[1], ps[0]]) * np.minimum(np.float32(s), np.float32(th_smooth))) * np.float32(lam)
+
+
+def expansion_graph(cur_cost, cur_label, prop_cost, plane, region, coeff, lam=1.0, th_smooth=1.0):
+    """The graph FastGCStereo::expansionMoveBK builds (FastGCStereo.h:424-549) for the move `plane` on `region`: returns
+    (tr, konst, cap): tr float32 [h][w] = the NET terminal capacity of every node as the BK library holds it after the reference's
+    sequence of Graph::add_tweights calls (float, the same operations in the same order), konst = the part of the flow value those
+    calls add (`flow += min(cap_source, cap_sink)`), cap float32 [4][h][w] = capacities of the forward arcs (GE, EG, LG, GG)."""
+    x0, y0, w, h = (int(v) for v in region)
+    H, W = cur_cost.shape
+    sl = (slice(y0, y0 + h), slice(x0, x0 + w))
+    c00, c01, c10 = smoothness_terms_expansion(cur_label, plane, region, coeff, lam, th_smooth)   # :422
+    tr = np.zeros((h, w), np.float32)
+    konst = np.zeros((h, w), np.float64)
+
+    def add_tweights(sel, cap_source, cap_sink):   # Graph::add_tweights, element-wise on the nodes `sel`
+        nonlocal tr, konst
+        cs = np.where(tr > 0, (cap_source + tr).astype(np.float32), cap_source).astype(np.float32)
+        ck = np.where(tr > 0, cap_sink, (cap_sink - tr).astype(np.float32)).astype(np.float32)
+        konst = np.where(sel, konst + np.minimum(cs, ck).astype(np.float64), konst)
+        tr = np.where(sel, (cs - ck).astype(np.float32), tr)
+    every = np.ones((h, w), bool)
+    q = np.asarray(prop_cost, np.float32)
+    assert q.shape == (h, w)
+    with np.errstate(invalid="ignore"):
+        add_tweights(every, cur_cost[sl].astype(np.float32), q)               # :433
+    l1 = np.asarray(plane, np.float32)
+    ys, xs = np.mgrid[0:h, 0:w]
+    for k, (dx, dy) in enumerate(NEIGHBORS):                                  # outer boundary (:435-471), reference neighbour order
+        a = np.zeros((h, w), np.float32); b = np.zeros((h, w), np.float32); sel = np.zeros((h, w), bool)
+        for y in range(h):
+            for x in (range(w) if y in (0, h - 1) else sorted({0, w - 1})):
+                ps = (x0 + x, y0 + y)
+                pt = (ps[0] + dx, ps[1] + dy)
+                if x0 <= pt[0] < x0 + w and y0 <= pt[1] < y0 + h:
+                    continue
+                if not (0 <= pt[0] < W and 0 <= pt[1] < H):
+                    continue
+                lt = cur_label[pt[1], pt[0]]
+                a[y, x] = smoothness_term(cur_label[ps[1], ps[0]], lt, ps, k, coeff, lam, th_smooth)
+                b[y, x] = smoothness_term(l1, lt, ps, k, coeff, lam, th_smooth)
+                sel[y, x] = True
+        add_tweights(sel, a, b)
+    cap = np.zeros((4, h, w), np.float32)
+    zero = np.zeros((h, w), np.float32)
+    for fi, k in enumerate([1, 3, 6, 7]):                                     # GE, EG, LG, GG (:478-541)
+        dx, dy = NEIGHBORS[k]
+        B, C_, D = c10[k], c01[k], c00[k]
+        ok = (xs + dx >= 0) & (xs + dx < w) & (ys + dy < h)                   # pairs (i, j = i + n) inside the region
+        cap[fi] = np.where(ok, np.maximum(np.float32(0), (B + C_) - D), np.float32(0))   # add_edge(i, j, max(0, B + C - D), 0)
+        DmC = np.zeros((h, w), np.float32); is_j = np.zeros((h, w), bool)     # the pair's values moved to its node j
+        DmC[max(dy, 0):h, max(dx, 0):w + min(dx, 0)] = (D - C_)[0:h - max(dy, 0), max(-dx, 0):w - max(dx, 0)]
+        is_j[max(dy, 0):h, max(dx, 0):w + min(dx, 0)] = ok[0:h - max(dy, 0), max(-dx, 0):w - max(dx, 0)]
+        add_tweights(is_j, DmC, zero)                                         # add_tweights(j, D - C, 0): reached before the node's own pair
+        add_tweights(ok, C_, zero)                                            # add_tweights(i, C, 0)
+    return tr, float(konst.sum()), cap
+
+
+def expansion_move(cur_cost, cur_label, prop_cost, plane, region, coeff, lam=1.0, th_smooth=1.0):
+    """FastGCStereo::expansionMoveBK (FastGCStereo.h:411-597): (updateMask bool [h][w], flow as BK reports it)."""
+    from . import c_oracle
+    tr, konst, cap = expansion_graph(cur_cost, cur_label, prop_cost, plane, region, coeff, lam, th_smooth)
+    mask, mf = c_oracle.grid_mincut(tr, cap)
+    return mask, konst + mf
+
+
+def gc_step(energy, units, shareds, filts, kind, m, seed, cell_ids, cur_cost, cur_label, coeff, lam=1.0, th_smooth=1.0, planes=None, mode=0):
+    """One proposal step with doGC == true for the (disjoint) cells of a group: proposal, ComputeUnaryPotential, expansionMoveBK,
+    copyTo / setTo (FastGCStereo.h:47-59).  Returns (planes evaluated [n][4], flows [n])."""
+    used = np.zeros((len(units), 4), np.float32)
+    flows = np.zeros(len(units), np.float64)
+    for i, (u, t, f) in enumerate(zip(units, shareds, filts)):
+        if kind == 0:
+            pl = np.asarray(planes[i], dtype=np.float32)
+        else:
+            pl = pm_proposal(kind, m, pm_rng_state(seed, cell_ids[i]), cur_label, u, energy.MIN, energy.MAX)
+        used[i] = pl
+        q = energy.compute_unary_potential(f, t, pl, mode)
+        mask, flows[i] = expansion_move(cur_cost, cur_label, q, pl, t, coeff, lam, th_smooth)
+        sl = (slice(t[1], t[1] + t[3]), slice(t[0], t[0] + t[2]))
+        cur_cost[sl][mask] = q[mask]
+        cur_label[sl][mask] = pl
+    return used, flows
+
+
+def smoothness_cost(labeling, coeff, lam=1.0, th_smooth=1.0):
+    """StereoEnergy::computeSmoothnessCost (StereoEnergy.h:165-199): sum over the forward neighbour pairs of the image."""
+    lab = np.asarray(labeling, np.float32)
+    H, W = lab.shape[:2]
+    c00, _, _ = smoothness_terms_expansion(lab, np.zeros(4, np.float32), (0, 0, W, H), coeff, lam, th_smooth)
+    return float(sum(c00[k].astype(np.float64).sum() for k in FORWARD))

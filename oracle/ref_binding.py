@@ -50,6 +50,12 @@ def lib():
         L.ref_pm_group.argtypes = [vp, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip, ip, C.c_int, C.c_float, C.c_float, fp, C.c_int, u64p, C.c_int,
                                    fp, fp, fp, ip, C.c_int]
         L.ref_pm_init.argtypes = [vp, C.c_int, C.c_int, ip, fp, C.c_int, fp, fp, C.c_int]
+        L.ref_set_smoothness.argtypes = [vp] + [C.c_float] * 4
+        L.ref_smooth_coeff.argtypes = [vp, C.c_int, fp]
+        L.ref_smooth_terms_expansion.argtypes = [vp, C.c_int, fp, fp, ip, fp]
+        L.ref_gc_group.argtypes = [vp, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip, ip, C.c_int, fp, C.c_int, u64p, C.c_int, fp, fp, fp, ip, dp, C.c_int]
+        L.ref_smoothness_cost.argtypes = [vp, C.c_int, fp]
+        L.ref_smoothness_cost.restype = C.c_double
         _lib = L
     return _lib
 
@@ -171,6 +177,57 @@ class RefEnergy:
         if rc:
             raise RuntimeError(lib().ref_last_error().decode())
 
+    # ---- pairwise terms / graph-cut move ----
+    def set_smoothness(self, lam=1.0, omega=10.0, th_smooth=1.0, epsilon=0.01):
+        """params.lambda / omega / th_smooth / epsilon, then the reference's initSmoothnessCoeff() (StereoEnergy.h:131-163)."""
+        if lib().ref_set_smoothness(self.h, float(lam), float(omega), float(th_smooth), float(epsilon)):
+            raise RuntimeError(lib().ref_last_error().decode())
+
+    def smooth_coeff(self, mode=0):
+        """smoothnessCoeff[mode][k] without the margin: float32 [8][H][W] (k in the order of StereoEnergy::NB_*)."""
+        out = np.zeros((8, self.H, self.W), np.float32)
+        if lib().ref_smooth_coeff(self.h, int(mode), _p(out, C.c_float)) < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
+    def smooth_terms_expansion(self, labeling, plane, region, mode=0):
+        """computeSmoothnessTermsExpansion(.., onlyForward = true) as expansionMoveBK calls it (FastGCStereo.h:422):
+        returns (cost00, cost01, cost10), each float32 [8][rh][rw] (only the forward neighbours 1, 3, 6, 7 are filled)."""
+        lab, pl, rg = _f(labeling), _f(plane), _i4(region)
+        assert lab.shape == (self.H, self.W, 4)
+        out = np.zeros((3, 8, rg[3], rg[2]), np.float32)
+        if lib().ref_smooth_terms_expansion(self.h, int(mode), _p(lab, C.c_float), _p(pl, C.c_float), _p(rg, C.c_int), _p(out, C.c_float)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out[0], out[1], out[2]
+
+    def smoothness_cost(self, labeling, mode=0):
+        lab = _f(labeling)
+        return float(lib().ref_smoothness_cost(self.h, int(mode), _p(lab, C.c_float)))
+
+    def gc_group(self, units, shareds, filts, proposers, outer_iter, states, cur_cost, cur_label, list_planes=None, mode=0, nthreads=0):
+        """FastGCStereo.h:30-61 with doGC == true for the cells of one disjoint group: the reference's own proposers, energy and
+        FastGCStereo::expansionMoveBK (over oracle/maxflow/graph.h).  Arguments as pm_group.  Returns (planes, steps, flows [n][max_steps])."""
+        n = len(units)
+        u, sh, fl = _i4(units), _i4(shareds), _i4(filts)
+        kinds = np.ascontiguousarray([k for k, _ in proposers], dtype=np.int32)
+        Ks = np.ascontiguousarray([K for _, K in proposers], dtype=np.int32)
+        st = np.ascontiguousarray(states, dtype=np.uint64)
+        assert st.ndim == 2 and st.shape[0] == n
+        max_steps = st.shape[1]
+        list_steps = int(sum(K for k, K in proposers if k == 0))
+        lp = _f(list_planes if list_planes is not None else np.zeros((n, max(list_steps, 1), 4), np.float32))
+        assert list_steps == 0 or lp.shape == (n, list_steps, 4)
+        assert cur_cost.dtype == np.float32 and cur_cost.flags.c_contiguous and cur_label.dtype == np.float32 and cur_label.flags.c_contiguous
+        out = np.zeros((n, max_steps, 4), np.float32)
+        steps = np.zeros(n, np.int32)
+        flows = np.zeros((n, max_steps), np.float64)
+        rc = lib().ref_gc_group(self.h, mode, n, _p(u, C.c_int), _p(sh, C.c_int), _p(fl, C.c_int), len(proposers), _p(kinds, C.c_int),
+                                _p(Ks, C.c_int), int(outer_iter), _p(lp, C.c_float), list_steps, _p(st, C.c_uint64), max_steps,
+                                _p(cur_cost, C.c_float), _p(cur_label, C.c_float), _p(out, C.c_float), _p(steps, C.c_int), _p(flows, C.c_double), nthreads)
+        if rc:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out, steps, flows
+
     def create_random_label(self, x, y):
         out = np.empty(4, np.float32)
         lib().ref_create_random_label(self.h, int(x), int(y), _p(out, C.c_float))
@@ -282,3 +339,15 @@ def shim_sobel_x(src, scale):
     if L.shim_sobel_x(_p(src, C.c_float), src.shape[0], src.shape[1], float(scale), _p(out, C.c_float)):
         raise RuntimeError(L.ref_last_error().decode())
     return out
+
+
+def shim_grid_mincut(tr, cap):
+    """The BK stand-in oracle/maxflow/graph.h (what the compiled reference's expansionMoveBK runs on) on a grid given as arrays."""
+    tr, cap = _f(tr), _f(cap)
+    h, w = tr.shape
+    mask = np.empty((h, w), np.uint8)
+    L = lib()
+    L.shim_grid_mincut.restype = C.c_double
+    L.shim_grid_mincut.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ubyte)]
+    f = L.shim_grid_mincut(w, h, _p(tr, C.c_float), _p(cap, C.c_float), _p(mask, C.c_ubyte))
+    return mask.astype(bool), float(f)

@@ -13,15 +13,31 @@
 #include "CostVolumeEnergy.h"
 #include "LayerManager.h"
 #include "Proposer.h"
+#include "FastGCStereo.h"
 #include <omp.h>
 #include <malloc.h>
 
 namespace {
 
+// the reference's optimiser class with its protected graph-cut move and state opened up (nothing overridden)
+struct GCProbe : FastGCStereo {
+    using FastGCStereo::FastGCStereo;
+    using FastGCStereo::expansionMoveBK;
+    using PMStereoBase::currentCost_;
+    using PMStereoBase::currentLabeling_;
+    using PMStereoBase::currentLabeling_m_;
+};
+
 struct ref_ctx {
-    std::unique_ptr<StereoEnergy> energy;
+    std::unique_ptr<StereoEnergy> own;   // owner of the energy until the optimiser probe takes it over (setStereoEnergyCPU)
+    StereoEnergy* energy = nullptr;
+    std::unique_ptr<GCProbe> gc;
     cv::Mat im[2];
     int H, W, D, kind;
+    float max_disp, min_disp;
+};
+struct SmoothProbe : StereoEnergy {
+    static const std::vector<cv::Mat>& coeff_of(const StereoEnergy& e, int m) { return (e.*(&SmoothProbe::smoothnessCoeff))[m]; }
 };
 
 // protected members of the reference's classes, reached through pointers to members named via a derived class
@@ -60,7 +76,7 @@ void* ref_create(int kind, int H, int W, int D, const uchar* imL, const uchar* i
         mallopt(M_MMAP_THRESHOLD, 1 << 30);
         mallopt(M_TRIM_THRESHOLD, 1 << 30);
         auto c = std::make_unique<ref_ctx>();
-        c->H = H; c->W = W; c->D = D; c->kind = kind;
+        c->H = H; c->W = W; c->D = D; c->kind = kind; c->max_disp = max_disp; c->min_disp = min_disp;
         c->im[0] = cv::Mat(H, W, CV_8UC3, (void*)imL).clone();
         c->im[1] = cv::Mat(H, W, CV_8UC3, (void*)imR).clone();
         Parameters params(20.f, windR, "GF", eps);
@@ -68,10 +84,11 @@ void* ref_create(int kind, int H, int W, int D, const uchar* imL, const uchar* i
         if (kind == 0) {
             int sz[3] = {D, H, W};
             cv::Mat vL(3, sz, CV_32F, volL), vR(3, sz, CV_32F, volR);
-            c->energy = std::make_unique<CostVolumeEnergy>(c->im[0], c->im[1], vL, vR, params, max_disp, min_disp);
+            c->own = std::make_unique<CostVolumeEnergy>(c->im[0], c->im[1], vL, vR, params, max_disp, min_disp);
         } else {
-            c->energy = std::make_unique<NaiveStereoEnergy>(c->im[0], c->im[1], params, max_disp, min_disp);
+            c->own = std::make_unique<NaiveStereoEnergy>(c->im[0], c->im[1], params, max_disp, min_disp);
         }
+        c->energy = c->own.get();
         return c.release();
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
@@ -124,8 +141,8 @@ int ref_unary_group(void* h, int n, const int* frects, const int* trects, const 
 int ref_stats(void* h, int mode, double* out) {
     try {
         ref_ctx* c = (ref_ctx*)h;
-        const IJointFilter* f = c->kind == 0 ? EnergyProbe::filter_of(*static_cast<CostVolumeEnergy*>(c->energy.get()), mode).get()
-                                             : NaiveProbe::filter_of(*static_cast<NaiveStereoEnergy*>(c->energy.get()), mode).get();
+        const IJointFilter* f = c->kind == 0 ? EnergyProbe::filter_of(*static_cast<CostVolumeEnergy*>(c->energy), mode).get()
+                                             : NaiveProbe::filter_of(*static_cast<NaiveStereoEnergy*>(c->energy), mode).get();
         auto g = dynamic_cast<const GuidedImageFilter<double>*>(f);
         if (!g) throw std::runtime_error("not a guided filter");
         const cv::Mat* pl[9];
@@ -140,7 +157,7 @@ int ref_exi(void* h, int mode, float* out) {
     try {
         ref_ctx* c = (ref_ctx*)h;
         if (c->kind != 1) throw std::runtime_error("ExI exists for NaiveStereoEnergy only");
-        const cv::Mat& e = NaiveProbe::exi_of(*static_cast<NaiveStereoEnergy*>(c->energy.get()), mode);
+        const cv::Mat& e = NaiveProbe::exi_of(*static_cast<NaiveStereoEnergy*>(c->energy), mode);
         for (int y = 0; y < c->H; y++) std::memcpy(out + (size_t)y * c->W * 4, e.ptr<float>(y), sizeof(float) * 4 * c->W);
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
@@ -245,6 +262,146 @@ int ref_pm_group(void* h, int mode, int n, const int* units, const int* shareds,
         }
     }
     return failed ? -failed : 0;
+}
+// ---- pairwise terms and the graph-cut move ----------------------------------------------------------
+// The smoothness parameters live in the energy's public `params`; the coefficient maps are rebuilt by the reference's own
+// initSmoothnessCoeff() (StereoEnergy.h:131-163).
+int ref_set_smoothness(void* h, float lambda, float omega, float th_smooth, float epsilon) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        c->energy->params.lambda = lambda; c->energy->params.omega = omega;
+        c->energy->params.th_smooth = th_smooth; c->energy->params.epsilon = epsilon;
+        c->energy->initSmoothnessCoeff();
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// smoothnessCoeff[mode][k] without its 1-pixel margin: out [8][H][W]
+int ref_smooth_coeff(void* h, int mode, float* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        const std::vector<cv::Mat>& co = SmoothProbe::coeff_of(*c->energy, mode);
+        for (int k = 0; k < (int)co.size() && k < 8; k++)
+            for (int y = 0; y < c->H; y++)
+                memcpy(out + ((size_t)k * c->H + y) * c->W, co[k].ptr<float>(y + 1) + 1, (size_t)c->W * sizeof(float));
+        return (int)co.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// computeSmoothnessTermsExpansion(labeling0_m, label1, region, cost00, cost01, cost10, onlyForward = true, mode) (StereoEnergy.h:398-453),
+// called as expansionMoveBK does (FastGCStereo.h:422).  labeling [H][W][4]; the 1-pixel margin is zero (PMStereoBase.h:44-45).
+// out [3][8][rh][rw]: cost00 / cost01 / cost10 for the neighbours the reference fills (forward ones: NB_GE 1, NB_EG 3, NB_LG 6, NB_GG 7).
+int ref_smooth_terms_expansion(void* h, int mode, const float* labeling, const float plane[4], const int region[4], float* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        cv::Mat lab_m = cv::Mat::zeros(c->H + 2, c->W + 2, CV_32FC4);
+        cv::Mat(c->H, c->W, CV_32FC4, (void*)labeling).copyTo(lab_m(cv::Rect(1, 1, c->W, c->H)));
+        std::vector<cv::Mat> c00, c01, c10;
+        const cv::Rect rg(region[0], region[1], region[2], region[3]);
+        c->energy->computeSmoothnessTermsExpansion(lab_m, Plane(plane[0], plane[1], plane[2], plane[3]), rg, c00, c01, c10, true, mode);
+        const size_t n = (size_t)rg.width * rg.height;
+        memset(out, 0, 3 * 8 * n * sizeof(float));
+        const std::vector<cv::Mat>* all[3] = {&c00, &c01, &c10};
+        for (int t = 0; t < 3; t++)
+            for (int k = 0; k < (int)all[t]->size() && k < 8; k++) {
+                const cv::Mat& m = (*all[t])[k];
+                if (m.empty()) continue;
+                for (int y = 0; y < rg.height; y++) memcpy(out + ((size_t)t * 8 + k) * n + (size_t)y * rg.width, m.ptr<float>(y), (size_t)rg.width * sizeof(float));
+            }
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// One disjoint group of FastGCStereo::localExpansionMovesForLayer_CPU with doGC == true (FastGCStereo.h:30-61): the loop body is
+// re-typed as in ref_pm_group (same harness additions: per-(cell, step) cv::RNG states, list proposer), but the move itself is the
+// reference's OWN FastGCStereo::expansionMoveBK (FastGCStereo.h:411-597) -- graph construction, pairwise terms, boundary terms --
+// running on the reference's own state members, over oracle/maxflow/graph.h (the un-vendored BK library's interface, see there).
+// flows_out [n][max_steps]: the value expansionMoveBK returns (= energy of the move's minimum cut); masks are applied as at :58-59.
+int ref_gc_group(void* h, int mode, int n, const int* units, const int* shareds, const int* filts, int nprop, const int* prop_kind,
+                 const int* prop_K, int outer_iter, const float* list_planes, int list_steps, const uint64_t* states, int max_steps,
+                 float* cur_cost, float* cur_label, float* planes_out, int* steps_out, double* flows_out, int nthreads) {
+    ref_ctx* c = (ref_ctx*)h;
+    try {
+        if (!c->gc) {   // the reference's optimiser object; it takes the energy over exactly as main.cpp:386 does
+            Parameters prm = c->energy->params;
+            c->gc = std::make_unique<GCProbe>(c->im[0], c->im[1], prm, c->max_disp, c->min_disp);
+            if (c->own) c->gc->setStereoEnergyCPU(std::move(c->own));
+        }
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+    GCProbe& gc = *c->gc;
+    cv::Mat(c->H, c->W, CV_32F, cur_cost).copyTo(gc.currentCost_[mode]);
+    cv::Mat(c->H, c->W, CV_32FC4, cur_label).copyTo(gc.currentLabeling_[mode]);   // the view into currentLabeling_m_ (margin stays zero)
+    cv::Mat currentCost = gc.currentCost_[mode], currentLabeling = gc.currentLabeling_[mode];
+    cv::Mat proposalCost = cv::Mat(c->H, c->W, CV_32F);                                                  // :25
+    int failed = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        try {
+            cv::Rect unitRegion(units[4 * i], units[4 * i + 1], units[4 * i + 2], units[4 * i + 3]);
+            cv::Rect sharedRegion(shareds[4 * i], shareds[4 * i + 1], shareds[4 * i + 2], shareds[4 * i + 3]);
+            cv::Rect filterRegion(filts[4 * i], filts[4 * i + 1], filts[4 * i + 2], filts[4 * i + 3]);
+            cv::Mat subCurrentCost = currentCost(sharedRegion);                                           // :36-38
+            cv::Mat subProposalCost = proposalCost(sharedRegion);
+            cv::Mat subCurrentLabeling = currentLabeling(sharedRegion);
+            StereoEnergy::Reusable reusable;
+            int step = 0, list_at = 0;
+            for (int j = 0; j < nprop; j++) {                                                             // :41
+                IProposer* prop;
+                if (prop_kind[j] == 1) { ExpansionProposer proto(prop_K[j]); prop = proto.createInstance(); }
+                else if (prop_kind[j] == 2) { RandomProposer proto(prop_K[j], c->max_disp, c->min_disp); prop = proto.createInstance(); }
+                else { ListProposer proto(prop_K[j], list_planes + ((size_t)i * list_steps + list_at) * 4); prop = proto.createInstance(); list_at += prop_K[j]; }
+                prop->startIterations(currentLabeling, unitRegion, outer_iter);                           // :44
+                while (prop->isContinued()) {                                                             // :45
+                    if (step >= max_steps) throw std::runtime_error("more proposals than max_steps");
+                    cv::theRNG().state = states[(size_t)i * max_steps + step];
+                    Plane label = prop->getNextProposal();                                                // :47
+                    float* po = planes_out + ((size_t)i * max_steps + step) * 4;
+                    po[0] = label.a; po[1] = label.b; po[2] = label.c; po[3] = label.v;
+                    c->energy->ComputeUnaryPotential(filterRegion, sharedRegion, proposalCost(filterRegion), label, reusable, mode);   // :49
+                    cv::Mat updateMask = cv::Mat_<uchar>(sharedRegion.size());                            // :53
+                    const double flow = gc.expansionMoveBK(updateMask, label, sharedRegion, subProposalCost, mode);   // :54
+                    if (flows_out) flows_out[(size_t)i * max_steps + step] = flow;
+                    subProposalCost.copyTo(subCurrentCost, updateMask);                                   // :58
+                    subCurrentLabeling.setTo(label.toScalar(), updateMask);                               // :59
+                    step++;
+                }
+                delete prop;
+            }
+            steps_out[i] = step;
+        } catch (const std::exception& e) {
+#pragma omp critical
+            { g_err = e.what(); failed++; }
+        }
+    }
+    gc.currentCost_[mode].copyTo(cv::Mat(c->H, c->W, CV_32F, cur_cost));
+    gc.currentLabeling_[mode].copyTo(cv::Mat(c->H, c->W, CV_32FC4, cur_label));
+    return failed ? -failed : 0;
+}
+// the BK stand-in (oracle/maxflow/graph.h) on a grid graph given as arrays: tr [h][w] net terminal capacities, cap [4][h][w] forward
+// arcs (GE, EG, LG, GG); mask[s] = what_segment(s) == SOURCE; returns the flow of the residual network (no add_tweights constants:
+// positive tr is added as source weight, negative as sink weight)
+double shim_grid_mincut(int w, int h, const float* tr, const float* cap, uchar* mask) {
+    typedef Graph<float, float, double> G;
+    G g(w * h, 4 * w * h);
+    g.add_node(w * h);
+    const int dx[4] = {1, 0, -1, 1}, dy[4] = {0, 1, 1, 1};
+    for (int s = 0; s < w * h; s++) g.add_tweights(s, tr[s] > 0 ? tr[s] : 0.f, tr[s] < 0 ? -tr[s] : 0.f);
+    for (int d = 0; d < 4; d++)
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const int xx = x + dx[d], yy = y + dy[d];
+                if (xx >= 0 && xx < w && yy < h) g.add_edge(y * w + x, yy * w + xx, cap[((size_t)d * h + y) * w + x], 0);
+            }
+    const double f = g.maxflow();
+    for (int s = 0; s < w * h; s++) mask[s] = g.what_segment(s) == G::SOURCE;
+    return f;
+}
+// total energy of a labeling as the reference evaluates it: sum of currentCost + computeSmoothnessCost (StereoEnergy.h:165-199)
+double ref_smoothness_cost(void* h, int mode, const float* labeling) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        cv::Mat lab_m = cv::Mat::zeros(c->H + 2, c->W + 2, CV_32FC4);
+        cv::Mat(c->H, c->W, CV_32FC4, (void*)labeling).copyTo(lab_m(cv::Rect(1, 1, c->W, c->H)));
+        return c->energy->computeSmoothnessCost(lab_m, mode);
+    } catch (const std::exception& e) { g_err = e.what(); return -1.0; }
 }
 // initCurrentFast with a given label per unit region (FastGCStereo.h:101-113; the random draw of :105-106 is the caller's):
 // currentLabeling(unit) = label; ComputeUnaryPotential(unit +- windR, unit, currentCost(filterRegion), label)

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_capi.cu")
-DEPS = [SRC, os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_kernels.cuh"), os.path.join(ROOT, "include", "lexp_cuda.h"),
+DEPS = [SRC, os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_kernels.cuh"), os.path.join(ROOT, "localexpstereo_b200", "csrc", "lexp_gc.cuh"), os.path.join(ROOT, "include", "lexp_cuda.h"),
         os.path.join(HERE, "cuda_runtime.h"), os.path.abspath(__file__)]
 SO = os.path.join(HERE, "liblexp_emu.so")
 

@@ -369,3 +369,105 @@ def test_pm_phase_oracle_equals_the_reference_loop():
         assert np.isfinite(state["ora"][0]).all()
     finally:
         ref.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pairwise terms and the graph-cut move: the oracle's restatement against the reference's own StereoEnergy and
+# FastGCStereo::expansionMoveBK (compiled from FastGCStereo.h over oracle/maxflow/graph.h)
+# ------------------------------------------------------------------------------------------------------------------
+def test_smoothness_oracle_equals_the_reference():
+    """oracle.smoothness_coeff / smoothness_terms_expansion / smoothness_cost vs the reference's initSmoothnessCoeff,
+    computeSmoothnessTermsExpansion (as expansionMoveBK calls it) and computeSmoothnessCost: coefficients to 1 ulp of exp(),
+    zero pattern identical; with the same coefficients the three cost maps are bit-identical on interior and border regions."""
+    H, W, D, windR = 60, 84, 10, 12
+    imL, imR, volL, volR = make_scene(H, W, D, seed=6)
+    ref = R.RefEnergy(imL, imR, volL, volR, windR=windR, eps=1e-4, th_col=0.5, max_disp=D - 1, min_disp=0.0, kind=0)
+    try:
+        rng = O.CvRNG(12)
+        lab = np.zeros((H, W, 4), np.float32)
+        for y in range(0, H, 6):
+            for x in range(0, W, 6):
+                lab[y:y + 6, x:x + 6] = O.create_random_label(rng, x, y, 0.0, D - 1.0)
+        for (lam, omega, th, eps) in ((1.0, 10.0, 1.0, 0.01), (0.35, 4.0, 0.6, 0.1)):
+            ref.set_smoothness(lam, omega, th, eps)
+            for mode, im in ((0, imL), (1, imR)):
+                co_r, co_o = ref.smooth_coeff(mode), O.smoothness_coeff(im, omega, eps)
+                assert np.array_equal(co_r == 0, co_o == 0)
+                assert np.allclose(co_r, co_o, rtol=1e-6, atol=0)   # float exp of the shim vs exp in double
+                for region in [(10, 8, 25, 21), (0, 0, 19, 14), (W - 13, H - 17, 13, 17), (0, 0, W, H), (5, 5, 1, 1)]:
+                    plane = O.create_random_label(rng, region[0], region[1], 0.0, D - 1.0)
+                    got = O.smoothness_terms_expansion(lab, plane, region, co_r, lam, th)
+                    want = ref.smooth_terms_expansion(lab, plane, region, mode)
+                    for g, w_ in zip(got, want):
+                        assert np.array_equal(g, w_), (region, np.abs(g - w_).max())
+                assert abs(O.smoothness_cost(lab, co_r, lam, th) - ref.smoothness_cost(lab, mode)) <= 1e-6 * ref.smoothness_cost(lab, mode)
+    finally:
+        ref.close()
+
+
+def test_graph_cut_oracle_equals_the_reference_loop():
+    """oracle.gc_step (numpy graph of expansion_graph + the C grid minimum cut) vs oracle/_ref's ref_gc_group: the body of
+    FastGCStereo::localExpansionMovesForLayer_CPU with doGC == true driving the reference's own proposers, CostVolumeEnergy and
+    FastGCStereo::expansionMoveBK.  Same proposals, the same minimum-cut energy of every move (1e-6: only the order of the
+    double-precision flow sums differs), identical currentLabeling_, currentCost_ equal to 1 ulp -- over two iterations of two
+    layers, including the first groups whose current costs still hold COST_FOR_INVALID next to the pairwise terms."""
+    H, W, D, windR = 72, 96, 12, 12
+    imL, imR, volL, volR = make_scene(H, W, D)
+    ref = R.RefEnergy(imL, imR, volL, volR, windR=windR, eps=1e-4, th_col=0.5, max_disp=D - 1, min_disp=0.0, kind=0)
+    ora = O.CostVolumeEnergyOracle(imL, imR, volL, volR, windR, 1e-4, 0.5, D - 1)
+    lam, omega, th, eps = 0.7, 10.0, 1.0, 0.01
+    try:
+        ref.set_smoothness(lam, omega, th, eps)
+        coeff = ref.smooth_coeff(0)
+        rng = O.CvRNG(21)
+        lay0 = O.make_layer(W, H, windR, 8)
+        units0 = lay0["unit"]
+        labels = np.stack([O.create_random_label(rng, u[0] + rng.uniform_int(0, u[2]), u[1] + rng.uniform_int(0, u[3]), 0.0, D - 1.0) for u in units0])
+        cost_r, lab_r = np.full((H, W), np.inf, np.float32), np.zeros((H, W, 4), np.float32)
+        ref.pm_init(units0, labels, windR, cost_r, lab_r)
+        cost_o, lab_o = cost_r.copy(), lab_r.copy()
+        n_moves = 0
+        for it in range(2):
+            for li, (u, proposers) in enumerate([(8, [(1, 1), (2, 2)]), (22, [(1, 2)])]):
+                lay = O.make_layer(W, H, windR, u)
+                for gi, cells in enumerate(lay["groups"]):
+                    us = [lay["unit"][r] for r in cells]; ts = [lay["shared"][r] for r in cells]; fs = [lay["filter"][r] for r in cells]
+                    steps = [(k, (it + j if k == 2 else 0)) for k, K in proposers for j in range(K)]
+                    seeds = [10000 * it + 1000 * li + 10 * gi + s for s in range(len(steps))]
+                    states = np.array([[O.pm_rng_state(seeds[s], 100 * li + r) for s in range(len(steps))] for r in cells], dtype=np.uint64)
+                    planes, nsteps, flows = ref.gc_group(us, ts, fs, proposers, it, states, cost_r, lab_r)
+                    assert (nsteps == len(steps)).all()
+                    for s, (kind, m) in enumerate(steps):
+                        used, fl = O.gc_step(ora, us, ts, fs, kind, m, seeds[s], [100 * li + r for r in cells], cost_o, lab_o, coeff, lam, th)
+                        assert np.allclose(used, planes[:, s], rtol=3e-6, atol=1e-6)
+                        assert (np.abs(fl - flows[:, s]) <= 1e-6 * np.maximum(np.abs(flows[:, s]), 1e-3)).all(), (it, li, gi, s)
+                        n_moves += len(cells)
+            assert np.array_equal(lab_r, lab_o), (it, int((lab_r != lab_o).any(axis=2).sum()))
+            assert np.abs(cost_r - cost_o).max() <= 1e-6
+        assert n_moves > 500
+    finally:
+        ref.close()
+
+
+def test_maxflow_stand_in_on_random_graphs():
+    """oracle/maxflow/graph.h (the interface of the un-vendored BK library, used by the compiled reference) and the C grid minimum
+    cut of the oracle are two independent implementations: on random expansion-move-shaped grids they report the same flow and the
+    same SOURCE segment, and the cut they report has the value of the flow (max-flow = min-cut)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(5)
+    for (h, w) in [(1, 1), (1, 7), (6, 1), (9, 13), (24, 31)]:
+        for trial in range(3):
+            tr = (rng.random((h, w)) - 0.5).astype(np.float32) * np.float32(4)
+            cap = (rng.random((4, h, w)) * (rng.random((4, h, w)) < 0.8)).astype(np.float32)
+            mask, flow = c_oracle.grid_mincut(tr, cap)
+            # value of the cut (SOURCE = mask): source arcs into the sink side + sink arcs out of the source side + forward arcs S -> T
+            cut = float(np.maximum(tr, 0)[~mask].sum() + np.maximum(-tr, 0)[mask].sum())
+            for d, (dx, dy) in enumerate([(1, 0), (0, 1), (-1, 1), (1, 1)]):
+                for y in range(h):
+                    for x in range(w):
+                        xx, yy = x + dx, y + dy
+                        if 0 <= xx < w and yy < h and mask[y, x] and not mask[yy, xx]:
+                            cut += float(cap[d, y, x])
+            assert abs(cut - flow) <= 1e-4 * max(1.0, flow), (h, w, trial, cut, flow)
+            m2, f2 = R.shim_grid_mincut(tr, cap)
+            assert abs(f2 - flow) <= 1e-5 * max(1.0, flow) and np.array_equal(m2, mask), (h, w, trial)
