@@ -207,11 +207,25 @@ public:
             check(lexp_pm_sweep_iteration(sweep_, iteration, seed, &n));
             return n;
         }
+        // One iteration of the MAIN loop of FastGCStereo::run (FastGCStereo.h:171-184: localExpansionMovesForLayer_CPU with doGC == true)
+        // on the same device state: per proposal step the proposals, ComputeUnaryPotential, the pairwise terms
+        // (computeSmoothnessTermsExpansion), the graph of expansionMoveBK and its minimum cut, and the copyTo / setTo of the winners
+        // (FastGCStereo.h:47-59, 411-597) all run on the device.  The smoothness parameters are the energy's `params` (lambda, omega,
+        // th_smooth, epsilon: StereoEnergy.h:26-36), handed over by CudaCostVolumeEnergy::setSmoothness.  Single GPU.
+        int graphCutIteration(int iteration, uint64_t seed) {
+            int n = 0;
+            check(lexp_pm_sweep_gc_iteration(sweep_, iteration, seed, &n));
+            return n;
+        }
         // blocking: the state back into the caller's continuous H x W mats
         void get(cv::Mat& currentCost, cv::Mat& currentLabeling) const {
             check(lexp_pm_get(ctx_, mode_, reinterpret_cast<float*>(currentCost.data), reinterpret_cast<lexp_plane*>(currentLabeling.data)));
         }
     };
+
+    // Parameters::lambda / omega / th_smooth / epsilon of the pairwise term (StereoEnergy.h:26-36, main.cpp:286,350) for the device-side
+    // graph-cut iterations; the coefficient maps of initSmoothnessCoeff (StereoEnergy.h:131-163) are rebuilt on the device.
+    void setSmoothness(const Parameters& p) { check(lexp_set_smoothness(ctx_, p.lambda, p.omega, p.th_smooth, p.epsilon)); }
 
 private:
     // The reference declares `Reusable& reusable = Reusable()` (an MSVC extension binding a temporary to a non-const

@@ -275,6 +275,10 @@ LEXP_API int lexp_pairwise_terms(lexp_ctx* ctx, int mode, int n, const lexp_rect
 LEXP_API int lexp_plan_gc_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int kind, int m, uint64_t seed, const lexp_plane* planes,
                                int planes_on_device, lexp_plane* d_planes_out, double* d_flows_out);
 
+/* One iteration of the main (graph-cut) loop of FastGCStereo::run (FastGCStereo.h:171-184) over the schedule of a sweep object
+ * (lexp_pm_sweep_create with world == 1): lexp_plan_gc_step for every proposal step of every group.  Asynchronous. */
+LEXP_API int lexp_pm_sweep_gc_iteration(lexp_pm_sweep* sweep, int iteration, uint64_t seed, int* n_steps);
+
 /* LayerManager::addLayer (LayerManager.h:44-185): cell geometry of one layer.
  * Call with rect pointers == NULL to query counts.  group_of[r] = (i%4)*4 + (j%4) (LayerManager.h:168-173). */
 LEXP_API int lexp_layer_geometry(int width, int height, int windR, int unit_size, int* height_blocks,

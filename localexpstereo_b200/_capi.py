@@ -77,6 +77,7 @@ SYMBOLS = {
     "lexp_pm_sweep_num_init_labels": (C.c_int, [_P]),
     "lexp_pm_sweep_init": (C.c_int, [_P, _P]),
     "lexp_pm_sweep_iteration": (C.c_int, [_P, C.c_int, C.c_uint64, C.POINTER(C.c_int)]),
+    "lexp_pm_sweep_gc_iteration": (C.c_int, [_P, C.c_int, C.c_uint64, C.POINTER(C.c_int)]),
     "lexp_set_smoothness": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float]),
     "lexp_get_smooth_coeff": (C.c_int, [_P, C.c_int, _P]),
     "lexp_pairwise_terms": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),

@@ -1612,6 +1612,29 @@ int lexp_pm_sweep_iteration(lexp_pm_sweep* s, int iteration, uint64_t seed, int*
     return sweep_advance(s);
 }
 
+// One iteration of the main loop of FastGCStereo::run (FastGCStereo.h:171-184, doGC == true) over the sweep's schedule: every proposal
+// step is lexp_plan_gc_step (proposals -> unary costs -> expansionMoveBK -> copyTo / setTo), ordered by the stream.  Single GPU.
+int lexp_pm_sweep_gc_iteration(lexp_pm_sweep* s, int iteration, uint64_t seed, int* n_steps) {
+    if (!s || iteration < 0) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (s->world != 1) return fail(LEXP_ERR_INVALID, "the graph-cut iterations run on one GPU (the cell shard covers the PatchMatch phase)");
+    const float range = s->ctx->p.max_disp - s->ctx->p.min_disp;
+    int steps_done = 0;
+    for (auto& g : s->sched) {
+        if (!g.plan) continue;
+        int k = 0;
+        for (auto& pr : s->proposers[g.layer])
+            for (int it = 0; it < pr.second; it++, k++) {
+                if (pr.first == LEXP_PROP_RANDOM && (double)(range * exp2f(-(float)(iteration + it + 1))) < 0.1) break;   // Proposer.h:149-152
+                const int rc = lexp_plan_gc_step(s->ctx, g.plan, s->mode, pr.first, pr.first == LEXP_PROP_RANDOM ? iteration + it : 0,
+                                                 pm_launch_seed(seed, s->mode, iteration, g.layer, g.group, k), nullptr, 0, nullptr, nullptr);
+                if (rc) return rc;
+                steps_done++;
+            }
+    }
+    if (n_steps) *n_steps = steps_done;
+    return LEXP_OK;
+}
+
 // LayerManager::addLayer, LayerManager.h:88-185 (the #else branch that merges small edge cells).
 int lexp_layer_geometry(int width, int height, int windR, int u, int* hb_out, int* wb_out, lexp_rect* unit, lexp_rect* shared,
                         lexp_rect* filt, int* group_of) {

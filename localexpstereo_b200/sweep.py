@@ -331,6 +331,14 @@ class NativePMSweep:
         check(lib().lexp_pm_sweep_iteration(self._h, int(iteration), int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(n)))
         return n.value
 
+    def gc_iteration(self, iteration, seed):
+        """One iteration of the graph-cut loop (FastGCStereo.h:171-184) on the device; energy.set_smoothness first."""
+        import ctypes as C
+        from ._capi import check, lib
+        n = C.c_int(0)
+        check(lib().lexp_pm_sweep_gc_iteration(self._h, int(iteration), int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(n)))
+        return n.value
+
     def get(self, out_cost=None, out_labeling=None):
         return self.energy.pm_get(self.mode, out_cost=out_cost, out_labeling=out_labeling)
 
