@@ -313,6 +313,30 @@ int ensure_compact(lexp_plan* pl, size_t nout) {
     return LEXP_OK;
 }
 
+// Zero-copy output is taken only for host memory that CUDA itself knows as page-locked (cudaHostRegister / cudaHostAlloc) over the WHOLE
+// range [p, p + bytes): first and last byte must both be registered host memory with a device alias at the same offset.  A bare
+// cudaHostGetDevicePointer is not enough: it also succeeds for a buffer that merely starts inside somebody else's registration (the
+// kernel then writes past the end of the mapping: an illegal address), and on systems where the GPU can address pageable memory
+// (HMM / ATS) for memory nobody registered at all.  Returns the device alias of p, or nullptr (= take the staged path).
+void* mapped_alias(void* p, size_t bytes) {
+#ifdef LEXP_EMU
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess || !d) return nullptr;
+    void* e = nullptr;
+    if (bytes > 1 && (cudaHostGetDevicePointer(&e, static_cast<char*>(p) + bytes - 1, 0) != cudaSuccess || !e)) return nullptr;
+    return d;
+#else
+    cudaPointerAttributes a0{}, a1{};
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || a0.type != cudaMemoryTypeHost || !a0.devicePointer) { cudaGetLastError(); return nullptr; }
+    if (bytes > 1) {
+        char* last = static_cast<char*>(p) + bytes - 1;
+        if (cudaPointerGetAttributes(&a1, last) != cudaSuccess || a1.type != cudaMemoryTypeHost || !a1.devicePointer ||
+            static_cast<char*>(a1.devicePointer) - static_cast<char*>(a0.devicePointer) != (ptrdiff_t)(bytes - 1)) { cudaGetLastError(); return nullptr; }
+    }
+    return a0.devicePointer;
+#endif
+}
+
 int check_rects(const lexp_ctx* c, const lexp_rect& f, const lexp_rect& t) {
     const int H = c->p.height, W = c->p.width;
     if (f.width <= 0 || f.height <= 0 || t.width <= 0 || t.height <= 0) return fail(LEXP_ERR_INVALID, "empty rect");
@@ -616,6 +640,9 @@ int lexp_set_volume_device_ex(lexp_ctx* c, int mode, const float* vol, int trans
     if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
         return fail(LEXP_ERR_INVALID, "lexp_set_volume_device needs a device pointer");
     LEXP_CUDA(cudaSetDevice(c->p.device));
+    // the caller's volume was produced on a stream this library does not know (e.g. torch's): the context's own stream is
+    // non-blocking, so nothing orders its re-layout kernel behind that producer -- wait for the device once (one-time set-up call)
+    LEXP_CUDA(cudaDeviceSynchronize());
     int* d_flag = nullptr;
     { int rc = alloc_volume(c, mode, &d_flag); if (rc) return rc; }
     const int rc = ingest_slab(c, mode, vol, 0, c->p.ndisp, kernel_transform(mode, transform), d_flag);
@@ -803,14 +830,14 @@ int lexp_plan_eval_host_tiles(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_p
     c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
-    void* dptr = nullptr;
-    if (cudaHostGetDevicePointer(&dptr, tiles, 0) == cudaSuccess && dptr) {  // registered (mapped) buffer: the kernel writes it directly
+    void* dptr = mapped_alias(tiles, (size_t)pl->sum_s * sizeof(float));
+    if (dptr) {  // registered (mapped) buffer: the kernel writes it directly
         int rc = run_plan(c, pl, mode, pl->d_planes, reinterpret_cast<float*>(dptr), 0, 1, with_check);
         if (rc) return rc;
         LEXP_CUDA(cudaStreamSynchronize(c->stream));
         return LEXP_OK;
     }
-    cudaGetLastError();  // not a mapped buffer: compact device buffer, then one contiguous copy
+    // not a mapped buffer: compact device buffer, then one contiguous copy
     const size_t nout = (size_t)pl->sum_s;
     { int rc0 = ensure_compact(pl, nout); if (rc0) return rc0; }
     int rc = run_plan(c, pl, mode, pl->d_planes, pl->d_compact, 0, 1, with_check);
@@ -827,8 +854,14 @@ int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
     c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
     LEXP_CUDA(cudaSetDevice(c->p.device));
     {   // zero-copy path: the caller's image is page-locked + mapped (lexp_host_register)
-        void* dptr = nullptr;
-        if (cudaHostGetDevicePointer(&dptr, cost_image, 0) == cudaSuccess && dptr) {
+        // the calls write rows t.y .. t.y + t.height - 1 of the image: the range that must be mapped spans them all
+        int y_lo = INT_MAX, y_hi = -1, x_hi = 0;
+        for (const lexp_rect& t : pl->targ) { y_lo = std::min(y_lo, t.y); y_hi = std::max(y_hi, t.y + t.height - 1); x_hi = std::max(x_hi, t.x + t.width); }
+        char* lo = reinterpret_cast<char*>(cost_image) + (ptrdiff_t)y_lo * step_bytes;
+        const size_t span = step_bytes > 0 && y_hi >= y_lo ? (size_t)(y_hi - y_lo) * (size_t)step_bytes + (size_t)x_hi * sizeof(float) : 0;
+        void* dlo = span ? mapped_alias(lo, span) : nullptr;
+        void* dptr = dlo ? static_cast<char*>(dlo) - (ptrdiff_t)y_lo * step_bytes : nullptr;
+        if (dptr) {
             if (step_bytes % 4 != 0) return fail(LEXP_ERR_INVALID, "bad row pitch");
             LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
             int rc = run_plan(c, pl, mode, pl->d_planes, reinterpret_cast<float*>(dptr), step_bytes / 4, 0, with_check);
@@ -836,8 +869,7 @@ int lexp_plan_eval_host(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
             LEXP_CUDA(cudaStreamSynchronize(c->stream));
             return LEXP_OK;
         }
-        cudaGetLastError();  // not a mapped buffer: staged path below
-    }
+    }   // not a mapped buffer: staged path below
     const size_t nout = (size_t)pl->sum_s;
     { int rc0 = ensure_compact(pl, nout); if (rc0) return rc0; }
     LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));

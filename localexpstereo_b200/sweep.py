@@ -278,11 +278,14 @@ class GCSweep(PMSweep):
         super().__init__(energy, unit_sizes, proposers, 0, 1, mode)
         energy.set_smoothness(lam, omega, th_smooth, epsilon)
 
-    def gc_iteration(self, iteration, seed, list_planes=None, planes_out=None, flows_out=None):
+    def gc_iteration(self, iteration, seed, list_planes=None, planes_out=None, flows_out=None, layers=None):
         """list_planes / planes_out as PMSweep.iteration; flows_out: optional {(layer, group): device pointer of double [steps][n]}
-        receiving the minimum-cut energy of every move.  Returns the number of proposal steps issued."""
+        receiving the minimum-cut energy of every move; layers: restrict to these layer indices (timing).  Returns the number of
+        proposal steps issued."""
         E, n = self.energy, 0
         for (li, gi, g, _owners) in self.schedule:
+            if layers is not None and li not in layers:
+                continue
             steps = expand_proposers(self.proposers[li], iteration, E.MAX_DISPARITY, E.MIN_DISPARITY)
             li_at = 0
             for k, (kind, m) in enumerate(steps):

@@ -312,6 +312,7 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaGetLastError(); }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaGetLastError(); }
 typedef void* cudaEvent_t;   /* streams are synchronous here: events are always complete */
 enum { cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)malloc(8); return cudaSuccess; }

@@ -201,3 +201,11 @@ def test_gc_moves_never_raise_the_energy(devmem):
     finally:
         S.close()
         E.close()
+
+
+def test_gc_replay_r10_larger_cells(devmem):
+    """The R = 10 instantiation (windR 20) with three layers: cells of 30 x 30, 93 x 93 and 168 x 168 nodes (28 000 nodes in one CTA, 27
+    per thread): many relabelling rounds and long residual paths."""
+    import localexpstereo_b200 as L
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)]]
+    check_gc_result(run_gc_replay(devmem, 200, 260, 16, 20, [10, 31, 56], props, pm_iterations=1, gc_iterations=1, seed=9))
