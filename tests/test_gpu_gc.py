@@ -76,10 +76,10 @@ def test_pairwise_terms_equal_the_oracle_bit_for_bit():
         E.close()
 
 
-def run_gc_replay(devmem, H, W, D, windR, units, proposers, pm_iterations=1, gc_iterations=1, seed=1234, mode=0, smooth=SMOOTH):
+def run_gc_replay(devmem, H, W, D, windR, units, proposers, pm_iterations=1, gc_iterations=1, seed=1234, mode=0, smooth=SMOOTH, scene=None):
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import GCSweep, expand_proposers, pm_seed
-    imL, imR, volL, volR = make_scene(H, W, D)
+    imL, imR, volL, volR = scene if scene is not None else make_scene(H, W, D)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
     E = L.CostVolumeEnergy(imL, imR if mode else None, volL, volR if mode else None, prm, D - 1)
     Or = O.CostVolumeEnergyOracle(imL, imR if mode else None, volL, volR if mode else None, windR, 1e-4, 0.5, D - 1)
@@ -209,3 +209,17 @@ def test_gc_replay_r10_larger_cells(devmem):
     import localexpstereo_b200 as L
     props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)]]
     check_gc_result(run_gc_replay(devmem, 200, 260, 16, 20, [10, 31, 56], props, pm_iterations=1, gc_iterations=1, seed=9))
+
+
+def test_gc_replay_on_the_cones_crop(devmem):
+    """A pm iteration and a graph-cut iteration on the natural-image crop of data/MiddV2/cones that the golden vectors use (real
+    edges in the smoothness coefficients: values from epsilon to 1 next to each other)."""
+    import lexp_golden
+    import localexpstereo_b200 as L
+    G = lexp_golden.load()
+    H, W = G["imL"].shape[:2]
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 2)], [(L.PROP_EXPANSION, 2)], [(L.PROP_EXPANSION, 1)]]
+    r = run_gc_replay(devmem, H, W, G["D"], G["windR"], [6, 18, 40], props, pm_iterations=1, gc_iterations=1, seed=77,
+                      scene=(G["imL"], G["imR"], G["volL"], G["volR"]), smooth=dict(lam=1.0, omega=10.0, th_smooth=1.0, epsilon=0.01))
+    check_gc_result(r)
+    assert r["n_moves"] > 1000
