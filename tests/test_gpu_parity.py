@@ -294,6 +294,43 @@ def test_host_tile_output(scene):
     plan.close()
 
 
+def test_partially_registered_output_takes_the_staged_path(scene):
+    """Only the FIRST part of the cost image / tile buffer is page-locked (it starts inside somebody's registration): the zero-copy
+    path must not be taken -- a kernel writing through that alias would run past the end of the mapping (an illegal address on the
+    device) -- and the staged path must deliver the same pixels."""
+    from localexpstereo_b200.sweep import tile_offsets
+    L, E = scene["L"], scene["E"]
+    H, W, D = scene["H"], scene["W"], scene["D"]
+    lay = L.LayerManager(W, H, scene["windR"]).addLayer(11)
+    g = lay.disjointRegionSets[1]
+    fr = [lay.filterRegions[r] for r in g]
+    tr = [lay.sharedRegions[r] for r in g]
+    plan = E.make_plan(fr, tr)
+    rng = O.CvRNG(56)
+    planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+    ref = np.full((H, W), -7.0, np.float32)
+    plan.eval_host(planes, ref, True, 0)
+    part = np.full((H, W), -7.0, np.float32)
+    head = part[:max(1, min(t[1] for t in tr) + 2)]          # the image's first rows only: the range the calls write is longer
+    L.host_register(head)
+    try:
+        plan.eval_host(planes, part, True, 0)
+    finally:
+        L.host_unregister(head)
+    assert np.array_equal(part, ref)
+    _, total = tile_offsets(tr)
+    tiles_ref = np.full(total, -9.0, np.float32)
+    plan.eval_host_tiles(planes, tiles_ref, True, 0)
+    tiles = np.full(total, -9.0, np.float32)
+    L.host_register(tiles[:total // 2])
+    try:
+        plan.eval_host_tiles(planes, tiles, True, 0)
+    finally:
+        L.host_unregister(tiles[:total // 2])
+    assert np.array_equal(tiles, tiles_ref)
+    plan.close()
+
+
 def _textureless_guides(H, W):
     """Guides on which the 3x3 covariance is (nearly) singular: the FP32 hazard SURVEY.md section 7 names."""
     const = np.full((H, W, 3), 128, np.uint8)
