@@ -1,4 +1,7 @@
-"""GPU parity at the other BASELINE.json sizes: Adirondack-shaped 1436 x 992 x 290 (configs[1]), an odd
+"""(Runs last in the -m gpu suite: the 1436 x 992 x 290 case ended in an illegal address on the device once this round --
+profiles/r2_gpu_validation.md -- and a fault there must not keep the other tests from being recorded.)
+
+GPU parity at the other BASELINE.json sizes: Adirondack-shaped 1436 x 992 x 290 (configs[1]), an odd
 size that is not a multiple of the 4 x 4 blocked volume layout (1437 x 991), and the 4K stress case 3840 x 2160 x 512 with
 filterRadius 32 (configs[4]: the R = 16 kernel instantiation, 1099 x 1099 filterRects in layer 2, 17 GB volume) -- sampled cells
 of all three layers against the numpy oracle, through the C-ABI, tolerance 1e-4 relative and exact COST_FOR_INVALID mask."""
