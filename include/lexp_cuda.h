@@ -269,7 +269,9 @@ LEXP_API int lexp_pairwise_terms(lexp_ctx* ctx, int mode, int n, const lexp_rect
  * lexp_plan_pm_step), ComputeUnaryPotential on the cell's filterRect, then FastGCStereo::expansionMoveBK on its targetRect
  * (= sharedRegion): graph of FastGCStereo.h:424-549 from the unary costs, the pairwise terms and the boundary terms, its minimum cut,
  * and `copyTo / setTo` of cost and label where the proposal wins (FastGCStereo.h:53-59).  The cells of the plan must be pairwise
- * non-adjacent (a disjoint group of LayerManager, LayerManager.h:168-173).  lexp_plan_set_units first.  Asynchronous, stream ordered.
+ * non-adjacent (a disjoint group of LayerManager, LayerManager.h:168-173).  lexp_plan_set_units first.  Asynchronous and stream ordered
+ * for plans whose cells have at most LEXP_GC_BIG_NODES (default 32768) nodes: one CTA per cell; plans with larger cells (layer 2) run the
+ * same steps as phase kernels over all SMs with two flags read back per decision -- that form returns when the moves are done.
  * d_planes_out: optional device array [ncalls] (the plane every call evaluated); d_flows_out: optional device array double[ncalls]
  * (the value expansionMoveBK returns: the minimum-cut energy of the move). */
 LEXP_API int lexp_plan_gc_step(lexp_ctx* ctx, lexp_plan* plan, int mode, int kind, int m, uint64_t seed, const lexp_plane* planes,

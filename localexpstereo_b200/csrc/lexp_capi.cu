@@ -88,6 +88,10 @@ struct lexp_plan {
     // graph-cut move (lexp_plan_gc_step): region + scratch offset of every call
     GcCell* d_gc_cells = nullptr;
     long long gc_nodes = 0;       // sum of the calls' targetRect areas
+    int gc_max_nodes = 0;         // largest cell: above the context's gc_big_nodes the move runs as phase kernels over all SMs
+    GcBlock* d_gc_blocks = nullptr;   // block map of the phase kernels (lexp_gc.cuh)
+    int gc_nblocks = 0;
+    char* d_gc_ctl = nullptr;     // int done[ncalls], active[ncalls], g_flags[2] (padded to 8 bytes), double konst_part[nblocks], sink_part[nblocks]
 };
 
 struct lexp_ctx {
@@ -126,6 +130,8 @@ struct lexp_ctx {
     float* d_gc_scratch = nullptr;                 // kGcWords planes of gc_scratch_nodes words: the residual network of a group's moves
     long long gc_scratch_nodes = 0;
     int gc_threads = 1024, gc_relabel_every = 24, gc_max_rounds = 1 << 22;
+    int gc_big_nodes = 32768;                      // cells with more nodes run as phase kernels over all SMs (LEXP_GC_BIG_NODES)
+    int* h_gc_flags = nullptr;                     // pinned: the two decision flags of the phase path
     int64_t launches = 0;
     std::mutex mu;
     int tile_oh = 128;    // max output rows per work item
@@ -296,6 +302,8 @@ void release_plan_memory(lexp_plan* pl) {
     if (pl->h_compact) { cudaFreeHost(pl->h_compact); pl->h_compact = nullptr; }
     cudaFree(pl->d_calls); pl->d_calls = nullptr;
     cudaFree(pl->d_gc_cells); pl->d_gc_cells = nullptr;
+    cudaFree(pl->d_gc_blocks); pl->d_gc_blocks = nullptr;
+    cudaFree(pl->d_gc_ctl); pl->d_gc_ctl = nullptr;
 }
 
 // compact device buffer + pinned host mirror of the staged host paths: both or neither
@@ -500,6 +508,7 @@ int lexp_create(const lexp_params* params, lexp_ctx** out_ctx) {
     c->smem_cap = (size_t)env_int("LEXP_SMEM_CAP", 0);
     c->gc_threads = std::min(1024, std::max(32, env_int("LEXP_GC_THREADS", 1024) / 32 * 32));
     c->gc_relabel_every = std::max(1, env_int("LEXP_GC_RELABEL_EVERY", 24));
+    c->gc_big_nodes = std::max(0, env_int("LEXP_GC_BIG_NODES", 32768));
     if (env_int("LEXP_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0) {
         const size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
@@ -547,6 +556,7 @@ int lexp_destroy(lexp_ctx* c) {
         cudaFree(c->d_prop_cost[m]);
     }
     cudaFree(c->d_gc_scratch);
+    if (c->h_gc_flags) cudaFreeHost(c->h_gc_flags);
     cudaFree(c->d_sync_arena);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1303,6 +1313,88 @@ int upload_gc_cells(lexp_ctx* c, int n, const lexp_rect* regions, GcCell** d_cel
 }
 }  // namespace
 
+namespace {
+void gc_phase(int phase, lexp_ctx* c, lexp_plan* pl, const GcParams& gp, const GcPhaseCtl& ctl, int cur) {   // (no template: C linkage block)
+#define LEXP_GC_PHASE_CASE(PH) case PH: LEXP_LAUNCH((lexp_gc_phase_kernel<PH>), pl->gc_nblocks, kGcPhaseThreads, 0, c->stream, gp, ctl, cur); break;
+    switch (phase) {
+        LEXP_GC_PHASE_CASE(GC_PH_BUILD) LEXP_GC_PHASE_CASE(GC_PH_GATHER) LEXP_GC_PHASE_CASE(GC_PH_CLEAR) LEXP_GC_PHASE_CASE(GC_PH_RELAX)
+        LEXP_GC_PHASE_CASE(GC_PH_ACTIVE) LEXP_GC_PHASE_CASE(GC_PH_PUSH) LEXP_GC_PHASE_CASE(GC_PH_RELABEL) LEXP_GC_PHASE_CASE(GC_PH_APPLY)
+    }
+#undef LEXP_GC_PHASE_CASE
+    c->launches++;
+}
+// block map + control block of the phase kernels (once per plan)
+int ensure_gc_phase_plan(lexp_ctx* c, lexp_plan* pl) {
+    if (pl->d_gc_blocks) return LEXP_OK;
+    std::vector<GcBlock> blocks;
+    for (int i = 0; i < pl->ncalls; i++) {
+        const int n = pl->targ[i].width * pl->targ[i].height;
+        for (int first = 0; first < n; first += kGcPhaseThreads) blocks.push_back(GcBlock{i, first});
+    }
+    pl->gc_nblocks = (int)blocks.size();
+    const size_t ints = ((size_t)2 * pl->ncalls + 2 + 1) / 2 * 2;   // done, active, g_flags; doubles follow 8-byte aligned
+    LEXP_CUDA(cudaMalloc(&pl->d_gc_blocks, blocks.size() * sizeof(GcBlock)));
+    LEXP_CUDA(cudaMalloc(&pl->d_gc_ctl, ints * sizeof(int) + 2 * blocks.size() * sizeof(double)));
+    LEXP_CUDA(cudaMemcpyAsync(pl->d_gc_blocks, blocks.data(), blocks.size() * sizeof(GcBlock), cudaMemcpyHostToDevice, c->stream));
+    LEXP_CUDA(cudaStreamSynchronize(c->stream));   // `blocks` is local
+    if (!c->h_gc_flags) LEXP_CUDA(cudaHostAlloc(&c->h_gc_flags, 2 * sizeof(int), cudaHostAllocDefault));
+    return LEXP_OK;
+}
+// The expansion moves of a plan with large cells: the phases of lexp_gc_move_kernel as kernels over all SMs, all cells in lockstep, two
+// flags read back per decision (lexp_gc.cuh).  Blocking.
+int run_gc_phases(lexp_ctx* c, lexp_plan* pl, const GcParams& gp, double* d_flows_out) {
+    { int rc = ensure_gc_phase_plan(c, pl); if (rc) return rc; }
+    const size_t ints = ((size_t)2 * pl->ncalls + 2 + 1) / 2 * 2;
+    int* ibase = reinterpret_cast<int*>(pl->d_gc_ctl);
+    GcPhaseCtl ctl{};
+    ctl.blocks = pl->d_gc_blocks; ctl.done = ibase; ctl.active = ibase + pl->ncalls; ctl.g_flags = ibase + 2 * pl->ncalls;
+    ctl.konst_part = reinterpret_cast<double*>(pl->d_gc_ctl + ints * sizeof(int)); ctl.sink_part = ctl.konst_part + pl->gc_nblocks;
+    ctl.ncells = pl->ncalls;
+    LEXP_CUDA(cudaMemsetAsync(ibase, 0, ints * sizeof(int), c->stream));
+    gc_phase(GC_PH_BUILD, c, pl, gp, ctl, 0);
+    auto flag = [&](int which, int* out) -> cudaError_t {   // read a decision flag back (and leave it cleared for the next use)
+        cudaError_t e = cudaMemcpyAsync(c->h_gc_flags + which, ctl.g_flags + which, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctl.g_flags + which, 0, sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        *out = c->h_gc_flags[which];
+        return e;
+    };
+    int cur = 0, rounds = 0;
+    for (;;) {
+        gc_phase(GC_PH_GATHER, c, pl, gp, ctl, cur);    // global relabelling: pending pushes, then exact distances by relaxation passes
+        gc_phase(GC_PH_CLEAR, c, pl, gp, ctl, cur);
+        for (int changed = 1; changed;) {
+            for (int pass = 0; pass < 8; pass++) gc_phase(GC_PH_RELAX, c, pl, gp, ctl, cur);
+            LEXP_CUDA(flag(0, &changed));
+        }
+        gc_phase(GC_PH_ACTIVE, c, pl, gp, ctl, cur);
+        LEXP_LAUNCH(lexp_gc_phase_decide, (pl->ncalls + 127) / 128, 128, 0, c->stream, ctl);
+        c->launches++;
+        int any_active = 0;
+        LEXP_CUDA(flag(1, &any_active));
+        if (!any_active) break;
+        if (rounds >= c->gc_max_rounds) {   // bounded like every loop of the device path; reported by lexp_pm_get
+            const int two = 2;
+            LEXP_CUDA(cudaMemcpyAsync(gp.err_flag, &two, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            LEXP_CUDA(cudaStreamSynchronize(c->stream));
+            break;
+        }
+        for (int r = 0; r < c->gc_relabel_every; r++, rounds++) {
+            gc_phase(GC_PH_PUSH, c, pl, gp, ctl, cur);
+            gc_phase(GC_PH_RELABEL, c, pl, gp, ctl, cur);
+            cur ^= 1;
+        }
+    }
+    gc_phase(GC_PH_APPLY, c, pl, gp, ctl, cur);
+    if (d_flows_out) {
+        LEXP_LAUNCH(lexp_gc_phase_flows, (pl->ncalls + 127) / 128, 128, 0, c->stream, ctl, pl->gc_nblocks, d_flows_out);
+        c->launches++;
+    }
+    LEXP_CUDA(cudaGetLastError());
+    return LEXP_OK;
+}
+}  // namespace
+
 int lexp_set_smoothness(lexp_ctx* c, float lambda, float omega, float th_smooth, float epsilon) {
     if (!c) return fail(LEXP_ERR_INVALID, "null ctx");
     if (!(omega > 0.0f) || !(lambda >= 0.0f) || !(th_smooth >= 0.0f) || !(epsilon >= 0.0f)) return fail(LEXP_ERR_INVALID, "bad smoothness parameters");
@@ -1381,7 +1473,11 @@ int lexp_plan_gc_step(lexp_ctx* c, lexp_plan* pl, int mode, int kind, int m, uin
     { int rc = ensure_coef(c, mode); if (rc) return rc; }
     const int H = c->p.height, W = c->p.width;
     if (!c->d_prop_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_prop_cost[mode], (size_t)H * W * sizeof(float)));
-    if (!pl->d_gc_cells) { int rc = upload_gc_cells(c, pl->ncalls, pl->targ.data(), &pl->d_gc_cells, &pl->gc_nodes); if (rc) return rc; }
+    if (!pl->d_gc_cells) {
+        int rc = upload_gc_cells(c, pl->ncalls, pl->targ.data(), &pl->d_gc_cells, &pl->gc_nodes);
+        if (rc) return rc;
+        for (const lexp_rect& t : pl->targ) pl->gc_max_nodes = std::max(pl->gc_max_nodes, t.width * t.height);
+    }
     if (pl->gc_nodes > c->gc_scratch_nodes) {   // the residual network of the largest group so far
         LEXP_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->d_gc_scratch); c->d_gc_scratch = nullptr; c->gc_scratch_nodes = 0;
@@ -1411,6 +1507,7 @@ int lexp_plan_gc_step(lexp_ctx* c, lexp_plan* pl, int mode, int kind, int m, uin
     gp.flows_out = d_flows_out; gp.iters_out = nullptr; gp.err_flag = c->d_flags[mode] + kMaxPeers + 1;
     gp.H = H; gp.W = W; gp.lambda = c->sm_lambda; gp.th_smooth = c->sm_th;
     gp.relabel_every = c->gc_relabel_every; gp.max_rounds = c->gc_max_rounds;
+    if (pl->gc_max_nodes > c->gc_big_nodes) return run_gc_phases(c, pl, gp, d_flows_out);   // large cells: phase kernels over all SMs (blocking)
     LEXP_LAUNCH(lexp_gc_move_kernel, pl->ncalls, c->gc_threads, 0, c->stream, gp);
     LEXP_CUDA(cudaGetLastError());
     c->launches++;

@@ -27,7 +27,7 @@ __host__ __device__ __forceinline__ int gc_ref_index(int d) {
     return d == 0 ? 1 : d == 1 ? 3 : d == 2 ? 6 : d == 3 ? 7 : d == 4 ? 0 : d == 5 ? 2 : d == 6 ? 5 : 4;
 }
 constexpr int kGcInf = 1 << 30;     // height of a node from which the sink cannot be reached
-constexpr int kGcWords = 27;        // scratch words per node: excess, sink capacity, height, 8 residual capacities, 2 x 8 push slots
+constexpr int kGcWords = 28;        // scratch words per node: excess, sink capacity, height, 8 residual capacities, 2 x 8 push slots, proposed height
 
 // ---- f-2: smoothness coefficients --------------------------------------------------------------------------------------------
 // smoothnessCoeff[mode][k](p) = max(epsilon, exp(-sum_c |I_c(p + n_k) - I_c(p)| / omega)), zero where p + n_k lies outside the image
@@ -168,8 +168,7 @@ struct GcParams {
     int max_rounds;                  // safety bound on the total number of rounds
 };
 
-// The expansion move of one cell: graph construction (FastGCStereo.h:424-549), minimum cut, `subProposalCost.copyTo(subCurrentCost, mask);
-// subCurrentLabeling.setTo(label, mask)` (FastGCStereo.h:58-59).  One CTA per cell; thread t owns the nodes t, t + blockDim, ...
+// ---- the expansion move: per-node steps, shared by the one-CTA-per-cell kernel and the phase kernels of large cells -------------------
 //
 // Graph (FastGCStereo.h:430-549): node s = pixel of the region with terminal weights
 //     source S_s = currentCost(s) + sum_boundary cost00 + sum_{forward pairs (s, j)} C + sum_{forward pairs (i, s)} (D - C)
@@ -178,7 +177,8 @@ struct GcParams {
 // pair, StereoEnergy.h:441-449); boundary = neighbours outside the region but inside the image, which keep their label (:455-470).
 // Only S - T shapes the cut; BK's flow value is sum_s min(S_s, T_s) + maxflow of what remains (see oracle/maxflow/graph.h).
 //
-// Minimum cut: synchronous push-relabel, deterministic (no floating-point atomics): in a round every active node (excess > 0, finite
+// Minimum cut: synchronous push-relabel, deterministic (no floating-point atomics, relabels computed from the heights of the round's
+// start: nothing depends on the order in which threads run): in a round every active node (excess > 0, finite
 // height) first collects what its neighbours pushed to it in the previous round (push slots, double buffered), then pushes to the sink
 // and along admissible arcs (height(v) == height(u) + 1) and records the amounts in its own push slots; after a barrier the nodes that
 // still hold excess are relabelled.  Two neighbours never push along the same arc pair in the same round (the admissibility conditions
@@ -186,82 +186,227 @@ struct GcParams {
 // (distance to the sink in the residual graph, by chaotic relaxation); nodes that cannot reach the sink get height infinity and stop
 // being active.  The loop ends when no node is active right after such a global relabelling: the preflow is then maximum and
 // height == infinity marks exactly the nodes from which the sink is unreachable = BK's SOURCE segment = the update mask.
+struct GcView {       // the residual network of one cell inside the scratch planes
+    GcCell c;
+    int N;
+    long long SN;
+    float* ex;        // excess
+    float* snk;       // residual capacity to the sink
+    int* ht;          // height
+    float* res;       // res[d * SN + s]: residual capacity of the arc s -> s + n_d
+    float* pb;        // pb[(b * 8 + d) * SN + s]: amount s pushed along d in a round of parity b
+    int* hq;          // height proposed by the node's last relabel; committed (max with ht) by its owner in the next push phase
+};
+__device__ __forceinline__ GcView gc_view(const GcParams& P, const GcCell c) {
+    GcView V;
+    V.c = c; V.N = c.w * c.h; V.SN = P.scratch_nodes;
+    V.ex = P.scratch + c.node0;
+    V.snk = P.scratch + V.SN + c.node0;
+    V.ht = reinterpret_cast<int*>(P.scratch + 2 * V.SN) + c.node0;
+    V.res = P.scratch + 3 * V.SN + c.node0;
+    V.pb = P.scratch + 11 * V.SN + c.node0;
+    V.hq = reinterpret_cast<int*>(P.scratch + 27 * V.SN) + c.node0;
+    return V;
+}
+
+// Graph construction of node s.  The terminal weights are accumulated exactly as the reference's sequence of Graph::add_tweights calls does
+// (BK keeps only the NET capacity tr = source - sink in float and moves the common part min(source, sink) into the flow value): first
+// (currentCost, proposalCost) (:433), then the boundary terms in the reference's neighbour order (:455-470), then per forward direction
+// GE, EG, LG, GG the pair in which the node is `j` (D - C) and the pair in which it is `i` (C) (:478-541; the pair loops run over (y, x)
+// ascending, so a node is reached as `j` first).  With costs of 1e6 for invalid labels on both sides this keeps the small pairwise terms
+// that a plain sum of the source weights in float would round away.  Returns BK's `flow += min(cap_source, cap_sink)` of the node.
+__device__ __forceinline__ double gc_node_build(const GcParams& P, const GcView& V, const float4 l1, int s) {
+    const GcCell& c = V.c;
+    const int W = P.W, H = P.H;
+    const float lambda = P.lambda, th = P.th_smooth;
+    const long long SN = V.SN;
+    const int x = s % c.w, y = s / c.w, X = c.x + x, Y = c.y + y;
+    const size_t p = (size_t)Y * W + X;
+    const float4 L0p = P.cur_label[p];
+    const float4 cf = P.coef[p];
+    float tr = 0.0f;
+    double konst = 0.0;
+    auto add_tweights = [&](float cap_source, float cap_sink) {   // Graph::add_tweights of the BK library
+        if (tr > 0.0f) cap_source = __fadd_rn(cap_source, tr); else cap_sink = __fsub_rn(cap_sink, tr);
+        konst += (double)(cap_source < cap_sink ? cap_source : cap_sink);
+        tr = __fsub_rn(cap_source, cap_sink);
+    };
+    add_tweights(P.cur_cost[p], P.prop_cost[p]);                                                   // :433
+    if (x == 0 || x == c.w - 1 || y == 0 || y == c.h - 1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {   // the reference's neighbour order LE GE EL EG LL GL LG GG
+            const int d = k == 0 ? 4 : k == 1 ? 0 : k == 2 ? 5 : k == 3 ? 1 : k == 4 ? 7 : k == 5 ? 6 : k == 6 ? 2 : 3;
+            const int qx = x + gc_dx(d), qy = y + gc_dy(d), QX = X + gc_dx(d), QY = Y + gc_dy(d);
+            if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) continue;              // region.contains(pt)
+            if (QX < 0 || QX >= W || QY < 0 || QY >= H) continue;                  // !imageDomain.contains(pt)
+            const size_t q = (size_t)QY * W + QX;
+            const float4 L0q = P.cur_label[q];                                     // the neighbour keeps its label
+            const float co = d < 4 ? coef_of(cf, d) : coef_of(P.coef[q], d - 4);
+            add_tweights(boundary_term(L0p, L0q, X, Y, QX, QY, co, lambda, th), boundary_term(l1, L0q, X, Y, QX, QY, co, lambda, th));   // :466-469
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        {   // this node is `j` of the pair whose `i` is the backward neighbour (:485, :500, :517, :534)
+            const int qx = x - gc_dx(d), qy = y - gc_dy(d);
+            if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
+                const size_t q = (size_t)(c.y + qy) * W + (c.x + qx);
+                const PairTerms t = pair_terms(P.cur_label[q], L0p, l1, c.x + qx, c.y + qy, X, Y, true, coef_of(P.coef[q], d), lambda, th);
+                add_tweights(__fsub_rn(t.c00, t.c01), 0.0f);
+            }
+        }
+        float cap = 0.0f;
+        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
+        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {   // this node is `i` (:483-484)
+            const size_t q = (size_t)(c.y + qy) * W + (c.x + qx);
+            const PairTerms t = pair_terms(L0p, P.cur_label[q], l1, X, Y, c.x + qx, c.y + qy, true, coef_of(cf, d), lambda, th);
+            cap = fmaxf(0.0f, __fsub_rn(__fadd_rn(t.c10, t.c01), t.c00));
+            add_tweights(t.c01, 0.0f);
+        }
+        V.res[(size_t)d * SN + s] = cap;
+        V.res[(size_t)(d + 4) * SN + s] = 0.0f;
+    }
+#pragma unroll
+    for (int d = 0; d < 16; d++) V.pb[(size_t)d * SN + s] = 0.0f;
+    V.ex[s] = tr > 0.0f ? tr : 0.0f;
+    V.snk[s] = tr < 0.0f ? -tr : 0.0f;
+    V.ht[s] = kGcInf;
+    V.hq[s] = 0;
+    return konst;
+}
+// start of a global relabelling: apply the pushes still pending in the neighbours' slots of parity `cur`, reset the height
+__device__ __forceinline__ void gc_node_gather(const GcView& V, int s, int cur) {
+    const GcCell& c = V.c;
+    const int x = s % c.w, y = s / c.w;
+    float e = V.ex[s];
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
+        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
+            const float f = V.pb[(size_t)(cur * 8 + (d ^ 4)) * V.SN + (qy * c.w + qx)];
+            if (f > 0.0f) { e += f; V.res[(size_t)d * V.SN + s] += f; }
+        }
+    }
+    V.ex[s] = e;
+    V.ht[s] = V.snk[s] > 0.0f ? 1 : kGcInf;
+    V.hq[s] = 0;   // the exact distances replace whatever the last relabel proposed
+}
+__device__ __forceinline__ void gc_node_clear_slots(const GcView& V, int s, int cur) {
+#pragma unroll
+    for (int d = 0; d < 8; d++) V.pb[(size_t)(cur * 8 + d) * V.SN + s] = 0.0f;
+}
+// one pass of the chaotic relaxation h(v) = 1 + min over residual arcs v -> u of h(u) (converges to the BFS distances to the sink)
+__device__ __forceinline__ int gc_node_relax(const GcView& V, int s) {
+    const GcCell& c = V.c;
+    const int hv = V.ht[s];
+    if (hv == 1) return 0;
+    const int x = s % c.w, y = s / c.w;
+    int best = kGcInf;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
+        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h && V.res[(size_t)d * V.SN + s] > 0.0f) {
+            const int hu = V.ht[qy * c.w + qx];
+            if (hu < best) best = hu;
+        }
+    }
+    if (best < kGcInf && best + 1 < hv) { V.ht[s] = best + 1; return 1; }
+    return 0;
+}
+__device__ __forceinline__ int gc_node_active(const GcView& V, int s) { return V.ex[s] > 0.0f && V.ht[s] < kGcInf; }
+// (A) collect the previous round's pushes, push to the sink and along admissible arcs; returns whether the node held excess
+__device__ __forceinline__ int gc_node_push(const GcView& V, int s, int cur, double& to_sink) {
+    const GcCell& c = V.c;
+    const long long SN = V.SN;
+    const int x = s % c.w, y = s / c.w;
+    float e = V.ex[s];
+    float rs[8];
+    int hu[8];
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
+        rs[d] = 0.0f; hu[d] = kGcInf;
+        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
+            const int u = qy * c.w + qx;
+            rs[d] = V.res[(size_t)d * SN + s];
+            const float f = V.pb[(size_t)(cur * 8 + (d ^ 4)) * SN + u];
+            if (f > 0.0f) { e += f; rs[d] += f; }
+            hu[d] = max(V.ht[u], V.hq[u]);   // whether u has committed its proposal yet or not: the same value
+        }
+    }
+    const int hv = max(V.ht[s], V.hq[s]);
+    V.ht[s] = hv;                            // commit the height the last relabel proposed
+    float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int busy = 0;
+    if (e > 0.0f && hv < kGcInf) {
+        busy = 1;
+        const float cs = V.snk[s];
+        if (cs > 0.0f) {   // a node with sink capacity has height 1: the arc to the sink is admissible
+            const float f = e < cs ? e : cs;
+            e -= f; V.snk[s] = cs - f; to_sink += (double)f;
+        }
+#pragma unroll
+        for (int d = 0; d < 8; d++)
+            if (e > 0.0f && rs[d] > 0.0f && hv == hu[d] + 1) {
+                const float f = e < rs[d] ? e : rs[d];
+                e -= f; rs[d] -= f; out[d] = f;
+            }
+    }
+    V.ex[s] = e;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        V.res[(size_t)d * SN + s] = rs[d];
+        V.pb[(size_t)((cur ^ 1) * 8 + d) * SN + s] = out[d];
+    }
+    return busy;
+}
+// (B) relabel a node that still holds excess; an arc whose residual was created by a push of THIS round (still in the neighbour's push
+// slot) counts as well.  The new height is only PROPOSED (hq): all relabels of a round are computed from the same committed heights, so
+// the result does not depend on the order in which threads run; the owner commits it at the start of the next push phase, and readers
+// take max(ht, hq) -- heights only grow, so a stale proposal never exceeds the committed height.
+__device__ __forceinline__ void gc_node_relabel(const GcView& V, int s, int cur) {
+    const GcCell& c = V.c;
+    const int hv = V.ht[s];
+    if (!(V.ex[s] > 0.0f && hv < kGcInf)) return;
+    const int x = s % c.w, y = s / c.w;
+    int best = V.snk[s] > 0.0f ? 0 : kGcInf;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
+        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
+            const int u = qy * c.w + qx;
+            if (V.res[(size_t)d * V.SN + s] > 0.0f || V.pb[(size_t)((cur ^ 1) * 8 + (d ^ 4)) * V.SN + u] > 0.0f) {
+                const int hq = V.ht[u];
+                if (hq < best) best = hq;
+            }
+        }
+    }
+    const int hn = (best >= kGcInf || best + 1 > V.N + 1) ? kGcInf : best + 1;
+    if (hn > hv) V.hq[s] = hn;   // proposed, not written to ht: every node of this phase sees the heights of the phase's start
+}
+// the move: `updateMask = what_segment(s) == SOURCE` (FastGCStereo.h:553-557), copyTo / setTo (:58-59); valid right after a global
+// relabelling with no active node left: height == infinity <=> the sink is unreachable from the node
+__device__ __forceinline__ void gc_node_apply(const GcParams& P, const GcView& V, const float4 l1, int s) {
+    if (V.ht[s] >= kGcInf) {
+        const int x = s % V.c.w, y = s / V.c.w;
+        const size_t p = (size_t)(V.c.y + y) * P.W + (V.c.x + x);
+        P.cur_cost[p] = P.prop_cost[p];
+        P.cur_label[p] = l1;
+    }
+}
+
+// The expansion move of one cell by ONE CTA (cells up to a few 10^4 nodes: layers 0 and 1): graph construction, minimum cut, copyTo / setTo.
+// Thread t owns the nodes t, t + blockDim, ...; the phases are separated by __syncthreads().
 __global__ void __launch_bounds__(1024) lexp_gc_move_kernel(const GcParams P) {
     __shared__ int s_flag[3];
     __shared__ double s_red[1024];
-    const GcCell c = P.cells[blockIdx.x];
+    const GcView V = gc_view(P, P.cells[blockIdx.x]);
     const Plane4 plv = P.planes[blockIdx.x];
     const float4 l1 = make_float4(plv.a, plv.b, plv.c, plv.v);
-    const int N = c.w * c.h, T = blockDim.x, tid = threadIdx.x;
-    const long long SN = P.scratch_nodes;
-    float* ex = P.scratch + c.node0;                                   // excess
-    float* snk = P.scratch + SN + c.node0;                             // residual capacity to the sink
-    int* ht = reinterpret_cast<int*>(P.scratch + 2 * SN) + c.node0;    // height
-    float* res = P.scratch + 3 * SN + c.node0;                         // res[d * SN + s]: residual capacity of the arc s -> s + n_d
-    float* pb = P.scratch + 11 * SN + c.node0;                         // pb[(b * 8 + d) * SN + s]: amount s pushed along d in a round of parity b
-    const float lambda = P.lambda, th = P.th_smooth;
-    const int W = P.W, H = P.H;
+    const int N = V.N, T = blockDim.x, tid = threadIdx.x;
 
-    // ---- graph construction -------------------------------------------------------------------------------------------------
-    // The terminal weights of a node are accumulated exactly as the reference's sequence of Graph::add_tweights calls does (BK keeps only
-    // the NET capacity tr = source - sink in float and moves the common part min(source, sink) into the flow value): first
-    // (currentCost, proposalCost) (:433), then the boundary terms in the reference's neighbour order (:455-470), then per forward
-    // direction GE, EG, LG, GG the pair in which the node is `j` (D - C) and the pair in which it is `i` (C) (:478-541; the pair loops
-    // run over (y, x) ascending, so a node is reached as `j` first).  With costs of 1e6 for invalid labels on both sides this keeps
-    // the small pairwise terms that a plain sum of the source weights in float would round away.
     double konst = 0.0;   // BK's `flow += min(cap_source, cap_sink)` over this thread's nodes
-    for (int s = tid; s < N; s += T) {
-        const int x = s % c.w, y = s / c.w, X = c.x + x, Y = c.y + y;
-        const size_t p = (size_t)Y * W + X;
-        const float4 L0p = P.cur_label[p];
-        const float4 cf = P.coef[p];
-        float tr = 0.0f;
-        auto add_tweights = [&](float cap_source, float cap_sink) {   // Graph::add_tweights of the BK library
-            if (tr > 0.0f) cap_source = __fadd_rn(cap_source, tr); else cap_sink = __fsub_rn(cap_sink, tr);
-            konst += (double)(cap_source < cap_sink ? cap_source : cap_sink);
-            tr = __fsub_rn(cap_source, cap_sink);
-        };
-        add_tweights(P.cur_cost[p], P.prop_cost[p]);                                                   // :433
-        if (x == 0 || x == c.w - 1 || y == 0 || y == c.h - 1) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {   // the reference's neighbour order LE GE EL EG LL GL LG GG
-                const int d = k == 0 ? 4 : k == 1 ? 0 : k == 2 ? 5 : k == 3 ? 1 : k == 4 ? 7 : k == 5 ? 6 : k == 6 ? 2 : 3;
-                const int qx = x + gc_dx(d), qy = y + gc_dy(d), QX = X + gc_dx(d), QY = Y + gc_dy(d);
-                if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) continue;              // region.contains(pt)
-                if (QX < 0 || QX >= W || QY < 0 || QY >= H) continue;                  // !imageDomain.contains(pt)
-                const size_t q = (size_t)QY * W + QX;
-                const float4 L0q = P.cur_label[q];                                     // the neighbour keeps its label
-                const float co = d < 4 ? coef_of(cf, d) : coef_of(P.coef[q], d - 4);
-                add_tweights(boundary_term(L0p, L0q, X, Y, QX, QY, co, lambda, th), boundary_term(l1, L0q, X, Y, QX, QY, co, lambda, th));   // :466-469
-            }
-        }
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            {   // this node is `j` of the pair whose `i` is the backward neighbour (:485, :500, :517, :534)
-                const int qx = x - gc_dx(d), qy = y - gc_dy(d);
-                if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
-                    const size_t q = (size_t)(c.y + qy) * W + (c.x + qx);
-                    const PairTerms t = pair_terms(P.cur_label[q], L0p, l1, c.x + qx, c.y + qy, X, Y, true, coef_of(P.coef[q], d), lambda, th);
-                    add_tweights(__fsub_rn(t.c00, t.c01), 0.0f);
-                }
-            }
-            float cap = 0.0f;
-            const int qx = x + gc_dx(d), qy = y + gc_dy(d);
-            if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {   // this node is `i` (:483-484)
-                const size_t q = (size_t)(c.y + qy) * W + (c.x + qx);
-                const PairTerms t = pair_terms(L0p, P.cur_label[q], l1, X, Y, c.x + qx, c.y + qy, true, coef_of(cf, d), lambda, th);
-                cap = fmaxf(0.0f, __fsub_rn(__fadd_rn(t.c10, t.c01), t.c00));
-                add_tweights(t.c01, 0.0f);
-            }
-            res[(size_t)d * SN + s] = cap;
-            res[(size_t)(d + 4) * SN + s] = 0.0f;
-        }
-#pragma unroll
-        for (int d = 0; d < 16; d++) pb[(size_t)d * SN + s] = 0.0f;
-        ex[s] = tr > 0.0f ? tr : 0.0f;
-        snk[s] = tr < 0.0f ? -tr : 0.0f;
-        ht[s] = kGcInf;
-    }
+    for (int s = tid; s < N; s += T) konst += gc_node_build(P, V, l1, s);
     __syncthreads();
 
     double to_sink = 0.0;
@@ -269,43 +414,14 @@ __global__ void __launch_bounds__(1024) lexp_gc_move_kernel(const GcParams P) {
     bool done = false;
     while (!done) {
         // ---- global relabelling: apply the pending pushes, then exact distances to the sink --------------------------------------
-        for (int s = tid; s < N; s += T) {
-            const int x = s % c.w, y = s / c.w;
-            float e = ex[s];
-#pragma unroll
-            for (int d = 0; d < 8; d++) {
-                const int qx = x + gc_dx(d), qy = y + gc_dy(d);
-                if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
-                    const float f = pb[(size_t)(cur * 8 + (d ^ 4)) * SN + (qy * c.w + qx)];
-                    if (f > 0.0f) { e += f; res[(size_t)d * SN + s] += f; }
-                }
-            }
-            ex[s] = e;
-            ht[s] = snk[s] > 0.0f ? 1 : kGcInf;
-        }
+        for (int s = tid; s < N; s += T) gc_node_gather(V, s, cur);
         __syncthreads();
-        for (int s = tid; s < N; s += T)
-#pragma unroll
-            for (int d = 0; d < 8; d++) pb[(size_t)(cur * 8 + d) * SN + s] = 0.0f;
-        for (;;) {   // chaotic relaxation of h(v) = 1 + min over residual arcs v -> u of h(u): converges to the BFS distances
+        for (int s = tid; s < N; s += T) gc_node_clear_slots(V, s, cur);
+        for (;;) {
             if (tid == 0) s_flag[0] = 0;
             __syncthreads();
             int changed = 0;
-            for (int s = tid; s < N; s += T) {
-                int hv = ht[s];
-                if (hv == 1) continue;
-                const int x = s % c.w, y = s / c.w;
-                int best = kGcInf;
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    const int qx = x + gc_dx(d), qy = y + gc_dy(d);
-                    if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h && res[(size_t)d * SN + s] > 0.0f) {
-                        const int hu = ht[qy * c.w + qx];
-                        if (hu < best) best = hu;
-                    }
-                }
-                if (best < kGcInf && best + 1 < hv) { ht[s] = best + 1; changed = 1; }
-            }
+            for (int s = tid; s < N; s += T) changed |= gc_node_relax(V, s);
             if (changed) s_flag[0] = 1;
             __syncthreads();
             const int any = s_flag[0];
@@ -317,7 +433,7 @@ __global__ void __launch_bounds__(1024) lexp_gc_move_kernel(const GcParams P) {
         __syncthreads();
         {
             int active = 0;
-            for (int s = tid; s < N; s += T) if (ex[s] > 0.0f && ht[s] < kGcInf) active = 1;
+            for (int s = tid; s < N; s += T) active |= gc_node_active(V, s);
             if (active) s_flag[1] = 1;
         }
         __syncthreads();
@@ -331,90 +447,20 @@ __global__ void __launch_bounds__(1024) lexp_gc_move_kernel(const GcParams P) {
         if (tid == 0) { s_flag[1] = 0; s_flag[2] = 0; }
         __syncthreads();
         for (int r = 0; r < P.relabel_every; r++, rounds++) {
-            // (A) collect the previous round's pushes, push to the sink and along admissible arcs
             int busy = 0;
-            for (int s = tid; s < N; s += T) {
-                const int x = s % c.w, y = s / c.w;
-                float e = ex[s];
-                float rs[8];
-                int hu[8];
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    const int qx = x + gc_dx(d), qy = y + gc_dy(d);
-                    rs[d] = 0.0f; hu[d] = kGcInf;
-                    if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
-                        const int u = qy * c.w + qx;
-                        rs[d] = res[(size_t)d * SN + s];
-                        const float f = pb[(size_t)(cur * 8 + (d ^ 4)) * SN + u];
-                        if (f > 0.0f) { e += f; rs[d] += f; }
-                        hu[d] = ht[u];
-                    }
-                }
-                const int hv = ht[s];
-                float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (e > 0.0f && hv < kGcInf) {
-                    busy = 1;
-                    const float cs = snk[s];
-                    if (cs > 0.0f) {   // a node with sink capacity has height 1: the arc to the sink is admissible
-                        const float f = e < cs ? e : cs;
-                        e -= f; snk[s] = cs - f; to_sink += (double)f;
-                    }
-#pragma unroll
-                    for (int d = 0; d < 8; d++)
-                        if (e > 0.0f && rs[d] > 0.0f && hv == hu[d] + 1) {
-                            const float f = e < rs[d] ? e : rs[d];
-                            e -= f; rs[d] -= f; out[d] = f;
-                        }
-                }
-                ex[s] = e;
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    res[(size_t)d * SN + s] = rs[d];
-                    pb[(size_t)((cur ^ 1) * 8 + d) * SN + s] = out[d];
-                }
-            }
+            for (int s = tid; s < N; s += T) busy |= gc_node_push(V, s, cur, to_sink);
             if (busy) s_flag[1 + (r & 1)] = 1;
             __syncthreads();
             const int any_busy = s_flag[1 + (r & 1)];
             if (tid == 0) s_flag[1 + ((r + 1) & 1)] = 0;   // next round's flag: last read before the previous round's second barrier
-            // (B) relabel the nodes that still hold excess (heights only grow: concurrent relabels of neighbours stay valid); an arc
-            // whose residual was created by a push of THIS round (still in the neighbour's push slot) counts as well
-            for (int s = tid; s < N; s += T) {
-                const int hv = ht[s];
-                if (ex[s] > 0.0f && hv < kGcInf) {
-                    const int x = s % c.w, y = s / c.w;
-                    int best = snk[s] > 0.0f ? 0 : kGcInf;
-#pragma unroll
-                    for (int d = 0; d < 8; d++) {
-                        const int qx = x + gc_dx(d), qy = y + gc_dy(d);
-                        if (qx >= 0 && qx < c.w && qy >= 0 && qy < c.h) {
-                            const int u = qy * c.w + qx;
-                            if (res[(size_t)d * SN + s] > 0.0f || pb[(size_t)((cur ^ 1) * 8 + (d ^ 4)) * SN + u] > 0.0f) {
-                                const int hq = ht[u];
-                                if (hq < best) best = hq;
-                            }
-                        }
-                    }
-                    const int hn = (best >= kGcInf || best + 1 > N + 1) ? kGcInf : best + 1;
-                    if (hn > hv) ht[s] = hn;
-                }
-            }
+            for (int s = tid; s < N; s += T) gc_node_relabel(V, s, cur);
             __syncthreads();
             cur ^= 1;
             if (!any_busy) { rounds++; break; }
         }
     }
 
-    // ---- the move: `updateMask = what_segment(s) == SOURCE` (FastGCStereo.h:553-557), copyTo / setTo (:58-59) ---------------------
-    // (the loop ends right after a global relabelling: height == infinity <=> the sink is unreachable from the node)
-    for (int s = tid; s < N; s += T) {
-        if (ht[s] >= kGcInf) {
-            const int x = s % c.w, y = s / c.w;
-            const size_t p = (size_t)(c.y + y) * W + (c.x + x);
-            P.cur_cost[p] = P.prop_cost[p];
-            P.cur_label[p] = l1;
-        }
-    }
+    for (int s = tid; s < N; s += T) gc_node_apply(P, V, l1, s);
     if (P.flows_out) {
         s_red[tid] = konst + to_sink;
         __syncthreads();
@@ -425,6 +471,73 @@ __global__ void __launch_bounds__(1024) lexp_gc_move_kernel(const GcParams P) {
         }
     }
     if (P.iters_out && tid == 0) P.iters_out[blockIdx.x] = rounds;
+}
+
+// ---- large cells (layer 2: 3 * 10^5 nodes): the same steps as PHASE KERNELS over all SMs --------------------------------------------------
+// One CTA per cell leaves 140 SMs idle when a group has 4-6 cells.  Here every phase of the loop above is a kernel of its own whose blocks
+// of kGcPhaseThreads threads each own a run of consecutive nodes of one cell (block map built with the plan); the host issues the phases
+// in the same order for all cells of the plan in lockstep and reads two flags back per decision (did a relaxation pass change a height?
+// is any node active after the global relabelling?).  A cell that has finished (`done`) is skipped by every later phase; a round in which
+// a cell has nothing to push is a no-op, so the result is identical to the one-CTA kernel's (same arithmetic, same rounds, same relabelling
+// points) -- the emulator tests compare the two paths bit for bit.
+constexpr int kGcPhaseThreads = 256;
+struct GcBlock { int cell, first; };   // block b of a phase kernel: nodes [first, first + kGcPhaseThreads) of cell `cell`
+struct GcPhaseCtl {
+    const GcBlock* blocks;
+    int* done;            // [ncells] the cell's minimum cut is complete
+    int* active;          // [ncells] the cell has an active node (written by the `active` phase)
+    int* g_flags;         // [0]: a relaxation pass changed a height; [1]: some cell is still active
+    double* konst_part;   // [nblocks] BK's add_tweights constant, per block
+    double* sink_part;    // [nblocks] flow pushed into the sink so far, per block
+    int ncells;
+};
+enum { GC_PH_BUILD = 0, GC_PH_GATHER, GC_PH_CLEAR, GC_PH_RELAX, GC_PH_ACTIVE, GC_PH_PUSH, GC_PH_RELABEL, GC_PH_APPLY };
+
+template <int PHASE>
+__global__ void __launch_bounds__(kGcPhaseThreads) lexp_gc_phase_kernel(const GcParams P, const GcPhaseCtl C, int cur) {
+    __shared__ double s_red[kGcPhaseThreads];
+    const GcBlock b = C.blocks[blockIdx.x];
+    if (PHASE != GC_PH_BUILD && PHASE != GC_PH_APPLY && C.done[b.cell]) return;
+    const GcView V = gc_view(P, P.cells[b.cell]);
+    const int s = b.first + threadIdx.x;
+    const bool in = s < V.N;
+    const Plane4 plv = P.planes[b.cell];
+    const float4 l1 = make_float4(plv.a, plv.b, plv.c, plv.v);
+    if (PHASE == GC_PH_BUILD || PHASE == GC_PH_PUSH) {
+        double v = 0.0;
+        if (PHASE == GC_PH_BUILD) { if (in) v = gc_node_build(P, V, l1, s); }
+        else if (in) gc_node_push(V, s, cur, v);
+        s_red[threadIdx.x] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double f = 0.0;
+            for (int i = 0; i < kGcPhaseThreads; i++) f += s_red[i];
+            if (PHASE == GC_PH_BUILD) { C.konst_part[blockIdx.x] = f; C.sink_part[blockIdx.x] = 0.0; }
+            else if (f != 0.0) C.sink_part[blockIdx.x] += f;
+        }
+    } else if (in) {
+        if (PHASE == GC_PH_GATHER) gc_node_gather(V, s, cur);
+        if (PHASE == GC_PH_CLEAR) gc_node_clear_slots(V, s, cur);
+        if (PHASE == GC_PH_RELAX) { if (gc_node_relax(V, s)) C.g_flags[0] = 1; }
+        if (PHASE == GC_PH_ACTIVE) { if (gc_node_active(V, s)) C.active[b.cell] = 1; }
+        if (PHASE == GC_PH_RELABEL) gc_node_relabel(V, s, cur);
+        if (PHASE == GC_PH_APPLY) gc_node_apply(P, V, l1, s);
+    }
+}
+// after the `active` phase: cells without an active node are done; g_flags[1] = some cell goes on.  One thread per cell.
+__global__ void lexp_gc_phase_decide(const GcPhaseCtl C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.ncells || C.done[i]) return;
+    if (C.active[i]) { C.active[i] = 0; C.g_flags[1] = 1; }
+    else C.done[i] = 1;
+}
+// flow of every cell = sum over its blocks (in block order) of the add_tweights constant and the flow into the sink
+__global__ void lexp_gc_phase_flows(const GcPhaseCtl C, int nblocks, double* flows_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.ncells) return;
+    double f = 0.0;
+    for (int b = 0; b < nblocks; b++) if (C.blocks[b].cell == i) f += C.konst_part[b] + C.sink_part[b];
+    flows_out[i] = f;
 }
 
 }  // namespace lexp

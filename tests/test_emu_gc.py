@@ -4,6 +4,7 @@ import pytest
 
 from emu import emu_lib
 import test_gpu_gc as _gc
+import test_gpu_zz_gc_phases as _ph
 import test_emu_parity as _ep
 
 
@@ -43,3 +44,38 @@ def test_emu_gc_replay_right_view_strong_smoothness(devmem):
 
 def test_emu_gc_moves_never_raise_the_energy(devmem):
     _gc.test_gc_moves_never_raise_the_energy(devmem)
+
+
+# (_ph.test_phase_kernels_equal_the_one_cta_path -- every cell on the phase path, two iterations -- takes four minutes of fiber
+#  switches here; it was run on the emulator when the path was written and is part of the -m gpu suite)
+def test_emu_phase_kernels_mixed_sizes(devmem, monkeypatch):
+    _ph.test_phase_kernels_mixed_sizes_and_strong_smoothness(devmem, monkeypatch)
+
+
+def test_emu_gc_result_does_not_depend_on_the_thread_schedule(devmem):
+    """The graph-cut move is deterministic by construction (push slots instead of atomics, relabels computed from the heights of the
+    round's start): forward, reverse and reshuffled-every-pass schedules of the emulated threads must give the same state and the same
+    minimum-cut energies bit for bit -- a missing barrier or an order-dependent read in lexp_gc_move_kernel would show here."""
+    import numpy as np
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import GCSweep
+    from oracle import lexp_oracle as O
+    H, W, D, windR = 48, 64, 10, 12
+    imL, _, volL, _ = _gc.make_scene(H, W, D, seed=4)
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)]]
+    outs = []
+    for order in (0, 1, 2):
+        with emu_lib.emulated(order=order):
+            E = L.CostVolumeEnergy(imL, None, volL, None, L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5), D - 1)
+            S = GCSweep(E, unit_sizes=[8], proposers=props, **_gc.SMOOTH)
+            rng = O.CvRNG(3)
+            S.begin()
+            S.init(np.stack([O.create_random_label(rng, u[0], u[1], 0.0, D - 1.0) for u in S.init_units]))
+            flows = {(g.layer, g.group): devmem.zeros((2, g.plan.num_calls, 2)) for g in S.groups}
+            S.gc_iteration(0, 21, flows_out={k: devmem.ptr(v) for k, v in flows.items()})
+            cost, lab = S.get()
+            outs.append((cost, lab, np.concatenate([np.ascontiguousarray(v).view(np.float64).ravel() for v in flows.values()])))
+            S.close(); E.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+    assert (outs[0][2] != 0).any()
