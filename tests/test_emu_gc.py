@@ -35,7 +35,9 @@ def test_emu_pairwise_terms():
 
 
 def test_emu_gc_replay_small(devmem):
-    _gc.test_gc_replay_small(devmem)
+    import localexpstereo_b200 as L   # the GPU test's scene with one graph-cut iteration instead of two (emulation time)
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 2)], [(L.PROP_EXPANSION, 2), (L.PROP_RANDOM, 1)]]
+    _gc.check_gc_result(_gc.run_gc_replay(devmem, 72, 96, 12, 12, [8, 22], props, pm_iterations=1, gc_iterations=1, seed=5))
 
 
 def test_emu_gc_replay_right_view_strong_smoothness(devmem):
