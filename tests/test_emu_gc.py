@@ -1,9 +1,9 @@
-"""tests/test_gpu_gc.py (pairwise terms + graph-cut move on the device) on the CPU emulator of the kernel source: the graph
+"""tests/test_gpu_zz_gc.py (pairwise terms + graph-cut move on the device) on the CPU emulator of the kernel source: the graph
 construction, the deterministic push-relabel and the host-side schedule, without a GPU."""
 import pytest
 
 from emu import emu_lib
-import test_gpu_gc as _gc
+import test_gpu_zz_gc as _gc
 import test_gpu_zz_gc_phases as _ph
 import test_emu_parity as _ep
 

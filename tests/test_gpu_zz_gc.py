@@ -1,4 +1,7 @@
-"""Pairwise terms and the expansion move on the device: StereoEnergy::initSmoothnessCoeff,
+"""(Sorted after the unary / PatchMatch / drop-in tests in the -m gpu suite: the graph-cut kernels were reworked -- shared per-node steps,
+proposed heights -- after their last run on hardware.)
+
+Pairwise terms and the expansion move on the device: StereoEnergy::initSmoothnessCoeff,
 computeSmoothnessTermsExpansion (StereoEnergy.h:131-163, 398-453) and FastGCStereo::expansionMoveBK inside the graph-cut
 iterations of FastGCStereo::run (FastGCStereo.h:22-72 with doGC == true, 411-597), against the numpy / C oracle
 (oracle.smoothness_coeff, smoothness_terms_expansion, expansion_graph, gc_step) -- which tests/test_ref_pin.py holds against the

@@ -5,7 +5,7 @@ state must be bit-identical to the one-CTA path.  LEXP_GC_BIG_NODES = 0 sends ev
 import numpy as np
 import pytest
 
-import test_gpu_gc as G
+import test_gpu_zz_gc as G
 
 pytestmark = pytest.mark.gpu
 
