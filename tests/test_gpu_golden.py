@@ -47,6 +47,7 @@ def full():
     W, H, D, windR = 2048, 1536, 256, 20
     g = torch.Generator(device="cuda").manual_seed(1234)
     vol = torch.rand((D, H, W), generator=g, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()   # torch fills the volume on its own stream; the library's stream is non-blocking
     img = synth.synthetic_image(H, W, 42)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
     E = L.CostVolumeEnergy(img, None, vol, None, prm, D - 1)

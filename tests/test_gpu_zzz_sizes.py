@@ -40,6 +40,7 @@ def test_sampled_cells_of_every_layer(W, H, D, windR, picks):
     from localexpstereo_b200.sweep import v3_layer_units
     g = torch.Generator(device="cuda").manual_seed(99)
     vol = torch.rand((D, H, W), generator=g, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()   # torch fills the volume on its own stream; the library's stream is non-blocking
     img = synth.synthetic_image(H, W, 42)
     prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
     E = L.CostVolumeEnergy(img, None, vol, None, prm, D - 1)
