@@ -1333,11 +1333,19 @@ int ensure_gc_phase_plan(lexp_ctx* c, lexp_plan* pl) {
     }
     pl->gc_nblocks = (int)blocks.size();
     const size_t ints = ((size_t)2 * pl->ncalls + 2 + 1) / 2 * 2;   // done, active, g_flags; doubles follow 8-byte aligned
-    LEXP_CUDA(cudaMalloc(&pl->d_gc_blocks, blocks.size() * sizeof(GcBlock)));
-    LEXP_CUDA(cudaMalloc(&pl->d_gc_ctl, ints * sizeof(int) + 2 * blocks.size() * sizeof(double)));
-    LEXP_CUDA(cudaMemcpyAsync(pl->d_gc_blocks, blocks.data(), blocks.size() * sizeof(GcBlock), cudaMemcpyHostToDevice, c->stream));
-    LEXP_CUDA(cudaStreamSynchronize(c->stream));   // `blocks` is local
     if (!c->h_gc_flags) LEXP_CUDA(cudaHostAlloc(&c->h_gc_flags, 2 * sizeof(int), cudaHostAllocDefault));
+    GcBlock* d_blocks = nullptr;
+    char* d_ctl = nullptr;
+    cudaError_t e = cudaMalloc(&d_blocks, blocks.size() * sizeof(GcBlock));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ctl, ints * sizeof(int) + 2 * blocks.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(GcBlock), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // `blocks` is local
+    if (e != cudaSuccess) {   // both buffers or neither
+        cudaFree(d_blocks); cudaFree(d_ctl); pl->gc_nblocks = 0;
+        cudaGetLastError();
+        return fail(LEXP_ERR_CUDA, std::string("graph-cut phase plan: ") + cudaGetErrorString(e));
+    }
+    pl->d_gc_blocks = d_blocks; pl->d_gc_ctl = d_ctl;
     return LEXP_OK;
 }
 // The expansion moves of a plan with large cells: the phases of lexp_gc_move_kernel as kernels over all SMs, all cells in lockstep, two
