@@ -81,3 +81,7 @@ def test_emu_gc_result_does_not_depend_on_the_thread_schedule(devmem):
     for o in outs[1:]:
         assert np.array_equal(outs[0][0], o[0]) and np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
     assert (outs[0][2] != 0).any()
+
+
+def test_emu_gc_steps_on_the_image_based_energy(devmem):
+    _gc.test_gc_steps_on_the_image_based_energy(devmem)

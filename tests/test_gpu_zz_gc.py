@@ -226,3 +226,70 @@ def test_gc_replay_on_the_cones_crop(devmem):
                       scene=(G["imL"], G["imR"], G["volL"], G["volR"]), smooth=dict(lam=1.0, omega=10.0, th_smooth=1.0, epsilon=0.01))
     check_gc_result(r)
     assert r["n_moves"] > 1000
+
+
+def test_gc_steps_on_the_image_based_energy(devmem):
+    """BASELINE.json configs[0] (`-mode MiddV2`): FastGCStereo with NaiveStereoEnergy -- the reference's own demo -- whose iterations
+    are all graph-cut iterations.  The device state is seeded from the oracle's initCurrentFast (the device PatchMatch phase is a
+    cost-volume path), then expansion moves with device-side proposals run on the image-based unary term (lambda = 20, main.cpp:72);
+    replayed through the oracle as above."""
+    import lexp_golden
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import pm_seed
+    G = lexp_golden.load()
+    imL, imR = G["imL"], G["imR"]
+    H, W = imL.shape[:2]
+    D, windR = 64, 20
+    prm = L.Parameters(lambda_=20, windR=windR, filterName="GF", filter_param1=1e-4)
+    E = L.NaiveStereoEnergy(imL, imR, prm, D - 1)
+    Or = O.NaiveStereoEnergyOracle(imL, imR, windR, 1e-4, prm.th_col, prm.th_grad, prm.alpha, D - 1)
+    lam, omega, th, eps = 20.0, 10.0, 1.0, 0.01
+    E.set_smoothness(lam, omega, th, eps)
+    coeff = O.smoothness_coeff(imL, omega, eps)
+    plans = []
+    try:
+        lm = L.LayerManager(W, H, windR)
+        lay0 = lm.addLayer(5)                                   # main.cpp:304
+        rng = O.CvRNG(8)
+        units0 = lay0.unitRegions
+        labels = np.stack([O.create_random_label(rng, u[0] + rng.uniform_int(0, u[2]), u[1] + rng.uniform_int(0, u[3]), 0.0, D - 1.0) for u in units0])
+        cost_o, lab_o = np.full((H, W), np.inf, np.float32), np.zeros((H, W, 4), np.float32)
+        fr0 = [(max(x - windR, 0), max(y - windR, 0), min(x + w + windR, W) - max(x - windR, 0), min(y + h + windR, H) - max(y - windR, 0)) for (x, y, w, h) in units0]
+        O.pm_step(Or, units0, units0, fr0, 0, 0, 0, None, cost_o, lab_o, planes=labels, init=True)
+        E.pm_begin(0, cost_o, lab_o)
+        n_moves, worst_flow = 0, 0.0
+        lay1 = lm.addLayer(15)                                  # main.cpp:305
+        for li, (lay, gis, steps) in enumerate([(lay0, (0, 7), [(L.PROP_EXPANSION, 0), (L.PROP_RANDOM, 0)]), (lay1, (2, len(lay1.disjointRegionSets) - 1), [(L.PROP_EXPANSION, 0)])]):
+            for gi in gis:
+                g = lay.disjointRegionSets[gi]
+                us = [lay.unitRegions[r] for r in g]; ts = [lay.sharedRegions[r] for r in g]; fs = [lay.filterRegions[r] for r in g]
+                plan = E.make_plan(fs, ts); plans.append(plan)
+                plan.set_units(us, [1000 * li + r for r in g])
+                for k, (kind, m) in enumerate(steps):
+                    rec, flw = devmem.zeros((len(g), 4)), devmem.zeros((len(g), 2))
+                    plan.gc_step(kind, m, pm_seed(5, 0, 0, li, gi, k), d_planes_out=devmem.ptr(rec), d_flows_out=devmem.ptr(flw))
+                    E.sync()
+                    dev_planes = devmem.download(rec)
+                    flows_d = np.ascontiguousarray(devmem.download(flw)).view(np.float64)[:, 0]
+                    _, flows_o = O.gc_step(Or, us, ts, fs, 0, 0, 0, None, cost_o, lab_o, coeff, lam, th, planes=dev_planes)
+                    worst_flow = max(worst_flow, float((np.abs(flows_d - flows_o) / np.maximum(np.abs(flows_o), 1e-3)).max()))
+                    n_moves += len(g)
+        cost_d, lab_d = E.pm_get()
+        diff = (lab_d != lab_o).any(axis=2)
+        same = ~diff & np.isfinite(cost_o) & (cost_o != O.COST_FOR_INVALID)
+        err = np.abs(cost_d.astype(np.float64) - cost_o) / (REL_TOL * np.maximum(np.abs(cost_o), ABS_FLOOR))
+        e_d = float(cost_d.astype(np.float64).sum()) + O.smoothness_cost(lab_d, coeff, lam, th)
+        e_o = float(cost_o.astype(np.float64).sum()) + O.smoothness_cost(lab_o, coeff, lam, th)
+        print(f"naive gc: {n_moves} moves, min-cut energy max rel err {worst_flow:.1e}, final cost max err/tol {err[same].max():.3f}, {int(diff.sum())} labels differ, "
+              f"energy {e_d:.4f} vs {e_o:.4f}")
+        assert n_moves > 200 and worst_flow <= 1e-5, worst_flow
+        # With the truncated image-based cost many proposals evaluate to EXACTLY the current cost in the oracle (both planes leave the
+        # valid range: same clamped samples); the minimum cut then takes the proposal (BK's free nodes count as SOURCE), while the
+        # device's FP32 filter separates the two costs by 1e-5 relative and keeps the current label -- same energy, another label.
+        # The parity gates are the minimum-cut energy of every move, the costs wherever the labels agree, and the total energy.
+        assert err[same].max() <= 1.0 and diff.mean() <= 2e-2, (err[same].max(), int(diff.sum()))
+        assert abs(e_d - e_o) <= 1e-6 * abs(e_o), (e_d, e_o)
+    finally:
+        for p in plans:
+            p.close()
+        E.close()
