@@ -217,6 +217,8 @@ public:
             check(lexp_pm_sweep_gc_iteration(sweep_, iteration, seed, &n));
             return n;
         }
+        // data term (sum of currentCost_) and StereoEnergy::computeSmoothnessCost of the device state (what the reference's Evaluator logs)
+        void energy(double& dataTerm, double& smoothnessTerm) const { check(lexp_energy(ctx_, mode_, &dataTerm, &smoothnessTerm)); }
         // blocking: the state back into the caller's continuous H x W mats
         void get(cv::Mat& currentCost, cv::Mat& currentLabeling) const {
             check(lexp_pm_get(ctx_, mode_, reinterpret_cast<float*>(currentCost.data), reinterpret_cast<lexp_plane*>(currentLabeling.data)));

@@ -1468,6 +1468,31 @@ int lexp_pairwise_terms(lexp_ctx* c, int mode, int n, const lexp_rect* regions, 
     return LEXP_OK;
 }
 
+int lexp_energy(lexp_ctx* c, int mode, double* data_term, double* smoothness_term) {
+    if (!c || mode < 0 || mode > 1 || (!data_term && !smoothness_term)) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    { int rc = ensure_coef(c, mode); if (rc) return rc; }
+    const int H = c->p.height, W = c->p.width;
+    const int nblocks = (int)(((size_t)H * W + 255) / 256);
+    double* d_part = nullptr;
+    LEXP_CUDA(cudaMalloc(&d_part, (2 * (size_t)nblocks + 2) * sizeof(double)));
+    LEXP_LAUNCH(lexp_energy_kernel, nblocks, 256, 0, c->stream, c->d_cur_cost[mode], c->d_cur_label[mode], c->d_coef[mode], d_part, H, W, c->sm_lambda, c->sm_th);
+    LEXP_LAUNCH(lexp_energy_finish, 1, 1, 0, c->stream, d_part, nblocks, d_part + 2 * (size_t)nblocks);
+    c->launches += 2;
+    double h[2] = {0.0, 0.0};
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_part + 2 * (size_t)nblocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("lexp_energy: ") + cudaGetErrorString(e));
+    if (data_term) *data_term = h[0];
+    if (smoothness_term) *smoothness_term = h[1];
+    return LEXP_OK;
+}
+
 int lexp_plan_gc_step(lexp_ctx* c, lexp_plan* pl, int mode, int kind, int m, uint64_t seed, const lexp_plane* planes, int planes_on_device,
                       lexp_plane* d_planes_out, double* d_flows_out) {
     if (!c || !pl || pl->ctx != c || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");

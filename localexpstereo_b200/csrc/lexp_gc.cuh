@@ -106,6 +106,43 @@ __device__ __forceinline__ float boundary_term(const float4 ls, const float4 lt,
 }
 __device__ __forceinline__ float coef_of(const float4 c, int d) { return d == 0 ? c.x : d == 1 ? c.y : d == 2 ? c.z : c.w; }
 
+// StereoEnergy::computeSmoothnessCost (StereoEnergy.h:165-199) and the data term next to it: per pixel the float sum of cost00 over the
+// forward neighbours in the reference's order (GE, EG, LG, GG: the `cv::add(sumCost, cost00_nb, sumCost)` loop), then sums in double --
+// block-wise here, the blocks added up in order by lexp_energy_finish (deterministic).  part[2 b] = data, part[2 b + 1] = smoothness.
+__global__ void lexp_energy_kernel(const float* __restrict__ cur_cost, const float4* __restrict__ cur_label, const float4* __restrict__ coef,
+                                   double* __restrict__ part, int H, int W, float lambda, float th) {
+    __shared__ double s_d[256], s_s[256];
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double dv = 0.0, sv = 0.0;
+    if (p < (long long)H * W) {
+        const int X = (int)(p % W), Y = (int)(p / W);
+        dv = (double)cur_cost[p];
+        const float4 L0p = cur_label[p];
+        const float4 cf = coef[p];
+        float sum = 0.0f;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int QX = X + gc_dx(d), QY = Y + gc_dy(d);
+            const bool inside = QX >= 0 && QX < W && QY < H;
+            const float4 L0q = inside ? cur_label[(size_t)QY * W + QX] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum = __fadd_rn(sum, pair_terms(L0p, L0q, L0p, X, Y, QX, QY, inside, coef_of(cf, d), lambda, th).c00);
+        }
+        sv = (double)sum;
+    }
+    s_d[threadIdx.x] = dv; s_s[threadIdx.x] = sv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < (int)blockDim.x; i++) { a += s_d[i]; b += s_s[i]; }
+        part[2 * (size_t)blockIdx.x] = a; part[2 * (size_t)blockIdx.x + 1] = b;
+    }
+}
+__global__ void lexp_energy_finish(const double* __restrict__ part, int nblocks, double* __restrict__ out2) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblocks; i++) { a += part[2 * (size_t)i]; b += part[2 * (size_t)i + 1]; }
+    out2[0] = a; out2[1] = b;
+}
+
 struct GcCell {       // one expansion move = one cell of the group (region = its sharedRegion)
     int x, y, w, h;   // region (image coordinates)
     long long node0;  // first node of the region in the scratch arrays

@@ -359,6 +359,13 @@ class CostVolumeEnergy:
             at += 12 * n
         return res
 
+    def energy(self, mode=0):
+        """(data term, smoothness term) of the device state of view `mode`: sum of currentCost_ and
+        StereoEnergy::computeSmoothnessCost(currentLabeling_m) (StereoEnergy.h:165-199)."""
+        d, s = C.c_double(0.0), C.c_double(0.0)
+        check(lib().lexp_energy(self._h, mode, C.byref(d), C.byref(s)))
+        return d.value, s.value
+
     # --- PatchMatch phase state: currentCost_[mode] / currentLabeling_[mode] resident on the device ------------------------
     def pm_begin(self, mode=0, cost=None, labeling=None):
         """FastGCStereo::run, :137: currentCost_ = INFINITY (or `cost`), currentLabeling_ = `labeling` (or zeros)."""

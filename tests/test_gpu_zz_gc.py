@@ -199,6 +199,9 @@ def test_gc_moves_never_raise_the_energy(devmem):
             S.gc_iteration(it, 77)
             cost, lab = S.get()
             e = float(cost.astype(np.float64).sum()) + O.smoothness_cost(lab, coeff, SMOOTH["lam"], SMOOTH["th_smooth"])
+            data_d, smooth_d = E.energy()      # lexp_energy: the same two sums on the device (computeSmoothnessCost, StereoEnergy.h:165-199)
+            assert abs(data_d - float(cost.astype(np.float64).sum())) <= 1e-9 * abs(data_d)
+            assert abs(smooth_d - O.smoothness_cost(lab, coeff, SMOOTH["lam"], SMOOTH["th_smooth"])) <= 1e-6 * max(abs(smooth_d), 1e-9)
             assert prev is None or e <= prev * (1 + 1e-6), (it, e, prev)
             prev = e
     finally:
