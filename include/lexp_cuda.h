@@ -265,6 +265,11 @@ LEXP_API int lexp_get_smooth_coeff(lexp_ctx* ctx, int mode, float* out8_host);
  * per call, back to back, float[3][4][region.height][region.width] = cost00, cost01, cost10 for the forward neighbours NB_GE, NB_EG,
  * NB_LG, NB_GG (the only ones the reference fills with onlyForward).  Blocking. */
 LEXP_API int lexp_pairwise_terms(lexp_ctx* ctx, int mode, int n, const lexp_rect* regions, const lexp_plane* planes, float* out_host);
+/* initCurrentFast for any energy kind (FastGCStereo.h:101-113): for every call of the plan, currentLabeling(targetRect) = planes[call] and
+ * currentCost(targetRect) = its unary cost (ComputeUnaryPotential on the call's filterRect).  The cost-volume energy has the same step fused
+ * into lexp_plan_pm_step(.., LEXP_PM_INIT); this form also serves the image-based energy (`-mode MiddV2`), whose iterations are all
+ * graph-cut iterations.  Asynchronous, stream ordered (host planes are staged before the call returns). */
+LEXP_API int lexp_plan_init_step(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes, int planes_on_device);
 /* Energy of the current state of view `mode`, as the reference logs it (Evaluator / PMStereoBase.h:266): *data_term = sum of currentCost_,
  * *smoothness_term = StereoEnergy::computeSmoothnessCost(currentLabeling_m) (StereoEnergy.h:165-199).  Either pointer may be NULL.  Blocking. */
 LEXP_API int lexp_energy(lexp_ctx* ctx, int mode, double* data_term, double* smoothness_term);

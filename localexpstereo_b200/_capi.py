@@ -81,6 +81,7 @@ SYMBOLS = {
     "lexp_set_smoothness": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float]),
     "lexp_get_smooth_coeff": (C.c_int, [_P, C.c_int, _P]),
     "lexp_pairwise_terms": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "lexp_plan_init_step": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "lexp_energy": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lexp_plan_gc_step": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, _P]),
     "lexp_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P, _P, _P, _P]),

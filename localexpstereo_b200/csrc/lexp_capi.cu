@@ -1468,6 +1468,32 @@ int lexp_pairwise_terms(lexp_ctx* c, int mode, int n, const lexp_rect* regions, 
     return LEXP_OK;
 }
 
+int lexp_plan_init_step(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* planes, int planes_on_device) {
+    if (!c || !pl || pl->ctx != c || !planes || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    c->chain_ok = false;   // copies / other kernels around the fused launch: it is an ordinary one
+    const int H = c->p.height, W = c->p.width;
+    if (!c->d_prop_cost[mode]) LEXP_CUDA(cudaMalloc(&c->d_prop_cost[mode], (size_t)H * W * sizeof(float)));
+    if (!pl->d_gc_cells) {
+        int rc = upload_gc_cells(c, pl->ncalls, pl->targ.data(), &pl->d_gc_cells, &pl->gc_nodes);
+        if (rc) return rc;
+        for (const lexp_rect& t : pl->targ) pl->gc_max_nodes = std::max(pl->gc_max_nodes, t.width * t.height);
+    }
+    const Plane4* dp = reinterpret_cast<const Plane4*>(planes);
+    if (!planes_on_device) {
+        LEXP_CUDA(cudaMemcpyAsync(pl->d_planes, planes, (size_t)pl->ncalls * sizeof(Plane4), cudaMemcpyHostToDevice, c->stream));
+        dp = pl->d_planes;
+    }
+    { int rc = run_plan(c, pl, mode, dp, c->d_prop_cost[mode], W, 0, 1); if (rc) return rc; }   // ComputeUnaryPotential (:111)
+    c->chain_ok = false;
+    LEXP_LAUNCH(lexp_gc_assign_kernel, pl->ncalls, 256, 0, c->stream, pl->d_gc_cells, dp, c->d_prop_cost[mode], c->d_cur_cost[mode], c->d_cur_label[mode], W);
+    LEXP_CUDA(cudaGetLastError());
+    c->launches++;
+    return LEXP_OK;
+}
+
 int lexp_energy(lexp_ctx* c, int mode, double* data_term, double* smoothness_term) {
     if (!c || mode < 0 || mode > 1 || (!data_term && !smoothness_term)) return fail(LEXP_ERR_INVALID, "bad argument");
     if (!c->d_cur_cost[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
@@ -1739,6 +1765,12 @@ int lexp_pm_sweep_init(lexp_pm_sweep* s, const lexp_plane* labels) {
     if (s->init_plan) {
         std::vector<lexp_plane> mine;
         for (int r : s->init_index) mine.push_back(labels[r]);
+        if (s->ctx->p.energy_kind != 0) {   // the image-based energy has no PatchMatch-phase kernel: unary launch + assignment (single GPU)
+            if (s->world != 1) return fail(LEXP_ERR_INVALID, "the image-based energy runs on one GPU");
+            rc = lexp_plan_init_step(s->ctx, s->init_plan, s->mode, mine.data(), 0);
+            if (rc == LEXP_OK) rc = lexp_sync(s->ctx);   // `mine` is local and pageable
+            return rc;
+        }
         rc = sweep_step(s, s->init_plan, 0, LEXP_PROP_LIST, 0, 0, mine.data(), LEXP_PM_INIT, true, true);
         if (rc) return rc;
     }

@@ -187,6 +187,22 @@ __global__ void lexp_gc_propose_kernel(const CallInfo* __restrict__ calls, int n
     if (planes_out) planes_out[i] = planes[i];
 }
 
+// initCurrentFast for any energy (FastGCStereo.h:101-113): `currentLabeling(unit) = label; ComputeUnaryPotential(.., currentCost(filterRegion), ..)`
+// -- after the fused kernel has written the unary costs of the cells' labels into the proposalCost image, every cell's region takes them
+// unconditionally.  One CTA per cell.  (The cost-volume energy has this fused into its PatchMatch-phase kernel, pm_mode 2.)
+__global__ void lexp_gc_assign_kernel(const GcCell* __restrict__ cells, const Plane4* __restrict__ planes, const float* __restrict__ prop_cost,
+                                      float* __restrict__ cur_cost, float4* __restrict__ cur_label, int W) {
+    const GcCell c = cells[blockIdx.x];
+    const Plane4 pl = planes[blockIdx.x];
+    const float4 l1 = make_float4(pl.a, pl.b, pl.c, pl.v);
+    const int N = c.w * c.h;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+        const size_t p = (size_t)(c.y + s / c.w) * W + (c.x + s % c.w);
+        cur_cost[p] = prop_cost[p];
+        cur_label[p] = l1;
+    }
+}
+
 struct GcParams {
     const GcCell* cells;
     const Plane4* planes;            // [ncells] the proposal of every cell (label1)

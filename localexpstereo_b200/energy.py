@@ -220,6 +220,16 @@ class Plan:
         check(lib().lexp_plan_pm_step_ex(self.energy._h, self._h, mode, int(step_index), int(kind), int(m), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                          ptr, int(planes_on_device), int(d_planes_out) or None, 1 if init else 0, int(publish_epoch), we, int(wait_mask)))
 
+    def init_step(self, planes, planes_on_device=False, mode=0):
+        """initCurrentFast (FastGCStereo.h:101-113) for any energy kind: label and unary cost of every call's targetRect, unconditionally."""
+        if planes_on_device:
+            ptr = int(planes)
+        else:
+            self._pl_keep = _plane_array(planes)
+            assert len(self._pl_keep) == self.num_calls
+            ptr = self._pl_keep.ctypes.data
+        check(lib().lexp_plan_init_step(self.energy._h, self._h, mode, ptr, int(planes_on_device)))
+
     def gc_step(self, kind, m=0, seed=0, planes=None, planes_on_device=False, d_planes_out=0, d_flows_out=0, mode=0):
         """One proposal step of FastGCStereo.h:41-60 with doGC == true for all cells of the plan, asynchronous: proposal, unary cost,
         FastGCStereo::expansionMoveBK (graph of :424-549 + its minimum cut) and the copyTo / setTo of the winners -- on the device.

@@ -278,6 +278,13 @@ class GCSweep(PMSweep):
         super().__init__(energy, unit_sizes, proposers, 0, 1, mode)
         energy.set_smoothness(lam, omega, th_smooth, epsilon)
 
+    def init(self, labels):
+        """initCurrentFast; the image-based energy has no PatchMatch-phase kernel and takes the unary launch + assignment form."""
+        if getattr(self.energy, "ENERGY_KIND", 0) == 0:
+            return super().init(labels)
+        if self.init_plan is not None:
+            self.init_plan.init_step(labels, mode=self.mode)
+
     def gc_iteration(self, iteration, seed, list_planes=None, planes_out=None, flows_out=None, layers=None):
         """list_planes / planes_out as PMSweep.iteration; flows_out: optional {(layer, group): device pointer of double [steps][n]}
         receiving the minimum-cut energy of every move; layers: restrict to these layer indices (timing).  Returns the number of

@@ -83,5 +83,10 @@ def test_emu_gc_result_does_not_depend_on_the_thread_schedule(devmem):
     assert (outs[0][2] != 0).any()
 
 
-def test_emu_gc_steps_on_the_image_based_energy(devmem):
-    _gc.test_gc_steps_on_the_image_based_energy(devmem)
+def test_emu_gc_iteration_on_the_image_based_energy(devmem):
+    _gc.test_gc_iteration_on_the_image_based_energy(devmem)
+
+
+@pytest.mark.parametrize("naive", [False, True])
+def test_emu_native_sweep_object_runs_the_same_graph_cut_iteration(naive):
+    _gc.test_native_sweep_object_runs_the_same_graph_cut_iteration(naive)

@@ -79,13 +79,20 @@ def test_pairwise_terms_equal_the_oracle_bit_for_bit():
         E.close()
 
 
-def run_gc_replay(devmem, H, W, D, windR, units, proposers, pm_iterations=1, gc_iterations=1, seed=1234, mode=0, smooth=SMOOTH, scene=None):
+def run_gc_replay(devmem, H, W, D, windR, units, proposers, pm_iterations=1, gc_iterations=1, seed=1234, mode=0, smooth=SMOOTH, scene=None,
+                  naive=False):
     import localexpstereo_b200 as L
     from localexpstereo_b200.sweep import GCSweep, expand_proposers, pm_seed
     imL, imR, volL, volR = scene if scene is not None else make_scene(H, W, D)
-    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
-    E = L.CostVolumeEnergy(imL, imR if mode else None, volL, volR if mode else None, prm, D - 1)
-    Or = O.CostVolumeEnergyOracle(imL, imR if mode else None, volL, volR if mode else None, windR, 1e-4, 0.5, D - 1)
+    if naive:   # the image-based energy of `-mode MiddV2` (no cost volume, no device PatchMatch phase: graph-cut iterations only)
+        assert pm_iterations == 0
+        prm = L.Parameters(lambda_=smooth["lam"], windR=windR, filterName="GF", filter_param1=1e-4)
+        E = L.NaiveStereoEnergy(imL, imR, prm, D - 1)
+        Or = O.NaiveStereoEnergyOracle(imL, imR, windR, 1e-4, prm.th_col, prm.th_grad, prm.alpha, D - 1)
+    else:
+        prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+        E = L.CostVolumeEnergy(imL, imR if mode else None, volL, volR if mode else None, prm, D - 1)
+        Or = O.CostVolumeEnergyOracle(imL, imR if mode else None, volL, volR if mode else None, windR, 1e-4, 0.5, D - 1)
     S = GCSweep(E, unit_sizes=units, proposers=proposers, mode=mode, **smooth)
     coeff = O.smoothness_coeff(imR if mode else imL, smooth["omega"], smooth["epsilon"])
     lam, th = smooth["lam"], smooth["th_smooth"]
@@ -231,68 +238,113 @@ def test_gc_replay_on_the_cones_crop(devmem):
     assert r["n_moves"] > 1000
 
 
-def test_gc_steps_on_the_image_based_energy(devmem):
-    """BASELINE.json configs[0] (`-mode MiddV2`): FastGCStereo with NaiveStereoEnergy -- the reference's own demo -- whose iterations
-    are all graph-cut iterations.  The device state is seeded from the oracle's initCurrentFast (the device PatchMatch phase is a
-    cost-volume path), then expansion moves with device-side proposals run on the image-based unary term (lambda = 20, main.cpp:72);
-    replayed through the oracle as above."""
+def test_gc_iteration_on_the_image_based_energy(devmem):
+    """BASELINE.json configs[0] (`-mode MiddV2`): FastGCStereo with NaiveStereoEnergy -- the reference's own demo -- whose iterations are
+    all graph-cut iterations (lambda = 20, layers 5 / 15: main.cpp:72,304-305).  Entirely on the device: initCurrentFast as a unary launch +
+    assignment (lexp_plan_init_step: this energy has no PatchMatch-phase kernel), then a graph-cut iteration with device-side proposals
+    on the image-based unary term.
+    With the truncated image-based cost many proposals evaluate to EXACTLY the current cost in the oracle (both planes leave the valid
+    range: same clamped samples); the minimum cut then takes the proposal (BK's free nodes count as SOURCE) while the device's FP32
+    filter separates the two costs by 1e-5 relative and keeps the current label -- same energy, another label, and a different graph for
+    every later move.  So here every proposal step is checked ON ITS OWN: the oracle starts each step from the device's state before
+    the step (downloaded), evaluates the device's planes, and must arrive at the device's state after the step -- minimum-cut energies
+    to 1e-5, costs wherever the labels agree, labels up to those ties."""
     import lexp_golden
     import localexpstereo_b200 as L
-    from localexpstereo_b200.sweep import pm_seed
+    from localexpstereo_b200.sweep import GCSweep, expand_proposers, pm_seed
     G = lexp_golden.load()
     imL, imR = G["imL"], G["imR"]
     H, W = imL.shape[:2]
     D, windR = 64, 20
-    prm = L.Parameters(lambda_=20, windR=windR, filterName="GF", filter_param1=1e-4)
+    lam, omega, th, eps = 20.0, 10.0, 1.0, 0.01
+    prm = L.Parameters(lambda_=lam, windR=windR, filterName="GF", filter_param1=1e-4)
     E = L.NaiveStereoEnergy(imL, imR, prm, D - 1)
     Or = O.NaiveStereoEnergyOracle(imL, imR, windR, 1e-4, prm.th_col, prm.th_grad, prm.alpha, D - 1)
-    lam, omega, th, eps = 20.0, 10.0, 1.0, 0.01
-    E.set_smoothness(lam, omega, th, eps)
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1)]]
+    S = GCSweep(E, unit_sizes=[5, 15], proposers=props, lam=lam, omega=omega, th_smooth=th, epsilon=eps)
     coeff = O.smoothness_coeff(imL, omega, eps)
-    plans = []
     try:
-        lm = L.LayerManager(W, H, windR)
-        lay0 = lm.addLayer(5)                                   # main.cpp:304
         rng = O.CvRNG(8)
-        units0 = lay0.unitRegions
-        labels = np.stack([O.create_random_label(rng, u[0] + rng.uniform_int(0, u[2]), u[1] + rng.uniform_int(0, u[3]), 0.0, D - 1.0) for u in units0])
+        labels = np.stack([O.create_random_label(rng, u[0] + rng.uniform_int(0, u[2]), u[1] + rng.uniform_int(0, u[3]), 0.0, D - 1.0) for u in S.init_units])
+        S.begin()
+        S.init(labels)
+        cost_d, lab_d = S.get()
         cost_o, lab_o = np.full((H, W), np.inf, np.float32), np.zeros((H, W, 4), np.float32)
-        fr0 = [(max(x - windR, 0), max(y - windR, 0), min(x + w + windR, W) - max(x - windR, 0), min(y + h + windR, H) - max(y - windR, 0)) for (x, y, w, h) in units0]
-        O.pm_step(Or, units0, units0, fr0, 0, 0, 0, None, cost_o, lab_o, planes=labels, init=True)
-        E.pm_begin(0, cost_o, lab_o)
-        n_moves, worst_flow = 0, 0.0
-        lay1 = lm.addLayer(15)                                  # main.cpp:305
-        for li, (lay, gis, steps) in enumerate([(lay0, (0, 7), [(L.PROP_EXPANSION, 0), (L.PROP_RANDOM, 0)]), (lay1, (2, len(lay1.disjointRegionSets) - 1), [(L.PROP_EXPANSION, 0)])]):
-            for gi in gis:
-                g = lay.disjointRegionSets[gi]
-                us = [lay.unitRegions[r] for r in g]; ts = [lay.sharedRegions[r] for r in g]; fs = [lay.filterRegions[r] for r in g]
-                plan = E.make_plan(fs, ts); plans.append(plan)
-                plan.set_units(us, [1000 * li + r for r in g])
-                for k, (kind, m) in enumerate(steps):
-                    rec, flw = devmem.zeros((len(g), 4)), devmem.zeros((len(g), 2))
-                    plan.gc_step(kind, m, pm_seed(5, 0, 0, li, gi, k), d_planes_out=devmem.ptr(rec), d_flows_out=devmem.ptr(flw))
-                    E.sync()
-                    dev_planes = devmem.download(rec)
-                    flows_d = np.ascontiguousarray(devmem.download(flw)).view(np.float64)[:, 0]
-                    _, flows_o = O.gc_step(Or, us, ts, fs, 0, 0, 0, None, cost_o, lab_o, coeff, lam, th, planes=dev_planes)
-                    worst_flow = max(worst_flow, float((np.abs(flows_d - flows_o) / np.maximum(np.abs(flows_o), 1e-3)).max()))
-                    n_moves += len(g)
-        cost_d, lab_d = E.pm_get()
-        diff = (lab_d != lab_o).any(axis=2)
-        same = ~diff & np.isfinite(cost_o) & (cost_o != O.COST_FOR_INVALID)
-        err = np.abs(cost_d.astype(np.float64) - cost_o) / (REL_TOL * np.maximum(np.abs(cost_o), ABS_FLOOR))
-        e_d = float(cost_d.astype(np.float64).sum()) + O.smoothness_cost(lab_d, coeff, lam, th)
-        e_o = float(cost_o.astype(np.float64).sum()) + O.smoothness_cost(lab_o, coeff, lam, th)
-        print(f"naive gc: {n_moves} moves, min-cut energy max rel err {worst_flow:.1e}, final cost max err/tol {err[same].max():.3f}, {int(diff.sum())} labels differ, "
-              f"energy {e_d:.4f} vs {e_o:.4f}")
-        assert n_moves > 200 and worst_flow <= 1e-5, worst_flow
-        # With the truncated image-based cost many proposals evaluate to EXACTLY the current cost in the oracle (both planes leave the
-        # valid range: same clamped samples); the minimum cut then takes the proposal (BK's free nodes count as SOURCE), while the
-        # device's FP32 filter separates the two costs by 1e-5 relative and keeps the current label -- same energy, another label.
-        # The parity gates are the minimum-cut energy of every move, the costs wherever the labels agree, and the total energy.
-        assert err[same].max() <= 1.0 and diff.mean() <= 2e-2, (err[same].max(), int(diff.sum()))
-        assert abs(e_d - e_o) <= 1e-6 * abs(e_o), (e_d, e_o)
+        R = windR
+        fr0 = [(max(x - R, 0), max(y - R, 0), min(x + w + R, W) - max(x - R, 0), min(y + h + R, H) - max(y - R, 0)) for (x, y, w, h) in S.init_units]
+        O.pm_step(Or, S.init_units, S.init_units, fr0, 0, 0, 0, None, cost_o, lab_o, planes=labels, init=True)
+        assert np.array_equal(lab_d, lab_o) and np.array_equal(cost_d == O.COST_FOR_INVALID, cost_o == O.COST_FOR_INVALID)
+        ok = cost_o != O.COST_FOR_INVALID
+        assert (np.abs(cost_d[ok] - cost_o[ok]) <= REL_TOL * np.maximum(np.abs(cost_o[ok]), ABS_FLOOR)).all()
+        n_moves = n_diff = 0
+        worst_flow = worst_cost = 0.0
+        cell_base = np.cumsum([0] + [len(l.unitRegions) for l in S.lm.layers])
+        for g in S.groups:
+            if g.group not in (0, 5, len(S.lm.layers[g.layer].disjointRegionSets) - 1):   # three groups per layer (emulation time)
+                continue
+            lay = S.lm.layers[g.layer]
+            us = [lay.unitRegions[r] for r in g.cells]; ts = [lay.sharedRegions[r] for r in g.cells]; fs = [lay.filterRegions[r] for r in g.cells]
+            for k, (kind, m) in enumerate(expand_proposers(props[g.layer], 0, D - 1.0)):
+                pre_c, pre_l = S.get()
+                rec, flw = devmem.zeros((g.plan.num_calls, 4)), devmem.zeros((g.plan.num_calls, 2))
+                g.plan.gc_step(kind, m, pm_seed(3, 0, 0, g.layer, g.group, k), d_planes_out=devmem.ptr(rec), d_flows_out=devmem.ptr(flw))
+                E.sync()
+                post_c, post_l = S.get()
+                dev_planes = devmem.download(rec)
+                flows_d = np.ascontiguousarray(devmem.download(flw)).view(np.float64)[:, 0]
+                for i, u in enumerate(us):   # the device's proposer against the oracle's, on the same state
+                    mine = O.pm_proposal(kind, m, O.pm_rng_state(pm_seed(3, 0, 0, g.layer, g.group, k), cell_base[g.layer] + g.cells[i]), pre_l, u, 0.0, D - 1.0)
+                    assert np.allclose(mine, dev_planes[i], rtol=2e-6, atol=1e-6)
+                oc, ol = pre_c.copy(), pre_l.copy()
+                _, flows_o = O.gc_step(Or, us, ts, fs, 0, 0, 0, None, oc, ol, coeff, lam, th, planes=dev_planes)
+                worst_flow = max(worst_flow, float((np.abs(flows_d - flows_o) / np.maximum(np.abs(flows_o), 1e-3)).max()))
+                diff = (post_l != ol).any(axis=2)
+                same = ~diff & (oc != O.COST_FOR_INVALID)
+                assert np.array_equal((post_c == O.COST_FOR_INVALID)[~diff], (oc == O.COST_FOR_INVALID)[~diff])
+                worst_cost = max(worst_cost, float((np.abs(post_c[same].astype(np.float64) - oc[same]) / (REL_TOL * np.maximum(np.abs(oc[same]), ABS_FLOOR))).max()))
+                n_diff += int(diff.sum()); n_moves += len(us)
+        print(f"naive gc: {n_moves} moves, min-cut energy max rel err {worst_flow:.1e}, cost max err/tol {worst_cost:.3f}, {n_diff} label ties")
+        assert n_moves > 300 and worst_flow <= 1e-5 and worst_cost <= 1.0, (n_moves, worst_flow, worst_cost)
+        assert n_diff <= 2e-2 * H * W, n_diff
     finally:
-        for p in plans:
-            p.close()
+        S.close()
         E.close()
+
+
+@pytest.mark.parametrize("naive", [False, True])
+def test_native_sweep_object_runs_the_same_graph_cut_iteration(naive):
+    """lexp_pm_sweep_init / lexp_pm_sweep_gc_iteration (what CudaCostVolumeEnergy::PatchMatchPhase::init / graphCutIteration call) against
+    the Python schedule (sweep.GCSweep): same seeds, same launches -- bit-identical state.  For the image-based energy the native init
+    takes the unary launch + assignment form (lexp_plan_init_step)."""
+    import lexp_golden
+    import localexpstereo_b200 as L
+    from localexpstereo_b200.sweep import GCSweep, NativePMSweep
+    G = lexp_golden.load()
+    if naive:
+        imL, imR, D, windR = G["imL"][:72, :96], G["imR"][:72, :96], 32, 20
+        mk = lambda: L.NaiveStereoEnergy(imL, imR, L.Parameters(lambda_=20, windR=windR, filterName="GF", filter_param1=1e-4), D - 1)
+        units, smooth = [5, 15], dict(lam=20.0, omega=10.0, th_smooth=1.0, epsilon=0.01)
+    else:
+        H, W, D, windR = 64, 88, 12, 12
+        imL, _, volL, _ = make_scene(H, W, D, seed=2)
+        mk = lambda: L.CostVolumeEnergy(imL, None, volL, None, L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5), D - 1)
+        units, smooth = [8, 22], SMOOTH
+    props = [[(L.PROP_EXPANSION, 1), (L.PROP_RANDOM, 1)], [(L.PROP_EXPANSION, 1)]]
+    Ea, Eb = mk(), mk()
+    try:
+        A = GCSweep(Ea, unit_sizes=units, proposers=props, **smooth)
+        Eb.set_smoothness(**smooth)
+        B = NativePMSweep(Eb, unit_sizes=units, proposers=props)
+        rng = O.CvRNG(6)
+        labels = np.stack([O.create_random_label(rng, u[0], u[1], 0.0, D - 1.0) for u in A.init_units])
+        assert B.num_init_labels == len(labels)
+        A.begin(); B.begin()
+        A.init(labels); B.init(labels)
+        ca, la = A.get(); cb, lb = B.get()
+        assert np.array_equal(ca, cb) and np.array_equal(la, lb)
+        assert A.gc_iteration(0, 99) == B.gc_iteration(0, 99)
+        ca, la = A.get(); cb, lb = B.get()
+        assert np.array_equal(ca, cb) and np.array_equal(la, lb) and not np.array_equal(la[..., 2], labels[0][2] * np.ones_like(la[..., 2]))
+        A.close(); B.close()
+    finally:
+        Ea.close(); Eb.close()
