@@ -321,7 +321,7 @@ def test_native_sweep_object_runs_the_same_graph_cut_iteration(naive):
     from localexpstereo_b200.sweep import GCSweep, NativePMSweep
     G = lexp_golden.load()
     if naive:
-        imL, imR, D, windR = G["imL"][:72, :96], G["imR"][:72, :96], 32, 20
+        imL, imR, D, windR = G["imL"][:56, :72], G["imR"][:56, :72], 24, 20
         mk = lambda: L.NaiveStereoEnergy(imL, imR, L.Parameters(lambda_=20, windR=windR, filterName="GF", filter_param1=1e-4), D - 1)
         units, smooth = [5, 15], dict(lam=20.0, omega=10.0, th_smooth=1.0, epsilon=0.01)
     else:
