@@ -4,7 +4,10 @@
 //   f-2  StereoEnergy::initSmoothnessCoeff            (StereoEnergy.h:131-163)  -> lexp_smooth_coeff_kernel
 //        StereoEnergy::computeSmoothnessTermsExpansion (StereoEnergy.h:398-453)  -> pair_terms() / lexp_pairwise_kernel
 //        StereoEnergy::computeSmoothnessTerm           (StereoEnergy.h:234-239)  -> boundary_term()
-//   f-3  FastGCStereo::expansionMoveBK                 (FastGCStereo.h:411-597)  -> lexp_gc_move_kernel
+//        StereoEnergy::computeSmoothnessCost           (StereoEnergy.h:165-199)  -> lexp_energy_kernel
+//   f-3  FastGCStereo::expansionMoveBK                 (FastGCStereo.h:411-597)  -> gc_node_* steps, run by lexp_gc_move_kernel (one CTA per
+//                                                                                   cell) or lexp_gc_phase_kernel (large cells, all SMs)
+//        FastGCStereo::initCurrentFast                 (FastGCStereo.h:101-113)  -> lexp_gc_assign_kernel (any energy kind)
 //        (graph construction as there; the minimum cut itself is computed by a deterministic push-relabel instead of the un-vendored
 //         Boykov-Kolmogorov library -- the segmentation BK reports, `what_segment() == SOURCE`, is the complement of the set of nodes
 //         from which the sink is reachable in the residual graph of a maximum flow, which is the same set for every maximum flow)
