@@ -72,6 +72,16 @@ public:
         check(lexp_set_volume_host(ctx_, 0, volL.ptr<float>()));   // float[D][H][W], continuous (main.cpp:353-354)
         check(lexp_set_volume_host(ctx_, 1, volR.ptr<float>()));
     }
+    // The cost volumes straight from the reference's files (main.cpp:353-370: `im0.acrt`, raw float[ndisp][H][W]), streamed in slabs with
+    // fillOutOfView fused in; without `im1.acrt` the right volume is derived from the left file (convertVolumeL2R + both fills, :363-367).
+    // Replaces `loadMatBinary + fillOutOfView (+ convertVolumeL2R)` and the 2 x 17 GB of host memory they need at 4K.
+    CudaCostVolumeEnergy(const cv::Mat imL, const cv::Mat imR, const std::string& volLFile, const std::string& volRFileOrEmpty, int ndisp,
+                         Parameters params, float MAX_DISPARITY, float MIN_DISPARITY = 0, float MAX_VDISPARITY = 0, int device = 0)
+        : CudaCostVolumeEnergy(imL, imR, params, MAX_DISPARITY, MIN_DISPARITY, MAX_VDISPARITY, device, 0, ndisp) {
+        check(lexp_set_volume_file(ctx_, 0, volLFile.c_str(), LEXP_VOL_FILL));
+        if (volRFileOrEmpty.empty()) check(lexp_set_volume_file(ctx_, 1, volLFile.c_str(), LEXP_VOL_RIGHT_FROM_LEFT));
+        else check(lexp_set_volume_file(ctx_, 1, volRFileOrEmpty.c_str(), LEXP_VOL_FILL));
+    }
     ~CudaCostVolumeEnergy() override { lexp_destroy(ctx_); }
     CudaCostVolumeEnergy(const CudaCostVolumeEnergy&) = delete;
     CudaCostVolumeEnergy& operator=(const CudaCostVolumeEnergy&) = delete;
@@ -216,6 +226,12 @@ public:
             int n = 0;
             check(lexp_pm_sweep_gc_iteration(sweep_, iteration, seed, &n));
             return n;
+        }
+        // computeDisparities(currentLabeling_[mode]) of the device state (StereoEnergy.h:269-272) into a continuous H x W CV_32F mat, and
+        // the PFM file main.cpp:319,410 writes from it (cvutils::io::save_pfm_file, byte-identical)
+        void disparities(cv::Mat& disp) const { check(lexp_get_disparities(ctx_, mode_, reinterpret_cast<float*>(disp.data))); }
+        static void savePfm(const std::string& file, const cv::Mat& disp) {
+            check(lexp_save_pfm(file.c_str(), reinterpret_cast<const float*>(disp.data), disp.cols, disp.rows, (ptrdiff_t)disp.step));
         }
         // data term (sum of currentCost_) and StereoEnergy::computeSmoothnessCost of the device state (what the reference's Evaluator logs)
         void energy(double& dataTerm, double& smoothnessTerm) const { check(lexp_energy(ctx_, mode_, &dataTerm, &smoothnessTerm)); }

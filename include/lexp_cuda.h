@@ -270,6 +270,14 @@ LEXP_API int lexp_pairwise_terms(lexp_ctx* ctx, int mode, int n, const lexp_rect
  * into lexp_plan_pm_step(.., LEXP_PM_INIT); this form also serves the image-based energy (`-mode MiddV2`), whose iterations are all
  * graph-cut iterations.  Asynchronous, stream ordered (host planes are staged before the call returns). */
 LEXP_API int lexp_plan_init_step(lexp_ctx* ctx, lexp_plan* plan, int mode, const lexp_plane* planes, int planes_on_device);
+/* The reference's cost-volume file, raw float[ndisp][height][width] without a header (`loadMatBinary(.., "im0.acrt", volL, false)`,
+ * main.cpp:353-358,364), streamed from disk in slabs through page-locked buffers with the volume preparation `transform`
+ * (LEXP_VOL_*) fused in as for lexp_set_volume_host_ex: the 17 GB volume of the 4K configuration never exists in host memory. */
+LEXP_API int lexp_set_volume_file(lexp_ctx* ctx, int mode, const char* path, int transform);
+/* StereoEnergy::computeDisparities(currentLabeling_[mode]) (StereoEnergy.h:269-272): float[H][W] into host memory; blocking. */
+LEXP_API int lexp_get_disparities(lexp_ctx* ctx, int mode, float* out_host);
+/* cvutils::io::save_pfm_file (Utilities.hpp:84-137) for a 1-channel float image (disp0.pfm of main.cpp:319,410): byte-identical file. */
+LEXP_API int lexp_save_pfm(const char* path, const float* image, int width, int height, ptrdiff_t step_bytes);
 /* Energy of the current state of view `mode`, as the reference logs it (Evaluator / PMStereoBase.h:266): *data_term = sum of currentCost_,
  * *smoothness_term = StereoEnergy::computeSmoothnessCost(currentLabeling_m) (StereoEnergy.h:165-199).  Either pointer may be NULL.  Blocking. */
 LEXP_API int lexp_energy(lexp_ctx* ctx, int mode, double* data_term, double* smoothness_term);

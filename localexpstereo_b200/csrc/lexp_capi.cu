@@ -640,6 +640,56 @@ int lexp_set_volume_host_ex(lexp_ctx* c, int mode, const float* vol, int transfo
     return rc ? rc : rc2;
 }
 
+// The cost-volume file of the reference: raw float[D][H][W] without a header (`loadMatBinary(inputDir + "im0.acrt", volL, false)`,
+// main.cpp:353-358,364; Utilities.hpp:173-201).  Streamed: slabs of disparities are read into two page-locked buffers in turn and uploaded
+// on the context's stream while the next one is being read -- the 17 GB volume of the 4K configuration never has to exist in host memory.
+int lexp_set_volume_file(lexp_ctx* c, int mode, const char* path, int transform) {
+    if (!c || !path || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    { int rc = check_transform(mode, transform); if (rc) return rc; }
+    const int D = c->p.ndisp, H = c->p.height, W = c->p.width;
+    const size_t plane = (size_t)H * W;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(LEXP_ERR_INVALID, std::string("cost volume file not found: ") + path);
+    if (fseek(f, 0, SEEK_END) != 0 || (unsigned long long)ftell(f) != (unsigned long long)D * plane * sizeof(float)) {
+        fclose(f);
+        return fail(LEXP_ERR_INVALID, std::string("cost volume file is not float[D][H][W] of this context's size: ") + path);
+    }
+    rewind(f);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
+    if (cudaSetDevice(c->p.device) != cudaSuccess) { fclose(f); return fail(LEXP_ERR_CUDA, "cudaSetDevice"); }
+    int slab = (int)std::max<size_t>(8, std::min<size_t>((size_t)D, ((size_t)env_int("LEXP_UPLOAD_SLAB_MB", 512) << 20) / (plane * sizeof(float))));
+    slab = std::min(D, (slab + 7) / 8 * 8);
+    int* d_flag = nullptr;
+    { int rc = alloc_volume(c, mode, &d_flag); if (rc) { fclose(f); return rc; } }
+    float* stage = nullptr;
+    float* host[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    int rc = LEXP_OK;
+    cudaError_t e = cudaMalloc(&stage, (size_t)slab * plane * sizeof(float));
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaHostAlloc(&host[i], (size_t)slab * plane * sizeof(float), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    }
+    const int tk = kernel_transform(mode, transform);
+    for (int d_lo = 0, i = 0; d_lo < D && e == cudaSuccess && rc == LEXP_OK; d_lo += slab, i ^= 1) {
+        const int nd = std::min(slab, D - d_lo);
+        e = cudaEventSynchronize(copied[i]);   // the upload that last read this host buffer has finished (no-op the first time)
+        if (e != cudaSuccess) break;
+        if (fread(host[i], sizeof(float), (size_t)nd * plane, f) != (size_t)nd * plane) { rc = fail(LEXP_ERR_INVALID, std::string("short read: ") + path); break; }
+        e = cudaMemcpyAsync(stage, host[i], (size_t)nd * plane * sizeof(float), cudaMemcpyHostToDevice, c->stream);   // behind the previous slab's re-layout
+        if (e == cudaSuccess) e = cudaEventRecord(copied[i], c->stream);
+        if (e != cudaSuccess) break;
+        rc = ingest_slab(c, mode, stage, d_lo, nd, tk, d_flag);
+    }
+    fclose(f);
+    if (e != cudaSuccess && rc == LEXP_OK) rc = fail(LEXP_ERR_CUDA, std::string("volume file upload: ") + cudaGetErrorString(e));
+    const int rc2 = finish_volume(c, mode, d_flag);   // synchronises the stream
+    cudaFree(stage);
+    for (int i = 0; i < 2; i++) { if (host[i]) cudaFreeHost(host[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
+    return rc ? rc : rc2;
+}
+
 int lexp_set_volume_device_ex(lexp_ctx* c, int mode, const float* vol, int transform) {
     if (!c || !vol || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
     { int rc = check_transform(mode, transform); if (rc) return rc; }
@@ -1492,6 +1542,40 @@ int lexp_plan_init_step(lexp_ctx* c, lexp_plan* pl, int mode, const lexp_plane* 
     LEXP_CUDA(cudaGetLastError());
     c->launches++;
     return LEXP_OK;
+}
+
+int lexp_get_disparities(lexp_ctx* c, int mode, float* out_host) {
+    if (!c || !out_host || mode < 0 || mode > 1) return fail(LEXP_ERR_INVALID, "bad argument");
+    if (!c->d_cur_label[mode]) return fail(LEXP_ERR_STATE, "lexp_pm_begin has not been called for this view");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->chain_ok = false;   // copies / other kernels follow on the stream: the next fused launch is an ordinary one
+    LEXP_CUDA(cudaSetDevice(c->p.device));
+    const int H = c->p.height, W = c->p.width;
+    float* d = nullptr;
+    LEXP_CUDA(cudaMalloc(&d, (size_t)H * W * sizeof(float)));
+    dim3 blk(128), grd((W + 127) / 128, H);
+    LEXP_LAUNCH(lexp_disparity_kernel, grd, blk, 0, c->stream, c->d_cur_label[mode], d, H, W);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LEXP_ERR_CUDA, std::string("lexp_get_disparities: ") + cudaGetErrorString(e));
+    return LEXP_OK;
+}
+
+// cvutils::io::save_pfm_file (Utilities.hpp:84-137) for a 1-channel float image: "Pf\n<w> <h>\n<-1/255 as %lf>\n", rows bottom-up, native
+// (little-endian) floats -- the file main.cpp:319,410 writes as disp0.pfm.
+int lexp_save_pfm(const char* path, const float* image, int width, int height, ptrdiff_t step_bytes) {
+    if (!path || !image || width <= 0 || height <= 0 || step_bytes < (ptrdiff_t)width * 4) return fail(LEXP_ERR_INVALID, "bad argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(LEXP_ERR_INVALID, std::string("cannot open for writing: ") + path);
+    fprintf(f, "Pf\n%d %d\n%lf\n", width, height, -1.0 / 255.0);
+    bool ok = true;
+    for (int y = height - 1; y >= 0 && ok; y--)   // pfm stores rows in inverse order
+        ok = fwrite(reinterpret_cast<const char*>(image) + (ptrdiff_t)y * step_bytes, sizeof(float), (size_t)width, f) == (size_t)width;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? LEXP_OK : fail(LEXP_ERR_INVALID, std::string("write failed: ") + path);
 }
 
 int lexp_energy(lexp_ctx* c, int mode, double* data_term, double* smoothness_term) {

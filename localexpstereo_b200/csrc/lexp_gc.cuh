@@ -146,6 +146,15 @@ __global__ void lexp_energy_finish(const double* __restrict__ part, int nblocks,
     out2[0] = a; out2[1] = b;
 }
 
+// StereoEnergy::computeDisparities(labeling) = channelDot(coordinates, labeling) (StereoEnergy.h:269-272): the disparity map the
+// reference writes as disp0.pfm (main.cpp:319,410)
+__global__ void lexp_disparity_kernel(const float4* __restrict__ cur_label, float* __restrict__ disp, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t p = (size_t)y * W + x;
+    disp[p] = gc_disp(cur_label[p], (float)x, (float)y);
+}
+
 struct GcCell {       // one expansion move = one cell of the group (region = its sharedRegion)
     int x, y, w, h;   // region (image coordinates)
     long long node0;  // first node of the region in the scratch arrays

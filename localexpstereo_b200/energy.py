@@ -130,6 +130,12 @@ def host_register(array: np.ndarray):
     check(lib().lexp_host_register(array.ctypes.data, array.nbytes))
 
 
+def save_pfm_file(path, image: np.ndarray):
+    """cvutils::io::save_pfm_file (Utilities.hpp:84-137) for a 1-channel float32 image."""
+    assert image.dtype == np.float32 and image.ndim == 2 and image.strides[1] == 4
+    check(lib().lexp_save_pfm(str(path).encode(), image.ctypes.data, image.shape[1], image.shape[0], image.strides[0]))
+
+
 def host_unregister(array: np.ndarray):
     check(lib().lexp_host_unregister(array.ctypes.data))
 
@@ -306,6 +312,10 @@ class CostVolumeEnergy:
             assert tuple(vol.shape) == (self.ndisp, self.height, self.width) and vol.is_contiguous() and vol.is_cuda
             check(lib().lexp_set_volume_device_ex(self._h, mode, vol.data_ptr(), int(transform)))
 
+    def set_volume_file(self, mode, path, transform=VOL_PLAIN):
+        """The reference's `.acrt` cost-volume file (raw float[D][H][W], main.cpp:353-364), streamed from disk in slabs."""
+        check(lib().lexp_set_volume_file(self._h, mode, str(path).encode(), int(transform)))
+
     def set_volume(self, mode, vol, transform=VOL_PLAIN):
         """(Re)load the cost volume of a view with the reference's volume preparation fused into the upload (main.cpp:146-199):
         VOL_FILL = fillOutOfView(vol, mode); VOL_RIGHT_FROM_LEFT (mode 1) = the right volume derived from the LEFT one,
@@ -368,6 +378,12 @@ class CostVolumeEnergy:
             res.append((blk[0], blk[1], blk[2]))
             at += 12 * n
         return res
+
+    def computeDisparities(self, mode=0) -> np.ndarray:
+        """StereoEnergy::computeDisparities of the device state (StereoEnergy.h:269-272)."""
+        out = np.empty((self.height, self.width), np.float32)
+        check(lib().lexp_get_disparities(self._h, mode, out.ctypes.data))
+        return out
 
     def energy(self, mode=0):
         """(data term, smoothness term) of the device state of view `mode`: sum of currentCost_ and

@@ -56,6 +56,10 @@ def lib():
         L.ref_gc_group.argtypes = [vp, C.c_int, C.c_int, ip, ip, ip, C.c_int, ip, ip, C.c_int, fp, C.c_int, u64p, C.c_int, fp, fp, fp, ip, dp, C.c_int]
         L.ref_smoothness_cost.argtypes = [vp, C.c_int, fp]
         L.ref_smoothness_cost.restype = C.c_double
+        L.ref_save_pfm.argtypes = [C.c_char_p, fp, C.c_int, C.c_int]
+        L.ref_read_pfm.argtypes = [C.c_char_p, fp, C.c_int, C.c_int]
+        L.ref_load_acrt.argtypes = [C.c_char_p, fp, C.c_int, C.c_int, C.c_int]
+        L.ref_disparities.argtypes = [vp, fp, fp]
         _lib = L
     return _lib
 
@@ -228,6 +232,14 @@ class RefEnergy:
             raise RuntimeError(lib().ref_last_error().decode())
         return out, steps, flows
 
+    def disparities(self, labeling):
+        """StereoEnergy::computeDisparities (StereoEnergy.h:269-272)."""
+        lab = _f(labeling)
+        out = np.empty((self.H, self.W), np.float32)
+        if lib().ref_disparities(self.h, _p(lab, C.c_float), _p(out, C.c_float)):
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out
+
     def create_random_label(self, x, y):
         out = np.empty(4, np.float32)
         lib().ref_create_random_label(self.h, int(x), int(y), _p(out, C.c_float))
@@ -351,3 +363,25 @@ def shim_grid_mincut(tr, cap):
     L.shim_grid_mincut.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_ubyte)]
     f = L.shim_grid_mincut(w, h, _p(tr, C.c_float), _p(cap, C.c_float), _p(mask, C.c_ubyte))
     return mask.astype(bool), float(f)
+
+
+def save_pfm(path, img):
+    """cvutils::io::save_pfm_file of the reference (Utilities.hpp:84-137)."""
+    a = _f(img)
+    if lib().ref_save_pfm(str(path).encode(), _p(a, C.c_float), a.shape[0], a.shape[1]):
+        raise RuntimeError(lib().ref_last_error().decode())
+
+
+def read_pfm(path, H, W):
+    out = np.empty((H, W), np.float32)
+    if lib().ref_read_pfm(str(path).encode(), _p(out, C.c_float), H, W):
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out
+
+
+def load_acrt(path, D, H, W):
+    """cvutils::io::loadMatBinary(path, vol, false) as main.cpp:353-358 reads im0.acrt."""
+    out = np.empty((D, H, W), np.float32)
+    if lib().ref_load_acrt(str(path).encode(), _p(out, C.c_float), D, H, W):
+        raise RuntimeError("loadMatBinary failed")
+    return out

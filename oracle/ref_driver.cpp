@@ -394,6 +394,35 @@ double shim_grid_mincut(int w, int h, const float* tr, const float* cap, uchar* 
     for (int s = 0; s < w * h; s++) mask[s] = g.what_segment(s) == G::SOURCE;
     return f;
 }
+// ---- file formats either side of the path: the reference's own cvutils::io functions --------------------
+int ref_save_pfm(const char* path, const float* img, int H, int W) {
+    try { cvutils::io::save_pfm_file(path, cv::Mat(H, W, CV_32F, (void*)img)); return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int ref_read_pfm(const char* path, float* out, int H, int W) {
+    try {
+        cv::Mat m = cvutils::io::read_pfm_file(path);
+        if (m.empty() || m.rows != H || m.cols != W || m.channels() != 1) { g_err = "read_pfm_file: absent or wrong shape"; return -1; }
+        for (int y = 0; y < H; y++) memcpy(out + (size_t)y * W, m.ptr<float>(y), (size_t)W * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// loadMatBinary(path, vol, readHeader = false) into a D x H x W float volume, as main.cpp:353-358
+int ref_load_acrt(const char* path, float* out, int D, int H, int W) {
+    try {
+        int sizes[] = {D, H, W};
+        cv::Mat vol(3, sizes, CV_32F, out);
+        return cvutils::io::loadMatBinary(path, vol, false) ? 0 : -1;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// StereoEnergy::computeDisparities(labeling) (StereoEnergy.h:269-272); labeling [H][W][4], out [H][W]
+int ref_disparities(void* h, const float* labeling, float* out) {
+    try {
+        ref_ctx* c = (ref_ctx*)h;
+        cv::Mat d = c->energy->computeDisparities(cv::Mat(c->H, c->W, CV_32FC4, (void*)labeling));
+        for (int y = 0; y < c->H; y++) memcpy(out + (size_t)y * c->W, d.ptr<float>(y), (size_t)c->W * sizeof(float));
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // total energy of a labeling as the reference evaluates it: sum of currentCost + computeSmoothnessCost (StereoEnergy.h:165-199)
 double ref_smoothness_cost(void* h, int mode, const float* labeling) {
     try {

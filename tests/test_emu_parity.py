@@ -54,6 +54,7 @@ def devmem():
 test_emu_device_image_and_tile_outputs = _p.test_device_image_and_tile_outputs
 test_emu_host_tile_output = _p.test_host_tile_output
 test_emu_partially_registered_output = _p.test_partially_registered_output_takes_the_staged_path
+test_emu_volume_file_disparity_map_and_pfm = _p.test_volume_file_disparity_map_and_pfm
 test_emu_stats_match_oracle = _p.test_stats_match_oracle
 test_emu_cells_of_a_layer = _p.test_cells_of_a_layer
 test_emu_single_cell_virtuals = _p.test_single_cell_virtuals

@@ -429,3 +429,64 @@ def test_volume_preparation_on_the_device(devmem):
     finally:
         for E in (ref, got, dev):
             E.close()
+
+
+def test_volume_file_disparity_map_and_pfm(tmp_path):
+    """SURVEY.md 8 f-4, the formats either side of the path: the reference's cost-volume file (`im0.acrt`: raw float[D][H][W],
+    main.cpp:353-364) streamed from disk in several slabs with the volume preparation fused in must give exactly the costs of the
+    same array uploaded from memory; computeDisparities of the device state (StereoEnergy.h:269-272) and the PFM file the
+    reference writes from it (main.cpp:319,410; Utilities.hpp:84-137: header "Pf / w h / -1/255", rows bottom-up)."""
+    import os
+    import localexpstereo_b200 as L
+    H, W, D, windR = 66, 91, 19, 12
+    imL, imR, volL, _ = make_scene(H, W, D, seed=12)
+    path = os.path.join(str(tmp_path), "im0.acrt")
+    volL.tofile(path)
+    prm = L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5)
+    old = os.environ.get("LEXP_UPLOAD_SLAB_MB")
+    os.environ["LEXP_UPLOAD_SLAB_MB"] = "0"      # 8 disparities per slab: three slabs, the last one ragged
+    A = L.CostVolumeEnergy(imL, imR, None, None, prm, D - 1)
+    B = L.CostVolumeEnergy(imL, imR, None, None, prm, D - 1)
+    try:
+        A.set_volume(0, volL, L.VOL_FILL); A.set_volume(1, volL, L.VOL_RIGHT_FROM_LEFT)
+        B.set_volume_file(0, path, L.VOL_FILL); B.set_volume_file(1, path, L.VOL_RIGHT_FROM_LEFT)
+    finally:
+        if old is None:
+            os.environ.pop("LEXP_UPLOAD_SLAB_MB")
+        else:
+            os.environ["LEXP_UPLOAD_SLAB_MB"] = old
+    try:
+        lay = L.LayerManager(W, H, windR).addLayer(9)
+        rng = O.CvRNG(2)
+        for mode in (0, 1):
+            g = lay.disjointRegionSets[2 + mode]
+            planes = random_planes(rng, [lay.unitRegions[r] for r in g], D)
+            fr, tr = [lay.filterRegions[r] for r in g], [lay.sharedRegions[r] for r in g]
+            ia, ib = np.full((H, W), -7.0, np.float32), np.full((H, W), -7.0, np.float32)
+            A.ComputeUnaryPotentialBatch(fr, tr, ia, planes, mode=mode)
+            B.ComputeUnaryPotentialBatch(fr, tr, ib, planes, mode=mode)
+            assert np.array_equal(ia, ib) and (ia != -7.0).any()
+        with open(os.path.join(str(tmp_path), "short.acrt"), "wb") as f:
+            f.write(volL.tobytes()[:-4])
+        with pytest.raises(L.LexpError):
+            B.set_volume_file(0, os.path.join(str(tmp_path), "short.acrt"))          # not float[D][H][W] of this size
+        with pytest.raises(L.LexpError):
+            B.set_volume_file(0, os.path.join(str(tmp_path), "absent.acrt"))
+        # disparity map of a labeling + the PFM file
+        lab = np.zeros((H, W, 4), np.float32)
+        for y in range(0, H, 5):
+            for x in range(0, W, 7):
+                lab[y:y + 5, x:x + 7] = O.create_random_label(rng, x, y, 0.0, D - 1.0)
+        B.pm_begin(0, np.zeros((H, W), np.float32), lab)
+        disp = B.computeDisparities(0)
+        xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+        want = ((xs * lab[..., 0] + ys * lab[..., 1]) + lab[..., 2]) + np.float32(0) * lab[..., 3]   # channelDot(coordinates, labeling)
+        assert np.array_equal(disp, want)
+        pfm = os.path.join(str(tmp_path), "disp0.pfm")
+        L.save_pfm_file(pfm, disp)
+        raw = open(pfm, "rb").read()
+        head = ("Pf\n%d %d\n%f\n" % (W, H, -1.0 / 255.0)).encode()
+        assert raw.startswith(head) and len(raw) == len(head) + H * W * 4
+        assert np.array_equal(np.frombuffer(raw[len(head):], np.float32).reshape(H, W)[::-1], disp)
+    finally:
+        A.close(); B.close()

@@ -471,3 +471,46 @@ def test_maxflow_stand_in_on_random_graphs():
             assert abs(cut - flow) <= 1e-4 * max(1.0, flow), (h, w, trial, cut, flow)
             m2, f2 = R.shim_grid_mincut(tr, cap)
             assert abs(f2 - flow) <= 1e-5 * max(1.0, flow) and np.array_equal(m2, mask), (h, w, trial)
+
+
+def test_file_formats_equal_the_reference(tmp_path):
+    """The product's PFM writer, volume-file reader and disparity map against the reference's own cvutils::io::save_pfm_file /
+    read_pfm_file / loadMatBinary and StereoEnergy::computeDisparities (compiled in oracle/_ref): byte-identical PFM file, the file
+    the reference reads back, the same volume from the same `.acrt` bytes.  (Host-side functions of the product library: the
+    emulator build of the same source is loaded here; no kernel runs except the disparity map's.)"""
+    import os
+    from emu import emu_lib
+    import localexpstereo_b200 as L
+    H, W, D, windR = 40, 56, 9, 8
+    imL, imR, volL, volR = make_scene(H, W, D, seed=3)
+    ref = R.RefEnergy(imL, imR, volL, volR, windR=windR, eps=1e-4, th_col=0.5, max_disp=D - 1, min_disp=0.0, kind=0)
+    with emu_lib.emulated():
+        E = L.CostVolumeEnergy(imL, None, volL, None, L.Parameters(windR=windR, filterName="GF", filter_param1=1e-4, th_col=0.5), D - 1)
+        try:
+            rng = O.CvRNG(9)
+            lab = np.zeros((H, W, 4), np.float32)
+            for y in range(0, H, 4):
+                for x in range(0, W, 8):
+                    lab[y:y + 4, x:x + 8] = O.create_random_label(rng, x, y, 0.0, D - 1.0)
+            E.pm_begin(0, np.zeros((H, W), np.float32), lab)
+            disp = E.computeDisparities(0)
+            assert np.array_equal(disp, ref.disparities(lab))
+            a, b = os.path.join(str(tmp_path), "a.pfm"), os.path.join(str(tmp_path), "b.pfm")
+            L.save_pfm_file(a, disp)
+            R.save_pfm(b, disp)
+            assert open(a, "rb").read() == open(b, "rb").read()
+            assert np.array_equal(R.read_pfm(a, H, W), disp)
+            acrt = os.path.join(str(tmp_path), "im0.acrt")
+            volL.tofile(acrt)
+            assert np.array_equal(R.load_acrt(acrt, D, H, W), volL)          # what the reference would have loaded
+            E.set_volume_file(0, acrt)                                          # and what the product ingests from the same bytes
+            f, t = (4, 4, 40, 30), (10, 8, 20, 16)
+            p = np.array([0.02, -0.01, 3.5, 0], np.float32)
+            img = np.zeros((H, W), np.float32)
+            E.ComputeUnaryPotential(f, t, img[f[1]:f[1] + f[3], f[0]:f[0] + f[2]], p)
+            got = img[t[1]:t[1] + t[3], t[0]:t[0] + t[2]]
+            want = ref.unary_target(f, t, p)
+            assert np.allclose(got, want, rtol=1e-4, atol=1e-7)
+        finally:
+            E.close()
+            ref.close()
